@@ -1,0 +1,324 @@
+// pvp_context.cu -- context, error reporting, pose helpers, .bin I/O and memory helpers of
+// libpvp_b200.so (the parts of include/pvp_b200.h that launch no hot-path kernel).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cmath>
+
+#include "pvp_internal.h"
+
+namespace pvp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
+    return e == cudaErrorMemoryAllocation ? PVP_ERR_NOMEM : PVP_ERR_CUDA;
+}
+
+int ensure_queue(pvp_ctx *ctx, unsigned long long entries)
+{
+    if (ctx->queue.capacity >= entries) return PVP_OK;
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->queue.pix) cudaFree(ctx->queue.pix);
+    if (ctx->queue.diff) cudaFree(ctx->queue.diff);
+    if (ctx->queue.pair) cudaFree(ctx->queue.pair);
+    ctx->queue = {nullptr, nullptr, nullptr, 0};
+    PVP_CUDA(cudaMalloc(&ctx->queue.pix, entries * sizeof(uint32_t)));
+    PVP_CUDA(cudaMalloc(&ctx->queue.diff, entries * sizeof(float)));
+    PVP_CUDA(cudaMalloc(&ctx->queue.pair, entries * sizeof(uint16_t)));
+    ctx->queue.capacity = entries;
+    return PVP_OK;
+}
+
+int ensure_pairs(pvp_ctx *ctx, int n_pairs)
+{
+    if (ctx->pairs_cap >= n_pairs) return PVP_OK;
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pairs_dev) cudaFree(ctx->pairs_dev);
+    if (ctx->pairs_pinned) cudaFreeHost(ctx->pairs_pinned);
+    ctx->pairs_dev = nullptr; ctx->pairs_pinned = nullptr; ctx->pairs_cap = 0;
+    int cap = n_pairs < 64 ? 64 : n_pairs;
+    PVP_CUDA(cudaMalloc(&ctx->pairs_dev, sizeof(pvp_pair) * (size_t)cap));
+    PVP_CUDA(cudaMallocHost(&ctx->pairs_pinned, sizeof(pvp_pair) * (size_t)cap));
+    ctx->pairs_cap = cap;
+    return PVP_OK;
+}
+
+// Pair table -> device through the pinned staging buffer; the event keeps a later call from
+// overwriting the staging area while this copy is still in flight.
+int upload_pairs(pvp_ctx *ctx, const pvp_pair *pairs, int n_pairs)
+{
+    int rc = ensure_pairs(ctx, n_pairs);
+    if (rc) return rc;
+    PVP_CUDA(cudaEventSynchronize(ctx->ev_pairs));
+    memcpy(ctx->pairs_pinned, pairs, sizeof(pvp_pair) * (size_t)n_pairs);
+    PVP_CUDA(cudaMemcpyAsync(ctx->pairs_dev, ctx->pairs_pinned, sizeof(pvp_pair) * (size_t)n_pairs,
+                             cudaMemcpyHostToDevice, ctx->stream));
+    PVP_CUDA(cudaEventRecord(ctx->ev_pairs, ctx->stream));
+    return PVP_OK;
+}
+
+}  // namespace pvp
+
+using namespace pvp;
+
+extern "C" {
+
+int pvp_version(void) { return PVP_VERSION; }
+
+const char *pvp_last_error(void) { return g_err; }
+
+int pvp_ctx_create(int device, void *stream, pvp_ctx **out)
+{
+    PVP_REQUIRE(out != nullptr, "pvp_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("pvp_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return PVP_ERR_CUDA;
+    }
+    PVP_REQUIRE(device >= 0 && device < ndev, "pvp_ctx_create: device %d out of range [0,%d)", device, ndev);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    PVP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("pvp_ctx_create: device %d is sm_%d%d; libpvp_b200 is built for sm_100a only", device, prop.major,
+                  prop.minor);
+        return PVP_ERR_CUDA;
+    }
+    pvp_ctx *ctx = new (std::nothrow) pvp_ctx();
+    if (!ctx) { set_error("pvp_ctx_create: out of host memory"); return PVP_ERR_NOMEM; }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        PVP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    PVP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    PVP_CUDA(cudaEventCreate(&ctx->ev_a));
+    PVP_CUDA(cudaEventCreate(&ctx->ev_b));
+    for (int i = 0; i < 2; ++i) {
+        PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+        PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+    }
+    PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_pairs, cudaEventDisableTiming));
+    PVP_CUDA(cudaMalloc(&ctx->ctl_dev, sizeof(Ctl)));
+    PVP_CUDA(cudaMemset(ctx->ctl_dev, 0, sizeof(Ctl)));
+    *out = ctx;
+    return PVP_OK;
+}
+
+int pvp_ctx_destroy(pvp_ctx *ctx)
+{
+    if (!ctx) return PVP_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->queue.pix) cudaFree(ctx->queue.pix);
+    if (ctx->queue.diff) cudaFree(ctx->queue.diff);
+    if (ctx->queue.pair) cudaFree(ctx->queue.pair);
+    if (ctx->pairs_dev) cudaFree(ctx->pairs_dev);
+    if (ctx->pairs_pinned) cudaFreeHost(ctx->pairs_pinned);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
+        cudaEventDestroy(ctx->ev_copy[i]);
+        cudaEventDestroy(ctx->ev_done[i]);
+    }
+    if (ctx->ctl_dev) cudaFree(ctx->ctl_dev);
+    cudaEventDestroy(ctx->ev_a);
+    cudaEventDestroy(ctx->ev_b);
+    cudaEventDestroy(ctx->ev_pairs);
+    cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PVP_OK;
+}
+
+int pvp_ctx_set_stream(pvp_ctx *ctx, void *stream)
+{
+    PVP_REQUIRE(ctx != nullptr, "pvp_ctx_set_stream: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        PVP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return PVP_OK;
+}
+
+int pvp_ctx_sync(pvp_ctx *ctx)
+{
+    PVP_REQUIRE(ctx != nullptr, "pvp_ctx_sync: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PVP_OK;
+}
+
+int pvp_ctx_set_option(pvp_ctx *ctx, const char *key, int64_t value)
+{
+    PVP_REQUIRE(ctx != nullptr && key != nullptr, "pvp_ctx_set_option: NULL argument");
+    if (!strcmp(key, "dda_variant")) ctx->opt_dda_variant = value;
+    else if (!strcmp(key, "max_queue")) { PVP_REQUIRE(value >= 1024, "max_queue must be >= 1024"); ctx->opt_max_queue = value; }
+    else if (!strcmp(key, "ctas_per_sm")) ctx->opt_ctas_per_sm = value;
+    else { set_error("pvp_ctx_set_option: unknown key '%s'", key); return PVP_ERR_INVALID; }
+    return PVP_OK;
+}
+
+int pvp_dev_malloc(pvp_ctx *ctx, size_t bytes, void **out_dev)
+{
+    PVP_REQUIRE(ctx && out_dev, "pvp_dev_malloc: NULL argument");
+    DeviceGuard guard(ctx->device);
+    PVP_CUDA(cudaMalloc(out_dev, bytes));
+    return PVP_OK;
+}
+
+int pvp_dev_free(pvp_ctx *ctx, void *dev)
+{
+    PVP_REQUIRE(ctx != nullptr, "pvp_dev_free: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    PVP_CUDA(cudaFree(dev));
+    return PVP_OK;
+}
+
+int pvp_dev_memset(pvp_ctx *ctx, void *dev, int value, size_t bytes)
+{
+    PVP_REQUIRE(ctx != nullptr, "pvp_dev_memset: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    PVP_CUDA(cudaMemsetAsync(dev, value, bytes, ctx->stream));
+    return PVP_OK;
+}
+
+int pvp_memcpy_h2d(pvp_ctx *ctx, void *dst_dev, const void *src, size_t bytes)
+{
+    PVP_REQUIRE(ctx != nullptr, "pvp_memcpy_h2d: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    PVP_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PVP_OK;
+}
+
+int pvp_memcpy_d2h(pvp_ctx *ctx, void *dst, const void *src_dev, size_t bytes)
+{
+    PVP_REQUIRE(ctx != nullptr, "pvp_memcpy_d2h: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    PVP_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PVP_OK;
+}
+
+int pvp_host_alloc_pinned(size_t bytes, void **out)
+{
+    PVP_REQUIRE(out != nullptr, "pvp_host_alloc_pinned: out is NULL");
+    PVP_CUDA(cudaMallocHost(out, bytes));
+    return PVP_OK;
+}
+
+int pvp_host_free_pinned(void *p)
+{
+    PVP_CUDA(cudaFreeHost(p));
+    return PVP_OK;
+}
+
+// ---- pose: host code, glibc libm, fp32, no contraction (x86-64 baseline ISA has no FMA) ----
+
+static inline float h_deg2rad(float deg) { return deg * 3.14159265358979323846f / 180.0f; }  // ray_voxel.cpp:60-62
+
+// R = Rz(yaw) * Ry(roll) * Rx(pitch), each 3x3 product a left-to-right 3-term sum (ray_voxel.cpp:84-135).
+void pvp_rotation_matrix(float yaw_deg, float pitch_deg, float roll_deg, float R[9])
+{
+    const float y = h_deg2rad(yaw_deg), p = h_deg2rad(pitch_deg), r = h_deg2rad(roll_deg);
+    const float cy = cosf(y), sy = sinf(y), cr = cosf(r), sr = sinf(r), cp = cosf(p), sp = sinf(p);
+    const float A[9] = {cy, -sy, 0.f, sy, cy, 0.f, 0.f, 0.f, 1.f};     // about z by yaw
+    const float B[9] = {cr, 0.f, sr, 0.f, 1.f, 0.f, -sr, 0.f, cr};     // about y by ROLL
+    const float Cm[9] = {1.f, 0.f, 0.f, 0.f, cp, -sp, 0.f, sp, cp};    // about x by PITCH
+    float AB[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            volatile float s = A[i * 3] * B[j];
+            s = s + A[i * 3 + 1] * B[3 + j];
+            s = s + A[i * 3 + 2] * B[6 + j];
+            AB[i * 3 + j] = s;
+        }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            volatile float s = AB[i * 3] * Cm[j];
+            s = s + AB[i * 3 + 1] * Cm[3 + j];
+            s = s + AB[i * 3 + 2] * Cm[6 + j];
+            R[i * 3 + j] = s;
+        }
+}
+
+float pvp_focal_length(float fov_degrees, int width)
+{
+    const float fov_rad = h_deg2rad(fov_degrees);
+    return ((float)width * 0.5f) / tanf(fov_rad * 0.5f);  // ray_voxel.cpp:491
+}
+
+// ---- .bin ------------------------------------------------------------------
+
+size_t pvp_grid_bytes(const pvp_grid_desc *g)
+{
+    if (!g || g->n <= 0 || g->slab_hi < g->slab_lo) return 0;
+    size_t elem = g->accum_mode == PVP_ACCUM_FIXED ? 8 : 4;
+    return (size_t)(g->slab_hi - g->slab_lo) * (size_t)g->n * (size_t)g->n * elem;
+}
+
+int pvp_write_bin(const char *path, int32_t n, float voxel_size, const float *grid_host)
+{
+    PVP_REQUIRE(path && grid_host && n > 0, "pvp_write_bin: bad argument");
+    FILE *f = fopen(path, "wb");
+    if (!f) { set_error("Cannot open output file: %s", path); return PVP_ERR_IO; }
+    size_t count = (size_t)n * n * n;
+    bool ok = fwrite(&n, sizeof(int32_t), 1, f) == 1 && fwrite(&voxel_size, sizeof(float), 1, f) == 1 &&
+              fwrite(grid_host, sizeof(float), count, f) == count;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { set_error("pvp_write_bin: short write to %s", path); return PVP_ERR_IO; }
+    return PVP_OK;
+}
+
+int pvp_read_bin_header(const char *path, int32_t *n, float *voxel_size)
+{
+    PVP_REQUIRE(path && n && voxel_size, "pvp_read_bin_header: NULL argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_error("pvp_read_bin_header: cannot open %s", path); return PVP_ERR_IO; }
+    bool ok = fread(n, sizeof(int32_t), 1, f) == 1 && fread(voxel_size, sizeof(float), 1, f) == 1;
+    fclose(f);
+    if (!ok || *n <= 0) { set_error("pvp_read_bin_header: %s is not a voxel grid .bin", path); return PVP_ERR_FORMAT; }
+    return PVP_OK;
+}
+
+int pvp_read_bin(const char *path, int32_t n, float *grid_host)
+{
+    PVP_REQUIRE(path && grid_host && n > 0, "pvp_read_bin: bad argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_error("pvp_read_bin: cannot open %s", path); return PVP_ERR_IO; }
+    int32_t fn = 0; float vs = 0.f;
+    size_t count = (size_t)n * n * n;
+    bool ok = fread(&fn, sizeof(int32_t), 1, f) == 1 && fread(&vs, sizeof(float), 1, f) == 1 && fn == n &&
+              fread(grid_host, sizeof(float), count, f) == count;
+    fclose(f);
+    if (!ok) { set_error("pvp_read_bin: %s truncated or N mismatch", path); return PVP_ERR_FORMAT; }
+    return PVP_OK;
+}
+
+}  // extern "C"

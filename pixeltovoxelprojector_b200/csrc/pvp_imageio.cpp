@@ -1,0 +1,231 @@
+// pvp_imageio.cpp -- host image decode feeding K1: the stbi_load(path,&w,&h,&c,1) call of
+// load_image_gray (ray_voxel.cpp:195) WITHOUT the unseeded noise of :206-215.
+//
+// stb_image is an un-vendored, un-pinned dependency of the reference.  This is a
+// from-scratch decoder for the lossless formats, following stb_image's PUBLISHED conversion
+// rules so the gray bytes are the ones the reference would see:
+//   - colour -> gray:   y = (77 r + 150 g + 29 b) >> 8  (integer, alpha ignored)
+//   - 16-bit -> 8-bit:  v >> 8, applied after the colour conversion
+//   - gray bit depths 1/2/4: scaled by 255/85/17
+// Formats: binary PNM (P5, P6; maxval <= 65535) and non-interlaced PNG (all colour types, 8/16
+// bit and sub-byte gray/palette).  Anything else (JPEG, BMP, interlaced PNG ...) fails to load,
+// which the pipeline treats like the reference treats a failed stbi_load: the frame is skipped
+// (ray_voxel.cpp:470-473).  JPEG parity is unpinned by design (stb's IDCT != libjpeg).
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <vector>
+
+#include "pvp_internal.h"
+
+namespace {
+
+struct Decoded {
+    int w = 0, h = 0;
+    std::vector<uint8_t> gray;
+};
+
+bool read_file(const char *path, std::vector<uint8_t> &out)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (n <= 0) { fclose(f); return false; }
+    out.resize((size_t)n);
+    bool ok = fread(out.data(), 1, (size_t)n, f) == (size_t)n;
+    fclose(f);
+    return ok;
+}
+
+inline uint8_t luma8(unsigned r, unsigned g, unsigned b) { return (uint8_t)((r * 77 + g * 150 + b * 29) >> 8); }
+inline uint16_t luma16(unsigned r, unsigned g, unsigned b) { return (uint16_t)((r * 77 + g * 150 + b * 29) >> 8); }
+
+// ---- PNM -------------------------------------------------------------------
+bool pnm_token(const std::vector<uint8_t> &d, size_t &pos, int &val)
+{
+    for (;;) {
+        while (pos < d.size() && (d[pos] == ' ' || d[pos] == '\t' || d[pos] == '\n' || d[pos] == '\r')) ++pos;
+        if (pos < d.size() && d[pos] == '#') { while (pos < d.size() && d[pos] != '\n') ++pos; continue; }
+        break;
+    }
+    if (pos >= d.size() || d[pos] < '0' || d[pos] > '9') return false;
+    long v = 0;
+    while (pos < d.size() && d[pos] >= '0' && d[pos] <= '9') { v = v * 10 + (d[pos] - '0'); if (v > (1 << 30)) return false; ++pos; }
+    val = (int)v;
+    return true;
+}
+
+bool decode_pnm(const std::vector<uint8_t> &d, Decoded &out)
+{
+    if (d.size() < 7 || d[0] != 'P' || (d[1] != '5' && d[1] != '6')) return false;
+    const int comp = d[1] == '5' ? 1 : 3;
+    size_t pos = 2;
+    int w, h, maxv;
+    if (!pnm_token(d, pos, w) || !pnm_token(d, pos, h) || !pnm_token(d, pos, maxv)) return false;
+    if (w <= 0 || h <= 0 || maxv <= 0 || maxv > 65535) return false;
+    ++pos;  // the single whitespace byte after maxval
+    const int bps = maxv > 255 ? 2 : 1;
+    const size_t npx = (size_t)w * h;
+    if (pos + npx * comp * bps > d.size()) return false;
+    const uint8_t *p = d.data() + pos;
+    out.w = w; out.h = h; out.gray.resize(npx);
+    if (bps == 1) {
+        if (comp == 1) memcpy(out.gray.data(), p, npx);
+        else for (size_t i = 0; i < npx; ++i) out.gray[i] = luma8(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+    } else {  // big-endian 16 bit
+        auto rd = [&](size_t k) { return (unsigned)((p[2 * k] << 8) | p[2 * k + 1]); };
+        if (comp == 1) for (size_t i = 0; i < npx; ++i) out.gray[i] = (uint8_t)(rd(i) >> 8);
+        else for (size_t i = 0; i < npx; ++i) out.gray[i] = (uint8_t)(luma16(rd(3 * i), rd(3 * i + 1), rd(3 * i + 2)) >> 8);
+    }
+    return true;
+}
+
+// ---- PNG (non-interlaced) ----------------------------------------------------
+inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+inline int paeth(int a, int b, int c)
+{
+    int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    if (pa <= pb && pa <= pc) return a;
+    return pb <= pc ? b : c;
+}
+
+bool decode_png(const std::vector<uint8_t> &d, Decoded &out)
+{
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (d.size() < 33 || memcmp(d.data(), sig, 8) != 0) return false;
+    size_t pos = 8;
+    uint32_t w = 0, h = 0;
+    int depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, pal;
+    bool have_ihdr = false;
+    while (pos + 12 <= d.size()) {
+        const uint32_t len = be32(&d[pos]);
+        const uint8_t *type = &d[pos + 4];
+        if (pos + 12 + (size_t)len > d.size()) return false;
+        const uint8_t *body = &d[pos + 8];
+        if (!memcmp(type, "IHDR", 4)) {
+            if (len != 13) return false;
+            w = be32(body); h = be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12];
+            if (body[10] != 0 || body[11] != 0) return false;
+            have_ihdr = true;
+        } else if (!memcmp(type, "PLTE", 4)) {
+            pal.assign(body, body + len);
+        } else if (!memcmp(type, "IDAT", 4)) {
+            idat.insert(idat.end(), body, body + len);
+        } else if (!memcmp(type, "IEND", 4)) {
+            break;
+        }
+        pos += 12 + (size_t)len;
+    }
+    if (!have_ihdr || w == 0 || h == 0 || w > (1u << 24) || h > (1u << 24) || interlace != 0) return false;
+    int chans;
+    switch (ctype) {
+        case 0: chans = 1; break;
+        case 2: chans = 3; break;
+        case 3: chans = 1; break;
+        case 4: chans = 2; break;
+        case 6: chans = 4; break;
+        default: return false;
+    }
+    if (!(depth == 8 || depth == 16 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4)))) return false;
+    if (ctype == 3 && (depth == 16 || pal.size() < 3)) return false;
+    const size_t bpp_bits = (size_t)chans * depth;
+    const size_t stride = ((size_t)w * bpp_bits + 7) / 8;
+    const size_t fbpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;  // filter byte distance
+    std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+    uLongf raw_len = (uLongf)raw.size();
+    if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) return false;
+
+    // un-filter in place (row r occupies raw[r*(stride+1)+1 ...])
+    std::vector<uint8_t> zero(stride, 0);
+    for (size_t r = 0; r < h; ++r) {
+        uint8_t *cur = &raw[r * (stride + 1) + 1];
+        const uint8_t *up = r ? &raw[(r - 1) * (stride + 1) + 1] : zero.data();
+        const int ft = raw[r * (stride + 1)];
+        for (size_t i = 0; i < stride; ++i) {
+            const int a = i >= fbpp ? cur[i - fbpp] : 0, b = up[i], c = i >= fbpp ? up[i - fbpp] : 0;
+            int x = cur[i];
+            switch (ft) {
+                case 0: break;
+                case 1: x += a; break;
+                case 2: x += b; break;
+                case 3: x += (a + b) >> 1; break;
+                case 4: x += paeth(a, b, c); break;
+                default: return false;
+            }
+            cur[i] = (uint8_t)x;
+        }
+    }
+
+    out.w = (int)w; out.h = (int)h; out.gray.resize((size_t)w * h);
+    const int npal = (int)(pal.size() / 3);
+    static const int scale_tab[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
+    for (size_t r = 0; r < h; ++r) {
+        const uint8_t *row = &raw[r * (stride + 1) + 1];
+        uint8_t *o = &out.gray[r * (size_t)w];
+        for (size_t x = 0; x < w; ++x) {
+            if (depth == 16) {
+                auto rd = [&](size_t k) { return (unsigned)((row[2 * k] << 8) | row[2 * k + 1]); };
+                unsigned y;
+                if (chans <= 2) y = rd(x * chans);
+                else y = luma16(rd(x * chans), rd(x * chans + 1), rd(x * chans + 2));
+                o[x] = (uint8_t)(y >> 8);
+            } else if (depth == 8) {
+                if (ctype == 3) {
+                    int idx = row[x];
+                    if (idx >= npal) idx = 0;
+                    o[x] = luma8(pal[3 * idx], pal[3 * idx + 1], pal[3 * idx + 2]);
+                } else if (chans <= 2) {
+                    o[x] = row[x * chans];
+                } else {
+                    o[x] = luma8(row[x * chans], row[x * chans + 1], row[x * chans + 2]);
+                }
+            } else {  // 1/2/4 bit gray or palette
+                const size_t bit = x * depth;
+                int v = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+                if (ctype == 3) {
+                    if (v >= npal) v = 0;
+                    o[x] = luma8(pal[3 * v], pal[3 * v + 1], pal[3 * v + 2]);
+                } else {
+                    o[x] = (uint8_t)(v * scale_tab[depth]);
+                }
+            }
+        }
+    }
+    return true;
+}
+
+bool decode_any(const char *path, Decoded &out)
+{
+    std::vector<uint8_t> data;
+    if (!read_file(path, data)) return false;
+    if (data.size() >= 2 && data[0] == 'P') return decode_pnm(data, out);
+    return decode_png(data, out);
+}
+
+}  // namespace
+
+extern "C" {
+
+// Decode `path` to 8-bit gray.  out may be NULL (size query).  Returns PVP_ERR_IO when the file
+// cannot be decoded (the reference's `stbi_load` == NULL case).
+int pvp_load_image_gray(const char *path, uint8_t *out, int64_t cap, int *width, int *height)
+{
+    if (!path || !width || !height) { pvp::set_error("pvp_load_image_gray: NULL argument"); return PVP_ERR_INVALID; }
+    Decoded d;
+    if (!decode_any(path, d)) { pvp::set_error("Failed to load image: %s", path); return PVP_ERR_IO; }
+    *width = d.w; *height = d.h;
+    if (out) {
+        if (cap < (int64_t)d.gray.size()) { pvp::set_error("pvp_load_image_gray: buffer too small"); return PVP_ERR_INVALID; }
+        memcpy(out, d.gray.data(), d.gray.size());
+    }
+    return PVP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// pvp_internal.h -- host-side context shared by the translation units of libpvp_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/pvp_b200.h"
+
+namespace pvp {
+
+// Device-resident control block of the ray queue and the run counters.
+struct Ctl {
+    unsigned long long count;      // entries appended by the compaction kernel
+    unsigned long long head;       // next entry to be claimed by the traversal kernel
+    unsigned long long n_rays;
+    unsigned long long n_steps;
+    unsigned long long n_written;
+    unsigned long long n_atomics;
+    unsigned long long img_rays;   // path B
+    unsigned long long img_samples;
+};
+
+// SoA ray queue: one entry per motion pixel of the batch.
+struct Queue {
+    uint32_t *pix;    // v*width + u
+    float *diff;      // |prev - curr| (the value accumulated, ray_voxel.cpp:500)
+    uint16_t *pair;   // index into the batch's pair table
+    unsigned long long capacity;
+};
+
+}  // namespace pvp
+
+struct pvp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // H2D staging for the *_host entry points
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+
+    pvp::Ctl *ctl_dev = nullptr;
+    pvp::Queue queue = {nullptr, nullptr, nullptr, 0};
+    pvp_pair *pairs_dev = nullptr;
+    pvp_pair *pairs_pinned = nullptr;
+    int pairs_cap = 0;
+    cudaEvent_t ev_pairs = nullptr;  // guards reuse of pairs_pinned
+
+    void *stage_dev[2] = {nullptr, nullptr};  // frame staging buffers for *_host
+    size_t stage_bytes = 0;
+
+    // options (pvp_ctx_set_option)
+    int64_t opt_dda_variant = 0;       // 0 = default
+    int64_t opt_max_queue = 64ll << 20;  // ray-queue capacity in entries per batch
+    int64_t opt_ctas_per_sm = 0;       // 0 = occupancy query
+};
+
+namespace pvp {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define PVP_CUDA(expr)                                                              \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return pvp::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define PVP_REQUIRE(cond, ...)        \
+    do {                              \
+        if (!(cond)) {                \
+            pvp::set_error(__VA_ARGS__); \
+            return PVP_ERR_INVALID;   \
+        }                             \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensure_queue(pvp_ctx *ctx, unsigned long long entries);
+int ensure_pairs(pvp_ctx *ctx, int n_pairs);
+int upload_pairs(pvp_ctx *ctx, const pvp_pair *pairs, int n_pairs);
+
+}  // namespace pvp

@@ -1,0 +1,516 @@
+// pvp_motion.cu -- path A of libpvp_b200.so: the per-frame motion pipeline of ray_voxel.cpp
+// (:484-531) as sm_100a kernels.
+//
+//   K1  motion_compact_kernel   diff / threshold (:236-255, :496-503) fused with compaction of
+//                               the motion pixels into an SoA ray queue.  HBM-bound: 2 B/pixel
+//                               (u8) read with 16 B vector loads, ~10 B written per motion pixel.
+//   K2  dda_accumulate_kernel   persistent warps pull 32-entry chunks from the queue, build the
+//                               camera ray (:506-515), run the Amanatides-Woo walk (:274-395) and
+//                               accumulate (:523-529) with RED atomics.  Bound by L2 atomic
+//                               throughput (grid L2-resident) or HBM sector traffic (not resident).
+//
+// Stage-level kernels (detect_motion / pixel_rays / cast_rays) expose the same device functions
+// for the bit-exact parity tests.
+#include <algorithm>
+#include <vector>
+
+#include "pvp_device.cuh"
+#include "pvp_internal.h"
+
+namespace pvp {
+
+// ------------------------------------------------------------------------------------------
+// K1: diff / threshold / compact
+// ------------------------------------------------------------------------------------------
+
+constexpr int K1_THREADS = 256;
+
+template <typename T> struct FrameVec;
+template <> struct FrameVec<uint8_t> { static constexpr int PX = 16; using V = uint4; };
+template <> struct FrameVec<float> { static constexpr int PX = 4; using V = float4; };
+
+template <typename T>
+__device__ __forceinline__ void load_px(const T *__restrict__ p, long long first, long long n_pix, bool vec_ok,
+                                        T (&out)[FrameVec<T>::PX])
+{
+    constexpr int PX = FrameVec<T>::PX;
+    if (vec_ok && first + PX <= n_pix) {
+        typename FrameVec<T>::V v = __ldg(reinterpret_cast<const typename FrameVec<T>::V *>(p + first));
+        memcpy(out, &v, sizeof(v));
+    } else {
+#pragma unroll
+        for (int k = 0; k < PX; ++k) out[k] = (first + k < n_pix) ? __ldg(p + first + k) : T(0);
+    }
+}
+
+// grid = (ceil(n_pix / (K1_THREADS*PX)), n_pairs).  Queue order: pair-major inside a CTA's
+// reservation, pixel order inside a CTA, so 32 consecutive entries are (almost always) 32
+// neighbouring pixels of one frame -- coherent rays for K2's warps.
+template <typename T>
+__global__ void __launch_bounds__(K1_THREADS)
+motion_compact_kernel(const T *__restrict__ frames, long long frame_stride, const pvp_pair *__restrict__ pairs,
+                      long long n_pix, float threshold, bool vec_ok, Queue q, Ctl *__restrict__ ctl)
+{
+    constexpr int PX = FrameVec<T>::PX;
+    const int pair = blockIdx.y;
+    const T *prev = frames + (long long)pairs[pair].prev * frame_stride;
+    const T *curr = frames + (long long)pairs[pair].curr * frame_stride;
+    const long long first = ((long long)blockIdx.x * K1_THREADS + threadIdx.x) * PX;
+
+    T a[PX], b[PX];
+    float d[PX];
+    unsigned mask = 0;
+    if (first < n_pix) {
+        load_px<T>(prev, first, n_pix, vec_ok, a);
+        load_px<T>(curr, first, n_pix, vec_ok, b);
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+            d[k] = motion_diff(a[k], b[k]);
+            if (first + k < n_pix && motion_casts_ray(d[k], threshold)) mask |= 1u << k;
+        }
+    }
+    const int cnt = __popc(mask);
+
+    // CTA-wide exclusive scan of cnt: ballot fast-out, shuffle scan per warp, smem across warps.
+    __shared__ unsigned warp_tot[K1_THREADS / 32];
+    __shared__ unsigned long long cta_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = cnt;
+    if (__ballot_sync(0xffffffffu, cnt != 0) != 0) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int w = 0; w < K1_THREADS / 32; ++w) { unsigned c = warp_tot[w]; warp_tot[w] = tot; tot += c; }
+        cta_base = tot ? atomicAdd(&ctl->count, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (cnt == 0) return;
+    unsigned long long pos = cta_base + warp_tot[warp] + (unsigned)(incl - cnt);
+    // the host sizes the queue for the worst case (n_pairs * n_pix), so pos < capacity always
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+        if (mask & (1u << k)) {
+            q.pix[pos] = (uint32_t)(first + k);
+            q.diff[pos] = d[k];
+            q.pair[pos] = (uint16_t)pair;
+            ++pos;
+        }
+    }
+}
+
+// detect_motion as a stand-alone stage (ray_voxel.cpp:236-255): mask + diff image.
+template <typename T>
+__global__ void detect_motion_kernel(const T *__restrict__ prev, const T *__restrict__ next, long long n, float threshold,
+                                     uint8_t *__restrict__ changed, float *__restrict__ diff)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float d = motion_diff(prev[i], next[i]);
+        diff[i] = d;
+        changed[i] = (d > threshold) ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: ray set-up + DDA + accumulate
+// ------------------------------------------------------------------------------------------
+
+constexpr int K2_THREADS = 256;
+
+template <int MODE> struct Accum;
+template <> struct Accum<PVP_ACCUM_F32> {
+    using cell = float;
+    using val = float;
+    __device__ static __forceinline__ val make(float diff, const GridP &) { return diff; }
+    __device__ static __forceinline__ void add(cell *p, val v) { atomicAdd(p, v); }  // RED.E.ADD.F32
+};
+template <> struct Accum<PVP_ACCUM_FIXED> {
+    using cell = unsigned long long;
+    using val = unsigned long long;
+    __device__ static __forceinline__ val make(float diff, const GridP &g) { return (unsigned long long)quantize_fixed(diff, g.fixed_scale); }
+    __device__ static __forceinline__ void add(cell *p, val v) { atomicAdd(p, v); }  // RED.E.ADD.64
+};
+
+// Variant 0: one ray per lane, one RED per voxel step.
+template <int MODE>
+__global__ void __launch_bounds__(K2_THREADS)
+dda_accumulate_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
+                      int width, int height, Ctl *__restrict__ ctl)
+{
+    using A = Accum<MODE>;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long count = ctl->count;
+    const int N = g.n;
+    const long long sx_stride = (long long)N * N;
+    unsigned long long my_steps = 0, my_written = 0;
+
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->head, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const unsigned long long i = base + lane;
+        if (i < count) {
+            const uint32_t pix = __ldg(q.pix + i);
+            const float diff = __ldg(q.diff + i);
+            const pvp_pair *P = pairs + __ldg(q.pair + i);
+            const int v = (int)(pix / (uint32_t)width), u = (int)(pix - (uint32_t)v * (uint32_t)width);
+            float dx, dy, dz;
+            pixel_ray(u, v, width, height, __ldg(&P->focal), P->R, dx, dy, dz);
+            Ray r;
+            if (ray_setup(__ldg(&P->cam[0]), __ldg(&P->cam[1]), __ldg(&P->cam[2]), dx, dy, dz, g, r)) {
+                const typename A::val val = A::make(diff, g);
+                while (r.t_cur <= r.t_end) {
+                    ++my_steps;
+                    if (r.ix >= g.slab_lo && r.ix < g.slab_hi) {
+                        A::add(grid + ((long long)(r.ix - g.slab_lo) * sx_stride + (long long)r.iy * N + r.iz), val);
+                        ++my_written;
+                    }
+                    if (!ray_advance(r, N)) break;
+                }
+            }
+        }
+    }
+    // counters: one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+        my_written += __shfl_xor_sync(0xffffffffu, my_written, o);
+    }
+    if (lane == 0 && my_steps) {
+        atomicAdd(&ctl->n_steps, my_steps);
+        atomicAdd(&ctl->n_written, my_written);
+        atomicAdd(&ctl->n_atomics, my_written);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->n_rays, count);
+}
+
+// Ray set-up of ray_voxel.cpp:506-515 as a stage.
+__global__ void pixel_rays_kernel(const uint32_t *__restrict__ pix, long long n, int width, int height, pvp_pair pose,
+                                  float *__restrict__ dirs)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t p = pix[i];
+        const int v = (int)(p / (uint32_t)width), u = (int)(p - (uint32_t)v * (uint32_t)width);
+        float dx, dy, dz;
+        pixel_ray(u, v, width, height, pose.focal, pose.R, dx, dy, dz);
+        dirs[3 * i] = dx; dirs[3 * i + 1] = dy; dirs[3 * i + 2] = dz;
+    }
+}
+
+// cast_ray_into_grid (ray_voxel.cpp:274-395) as a stage: counts, and optionally the step lists.
+__global__ void cast_rays_kernel(const float *__restrict__ origins, const float *__restrict__ dirs, long long n, GridP g,
+                                 int32_t *__restrict__ counts, const long long *__restrict__ offsets,
+                                 int32_t *__restrict__ vox, float *__restrict__ tt)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Ray r;
+        int c = 0;
+        if (ray_setup(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], g, r)) {
+            long long o = offsets ? offsets[i] : 0;
+            while (r.t_cur <= r.t_end) {
+                if (offsets) {
+                    if (vox) { vox[3 * (o + c)] = r.ix; vox[3 * (o + c) + 1] = r.iy; vox[3 * (o + c) + 2] = r.iz; }
+                    if (tt) tt[o + c] = r.t_cur;
+                }
+                ++c;
+                if (!ray_advance(r, g.n)) break;
+            }
+        }
+        counts[i] = c;
+    }
+}
+
+__global__ void fixed_to_f32_kernel(const long long *__restrict__ src, float *__restrict__ dst, long long n, double inv)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = (float)((double)src[i] * inv);
+}
+
+__global__ void fixed_to_f64_kernel(const long long *__restrict__ src, double *__restrict__ dst, long long n, double inv)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = (double)src[i] * inv;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+
+// Host evaluation of ray_voxel.cpp:284-290 in fp32 (volatile blocks any re-association).
+static int make_gridp(const pvp_grid_desc *d, GridP *g)
+{
+    PVP_REQUIRE(d != nullptr, "grid descriptor is NULL");
+    PVP_REQUIRE(d->n > 0 && d->n <= 2048, "grid n=%d out of range (1..2048)", d->n);
+    PVP_REQUIRE(d->slab_lo >= 0 && d->slab_lo <= d->slab_hi && d->slab_hi <= d->n, "bad slab [%d,%d) for n=%d",
+                d->slab_lo, d->slab_hi, d->n);
+    PVP_REQUIRE(d->accum_mode == PVP_ACCUM_F32 || d->accum_mode == PVP_ACCUM_FIXED, "bad accum_mode %d", d->accum_mode);
+    PVP_REQUIRE(d->accum_mode == PVP_ACCUM_F32 || (d->frac_bits >= 0 && d->frac_bits <= 40), "frac_bits %d out of range",
+                d->frac_bits);
+    g->n = d->n; g->slab_lo = d->slab_lo; g->slab_hi = d->slab_hi; g->vs = d->voxel_size;
+    volatile float extent = (float)d->n * d->voxel_size;
+    volatile float half = 0.5f * extent;
+    for (int a = 0; a < 3; ++a) {
+        volatile float lo = d->center[a] - half, hi = d->center[a] + half;
+        g->gmin[a] = lo; g->gmax[a] = hi;
+    }
+    g->fixed_scale = (float)((long long)1 << (d->accum_mode == PVP_ACCUM_FIXED ? d->frac_bits : 0));
+    return PVP_OK;
+}
+
+static int k2_grid_size(pvp_ctx *ctx, const void *kernel)
+{
+    int per_sm = 0;
+    if (ctx->opt_ctas_per_sm > 0) per_sm = (int)ctx->opt_ctas_per_sm;
+    else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, K2_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    return ctx->sm_count * per_sm;  // persistent: every CTA resident, a multiple of the SM count
+}
+
+template <typename T>
+static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_stride, long long n_pix, int n_pairs, float threshold)
+{
+    constexpr int PX = FrameVec<T>::PX;
+    const bool vec_ok = ((uintptr_t)frames_dev % sizeof(typename FrameVec<T>::V) == 0) && (frame_stride % PX == 0);
+    dim3 grid((unsigned)((n_pix + (long long)K1_THREADS * PX - 1) / ((long long)K1_THREADS * PX)), (unsigned)n_pairs);
+    motion_compact_kernel<T><<<grid, K1_THREADS, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, n_pix,
+                                                                   threshold, vec_ok, ctx->queue, ctx->ctl_dev);
+    PVP_CUDA(cudaGetLastError());
+    return PVP_OK;
+}
+
+static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, void *grid_dev, int width, int height)
+{
+    if (accum_mode == PVP_ACCUM_F32) {
+        auto k = dda_accumulate_kernel<PVP_ACCUM_F32>;
+        k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (float *)grid_dev, width,
+                                                                               height, ctx->ctl_dev);
+    } else {
+        auto k = dda_accumulate_kernel<PVP_ACCUM_FIXED>;
+        k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g,
+                                                                               (unsigned long long *)grid_dev, width, height, ctx->ctl_dev);
+    }
+    PVP_CUDA(cudaGetLastError());
+    return PVP_OK;
+}
+
+static int validate_pairs(const pvp_pair *pairs, int n_pairs, long long n_frames)
+{
+    for (int i = 0; i < n_pairs; ++i)
+        PVP_REQUIRE(pairs[i].prev >= 0 && pairs[i].curr >= 0 && (n_frames < 0 || (pairs[i].prev < n_frames && pairs[i].curr < n_frames)),
+                    "pair %d references frames (%d,%d) outside [0,%lld)", i, pairs[i].prev, pairs[i].curr, n_frames);
+    return PVP_OK;
+}
+
+static int fetch_stats(pvp_ctx *ctx, pvp_stats *stats)
+{
+    if (!stats) return PVP_OK;
+    Ctl h;
+    PVP_CUDA(cudaMemcpyAsync(&h, ctx->ctl_dev, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
+    PVP_CUDA(cudaMemsetAsync(&ctx->ctl_dev->n_rays, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    stats->n_rays += h.n_rays; stats->n_steps += h.n_steps; stats->n_written += h.n_written; stats->n_atomics += h.n_atomics;
+    return PVP_OK;
+}
+
+// One device-resident batch: K1 over all pairs, then K2 over the queue.  Batches are split so
+// the worst-case queue (every pixel of every pair moves) fits the configured capacity.
+static int run_batches(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, long long frame_stride, int width, int height,
+                       const pvp_pair *pairs, int n_pairs, float threshold, void *grid_dev, const GridP &g, int accum_mode)
+{
+    const long long n_pix = (long long)width * height;
+    long long per_batch = std::max<long long>(1, ctx->opt_max_queue / n_pix);
+    per_batch = std::min<long long>(per_batch, 65535);  // pair id is 16 bit in the queue
+    for (int p0 = 0; p0 < n_pairs; p0 += (int)per_batch) {
+        const int np = (int)std::min<long long>(per_batch, n_pairs - p0);
+        int rc = ensure_queue(ctx, (unsigned long long)np * (unsigned long long)n_pix);
+        if (rc) return rc;
+        rc = upload_pairs(ctx, pairs + p0, np);
+        if (rc) return rc;
+        PVP_CUDA(cudaMemsetAsync(ctx->ctl_dev, 0, 2 * sizeof(unsigned long long), ctx->stream));  // count, head
+        rc = frame_dtype == PVP_FRAME_U8 ? launch_k1<uint8_t>(ctx, frames_dev, frame_stride, n_pix, np, threshold)
+                                         : launch_k1<float>(ctx, frames_dev, frame_stride, n_pix, np, threshold);
+        if (rc) return rc;
+        rc = launch_k2(ctx, g, accum_mode, grid_dev, width, height);
+        if (rc) return rc;
+    }
+    return PVP_OK;
+}
+
+static int check_common(pvp_ctx *ctx, const void *frames, int frame_dtype, long long frame_stride, int width, int height,
+                        const pvp_pair *pairs, int n_pairs, void *grid_dev)
+{
+    PVP_REQUIRE(ctx != nullptr, "ctx is NULL");
+    PVP_REQUIRE(n_pairs >= 0, "n_pairs < 0");
+    PVP_REQUIRE(n_pairs == 0 || (frames && pairs), "frames / pairs is NULL");
+    PVP_REQUIRE(grid_dev != nullptr, "grid_dev is NULL");
+    PVP_REQUIRE(frame_dtype == PVP_FRAME_U8 || frame_dtype == PVP_FRAME_F32, "bad frame_dtype %d", frame_dtype);
+    PVP_REQUIRE(width > 0 && height > 0 && (long long)width * height < (1ll << 32), "bad frame size %dx%d", width, height);
+    PVP_REQUIRE(frame_stride >= (long long)width * height, "frame_stride smaller than a frame");
+    return PVP_OK;
+}
+
+}  // namespace pvp
+
+using namespace pvp;
+
+extern "C" {
+
+int pvp_detect_motion(pvp_ctx *ctx, const void *prev_dev, const void *next_dev, int frame_dtype, int64_t n_pixels,
+                      float threshold, uint8_t *changed_dev, float *diff_dev)
+{
+    PVP_REQUIRE(ctx && prev_dev && next_dev && changed_dev && diff_dev, "pvp_detect_motion: NULL argument");
+    PVP_REQUIRE(frame_dtype == PVP_FRAME_U8 || frame_dtype == PVP_FRAME_F32, "pvp_detect_motion: bad frame_dtype %d", frame_dtype);
+    if (n_pixels <= 0) return PVP_OK;
+    DeviceGuard guard(ctx->device);
+    int blocks = (int)std::min<long long>((n_pixels + 255) / 256, (long long)ctx->sm_count * 8);
+    if (frame_dtype == PVP_FRAME_U8)
+        detect_motion_kernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>((const uint8_t *)prev_dev, (const uint8_t *)next_dev, n_pixels,
+                                                                       threshold, changed_dev, diff_dev);
+    else
+        detect_motion_kernel<float><<<blocks, 256, 0, ctx->stream>>>((const float *)prev_dev, (const float *)next_dev, n_pixels,
+                                                                     threshold, changed_dev, diff_dev);
+    PVP_CUDA(cudaGetLastError());
+    return PVP_OK;
+}
+
+int pvp_pixel_rays(pvp_ctx *ctx, const uint32_t *pix_dev, int64_t n, int width, int height, const pvp_pair *pose, float *dirs_dev)
+{
+    PVP_REQUIRE(ctx && pix_dev && pose && dirs_dev, "pvp_pixel_rays: NULL argument");
+    PVP_REQUIRE(width > 0 && height > 0, "pvp_pixel_rays: bad frame size");
+    if (n <= 0) return PVP_OK;
+    DeviceGuard guard(ctx->device);
+    int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 8);
+    pixel_rays_kernel<<<blocks, 256, 0, ctx->stream>>>(pix_dev, n, width, height, *pose, dirs_dev);
+    PVP_CUDA(cudaGetLastError());
+    return PVP_OK;
+}
+
+int pvp_cast_rays(pvp_ctx *ctx, const float *origins_dev, const float *dirs_dev, int64_t n, const pvp_grid_desc *grid,
+                  int32_t *counts_dev, const int64_t *offsets_dev, int32_t *vox_dev, float *t_dev)
+{
+    PVP_REQUIRE(ctx && origins_dev && dirs_dev && counts_dev, "pvp_cast_rays: NULL argument");
+    GridP g;
+    int rc = make_gridp(grid, &g);
+    if (rc) return rc;
+    if (n <= 0) return PVP_OK;
+    DeviceGuard guard(ctx->device);
+    int blocks = (int)std::min<long long>((n + 127) / 128, (long long)ctx->sm_count * 16);
+    cast_rays_kernel<<<blocks, 128, 0, ctx->stream>>>(origins_dev, dirs_dev, n, g, counts_dev, (const long long *)offsets_dev, vox_dev, t_dev);
+    PVP_CUDA(cudaGetLastError());
+    return PVP_OK;
+}
+
+int pvp_motion_accumulate(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, int64_t frame_stride, int width, int height,
+                          const pvp_pair *pairs, int n_pairs, float threshold, void *grid_dev, const pvp_grid_desc *grid,
+                          pvp_stats *stats)
+{
+    int rc = check_common(ctx, frames_dev, frame_dtype, frame_stride, width, height, pairs, n_pairs, grid_dev);
+    if (rc) return rc;
+    GridP g;
+    if ((rc = make_gridp(grid, &g))) return rc;
+    if ((rc = validate_pairs(pairs, n_pairs, -1))) return rc;
+    DeviceGuard guard(ctx->device);
+    if (n_pairs > 0) {
+        rc = run_batches(ctx, frames_dev, frame_dtype, frame_stride, width, height, pairs, n_pairs, threshold, grid_dev, g, grid->accum_mode);
+        if (rc) return rc;
+    }
+    return fetch_stats(ctx, stats);
+}
+
+int pvp_motion_accumulate_host(pvp_ctx *ctx, const void *frames_host, int frame_dtype, int64_t frame_stride, int width, int height,
+                               int n_frames, const pvp_pair *pairs, int n_pairs, float threshold, void *grid_dev,
+                               const pvp_grid_desc *grid, pvp_stats *stats)
+{
+    int rc = check_common(ctx, frames_host, frame_dtype, frame_stride, width, height, pairs, n_pairs, grid_dev);
+    if (rc) return rc;
+    GridP g;
+    if ((rc = make_gridp(grid, &g))) return rc;
+    if ((rc = validate_pairs(pairs, n_pairs, n_frames))) return rc;
+    if (n_pairs == 0) return fetch_stats(ctx, stats);
+    DeviceGuard guard(ctx->device);
+
+    // Chunk the pair list; each chunk needs the frames [fmin, fmax] of its pairs on the device.
+    // Two staging buffers: the copy stream fills buffer k+1 while the kernels of chunk k run.
+    const size_t elem = frame_dtype == PVP_FRAME_U8 ? 1 : 4;
+    const long long n_pix = (long long)width * height;
+    const long long queue_pairs = std::max<long long>(1, ctx->opt_max_queue / n_pix);
+    const int chunk_pairs = (int)std::min<long long>(std::min<long long>(queue_pairs, 65535), 64);
+
+    struct Chunk { int p0, np, fmin, fmax; };
+    std::vector<Chunk> chunks;
+    size_t max_frames = 0;
+    for (int p0 = 0; p0 < n_pairs; p0 += chunk_pairs) {
+        Chunk c{p0, std::min(chunk_pairs, n_pairs - p0), INT32_MAX, -1};
+        for (int i = 0; i < c.np; ++i) {
+            c.fmin = std::min(c.fmin, std::min(pairs[p0 + i].prev, pairs[p0 + i].curr));
+            c.fmax = std::max(c.fmax, std::max(pairs[p0 + i].prev, pairs[p0 + i].curr));
+        }
+        max_frames = std::max(max_frames, (size_t)(c.fmax - c.fmin + 1));
+        chunks.push_back(c);
+    }
+    const size_t need = max_frames * (size_t)frame_stride * elem;
+    if (ctx->stage_bytes < need) {
+        PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+        PVP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
+            ctx->stage_dev[i] = nullptr;
+        }
+        ctx->stage_bytes = 0;
+        for (int i = 0; i < 2; ++i) PVP_CUDA(cudaMalloc(&ctx->stage_dev[i], need));
+        ctx->stage_bytes = need;
+    }
+
+    std::vector<pvp_pair> local;
+    // order the copy stream behind whatever the caller already enqueued that touches the buffers
+    PVP_CUDA(cudaEventRecord(ctx->ev_done[0], ctx->stream));
+    PVP_CUDA(cudaEventRecord(ctx->ev_done[1], ctx->stream));
+    for (size_t c = 0; c < chunks.size(); ++c) {
+        const Chunk &ch = chunks[c];
+        const int buf = (int)(c & 1);
+        const size_t bytes = (size_t)(ch.fmax - ch.fmin + 1) * (size_t)frame_stride * elem;
+        PVP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[buf], 0));  // buffer free again?
+        PVP_CUDA(cudaMemcpyAsync(ctx->stage_dev[buf], (const char *)frames_host + (size_t)ch.fmin * (size_t)frame_stride * elem, bytes,
+                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+        PVP_CUDA(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
+        PVP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+        local.assign(pairs + ch.p0, pairs + ch.p0 + ch.np);
+        for (auto &p : local) { p.prev -= ch.fmin; p.curr -= ch.fmin; }
+        rc = run_batches(ctx, ctx->stage_dev[buf], frame_dtype, frame_stride, width, height, local.data(), ch.np, threshold, grid_dev, g,
+                         grid->accum_mode);
+        if (rc) return rc;
+        PVP_CUDA(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
+    }
+    return fetch_stats(ctx, stats);
+}
+
+int pvp_fixed_to_f32(pvp_ctx *ctx, const int64_t *src_dev, float *dst_dev, int64_t n, int frac_bits)
+{
+    PVP_REQUIRE(ctx && src_dev && dst_dev && frac_bits >= 0 && frac_bits <= 62, "pvp_fixed_to_f32: bad argument");
+    if (n <= 0) return PVP_OK;
+    DeviceGuard guard(ctx->device);
+    int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    fixed_to_f32_kernel<<<blocks, 256, 0, ctx->stream>>>((const long long *)src_dev, dst_dev, n, 1.0 / (double)(1ll << frac_bits));
+    PVP_CUDA(cudaGetLastError());
+    return PVP_OK;
+}
+
+int pvp_fixed_to_f64(pvp_ctx *ctx, const int64_t *src_dev, double *dst_dev, int64_t n, int frac_bits)
+{
+    PVP_REQUIRE(ctx && src_dev && dst_dev && frac_bits >= 0 && frac_bits <= 62, "pvp_fixed_to_f64: bad argument");
+    if (n <= 0) return PVP_OK;
+    DeviceGuard guard(ctx->device);
+    int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    fixed_to_f64_kernel<<<blocks, 256, 0, ctx->stream>>>((const long long *)src_dev, dst_dev, n, 1.0 / (double)(1ll << frac_bits));
+    PVP_CUDA(cudaGetLastError());
+    return PVP_OK;
+}
+
+}  // extern "C"

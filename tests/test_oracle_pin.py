@@ -1,0 +1,178 @@
+"""Pin the C restatement (oracle/pvp_oracle.c) to the reference: against the committed golden vectors
+(generated from oracle/_ref by tests/golden/make_golden.py) and, where oracle/_ref exists, against the
+compiled reference itself on fresh random inputs.  Everything is bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import bits, golden
+
+
+def test_pose_golden(oracle):
+    g = golden("pose_golden.npz")
+    for ypr, R, fov, w, f in zip(g["ypr"], g["R"], g["fov"], g["width"], g["focal"]):
+        assert np.array_equal(bits(oracle.rotation_matrix(*ypr)), bits(R))
+        assert bits(np.float32(oracle.focal_length(fov, int(w)))) == bits(np.float32(f))
+
+
+def test_rays_golden(oracle):
+    g = golden("rays_golden.npz")
+    off = np.concatenate([[0], np.cumsum(g["counts"])])
+    for i in range(len(g["N"])):
+        vox, t = oracle.cast_ray(g["cam"][i], g["dir"][i], int(g["N"][i]), g["voxel_size"][i], g["center"][i], want_t=True)
+        assert len(vox) == g["counts"][i], i
+        assert np.array_equal(vox, g["vox"][off[i]:off[i + 1]]), i
+        assert np.array_equal(bits(t), bits(g["t"][off[i]:off[i + 1]])), i
+
+
+def test_pair_golden(oracle):
+    g = golden("pair_golden.npz")
+    N = int(g["N"])
+    prev, curr = g["prev"], g["curr"]
+    changed, diff = oracle.detect_motion(prev.astype(np.float32), curr.astype(np.float32), float(g["threshold"]))
+    assert np.array_equal(changed, g["changed"]) and np.array_equal(bits(diff), bits(g["diff"]))
+    R = oracle.rotation_matrix(*g["ypr"])
+    f = oracle.focal_length(g["fov"], prev.shape[1])
+    assert np.array_equal(bits(R), bits(g["R"])) and bits(np.float32(f)) == bits(g["focal"])
+    for frames in ((prev, curr), (prev.astype(np.float32), curr.astype(np.float32))):
+        grid = np.zeros((N, N, N), np.float32)
+        nr, ns, nw = oracle.accumulate_pair(frames[0], frames[1], g["cam"], R, f, grid, N, g["voxel_size"], g["center"], float(g["threshold"]))
+        assert (nr, ns, nw) == (int(g["n_rays"]), int(g["n_steps"]), int(g["n_steps"]))
+        nz = np.flatnonzero(grid)
+        assert np.array_equal(nz, g["nz_index"]) and np.array_equal(bits(grid.reshape(-1)[nz]), bits(g["nz_value"]))
+    # fixed point: integer inputs => identical values after conversion
+    gi = np.zeros((N, N, N), np.int64)
+    oracle.accumulate_pair(prev, curr, g["cam"], R, f, gi, N, g["voxel_size"], g["center"], float(g["threshold"]), accum_mode=1, frac_bits=16)
+    gf = oracle.fixed_to_f32(gi, 16)
+    assert np.array_equal(np.flatnonzero(gf), g["nz_index"]) and np.array_equal(gf.reshape(-1)[g["nz_index"]], g["nz_value"])
+    # slabs partition the grid
+    parts = []
+    for lo, hi in ((0, 13), (13, 14), (14, N)):
+        s = np.zeros((hi - lo, N, N), np.float32)
+        oracle.accumulate_pair(prev, curr, g["cam"], R, f, s, N, g["voxel_size"], g["center"], float(g["threshold"]), slab=(lo, hi))
+        parts.append(s)
+    assert np.array_equal(np.concatenate(parts).reshape(-1)[g["nz_index"]], g["nz_value"])
+
+
+def test_process_image_golden(oracle):
+    g = golden("process_image_golden.npz")
+    img = g["image"]
+    H, W = img.shape
+    for name in g["names"]:
+        grid = np.zeros_like(g[f"{name}_grid_out"])
+        tex = g[f"{name}_tex_in"].copy()
+        oracle.process_image(img, g["earth_position"], g[f"{name}_pointing"], float(g["fov"]), W, H, grid, g["extent"], float(g["max_distance"]),
+                             int(g["num_steps"]), tex, *g["sky"], bool(g[f"{name}_update"]), bool(g[f"{name}_bgsub"]))
+        assert np.array_equal(bits(grid), bits(g[f"{name}_grid_out"])), name
+        assert np.array_equal(bits(tex), bits(g[f"{name}_tex_out"])), name
+
+
+def test_process_image_strided_and_empty_grid(oracle):
+    g = golden("process_image_golden.npz")
+    img = g["image"]
+    H, W = img.shape
+    name = "update"
+    want = g[f"{name}_grid_out"]
+    big = np.zeros((want.shape[0], want.shape[1] * 2, want.shape[2]))
+    view = big[:, ::2, :]
+    tex = np.asfortranarray(g[f"{name}_tex_in"].copy())
+    oracle.process_image(img, g["earth_position"], g[f"{name}_pointing"], float(g["fov"]), W, H, view, g["extent"], float(g["max_distance"]),
+                         int(g["num_steps"]), tex, *g["sky"], True, False)
+    assert np.array_equal(view, want) and np.array_equal(tex, g[f"{name}_tex_out"]) and not big[:, 1::2, :].any()
+    tex2 = g[f"{name}_tex_in"].copy()
+    nr, ns = oracle.process_image(img, g["earth_position"], g[f"{name}_pointing"], float(g["fov"]), W, H, np.zeros((0,)), g["extent"],
+                                  float(g["max_distance"]), int(g["num_steps"]), tex2, *g["sky"], True, False)
+    assert ns == 0 and np.array_equal(tex2, g[f"{name}_tex_out"])
+
+
+# ---- against the compiled reference itself (only where oracle/_ref exists) -------------------
+def test_pose_vs_reference(oracle, reflib):
+    rng = np.random.default_rng(1)
+    for _ in range(1500):
+        ypr = rng.uniform(-360, 360, 3).astype(np.float32)
+        assert np.array_equal(bits(oracle.rotation_matrix(*ypr)), bits(reflib.rotation_matrix(*ypr)))
+        fov, w = np.float32(rng.uniform(1, 179)), int(rng.integers(1, 8192))
+        assert bits(np.float32(oracle.focal_length(fov, w))) == bits(np.float32(reflib.focal_length(fov, w)))
+
+
+def test_pixel_rays_vs_reference(oracle, reflib):
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        W, H = int(rng.integers(2, 4000)), int(rng.integers(2, 3000))
+        R = reflib.rotation_matrix(*rng.uniform(-180, 180, 3).astype(np.float32))
+        f = reflib.focal_length(np.float32(rng.uniform(20, 120)), W)
+        for _ in range(10):
+            u, v = int(rng.integers(0, W)), int(rng.integers(0, H))
+            assert np.array_equal(bits(oracle.pixel_ray(u, v, W, H, f, R)), bits(reflib.pixel_ray(u, v, W, H, f, R)))
+
+
+def test_cast_ray_vs_reference(oracle, reflib):
+    rng = np.random.default_rng(3)
+    steps = 0
+    for k in range(2500):
+        N = int(rng.integers(1, 160))
+        vs = np.float32(rng.uniform(0.05, 12))
+        center = rng.uniform(-200, 200, 3).astype(np.float32)
+        half = N * vs / 2
+        cam = (center + rng.uniform(-1.8, 1.8, 3) * half).astype(np.float32)
+        d = ((center + rng.uniform(-1, 1, 3) * half) - cam).astype(np.float32) if k % 2 else rng.normal(size=3).astype(np.float32)
+        if k % 7 == 0:
+            d[rng.integers(0, 3)] = rng.choice([0.0, -0.0, 1e-13])
+        if k % 13 == 0:
+            cam = (center - half + vs * rng.integers(0, N + 1, 3)).astype(np.float32)
+            d = rng.choice([-1.0, 1.0, 0.0], 3).astype(np.float32)
+        nrm = np.linalg.norm(d)
+        if nrm > 0:
+            d = (d / nrm).astype(np.float32)
+        a, ta = oracle.cast_ray(cam, d, N, vs, center, want_t=True)
+        b, tb = reflib.cast_ray(cam, d, N, vs, center, want_t=True)
+        assert a.shape == b.shape and np.array_equal(a, b) and np.array_equal(bits(ta), bits(tb)), k
+        steps += len(a)
+    assert steps > 20000
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_accumulate_pair_vs_reference(oracle, reflib, dense):
+    rng = np.random.default_rng(4 + dense)
+    H, W, N = 54, 72, 72
+    vs, center = np.float32(3.0), np.array([5, -3, 400], np.float32)
+    prev = rng.integers(0, 256, (H, W)).astype(np.float32)
+    curr = rng.integers(0, 256, (H, W)).astype(np.float32) if dense else prev.copy()
+    if not dense:
+        curr[20:30, 30:44] += 50
+    prev += rng.uniform(-1, 1, prev.shape).astype(np.float32)  # float frames with (seeded) loader-style noise
+    curr += rng.uniform(-1, 1, curr.shape).astype(np.float32)
+    R = reflib.rotation_matrix(20, -10, 170)   # roll 170 -> looks towards +z
+    f = reflib.focal_length(70, W)
+    cam = np.array([10, 20, 250], np.float32)  # outside, below the min-z face
+    g1, g2 = np.zeros((N, N, N), np.float32), np.zeros((N, N, N), np.float32)
+    s1 = oracle.accumulate_pair(prev, curr, cam, R, f, g1, N, vs, center, 2.0)
+    s2 = reflib.accumulate_pair(prev, curr, cam, R, f, g2, N, vs, center, 2.0)
+    assert s1[:2] == s2 and s1[1] > 0
+    assert np.array_equal(bits(g1), bits(g2))
+
+
+def test_process_image_vs_reference(oracle):
+    from oracle import REF_DIR, ref_process_image_module
+    if not os.path.isdir(REF_DIR):
+        pytest.skip("oracle/_ref not built")
+    m = ref_process_image_module()
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        H, W = int(rng.integers(8, 40)), int(rng.integers(8, 40))
+        img = rng.random((H, W))
+        img[img < 0.3] = 0
+        pos = rng.uniform(-5, 5, 3)
+        pointing = rng.normal(size=3) if trial else np.array([0.0, 0.0, -3.0])
+        ext = [(-8.0, 9.0), (-7.0, 6.5), (-6.0, 8.0)] if trial % 2 else [(10.0, 30.0), (-10.0, 10.0), (-10.0, 10.0)]
+        shape = (int(rng.integers(4, 20)), int(rng.integers(4, 20)), int(rng.integers(4, 20)))
+        sky = (float(rng.uniform(0, 6.28)), float(rng.uniform(-1.5, 1.5)), float(rng.uniform(0.5, 6.0)), float(rng.uniform(0.5, 3.0)))
+        for upd, bg in ((True, False), (False, True)):
+            g1, g2 = np.zeros(shape), np.zeros(shape)
+            t1 = rng.random((16, 24)) * 0.4
+            t2 = t1.copy()
+            m.process_image_cpp(img, list(pos), list(pointing), 0.9, W, H, g1, ext, 60.0, 300, t1, *sky, upd, bg)
+            oracle.process_image(img, pos, pointing, 0.9, W, H, g2, ext, 60.0, 300, t2, *sky, upd, bg)
+            assert np.array_equal(bits(g1), bits(g2)) and np.array_equal(bits(t1), bits(t2)), (trial, upd, bg)
