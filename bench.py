@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: voxel-steps/s and frames/s, 512^3 grid, 1080p).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the motion pipeline (K1 diff/threshold/compact + K2 DDA/accumulate) over one batch of
+synthetic frame pairs.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # the configuration BASELINE.json's metric is quoted on: 1080p frames into a 512^3 fp32 grid, one camera whose
+    # pose changes every frame, dense motion (iid uint8 frames: ~98 % of the pixels cast a ray)
+    "1080p_dense_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=72, motion="dense", accum="f32"),
+    # BASELINE config[1]: 256^3 grid (L2 resident)
+    "1080p_dense_256": dict(H=1080, W=1920, N=256, voxel_size=4.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=72, motion="dense", accum="f32"),
+    # sparse motion (moving blobs, ~1 % of the pixels): frames/s matters, many pairs per step
+    "1080p_sparse_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=72, motion="sparse", accum="f32"),
+    "1080p_dense_512_fixed": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=72, motion="dense", accum="fixed"),
+    # small smoke-sized case for CPU-side checks of this script
+    "tiny": dict(H=120, W=160, N=64, voxel_size=16.0, center=(0.0, 0.0, 500.0), pairs_per_step=2, pool=8, motion="dense", accum="f32"),
+}
+ALGO_BYTES_PER_STEP = {"f32": 8, "fixed": 16}   # one atomic RMW: 4 B read + 4 B write (fp32), 8 + 8 (int64) -- SURVEY 8d
+
+
+def make_inputs(wl, seed):
+    from pixeltovoxelprojector_b200 import synth
+    F = wl["pool"]
+    if wl["motion"] == "dense":
+        frames = synth.dense_frames(F, wl["H"], wl["W"], seed=seed)
+    else:
+        frames = synth.sparse_frames(F, wl["H"], wl["W"], seed=seed, blobs=6)
+    poses = synth.orbit_poses(F, wl["N"], wl["voxel_size"], wl["center"], seed=seed + 1)
+    return frames, poses
+
+
+def step_pairs(step, wl):
+    """Frame indices of step `step`: B consecutive pairs out of the pool, wrapping."""
+    B, F = wl["pairs_per_step"], wl["pool"]
+    start = (step * B) % (F - B)
+    return start, [(start + i, start + i + 1) for i in range(B)]
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region (pynvml, 100 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop, self._t = [], set(), None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_reference(wl, frames, poses, pairs, rows=None):
+    """Time the reference CPU implementation (oracle/_ref = the unmodified ray_voxel.cpp compiled; else the C port) on
+    the given pairs, optionally restricted to a band of rows (pixels outside the band are made motion-free).
+    Returns (voxel_steps, seconds, kind).  The reference is serial: 1 thread."""
+    import oracle
+    use_ref = oracle.have_ref()
+    lib = oracle.RefLib() if use_ref else oracle.Oracle()
+    N = wl["N"]
+    grid = np.zeros((N, N, N), np.float32)
+    steps, secs = 0, 0.0
+    for (p, c) in pairs:
+        prev, curr = frames[p].astype(np.float32), frames[c].astype(np.float32)
+        if rows is not None:
+            keep = np.zeros(prev.shape[0], bool)
+            keep[rows[0]:rows[1]] = True
+            curr = np.where(keep[:, None], curr, prev)
+        R = lib.rotation_matrix(poses[c].yaw, poses[c].pitch, poses[c].roll)
+        f = lib.focal_length(poses[c].fov_degrees, wl["W"])
+        t0 = time.perf_counter()
+        if use_ref:
+            _, ns = lib.accumulate_pair(prev, curr, np.array(poses[c].camera_position, np.float32), R, f, grid, N, wl["voxel_size"], wl["center"], 2.0)
+        else:
+            _, ns, _ = lib.accumulate_pair(prev, curr, np.array(poses[c].camera_position, np.float32), R, f, grid, N, wl["voxel_size"], np.array(wl["center"], np.float32), 2.0)
+        secs += time.perf_counter() - t0
+        steps += ns
+    return steps, secs, ("reference" if use_ref else "port")
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames, poses = make_inputs(wl, seed=1000)
+    H = wl["H"]
+    bands = 4   # each step = one quarter of the rows of one frame pair (bounded sample of the same workload)
+
+    def one(step):
+        _, pairs = step_pairs(step // bands, wl)
+        b = step % bands
+        return cpu_reference(wl, frames, poses, pairs[:1], rows=(H * b // bands, H * (b + 1) // bands))
+
+    for s in range(args.warmup):
+        one(s)
+    tot_steps, tot_s, kind = 0, 0.0, "port"
+    for s in range(args.steps):
+        st, sec, kind = one(args.warmup + s)
+        tot_steps += st
+        tot_s += sec
+    v = tot_steps / tot_s if tot_s > 0 else 0.0
+    sample = f"per step: rows [b*{H // bands},(b+1)*{H // bands}) of one {wl['W']}x{H} frame pair, {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": "voxel_steps_per_sec", "value": v, "unit": "voxel-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl),
+        "cpu_baseline": {"value": v, "unit": "voxel-steps/s", "cores": 1, "kind": kind, "sample": sample,
+                         "note": "ray_voxel.cpp is single-threaded (no OpenMP/threads, SURVEY 2): 1 of %d host cores" % (os.cpu_count() or 1)},
+        "e2e": {"value": v, "unit": "voxel-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_s": (args.steps / bands) / tot_s if tot_s > 0 else 0.0,
+    }))
+
+
+def workload_config(args, wl):
+    return {"workload": args.workload, "frame": f"{wl['W']}x{wl['H']} uint8", "grid": f"{wl['N']}^3 {wl['accum']}", "voxel_size": wl["voxel_size"],
+            "pairs_per_step": wl["pairs_per_step"], "motion": wl["motion"], "camera": "pose changes every frame (orbit inside the grid)",
+            "parallelism": f"frames sharded over {args.gpus} GPU(s), private grids, one NCCL reduce per run" if args.gpus > 1 else "1 GPU",
+            "l2": "256 MiB buffer written between timed steps (L2 flush); frame pool 149 MB and grid > L2" if wl["N"] >= 512 else
+                  "256 MiB buffer written between timed steps (L2 flush)"}
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import pixeltovoxelprojector_b200 as pvp
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = pvp.default_context(dev)
+
+    frames_np, poses = make_inputs(wl, seed=1000 + rank)   # weak scaling: every rank has its own frames, same shape
+    frames_dev = torch.as_tensor(frames_np, device=dev)
+    frames_pin = torch.as_tensor(frames_np).pin_memory()
+    grid = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    B, H, W = wl["pairs_per_step"], wl["H"], wl["W"]
+    pair_tabs = {}
+
+    def pairs_for(step, rebase=False):
+        start, idx = step_pairs(step, wl)
+        key = (start, rebase)
+        if key not in pair_tabs:
+            if rebase:
+                pair_tabs[key] = pvp.make_pairs(poses[start:start + B + 1], W)[0]
+            else:
+                pair_tabs[key] = pvp.make_pairs(poses, W, pairs=idx)[0]
+        return start, pair_tabs[key]
+
+    def step_device(step):
+        _, tab = pairs_for(step)
+        pvp.accumulate_motion(frames_dev, tab, grid, 2.0, ctx=ctx, n_pairs=B, want_stats=False)
+
+    def step_e2e(step):
+        start, tab = pairs_for(step, rebase=True)
+        return pvp.accumulate_motion(frames_pin[start:start + B + 1], tab, grid, 2.0, ctx=ctx, n_pairs=B, want_stats=True)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up -------------------------------------------------------------------------------------------------
+    for s in range(args.warmup):
+        step_device(s)
+        step_e2e(s)
+    pvp.accumulate_motion(frames_dev, pairs_for(0)[1], grid, 2.0, ctx=ctx, n_pairs=0, want_stats=True)  # drain counters
+    grid.zero_()
+    ctx.get_profile(reset=True)
+
+    # ---- timed region 1: inputs resident in HBM (`value`) ------------------------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
+    ctx.profile(True)
+    barrier()
+    with ClockSampler(local) as clocks:
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)            # L2 flush, outside the timed events
+            ev[s][0].record()
+            step_device(args.warmup + s)
+            ev[s][1].record()
+        ev[-1][0].record()
+        if world > 1:                        # the run's single grid merge over NVLink (SURVEY 8e mode 1)
+            dist.reduce(grid.data, dst=0)
+        ev[-1][1].record()
+        barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    prof = ctx.get_profile(reset=True)
+    ctx.profile(False)
+    stats = pvp.accumulate_motion(frames_dev, pairs_for(0)[1], grid, 2.0, ctx=ctx, n_pairs=0, want_stats=True)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([stats["n_steps"], stats["n_rays"], stats["n_atomics"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max, all_steps, all_rays = float(t.item()), float(tot[0].item()), float(tot[1].item())
+
+    # ---- timed region 2: end to end through the public API with HOST (pinned) frames ------------------------------
+    grid.zero_()
+    e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_steps = 0
+    barrier()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        e_ev[s][0].record()
+        e_steps += step_e2e(args.warmup + s)["n_steps"]      # H2D of B+1 frames inside; D2H of the step's counters
+        e_ev[s][1].record()
+    barrier()
+    e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e_ev)], dtype=torch.float64, device=dev)
+    e_tot = torch.tensor([float(e_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e_tot, op=dist.ReduceOp.SUM)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K2), live CUDA-event timing ---------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    k2_s = prof["ms_k2"] * 1e-3
+    per_rank_steps = stats["n_steps"]
+    achieved = ALGO_BYTES_PER_STEP[wl["accum"]] * per_rank_steps / k2_s / 1e9 if k2_s > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                "kernel": "dda_accumulate_kernel (K2)", "peak_source": peak_src,
+                "algorithmic_bytes_per_voxel_step": ALGO_BYTES_PER_STEP[wl["accum"]],
+                "voxel_steps_per_launch": per_rank_steps / max(1, prof["launches_k2"]), "avg_launch_ms": prof["ms_k2"] / max(1, prof["launches_k2"]),
+                "k2_share_of_step": prof["ms_k2"] / ms if ms > 0 else None, "k1_ms_total": prof["ms_k1"]}
+    # L2-atomic roofline: measured peak of independent red.global.add on this GPU, same run
+    l2 = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import atomic_roofline
+        elem = 4 if wl["accum"] == "f32" else 8
+        buf = torch.zeros(grid.data.numel() * grid.data.element_size() // 8, dtype=torch.int64, device=dev)  # same footprint as the grid
+        nbytes = buf.numel() * 8
+        peak_ops = {name: atomic_roofline.measure(ctx, buf, nbytes, elem, pat, 1 << 30) for pat, name in ((0, "random_per_lane"), (3, "random_line_per_warp"))}
+        k2_rate = per_rank_steps / k2_s if k2_s > 0 else 0.0
+        l2 = {"unit": "atomic adds/s", "buffer_bytes": nbytes, "peak_random_per_lane": peak_ops["random_per_lane"],
+              "peak_coalesced_line_per_warp": peak_ops["random_line_per_warp"], "achieved_voxel_steps_per_s_in_k2": k2_rate,
+              "frac_of_random_peak": k2_rate / peak_ops["random_per_lane"]}
+    except Exception as e:  # the micro-benchmark must never break the bench line
+        l2 = {"error": repr(e)}
+
+    # ---- CPU baseline on this box's host cores (bounded sample: one frame pair of the same workload) -------------
+    _, p0 = step_pairs(args.warmup, wl)
+    c_steps, c_s, kind = cpu_reference(wl, frames_np, poses, p0[:1])
+    cpu = {"value": c_steps / c_s, "unit": "voxel-steps/s", "cores": 1, "kind": kind,
+           "sample": f"one {W}x{H} frame pair of the workload ({c_steps} voxel-steps, {c_s:.1f} s); reference is single-threaded: 1 of {os.cpu_count()} host cores"}
+
+    value = all_steps / (ms_max * 1e-3)
+    e_value = float(e_tot.item()) / (float(e_ms.item()) * 1e-3)
+    frames_total = args.steps * B * world
+    line = {
+        "metric": "voxel_steps_per_sec", "value": value, "unit": "voxel-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, wl),
+        "frames_per_s": frames_total / (ms_max * 1e-3), "rays_per_s": all_rays / (ms_max * 1e-3), "voxel_steps_per_ray": all_steps / max(1.0, all_rays),
+        "e2e": {"value": e_value, "unit": "voxel-steps/s", "h2d_bytes_per_step": (B + 1) * H * W, "d2h_bytes_per_step": 32,
+                "frames_per_s": frames_total / (float(e_ms.item()) * 1e-3), "api": "pixeltovoxelprojector_b200.accumulate_motion(pinned host frames) -> pvp_motion_accumulate_host"},
+        "gpu_launches": int(prof["launches_k1"] + prof["launches_k2"]),
+        "roofline": roofline, "l2_atomic_roofline": l2, "cpu_baseline": cpu, "clocks": clocks.summary(),
+        "atomics_per_voxel_step": float(tot[2].item()) / max(1.0, all_steps),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="1080p_dense_512", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

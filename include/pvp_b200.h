@@ -93,6 +93,17 @@ int pvp_ctx_sync(pvp_ctx *ctx);
 /* kernel variant selector for experiments: 0 = default; see DESIGN.md */
 int pvp_ctx_set_option(pvp_ctx *ctx, const char *key, int64_t value);
 
+/*
+ * Per-kernel accounting for bench.py: launch counts are always kept; with profiling enabled every
+ * K1/K2/K3 launch is bracketed by CUDA events on the context stream (live timing, no profiler).
+ */
+typedef struct pvp_profile {
+    uint64_t launches_k1, launches_k2, launches_k3, launches_other; /* kernels launched since the last reset */
+    double ms_k1, ms_k2, ms_k3;                                     /* summed event time (profiling enabled only) */
+} pvp_profile;
+int pvp_ctx_profile(pvp_ctx *ctx, int enable);
+int pvp_ctx_get_profile(pvp_ctx *ctx, pvp_profile *out, int reset); /* synchronises the stream */
+
 /* plain device-memory helpers for hosts that do not bring their own allocator (the CLI) */
 int pvp_dev_malloc(pvp_ctx *ctx, size_t bytes, void **out_dev);
 int pvp_dev_free(pvp_ctx *ctx, void *dev);

@@ -68,6 +68,14 @@ class ImageArgs(C.Structure):
                 ("accum_mode", C.c_int32), ("frac_bits", C.c_int32)]
 
 
+class Profile(C.Structure):
+    _fields_ = [("launches_k1", C.c_uint64), ("launches_k2", C.c_uint64), ("launches_k3", C.c_uint64), ("launches_other", C.c_uint64),
+                ("ms_k1", C.c_double), ("ms_k2", C.c_double), ("ms_k3", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class ImageStats(C.Structure):
     _fields_ = [("n_rays", C.c_uint64), ("n_samples", C.c_uint64)]
 
@@ -81,6 +89,8 @@ SIGNATURES = {
     "pvp_ctx_destroy": (C.c_int, [_P]),
     "pvp_ctx_set_stream": (C.c_int, [_P, _P]),
     "pvp_ctx_sync": (C.c_int, [_P]),
+    "pvp_ctx_profile": (C.c_int, [_P, C.c_int]),
+    "pvp_ctx_get_profile": (C.c_int, [_P, C.POINTER(Profile), C.c_int]),
     "pvp_ctx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "pvp_dev_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "pvp_dev_free": (C.c_int, [_P, _P]),

@@ -27,6 +27,32 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     return e == cudaErrorMemoryAllocation ? PVP_ERR_NOMEM : PVP_ERR_CUDA;
 }
 
+static cudaEvent_t pool_get(pvp_ctx *ctx)
+{
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+LaunchScope::LaunchScope(pvp_ctx *c, int k) : ctx(c), kind(k)
+{
+    uint64_t *cnt[4] = {&c->prof.launches_other, &c->prof.launches_k1, &c->prof.launches_k2, &c->prof.launches_k3};
+    ++*cnt[k];
+    if (c->profiling && k != 0) {
+        a = pool_get(c); b = pool_get(c);
+        cudaEventRecord(a, c->stream);
+    }
+}
+
+LaunchScope::~LaunchScope()
+{
+    if (a) {
+        cudaEventRecord(b, ctx->stream);
+        ctx->timed.push_back({a, b, kind});
+    }
+}
+
 int ensure_queue(pvp_ctx *ctx, unsigned long long entries)
 {
     if (ctx->queue.capacity >= entries) return PVP_OK;
@@ -141,6 +167,8 @@ int pvp_ctx_destroy(pvp_ctx *ctx)
         cudaEventDestroy(ctx->ev_done[i]);
     }
     if (ctx->ctl_dev) cudaFree(ctx->ctl_dev);
+    for (auto &t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
     cudaEventDestroy(ctx->ev_pairs);
@@ -170,6 +198,31 @@ int pvp_ctx_sync(pvp_ctx *ctx)
     PVP_REQUIRE(ctx != nullptr, "pvp_ctx_sync: ctx is NULL");
     DeviceGuard guard(ctx->device);
     PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PVP_OK;
+}
+
+int pvp_ctx_profile(pvp_ctx *ctx, int enable)
+{
+    PVP_REQUIRE(ctx != nullptr, "pvp_ctx_profile: ctx is NULL");
+    ctx->profiling = enable != 0;
+    return PVP_OK;
+}
+
+int pvp_ctx_get_profile(pvp_ctx *ctx, pvp_profile *out, int reset)
+{
+    PVP_REQUIRE(ctx && out, "pvp_ctx_get_profile: NULL argument");
+    DeviceGuard guard(ctx->device);
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &t : ctx->timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            if (t.kind == 1) ctx->prof.ms_k1 += ms; else if (t.kind == 2) ctx->prof.ms_k2 += ms; else ctx->prof.ms_k3 += ms;
+        }
+        ctx->ev_pool.push_back(t.a); ctx->ev_pool.push_back(t.b);
+    }
+    ctx->timed.clear();
+    *out = ctx->prof;
+    if (reset) ctx->prof = {0, 0, 0, 0, 0.0, 0.0, 0.0};
     return PVP_OK;
 }
 

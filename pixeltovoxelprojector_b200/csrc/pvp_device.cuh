@@ -153,7 +153,7 @@ __device__ __forceinline__ float motion_diff(float a, float b) { return fabsf(fs
 // The two filters between a pixel and a ray: changed (:252, :496) and pix_val >= 1e-3 (:501).
 __device__ __forceinline__ bool motion_casts_ray(float d, float threshold) { return (d > threshold) && !(d < 1e-3f); }
 
-// Fixed-point quantisation: rint(val * 2^frac_bits), nearest-even (oracle: o_quantize).
+// Fixed-point quantisation: rint(val * 2^frac_bits), nearest-even.
 __device__ __forceinline__ long long quantize_fixed(float val, float scale) { return __float2ll_rn(fmul(val, scale)); }
 
 }  // namespace pvp

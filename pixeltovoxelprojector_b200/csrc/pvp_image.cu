@@ -227,6 +227,7 @@ static int launch_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, v
 {
     const long long n_px = p.W * p.H;
     int blocks = (int)std::min<long long>((n_px + K3_THREADS - 1) / K3_THREADS, (long long)ctx->sm_count * 16);
+    LaunchScope scope(ctx, 3);
     if (accum_mode == PVP_ACCUM_F64)
         process_image_kernel<PVP_ACCUM_F64><<<blocks, K3_THREADS, 0, ctx->stream>>>(image_dev, (double *)grid_dev, (double *)tex_dev, p, ctx->ctl_dev);
     else

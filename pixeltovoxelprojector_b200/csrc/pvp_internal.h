@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/pvp_b200.h"
 
@@ -52,6 +53,13 @@ struct pvp_ctx {
     void *stage_dev[2] = {nullptr, nullptr};  // frame staging buffers for *_host
     size_t stage_bytes = 0;
 
+    // per-kernel accounting (pvp_ctx_profile / pvp_ctx_get_profile)
+    bool profiling = false;
+    pvp_profile prof = {0, 0, 0, 0, 0.0, 0.0, 0.0};
+    struct Timed { cudaEvent_t a, b; int kind; };
+    std::vector<Timed> timed;          // event pairs recorded since the last get_profile
+    std::vector<cudaEvent_t> ev_pool;  // recycled events
+
     // options (pvp_ctx_set_option)
     int64_t opt_dda_variant = 0;       // 0 = default
     int64_t opt_max_queue = 64ll << 20;  // ray-queue capacity in entries per batch
@@ -81,6 +89,13 @@ struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// RAII bracket around one kernel launch: counts it and, when profiling, times it with events.
+struct LaunchScope {
+    pvp_ctx *ctx; int kind; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(pvp_ctx *c, int k);
+    ~LaunchScope();
 };
 
 int ensure_queue(pvp_ctx *ctx, unsigned long long entries);

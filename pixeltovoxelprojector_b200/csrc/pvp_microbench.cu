@@ -63,6 +63,7 @@ extern "C" int pvp_atomic_microbench(pvp_ctx *ctx, void *buf_dev, size_t buf_byt
     const long long lanes = (long long)blocks * threads;
     const int iters = (int)std::max<long long>(1, n_ops / lanes);
     PVP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    ++ctx->prof.launches_other;
     if (elem == 4)
         atomic_bench_kernel<float><<<blocks, threads, 0, ctx->stream>>>((float *)buf_dev, buf_bytes / 4, pattern, iters);
     else if (elem == 8)

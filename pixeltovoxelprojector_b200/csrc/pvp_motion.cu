@@ -279,6 +279,7 @@ static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_strid
     constexpr int PX = FrameVec<T>::PX;
     const bool vec_ok = ((uintptr_t)frames_dev % sizeof(typename FrameVec<T>::V) == 0) && (frame_stride % PX == 0);
     dim3 grid((unsigned)((n_pix + (long long)K1_THREADS * PX - 1) / ((long long)K1_THREADS * PX)), (unsigned)n_pairs);
+    LaunchScope scope(ctx, 1);
     motion_compact_kernel<T><<<grid, K1_THREADS, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, n_pix,
                                                                    threshold, vec_ok, ctx->queue, ctx->ctl_dev);
     PVP_CUDA(cudaGetLastError());
@@ -287,6 +288,7 @@ static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_strid
 
 static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, void *grid_dev, int width, int height)
 {
+    LaunchScope scope(ctx, 2);
     if (accum_mode == PVP_ACCUM_F32) {
         auto k = dda_accumulate_kernel<PVP_ACCUM_F32>;
         k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (float *)grid_dev, width,
@@ -370,6 +372,7 @@ int pvp_detect_motion(pvp_ctx *ctx, const void *prev_dev, const void *next_dev, 
     if (n_pixels <= 0) return PVP_OK;
     DeviceGuard guard(ctx->device);
     int blocks = (int)std::min<long long>((n_pixels + 255) / 256, (long long)ctx->sm_count * 8);
+    LaunchScope scope(ctx, 0);
     if (frame_dtype == PVP_FRAME_U8)
         detect_motion_kernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>((const uint8_t *)prev_dev, (const uint8_t *)next_dev, n_pixels,
                                                                        threshold, changed_dev, diff_dev);
@@ -387,6 +390,7 @@ int pvp_pixel_rays(pvp_ctx *ctx, const uint32_t *pix_dev, int64_t n, int width, 
     if (n <= 0) return PVP_OK;
     DeviceGuard guard(ctx->device);
     int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 8);
+    LaunchScope scope(ctx, 0);
     pixel_rays_kernel<<<blocks, 256, 0, ctx->stream>>>(pix_dev, n, width, height, *pose, dirs_dev);
     PVP_CUDA(cudaGetLastError());
     return PVP_OK;
@@ -402,6 +406,7 @@ int pvp_cast_rays(pvp_ctx *ctx, const float *origins_dev, const float *dirs_dev,
     if (n <= 0) return PVP_OK;
     DeviceGuard guard(ctx->device);
     int blocks = (int)std::min<long long>((n + 127) / 128, (long long)ctx->sm_count * 16);
+    LaunchScope scope(ctx, 0);
     cast_rays_kernel<<<blocks, 128, 0, ctx->stream>>>(origins_dev, dirs_dev, n, g, counts_dev, (const long long *)offsets_dev, vox_dev, t_dev);
     PVP_CUDA(cudaGetLastError());
     return PVP_OK;
@@ -497,6 +502,7 @@ int pvp_fixed_to_f32(pvp_ctx *ctx, const int64_t *src_dev, float *dst_dev, int64
     if (n <= 0) return PVP_OK;
     DeviceGuard guard(ctx->device);
     int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    LaunchScope scope(ctx, 0);
     fixed_to_f32_kernel<<<blocks, 256, 0, ctx->stream>>>((const long long *)src_dev, dst_dev, n, 1.0 / (double)(1ll << frac_bits));
     PVP_CUDA(cudaGetLastError());
     return PVP_OK;
@@ -508,6 +514,7 @@ int pvp_fixed_to_f64(pvp_ctx *ctx, const int64_t *src_dev, double *dst_dev, int6
     if (n <= 0) return PVP_OK;
     DeviceGuard guard(ctx->device);
     int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    LaunchScope scope(ctx, 0);
     fixed_to_f64_kernel<<<blocks, 256, 0, ctx->stream>>>((const long long *)src_dev, dst_dev, n, 1.0 / (double)(1ll << frac_bits));
     PVP_CUDA(cudaGetLastError());
     return PVP_OK;

@@ -53,6 +53,15 @@ class Context:
     def set_option(self, key: str, value: int) -> None:
         check(self._lib.pvp_ctx_set_option(self.handle, key.encode(), int(value)))
 
+    def profile(self, enable: bool = True) -> None:
+        """Bracket every K1/K2/K3 launch with CUDA events on the context stream (live kernel timing)."""
+        check(self._lib.pvp_ctx_profile(self.handle, int(enable)))
+
+    def get_profile(self, reset: bool = True) -> dict:
+        p = _lib.Profile()
+        check(self._lib.pvp_ctx_get_profile(self.handle, C.byref(p), int(reset)))
+        return p.as_dict()
+
     def sync(self) -> None:
         check(self._lib.pvp_ctx_sync(self.handle))
 

@@ -1,0 +1,226 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol include/pvp_b200.h declares,
+the host-side logic (pose, metadata, image decode, .bin) matches the oracle, and the product fails loudly
+without a GPU.  No compute entry point is called here."""
+import ctypes as C
+import json
+import os
+import re
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bits, golden
+
+import pixeltovoxelprojector_b200 as pvp
+from pixeltovoxelprojector_b200 import _lib, synth
+
+HEADER = os.path.join(ROOT, "include", "pvp_b200.h")
+
+
+def declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(pvp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pvp_b200.h but not exported by libpvp_b200.so"
+    assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
+    assert lib.pvp_version() == 100
+
+
+def test_struct_layouts_match_header_sizes():
+    assert C.sizeof(_lib.Pair) == 60 and C.sizeof(_lib.GridDesc) == 36 and C.sizeof(_lib.Stats) == 32
+    assert C.sizeof(_lib.FrameInfo) == 4 * 10 + 512
+    opt = _lib.RunOptions()
+    _lib.load().pvp_run_options_default(C.byref(opt))
+    # the hard-coded constants of ray_voxel.cpp:434-447
+    assert (opt.grid.n, opt.grid.voxel_size, tuple(opt.grid.center), opt.threshold) == (500, 6.0, (0.0, 0.0, 500.0), 2.0)
+    assert (opt.grid.slab_lo, opt.grid.slab_hi, opt.shard_rank, opt.shard_count) == (0, 500, 0, 1)
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pvp.Context()
+    h = C.c_void_p()
+    rc = _lib.load().pvp_ctx_create(0, None, C.byref(h))
+    assert rc == -2 and b"no CPU fallback" in _lib.load().pvp_last_error()
+
+
+def test_host_pose_matches_oracle(oracle):
+    g = golden("pose_golden.npz")
+    for ypr, R, fov, w, f in zip(g["ypr"], g["R"], g["fov"], g["width"], g["focal"]):
+        assert np.array_equal(bits(pvp.rotation_matrix(*ypr)), bits(R))
+        assert bits(pvp.focal_length(fov, int(w))) == bits(np.float32(f))
+    rng = np.random.default_rng(7)
+    for _ in range(500):
+        ypr = rng.uniform(-720, 720, 3).astype(np.float32)
+        assert np.array_equal(bits(pvp.rotation_matrix(*ypr)), bits(oracle.rotation_matrix(*ypr)))
+
+
+def test_metadata_defaults_and_order(tmp_path):
+    entries = [{"camera_index": 2, "frame_index": 5, "camera_position": [1.5, -2, 3e2], "yaw": 10, "pitch": -1.25, "roll": 0.5,
+                "fov_degrees": 75.5, "image_file": "a b/é.pgm", "object_name": "ignored"},
+               {},
+               {"camera_position": [1, 2], "image_file": "x.pgm", "frame_index": 1.0}]
+    p = tmp_path / "m.json"
+    p.write_text(json.dumps(entries))
+    fr = pvp.load_metadata(str(p))
+    assert len(fr) == 3
+    assert (fr[0].camera_index, fr[0].frame_index, fr[0].camera_position, fr[0].yaw, fr[0].pitch, fr[0].roll, fr[0].fov_degrees) == \
+        (2, 5, (1.5, -2.0, 300.0), 10.0, -1.25, 0.5, 75.5)
+    assert fr[0].image_file == "a b/é.pgm"
+    # defaults of ray_voxel.cpp:157-163
+    assert (fr[1].camera_index, fr[1].frame_index, fr[1].yaw, fr[1].pitch, fr[1].roll, fr[1].fov_degrees, fr[1].image_file) == (0, 0, 0, 0, 0, 60.0, "")
+    assert fr[2].camera_position == (0.0, 0.0, 0.0) and fr[2].frame_index == 1  # short array is ignored (:168)
+    (tmp_path / "bad.json").write_text('{"not": "an array"}')
+    with pytest.raises(pvp.PvpError, match="top level is not an array"):
+        pvp.load_metadata(str(tmp_path / "bad.json"))
+    with pytest.raises(pvp.PvpError, match="Cannot open"):
+        pvp.load_metadata(str(tmp_path / "missing.json"))
+
+
+def _png(path, arr, ctype, depth=8, palette=None):
+    h, w = arr.shape[:2]
+    raw = b""
+    rows = arr.reshape(h, -1)
+    if depth == 16:
+        rows = rows.astype(">u2").view(np.uint8).reshape(h, -1)
+    elif depth < 8:
+        per = 8 // depth
+        pad = (-rows.shape[1]) % per
+        r = np.pad(rows, ((0, 0), (0, pad))).reshape(h, -1, per).astype(np.uint32)
+        rows = sum(r[:, :, k] << (8 - depth * (k + 1)) for k in range(per)).astype(np.uint8)
+    rng = np.random.default_rng(0)
+    prev = np.zeros(rows.shape[1], np.int32)
+    bpp = max(1, {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype] * depth // 8)
+    for y in range(h):  # exercise all five filter types
+        cur = rows[y].astype(np.int32)
+        ft = int(rng.integers(0, 5))
+        left = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        ul = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        if ft == 0: f = cur
+        elif ft == 1: f = cur - left
+        elif ft == 2: f = cur - prev
+        elif ft == 3: f = cur - ((left + prev) >> 1)
+        else:
+            p = left + prev - ul
+            pa, pb, pc = abs(p - left), abs(p - prev), abs(p - ul)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, ul))
+            f = cur - pred
+        raw += bytes([ft]) + (f & 255).astype(np.uint8).tobytes()
+        prev = cur
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+    comp = zlib.compress(raw)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+    if palette is not None:
+        out += chunk(b"PLTE", palette.astype(np.uint8).tobytes())
+    out += chunk(b"IDAT", comp[: len(comp) // 2]) + chunk(b"IDAT", comp[len(comp) // 2:]) + chunk(b"IEND", b"")
+    open(path, "wb").write(out)
+
+
+def luma(r, g, b):
+    return ((r.astype(np.uint32) * 77 + g.astype(np.uint32) * 150 + b.astype(np.uint32) * 29) >> 8)
+
+
+def test_image_decode_pnm_png(tmp_path):
+    rng = np.random.default_rng(3)
+    gray = rng.integers(0, 256, (13, 17), dtype=np.uint8)
+    rgb = rng.integers(0, 256, (13, 17, 3), dtype=np.uint8)
+    synth.write_pgm(str(tmp_path / "g.pgm"), gray)
+    synth.write_ppm(str(tmp_path / "c.ppm"), rgb)
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "g.pgm")), gray)
+    want = luma(rgb[..., 0], rgb[..., 1], rgb[..., 2]).astype(np.uint8)   # stb_image's integer luma
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "c.ppm")), want)
+    (tmp_path / "h.pgm").write_bytes(b"P5\n# comment\n17 13\n# another\n255\n" + gray.tobytes())
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "h.pgm")), gray)
+    g16 = rng.integers(0, 65536, (5, 7)).astype(np.uint16)
+    (tmp_path / "g16.pgm").write_bytes(b"P5\n7 5\n65535\n" + g16.astype(">u2").tobytes())
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "g16.pgm")), (g16 >> 8).astype(np.uint8))
+    # PNG: gray8, rgb8, rgba8, gray+alpha, gray16, rgb16, palette8, gray4, gray1
+    _png(tmp_path / "g.png", gray, 0)
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "g.png")), gray)
+    _png(tmp_path / "c.png", rgb, 2)
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "c.png")), want)
+    rgba = np.concatenate([rgb, rng.integers(0, 256, (13, 17, 1), dtype=np.uint8)], -1)
+    _png(tmp_path / "ca.png", rgba, 6)
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "ca.png")), want)
+    ga = np.stack([gray, 255 - gray], -1)
+    _png(tmp_path / "ga.png", ga, 4)
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "ga.png")), gray)
+    g16b = rng.integers(0, 65536, (13, 17)).astype(np.uint16)
+    _png(tmp_path / "g16.png", g16b, 0, depth=16)
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "g16.png")), (g16b >> 8).astype(np.uint8))
+    c16 = rng.integers(0, 65536, (13, 17, 3)).astype(np.uint16)
+    _png(tmp_path / "c16.png", c16, 2, depth=16)
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "c16.png")), (luma(c16[..., 0], c16[..., 1], c16[..., 2]) >> 8).astype(np.uint8))
+    pal = rng.integers(0, 256, (40, 3), dtype=np.uint8)
+    idx = rng.integers(0, 40, (13, 17), dtype=np.uint8)
+    _png(tmp_path / "p.png", idx, 3, palette=pal)
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "p.png")), luma(pal[idx, 0], pal[idx, 1], pal[idx, 2]).astype(np.uint8))
+    g4 = rng.integers(0, 16, (13, 17), dtype=np.uint8)
+    _png(tmp_path / "g4.png", g4, 0, depth=4)
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "g4.png")), g4 * 17)
+    g1 = rng.integers(0, 2, (13, 17), dtype=np.uint8)
+    _png(tmp_path / "g1.png", g1, 0, depth=1)
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "g1.png")), g1 * 255)
+    try:  # cross-check the PNG decoder against an independent one when PIL is present
+        from PIL import Image
+        Image.fromarray(gray).save(tmp_path / "pil.png")
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "pil.png")), gray)
+        Image.fromarray(rgb).save(tmp_path / "pilc.png", optimize=True)
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "pilc.png")), want)
+    except ImportError:
+        pass
+    for bad in ("nope.pgm",):
+        with pytest.raises(pvp.PvpError, match="Failed to load image"):
+            pvp.load_image_gray(str(tmp_path / bad))
+    (tmp_path / "junk.jpg").write_bytes(b"\xff\xd8\xff\xe0 not really a jpeg")
+    with pytest.raises(pvp.PvpError, match="Failed to load image"):
+        pvp.load_image_gray(str(tmp_path / "junk.jpg"))
+
+
+def test_bin_roundtrip_matches_reference_layout(tmp_path):
+    rng = np.random.default_rng(0)
+    grid = rng.random((7, 7, 7)).astype(np.float32)
+    path = str(tmp_path / "g.bin")
+    pvp.write_bin(path, grid, 6.0)
+    raw = open(path, "rb").read()
+    assert len(raw) == 8 + 4 * 7 ** 3                      # ray_voxel.cpp:549-552
+    assert struct.unpack("<if", raw[:8]) == (7, 6.0)
+    assert np.array_equal(np.frombuffer(raw[8:], np.float32).reshape(7, 7, 7), grid)   # voxelmotionviewer.py:41-51
+    back, vs = pvp.read_bin(path)
+    assert np.array_equal(back, grid) and vs == np.float32(6.0)
+    with pytest.raises(pvp.PvpError, match="Cannot open output file"):
+        pvp.write_bin(str(tmp_path / "no_such_dir" / "g.bin"), grid, 1.0)
+
+
+def test_cli_usage_error_without_gpu():
+    exe = os.path.join(ROOT, "pixeltovoxelprojector_b200", "ray_voxel")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    res = subprocess.run([exe, "only", "two"], capture_output=True, text=True)
+    assert res.returncode == 1 and "Usage:" in res.stderr and "<metadata.json> <image_folder> <output_voxel_bin>" in res.stderr
+
+
+def test_product_never_imports_oracle():
+    """The product path must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "pixeltovoxelprojector_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libref" not in out

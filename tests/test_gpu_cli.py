@@ -1,0 +1,91 @@
+"""End to end through the CLI boundary (B-2): metadata.json + image folder -> .bin, compared byte-for-value with the
+output of the reference CLI itself (tests/golden/cli_golden.npz: noise-off build of the unmodified ray_voxel.cpp)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, bits, golden
+
+import pixeltovoxelprojector_b200 as pvp
+from pixeltovoxelprojector_b200 import synth
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "pixeltovoxelprojector_b200", "ray_voxel")
+
+
+def materialise(tmp_path):
+    g = golden("cli_golden.npz")
+    for name, present in zip(g["names"], g["present"]):
+        if present:
+            synth.write_pgm(str(tmp_path / str(name)), g["img_" + str(name)])
+    meta = tmp_path / "metadata.json"
+    meta.write_text(str(g["metadata"]))
+    return g, str(meta)
+
+
+def check_bin(path, g):
+    grid, vs = pvp.read_bin(path)
+    assert grid.shape == (500, 500, 500) and vs == g["voxel_size"]
+    assert os.path.getsize(path) == 500_000_008                    # 8 + 4 N^3
+    flat = grid.reshape(-1)
+    nz = np.flatnonzero(flat)
+    assert np.array_equal(nz, g["nz_index"])
+    assert np.array_equal(bits(flat[nz]), bits(g["nz_value"]))
+
+
+def test_cli_binary_matches_reference_cli(tmp_path):
+    g, meta = materialise(tmp_path)
+    out = str(tmp_path / "voxel_grid.bin")
+    res = subprocess.run([EXE, meta, str(tmp_path), out], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout == str(g["stdout"]).replace(str(g["stdout"]).split("Saved voxel grid to ")[1].strip(), out)
+    # same diagnostics as the reference: one failed load (+ skip notice) and one size mismatch
+    assert res.stderr.count("Skipping frame due to load error.") == str(g["stderr"]).count("Skipping frame due to load error.") == 1
+    assert res.stderr.count("Images differ in size") == str(g["stderr"]).count("Images differ in size") == 1
+    check_bin(out, g)
+    # fixed-point mode writes the same float32 payload for integer frames
+    out2 = str(tmp_path / "fx.bin")
+    res = subprocess.run([EXE, meta, str(tmp_path), out2, "--fixed-point", "12", "--quiet", "--stats"], capture_output=True, text=True)
+    assert res.returncode == 0 and "voxel_steps=" in res.stderr
+    check_bin(out2, g)
+
+
+def test_cli_error_paths(tmp_path):
+    res = subprocess.run([EXE], capture_output=True, text=True)
+    assert res.returncode == 1 and res.stderr.startswith("Usage:")
+    res = subprocess.run([EXE, str(tmp_path / "nope.json"), str(tmp_path), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert res.returncode == 1 and "Cannot open" in res.stderr
+    (tmp_path / "empty.json").write_text("[]")
+    res = subprocess.run([EXE, str(tmp_path / "empty.json"), str(tmp_path), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert res.returncode == 1 and "No frames loaded." in res.stderr
+    g, meta = materialise(tmp_path)
+    res = subprocess.run([EXE, meta, str(tmp_path), str(tmp_path / "no_dir" / "o.bin"), "--quiet"], capture_output=True, text=True)
+    assert res.returncode == 1 and "Cannot open output file" in res.stderr
+
+
+def test_python_pipeline_sharded_equals_whole(tmp_path):
+    """Frame sharding (SURVEY 8e mode 1) on one GPU: the per-shard grids of 1, 2, 3 and 5 shards sum to the reference grid
+    (fixed point => bit-exact), and every shard resolves the skipped-frame pairing like the reference."""
+    g, meta = materialise(tmp_path)
+    whole = None
+    for count in (1, 2, 3, 5):
+        total = torch.zeros((500, 500, 500), dtype=torch.int64, device="cuda")
+        pairs = 0
+        for rank in range(count):
+            grid = pvp.VoxelGrid(accum="fixed", frac_bits=8)
+            rep = pvp.ray_voxel_accumulate(meta, str(tmp_path), grid, shard=(rank, count))
+            total += grid.data
+            pairs += rep["n_pairs"]
+            del grid
+        assert pairs == 5     # cam0: (0,1),(1,3),(3,4); cam3: (0,1) + the mismatched pair is not counted, (2,3) mismatched too
+        if whole is None:
+            whole = total
+            flat = pvp.VoxelGrid(accum="fixed", frac_bits=8, data=total).to_float32().cpu().numpy().reshape(-1)
+            nz = np.flatnonzero(flat)
+            assert np.array_equal(nz, g["nz_index"]) and np.array_equal(bits(flat[nz]), bits(g["nz_value"]))
+        else:
+            assert torch.equal(whole, total)

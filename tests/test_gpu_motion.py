@@ -1,0 +1,262 @@
+"""Parity of path A on the GPU, through the C ABI: motion masks, ray set-up, visited voxel lists (bit-exact),
+accumulated grids (bit-exact for integer-valued frames and for fixed point; rel. 1e-5 for float frames with
+fp32 atomics), slabs, the host-staged path, and size-independent properties at full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits, golden
+
+import pixeltovoxelprojector_b200 as pvp
+from pixeltovoxelprojector_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RTOL_F32_ATOMICS = 1e-5   # BASELINE.json north_star: fp32 atomics within a relative tolerance of 1e-5
+
+
+def grid_like(g, accum="f32", slab=None, frac_bits=16):
+    return pvp.VoxelGrid(int(g["N"]), float(g["voxel_size"]), tuple(float(c) for c in g["center"]), accum=accum, slab=slab, frac_bits=frac_bits)
+
+
+def pose_of(g, W):
+    return pvp.FramePose(tuple(float(c) for c in g["cam"]), *(float(a) for a in g["ypr"]), fov_degrees=float(g["fov"]))
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_detect_motion_bit_exact(ctx, oracle, dtype):
+    rng = np.random.default_rng(0)
+    for shape in ((1, 1), (7, 13), (480, 640), (1080, 1920)):
+        prev = rng.integers(0, 256, shape, dtype=np.uint8)
+        curr = np.where(rng.random(shape) < 0.5, prev, rng.integers(0, 256, shape, dtype=np.uint8)).astype(np.uint8)
+        if dtype == torch.float32:
+            prev = prev + rng.uniform(-1, 1, shape).astype(np.float32)
+            curr = curr + rng.uniform(-1, 1, shape).astype(np.float32)
+        want_c, want_d = oracle.detect_motion(prev.astype(np.float32), curr.astype(np.float32), 2.0)
+        c, d = pvp.detect_motion(torch.as_tensor(prev, device=DEV).to(dtype), torch.as_tensor(curr, device=DEV).to(dtype), 2.0)
+        assert np.array_equal(c.cpu().numpy(), want_c)
+        assert np.array_equal(bits(d.cpu().numpy()), bits(want_d))
+    with pytest.raises(ValueError, match="differ in size"):
+        pvp.detect_motion(torch.zeros((4, 4), device=DEV, dtype=dtype), torch.zeros((4, 5), device=DEV, dtype=dtype), 2.0)
+
+
+def test_pixel_rays_bit_exact(ctx, oracle):
+    rng = np.random.default_rng(1)
+    for W, H in ((640, 480), (1920, 1080), (3840, 2160), (4096, 4096), (17, 5)):
+        pose = pvp.FramePose((0, 0, 0), float(np.float32(rng.uniform(-180, 180))), float(np.float32(rng.uniform(-90, 90))),
+                             float(np.float32(rng.uniform(-180, 180))), fov_degrees=float(np.float32(rng.uniform(20, 120))))
+        pix = rng.integers(0, W * H, 4000)
+        pix[:4] = [0, W - 1, W * (H - 1), W * H - 1]
+        got = pvp.pixel_rays(torch.as_tensor(pix, device=DEV), W, H, pose).cpu().numpy()
+        R, f = oracle.rotation_matrix(pose.yaw, pose.pitch, pose.roll), oracle.focal_length(pose.fov_degrees, W)
+        want = np.stack([oracle.pixel_ray(int(p % W), int(p // W), W, H, f, R) for p in pix])
+        assert np.array_equal(bits(got), bits(want))
+
+
+def test_cast_rays_golden_bit_exact(ctx):
+    g = golden("rays_golden.npz")
+    off = np.concatenate([[0], np.cumsum(g["counts"])])
+    for i in range(len(g["N"])):
+        grid = pvp.VoxelGrid(int(g["N"][i]), float(g["voxel_size"][i]), tuple(float(c) for c in g["center"][i]))
+        counts, offsets, vox, t = pvp.cast_rays(torch.as_tensor(g["cam"][i:i + 1], device=DEV), torch.as_tensor(g["dir"][i:i + 1], device=DEV), grid)
+        assert int(counts[0]) == g["counts"][i], i
+        assert np.array_equal(vox.cpu().numpy(), g["vox"][off[i]:off[i + 1]]), i
+        assert np.array_equal(bits(t.cpu().numpy()), bits(g["t"][off[i]:off[i + 1]])), i
+
+
+@pytest.mark.parametrize("N,vs", [(64, 2.0), (256, 1.5), (500, 6.0)])
+def test_cast_rays_random_bit_exact(ctx, oracle, N, vs):
+    """Visited voxel indices must match the reference bit-exactly (order, count, t)."""
+    rng = np.random.default_rng(N)
+    n = 600
+    center = np.array([0, 0, 500], np.float32)
+    half = N * vs / 2
+    cam = (center + rng.uniform(-1.5, 1.5, (n, 3)) * half).astype(np.float32)
+    tgt = center + rng.uniform(-1, 1, (n, 3)) * half
+    d = (tgt - cam).astype(np.float32)
+    d[::9, rng.integers(0, 3)] = 0.0
+    d[::11] = rng.choice([-1.0, 1.0, 0.0, -0.0], (len(d[::11]), 3))
+    cam[::11] = (center - half + vs * rng.integers(0, N + 1, (len(cam[::11]), 3))).astype(np.float32)  # on lattice planes: ties
+    nrm = np.linalg.norm(d, axis=1, keepdims=True)
+    d = np.where(nrm > 0, d / np.maximum(nrm, 1e-30), d).astype(np.float32)
+    grid = pvp.VoxelGrid(N, vs, tuple(center))
+    counts, offsets, vox, t = pvp.cast_rays(torch.as_tensor(cam, device=DEV), torch.as_tensor(d, device=DEV), grid)
+    counts, offsets, vox, t = counts.cpu().numpy(), offsets.cpu().numpy(), vox.cpu().numpy(), t.cpu().numpy()
+    total = 0
+    for i in range(n):
+        w_vox, w_t = oracle.cast_ray(cam[i], d[i], N, vs, center, want_t=True)
+        assert counts[i] == len(w_vox), i
+        assert np.array_equal(vox[offsets[i]:offsets[i + 1]], w_vox), i
+        assert np.array_equal(bits(t[offsets[i]:offsets[i + 1]]), bits(w_t)), i
+        total += len(w_vox)
+    assert total > 20 * n // 4
+
+
+@pytest.mark.parametrize("accum", ["f32", "fixed"])
+@pytest.mark.parametrize("frames_on", ["device", "host"])
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+def test_pair_golden(ctx, accum, frames_on, dtype):
+    """ray_voxel.cpp:484-531 on the committed reference output: integer-valued frames => exact sums."""
+    g = golden("pair_golden.npz")
+    H, W = g["prev"].shape
+    frames = np.stack([g["prev"], g["curr"]])
+    frames = frames if dtype == "u8" else frames.astype(np.float32)
+    pairs, n = pvp.make_pairs([pose_of(g, W)] * 2, W)
+    assert np.array_equal(bits(np.array(pairs[0].R[:], np.float32)), bits(g["R"])) and bits(np.float32(pairs[0].focal)) == bits(g["focal"])
+    grid = grid_like(g, accum)
+    fr = torch.as_tensor(frames, device=DEV) if frames_on == "device" else frames
+    st = pvp.accumulate_motion(fr, pairs, grid, float(g["threshold"]))
+    assert (st["n_rays"], st["n_steps"], st["n_written"]) == (int(g["n_rays"]), int(g["n_steps"]), int(g["n_steps"]))
+    out = grid.to_float32().cpu().numpy().reshape(-1)
+    nz = np.flatnonzero(out)
+    assert np.array_equal(nz, g["nz_index"])
+    assert np.array_equal(bits(out[nz]), bits(g["nz_value"]))
+
+
+def test_slabs_partition_the_grid(ctx):
+    g = golden("pair_golden.npz")
+    H, W = g["prev"].shape
+    frames = torch.as_tensor(np.stack([g["prev"], g["curr"]]), device=DEV)
+    pairs, _ = pvp.make_pairs([pose_of(g, W)] * 2, W)
+    N = int(g["N"])
+    parts, written = [], 0
+    for lo, hi in ((0, 9), (9, 10), (10, 31), (31, N), (N, N)):
+        grid = grid_like(g, slab=(lo, hi))
+        st = pvp.accumulate_motion(frames, pairs, grid, float(g["threshold"]))
+        assert st["n_steps"] == int(g["n_steps"])   # every slab walks every ray in full
+        written += st["n_written"]
+        parts.append(grid.data)
+    assert written == int(g["n_steps"])
+    out = torch.cat(parts).cpu().numpy().reshape(-1)
+    assert np.array_equal(np.flatnonzero(out), g["nz_index"]) and np.array_equal(out[g["nz_index"]], g["nz_value"])
+
+
+def _scene(rng, F, H, W, N, vs, center, dense):
+    frames = synth.dense_frames(F, H, W, seed=int(rng.integers(1 << 30))) if dense else synth.sparse_frames(F, H, W, seed=int(rng.integers(1 << 30)), blobs=3)
+    poses = synth.orbit_poses(F, N, vs, center, seed=int(rng.integers(1 << 30)))
+    return frames, poses
+
+
+def _oracle_run(oracle, frames, poses, N, vs, center, thr, accum_mode=0, frac_bits=16, pair_idx=None):
+    grid = np.zeros((N, N, N), np.float32 if accum_mode == 0 else np.int64)
+    tot = np.zeros(3, np.int64)
+    W = frames.shape[2]
+    for (p, c) in (pair_idx or [(i - 1, i) for i in range(1, len(frames))]):
+        R = oracle.rotation_matrix(poses[c].yaw, poses[c].pitch, poses[c].roll)
+        f = oracle.focal_length(poses[c].fov_degrees, W)
+        tot += oracle.accumulate_pair(frames[p], frames[c], np.array(poses[c].camera_position, np.float32), R, f, grid, N, vs,
+                                      np.array(center, np.float32), thr, accum_mode=accum_mode, frac_bits=frac_bits)
+    return grid, tot
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_sequence_u8_bit_exact(ctx, oracle, dense):
+    """Multi-pair batch, moving camera, uint8 frames: every addend is an integer <= 255, so fp32 sums are exact and
+    order independent (< 2^24) -- the grid must equal the reference's serial sum bit for bit."""
+    rng = np.random.default_rng(10 + dense)
+    F, H, W, N, vs, center = 5, 60, 96, 96, 4.0, (0.0, 0.0, 500.0)
+    frames, poses = _scene(rng, F, H, W, N, vs, center, dense)
+    want, tot = _oracle_run(oracle, frames, poses, N, vs, center, 2.0)
+    assert want.max() < 2 ** 24 and tot[1] > 1000
+    pairs, n = pvp.make_pairs(poses, W)
+    for fr in (torch.as_tensor(frames, device=DEV), frames, torch.as_tensor(frames).pin_memory()):
+        grid = pvp.VoxelGrid(N, vs, center)
+        st = pvp.accumulate_motion(fr, pairs, grid, 2.0)
+        assert (st["n_rays"], st["n_steps"], st["n_written"]) == tuple(tot)
+        assert np.array_equal(bits(grid.data.cpu().numpy()), bits(want))
+
+
+def test_sequence_float_frames_tolerance_and_fixed_exact(ctx, oracle):
+    """Float frames (loader-style noise, seeded): fp32 atomics within rel 1e-5 of the serial reference sum;
+    fixed-point mode bit-exact against the oracle's fixed-point accumulation and run-to-run deterministic."""
+    rng = np.random.default_rng(12)
+    F, H, W, N, vs, center = 4, 48, 80, 80, 5.0, (0.0, 0.0, 500.0)
+    frames, poses = _scene(rng, F, H, W, N, vs, center, True)
+    frames = np.clip(frames.astype(np.float32) + rng.uniform(-1, 1, frames.shape).astype(np.float32), 0, 255)  # ray_voxel.cpp:213-218
+    want, tot = _oracle_run(oracle, frames, poses, N, vs, center, 2.0)
+    pairs, _ = pvp.make_pairs(poses, W)
+    grid = pvp.VoxelGrid(N, vs, center)
+    st = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, grid, 2.0)
+    assert (st["n_rays"], st["n_steps"]) == (tot[0], tot[1])
+    got = grid.data.cpu().numpy()
+    assert np.array_equal(got != 0, want != 0)                      # identical support (visited set)
+    np.testing.assert_allclose(got, want, rtol=RTOL_F32_ATOMICS, atol=0)
+    want_fx, _ = _oracle_run(oracle, frames, poses, N, vs, center, 2.0, accum_mode=1, frac_bits=20)
+    runs = []
+    for _ in range(2):
+        gfx = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=20)
+        pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, gfx, 2.0)
+        runs.append(gfx.data.cpu().numpy())
+    assert np.array_equal(runs[0], want_fx) and np.array_equal(runs[0], runs[1])
+    assert np.array_equal(bits(pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=20, data=torch.as_tensor(want_fx, device=DEV)).to_float32().cpu().numpy()),
+                          bits(oracle.fixed_to_f32(want_fx, 20)))
+
+
+def test_edge_cases(ctx, oracle):
+    N, vs, center = 32, 1.0, (0.0, 0.0, 0.0)
+    W, H = 16, 8
+    frames = np.zeros((3, H, W), np.uint8)
+    frames[1, 2, 3] = 2      # |d| == threshold: not changed
+    frames[2, 2, 3] = 5      # |5-2| = 3 > 2: one ray
+    inside = pvp.FramePose((0.3, 0.2, 0.1))
+    pairs, n = pvp.make_pairs([inside] * 3, W)
+    grid = pvp.VoxelGrid(N, vs, center)
+    assert pvp.accumulate_motion(torch.as_tensor(frames[:2], device=DEV), pairs, grid, 2.0, n_pairs=1)["n_rays"] == 0
+    st = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, grid, 2.0)
+    want, tot = _oracle_run(oracle, frames, [inside] * 3, N, vs, center, 2.0)
+    assert st["n_rays"] == 1 and st["n_steps"] == tot[1] > 0 and np.array_equal(grid.data.cpu().numpy(), want)
+    # zero pairs: a no-op that still reports counters
+    assert pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, grid, 2.0, n_pairs=0)["n_steps"] == 0
+    # camera outside the +z face looking in: every ray enters through a max face and is dropped (ray_voxel.cpp:329-334)
+    outside = pvp.FramePose((0.0, 0.0, 100.0))
+    p2, _ = pvp.make_pairs([outside] * 2, W)
+    g2 = pvp.VoxelGrid(N, vs, center)
+    st = pvp.accumulate_motion(torch.as_tensor(synth.dense_frames(2, H, W), device=DEV), p2, g2, 2.0)
+    assert st["n_rays"] > 100 and st["n_steps"] == 0 and not g2.data.any()
+    # N = 1 grid, odd sizes, unaligned frame stride (scalar-load path of K1)
+    for (h, w) in ((1, 1), (3, 5), (7, 33)):
+        fr = synth.dense_frames(3, h, w, seed=h * w)
+        pz = [pvp.FramePose((0.1, 0.1, 0.1), yaw=5.0 * i) for i in range(3)]
+        pp, _ = pvp.make_pairs(pz, w)
+        for n_ in (1, 5):
+            gg = pvp.VoxelGrid(n_, 2.0, (0, 0, 0))
+            pvp.accumulate_motion(torch.as_tensor(fr, device=DEV), pp, gg, 2.0)
+            w_, _ = _oracle_run(oracle, fr, pz, n_, 2.0, (0, 0, 0), 2.0)
+            assert np.array_equal(gg.data.cpu().numpy(), w_)
+    with pytest.raises(pvp.PvpError, match="outside"):
+        bad, _ = pvp.make_pairs([inside] * 2, W, pairs=[(0, 7)])
+        pvp.accumulate_motion(frames, bad, grid, 2.0)
+
+
+def test_full_size_properties_1080p_256(ctx):
+    """BASELINE config 2 shape (1080p -> 256^3): size-independent properties instead of a CPU oracle run.
+    (a) grid total == sum over rays of diff * steps (checked through the fixed-point grid, exactly);
+    (b) linearity: accumulating pairs A then B equals accumulating A+B in one batch;
+    (c) fixed-point determinism across runs; (d) fp32 result within 1e-5 of the fixed-point result."""
+    F, H, W, N, vs, center = 3, 1080, 1920, 256, 2.0, (0.0, 0.0, 500.0)
+    frames = torch.as_tensor(synth.sparse_frames(F, H, W, seed=5, blob=96, blobs=4), device=DEV)
+    poses = synth.orbit_poses(F, N, vs, center, seed=6)
+    pairs, n = pvp.make_pairs(poses, W)
+    gfx = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=8)
+    st = pvp.accumulate_motion(frames, pairs, gfx, 2.0)
+    assert st["n_rays"] > 10000 and st["n_steps"] > st["n_rays"] * 50
+    g2 = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=8)
+    a, _ = pvp.make_pairs(poses, W, pairs=[(0, 1)])
+    b, _ = pvp.make_pairs(poses, W, pairs=[(1, 2)])
+    sa = pvp.accumulate_motion(frames, a, g2, 2.0)
+    sb = pvp.accumulate_motion(frames, b, g2, 2.0)
+    assert sa["n_steps"] + sb["n_steps"] == st["n_steps"]
+    assert torch.equal(gfx.data, g2.data)
+    # (a): per-ray step counts from the stage API, diff from detect_motion
+    total = 0
+    for (p, c) in ((0, 1), (1, 2)):
+        ch, d = pvp.detect_motion(frames[p], frames[c], 2.0)
+        pix = torch.nonzero(ch.reshape(-1)).reshape(-1)
+        dirs = pvp.pixel_rays(pix, W, H, poses[c])
+        org = torch.tensor(poses[c].camera_position, device=DEV, dtype=torch.float32).expand(len(pix), 3)
+        counts, _, _, _ = pvp.cast_rays(org, dirs, pvp.VoxelGrid(N, vs, center, data=torch.zeros((N, N, N), device=DEV)), want_steps=False)
+        total += int((counts.to(torch.int64) * d.reshape(-1)[pix].to(torch.int64)).sum())
+    assert int(gfx.data.sum()) == total * 256
+    gf = pvp.VoxelGrid(N, vs, center)
+    pvp.accumulate_motion(frames, pairs, gf, 2.0)
+    torch.testing.assert_close(gf.data, gfx.to_float32(), rtol=RTOL_F32_ATOMICS, atol=0)

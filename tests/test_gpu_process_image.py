@@ -1,0 +1,126 @@
+"""Parity of path B (process_image_cpp) on the GPU: the reference module's own outputs (golden, generated with
+OMP_NUM_THREADS=1) and the oracle on fresh inputs.  Voxel indices are bit-reproducible; fp64 sums differ from the
+serial reference only by summation order (rtol 1e-12); fixed-point mode is bit-exact against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits, golden
+
+import pixeltovoxelprojector_b200 as pvp
+import process_image_cpp as dropin
+
+pytestmark = pytest.mark.gpu
+RTOL_F64_ATOMICS = 1e-12
+
+
+def call(fn, g, name, img, grid, tex, **kw):
+    H, W = g["image"].shape
+    return fn(img, list(g["earth_position"]), list(g[f"{name}_pointing"]), float(g["fov"]), W, H, grid, [tuple(r) for r in g["extent"]],
+              float(g["max_distance"]), int(g["num_steps"]), tex, *[float(s) for s in g["sky"]], bool(g[f"{name}_update"]), bool(g[f"{name}_bgsub"]), **kw)
+
+
+@pytest.mark.parametrize("name", ["update", "bgsub", "zenith"])
+def test_golden_numpy_dropin(ctx, name):
+    g = golden("process_image_golden.npz")
+    grid = np.zeros_like(g[f"{name}_grid_out"])
+    tex = g[f"{name}_tex_in"].copy()
+    assert call(dropin.process_image_cpp, g, name, g["image"], grid, tex) is None   # mutates in place, returns None
+    want_g, want_t = g[f"{name}_grid_out"], g[f"{name}_tex_out"]
+    assert np.array_equal(grid != 0, want_g != 0)                                   # identical visited voxels
+    np.testing.assert_allclose(grid, want_g, rtol=RTOL_F64_ATOMICS, atol=0)
+    assert np.array_equal(tex != 0, want_t != 0)
+    np.testing.assert_allclose(tex, want_t, rtol=RTOL_F64_ATOMICS, atol=0)
+
+
+def test_golden_device_tensors_and_fixed_point(ctx, oracle):
+    g = golden("process_image_golden.npz")
+    name = "update"
+    img = torch.as_tensor(g["image"], device="cuda")
+    grid = torch.zeros(g[f"{name}_grid_out"].shape, dtype=torch.float64, device="cuda")
+    tex = torch.as_tensor(g[f"{name}_tex_in"], device="cuda").clone()
+    call(pvp.process_image_cpp, g, name, img, grid, tex, want_stats=True)
+    from pixeltovoxelprojector_b200 import process_image as pi
+    np.testing.assert_allclose(grid.cpu().numpy(), g[f"{name}_grid_out"], rtol=RTOL_F64_ATOMICS, atol=0)
+    H, W = g["image"].shape
+    og, ot = np.zeros(grid.shape, np.int64), np.zeros(tex.shape, np.int64)
+    nr, ns = call(oracle.process_image, g, name, g["image"], og, ot, accum_mode=1, frac_bits=30)
+    assert pi.last_stats == {"n_rays": nr, "n_samples": ns}
+    runs = []
+    for _ in range(2):
+        gi = torch.zeros(grid.shape, dtype=torch.int64, device="cuda")
+        ti = torch.zeros(tex.shape, dtype=torch.int64, device="cuda")
+        call(pvp.process_image_cpp, g, name, img, gi, ti, accum_mode="fixed", frac_bits=30)
+        runs.append((gi.cpu().numpy(), ti.cpu().numpy()))
+    assert np.array_equal(runs[0][0], og) and np.array_equal(runs[0][1], ot)
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+
+
+def test_strides_empty_grid_and_errors(ctx):
+    g = golden("process_image_golden.npz")
+    name = "update"
+    want_g, want_t = g[f"{name}_grid_out"], g[f"{name}_tex_out"]
+    big = np.zeros((want_g.shape[0], want_g.shape[1] * 2, want_g.shape[2]))
+    view = big[:, ::2, :]                                     # strided view: updated in place like the reference
+    tex = np.asfortranarray(g[f"{name}_tex_in"].copy())       # F-order texture
+    call(dropin.process_image_cpp, g, name, g["image"], view, tex)
+    np.testing.assert_allclose(view, want_g, rtol=RTOL_F64_ATOMICS, atol=0)
+    np.testing.assert_allclose(tex, want_t, rtol=RTOL_F64_ATOMICS, atol=0)
+    assert not big[:, 1::2, :].any()
+    rev = np.zeros_like(want_g)[::-1]                         # negative stride: copy-in / copy-out
+    call(dropin.process_image_cpp, g, name, g["image"], rev, g[f"{name}_tex_in"].copy())
+    np.testing.assert_allclose(rev, want_g, rtol=RTOL_F64_ATOMICS, atol=0)
+    tex2 = g[f"{name}_tex_in"].copy()                         # empty grid of any ndim => voxel stage skipped (:152)
+    call(dropin.process_image_cpp, g, name, g["image"], np.zeros((0,)), tex2)
+    np.testing.assert_allclose(tex2, want_t, rtol=RTOL_F64_ATOMICS, atol=0)
+    with pytest.raises(ValueError, match="incorrect number of dimensions: 2; expected 3"):
+        call(dropin.process_image_cpp, g, name, g["image"], np.zeros((4, 4)), tex2)
+    with pytest.raises(TypeError):
+        dropin.process_image_cpp(g["image"])                  # arity
+    g32 = np.zeros(want_g.shape, np.float32)                  # forcecast: silently copied, caller sees no update
+    with pytest.warns(UserWarning, match="not float64"):
+        call(dropin.process_image_cpp, g, name, g["image"], g32, g[f"{name}_tex_in"].copy())
+    assert not g32.any()
+
+
+def test_random_scenes_vs_oracle(ctx, oracle):
+    rng = np.random.default_rng(9)
+    for trial in range(6):
+        H, W = int(rng.integers(8, 70)), int(rng.integers(8, 70))
+        img = rng.random((H, W))
+        img[img < 0.3] = 0
+        pos = rng.uniform(-5, 5, 3)
+        pointing = rng.normal(size=3) if trial else np.array([0.0, 0.0, -3.0])
+        ext = [(-8.0, 9.0), (-7.0, 6.5), (-6.0, 8.0)] if trial % 2 else [(10.0, 30.0), (-10.0, 10.0), (-10.0, 10.0)]
+        shape = tuple(int(x) for x in rng.integers(4, 40, 3))
+        sky = [float(rng.uniform(0, 6.28)), float(rng.uniform(-1.5, 1.5)), float(rng.uniform(0.5, 6.0)), float(rng.uniform(0.5, 3.0))]
+        for upd, bg in ((True, False), (False, True)):
+            g1, g2 = np.zeros(shape), np.zeros(shape)
+            t1 = rng.random((16, 24)) * 0.4
+            t2 = t1.copy()
+            oracle.process_image(img, pos, pointing, 0.9, W, H, g1, ext, 60.0, 300, t1, *sky, upd, bg)
+            dropin.process_image_cpp(img, list(pos), list(pointing), 0.9, W, H, g2, ext, 60.0, 300, t2, *sky, upd, bg)
+            assert np.array_equal(g1 != 0, g2 != 0), (trial, upd, bg)
+            np.testing.assert_allclose(g2, g1, rtol=RTOL_F64_ATOMICS, atol=0)
+            np.testing.assert_allclose(t2, t1, rtol=RTOL_F64_ATOMICS, atol=0)
+
+
+def test_full_size_properties_4096_512_fixed(ctx):
+    """BASELINE config 5 shape (4096^2 image -> 512^3 grid, fixed point): determinism, linearity in brightness
+    (2x image => exactly 2x grid) and conservation (grid total == n_samples * brightness for a constant image)."""
+    from pixeltovoxelprojector_b200 import process_image as pi
+    H = W = 4096
+    n = 512
+    ext = [(-256.0, 256.0), (-256.0, 256.0), (100.0, 612.0)]
+    args = ([0.0, 0.0, 0.0], [0.02, 0.01, 1.0], 0.8, W, H)
+    tail = (ext, 700.0, 700, None, 0.0, 0.0, 1.0, 1.0, False, False)
+    img = torch.full((H, W), 0.5, dtype=torch.float64, device="cuda")
+    grids = []
+    for scale in (1.0, 1.0, 2.0):
+        gi = torch.zeros((n, n, n), dtype=torch.int64, device="cuda")
+        ti = torch.zeros((8, 8), dtype=torch.int64, device="cuda")
+        pvp.process_image_cpp(img * scale, *args, gi, tail[0], tail[1], tail[2], ti, *tail[4:], accum_mode="fixed", frac_bits=20, want_stats=True)
+        grids.append(gi)
+        assert int(gi.sum()) == pi.last_stats["n_samples"] * int(0.5 * scale * (1 << 20))
+    assert pi.last_stats["n_rays"] == H * W and pi.last_stats["n_samples"] > 50 * H * W
+    assert torch.equal(grids[0], grids[1]) and torch.equal(grids[2], grids[0] * 2)
