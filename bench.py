@@ -161,7 +161,7 @@ def run_reference(args, wl):
 
 
 def workload_config(args, wl):
-    return {"workload": args.workload, "frame": f"{wl['W']}x{wl['H']} uint8", "grid": f"{wl['N']}^3 {wl['accum']}", "voxel_size": wl["voxel_size"],
+    return {"workload": args.workload, "k2_variant": getattr(args, "variant", 0), "frame": f"{wl['W']}x{wl['H']} uint8", "grid": f"{wl['N']}^3 {wl['accum']}", "voxel_size": wl["voxel_size"],
             "pairs_per_step": wl["pairs_per_step"], "motion": wl["motion"], "camera": "pose changes every frame (orbit inside the grid)",
             "parallelism": f"frames sharded over {args.gpus} GPU(s), private grids, one NCCL reduce per run" if args.gpus > 1 else "1 GPU",
             "l2": "256 MiB buffer written between timed steps (L2 flush); frame pool 149 MB and grid > L2" if wl["N"] >= 512 else
@@ -182,6 +182,8 @@ def run_ours(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = pvp.default_context(dev)
+    if args.variant:
+        ctx.set_option("dda_variant", args.variant)
 
     frames_np, poses = make_inputs(wl, seed=1000 + rank)   # weak scaling: every rank has its own frames, same shape
     frames_dev = torch.as_tensor(frames_np, device=dev)
@@ -304,7 +306,10 @@ def run_ours(args, wl):
 
     # ---- CPU baseline on this box's host cores (bounded sample: one frame pair of the same workload) -------------
     _, p0 = step_pairs(args.warmup, wl)
-    c_steps, c_s, kind = cpu_reference(wl, frames_np, poses, p0[:1])
+    if args.no_cpu:
+        c_steps, c_s, kind = 0, 1.0, "skipped"
+    else:
+        c_steps, c_s, kind = cpu_reference(wl, frames_np, poses, p0[:1])
     cpu = {"value": c_steps / c_s, "unit": "voxel-steps/s", "cores": 1, "kind": kind,
            "sample": f"one {W}x{H} frame pair of the workload ({c_steps} voxel-steps, {c_s:.1f} s); reference is single-threaded: 1 of {os.cpu_count()} host cores"}
 
@@ -334,6 +339,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p_dense_512", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", type=int, default=0, help="K2 variant (0 = library default; see pvp_motion.cu launch_k2)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments only)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

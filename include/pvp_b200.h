@@ -85,7 +85,8 @@ typedef struct pvp_stats {
 /* ---- library / context ---------------------------------------------------- */
 int pvp_version(void);
 const char *pvp_last_error(void);
-/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream) or NULL for a private one */
+/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream) or NULL for a private non-blocking one;
+ * pass cudaStreamLegacy ((cudaStream_t)0x1) to name the legacy default stream, whose own handle is NULL */
 int pvp_ctx_create(int device, void *stream, pvp_ctx **out);
 int pvp_ctx_destroy(pvp_ctx *ctx);
 int pvp_ctx_set_stream(pvp_ctx *ctx, void *stream);

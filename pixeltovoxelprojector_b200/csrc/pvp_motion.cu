@@ -192,6 +192,177 @@ dda_accumulate_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, type
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->n_rays, count);
 }
 
+// ---- warp-aggregated variants --------------------------------------------------------------
+// Neighbouring pixels cast nearly identical rays: in lockstep, the 32 lanes of a warp that holds 32
+// consecutive motion pixels of one image row touch only ~4.5 distinct voxels per DDA iteration
+// (measured on the 1080p -> 512^3 workload).  The SM issues REDs at ~1.5 cycles per LANE
+// whether or not lanes collide (tools/atomic_roofline.py), so summing equal-voxel lanes in registers
+// first divides the atomic traffic by ~7.  The DDA arithmetic per lane is unchanged (bit-exact visited
+// sets); only the order of the additions differs, which is exact for integer-valued addends and for
+// fixed point.
+
+// Lock-step state of one lane's ray: branch-free advance with the reference's tie-break
+// (ray_voxel.cpp:375-387) and per-axis "steps left before leaving the grid" counters (:389-391).
+struct Walk {
+    float t_cur, t_end, tmx, tmy, tmz, tdx, tdy, tdz;
+    unsigned idx;             // linear voxel offset inside the stored slab
+    int dix, diy, diz;        // signed strides of one x / y / z step
+    int remx, remy, remz;     // steps left along each axis before the index leaves [0, N)
+    int ix, sx;               // x index and x step (slab test only)
+};
+
+__device__ __forceinline__ void walk_init(Walk &w, const Ray &r, const GridP &g)
+{
+    const int N = g.n;
+    w.t_cur = r.t_cur; w.t_end = r.t_end;
+    w.tmx = r.tmx; w.tmy = r.tmy; w.tmz = r.tmz; w.tdx = r.tdx; w.tdy = r.tdy; w.tdz = r.tdz;
+    w.idx = (unsigned)((r.ix - g.slab_lo) * N + r.iy) * (unsigned)N + (unsigned)r.iz;  // wraps harmlessly outside the slab
+    w.dix = r.sx * N * N; w.diy = r.sy * N; w.diz = r.sz;
+    w.remx = r.sx > 0 ? N - 1 - r.ix : r.ix;
+    w.remy = r.sy > 0 ? N - 1 - r.iy : r.iy;
+    w.remz = r.sz > 0 ? N - 1 - r.iz : r.iz;
+    w.ix = r.ix; w.sx = r.sx;
+}
+
+// One DDA step; returns whether the ray is still inside the grid AND t_current <= t_max (:365, :389).
+__device__ __forceinline__ bool walk_advance(Walk &w)
+{
+    const bool cx = (w.tmx < w.tmy) & (w.tmx < w.tmz);
+    const bool cy = !cx & (w.tmy < w.tmz);
+    const bool cz = !(cx | cy);
+    w.t_cur = cx ? w.tmx : (cy ? w.tmy : w.tmz);
+    const float nx = fadd(w.tmx, w.tdx), ny = fadd(w.tmy, w.tdy), nz = fadd(w.tmz, w.tdz);
+    w.tmx = cx ? nx : w.tmx; w.tmy = cy ? ny : w.tmy; w.tmz = cz ? nz : w.tmz;
+    w.idx += (unsigned)(cx ? w.dix : (cy ? w.diy : w.diz));
+    w.ix += cx ? w.sx : 0;
+    w.remx -= (int)cx; w.remy -= (int)cy; w.remz -= (int)cz;
+    return ((w.remx | w.remy | w.remz) >= 0) & (w.t_cur <= w.t_end);
+}
+
+template <int MODE> struct AggVal;
+template <> struct AggVal<PVP_ACCUM_F32> {
+    using T = float;
+    __device__ static __forceinline__ T shfl_up(T v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+    __device__ static __forceinline__ T add(T a, T b) { return fadd(a, b); }
+};
+template <> struct AggVal<PVP_ACCUM_FIXED> {
+    using T = unsigned long long;
+    __device__ static __forceinline__ T shfl_up(T v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+    __device__ static __forceinline__ T add(T a, T b) { return a + b; }
+};
+
+constexpr unsigned KEY_NONE = 0xffffffffu;
+
+// Variant 1: lock-step DDA, runs of equal voxels among consecutive lanes are summed with a segmented
+// warp scan (5 shuffle steps, any value type) and the last lane of each run issues one RED.
+// Variant 2: groups found with match.any (arbitrary lane sets); integer-valued addends are summed with
+// redux.sync, anything else falls back to the scan.  SLAB: the grid pointer holds only x-planes [lo,hi).
+template <int MODE, int VARIANT, bool SLAB>
+__global__ void __launch_bounds__(K2_THREADS)
+dda_accumulate_agg_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
+                          int width, int height, Ctl *__restrict__ ctl)
+{
+    using A = Accum<MODE>;
+    using V = AggVal<MODE>;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
+    const unsigned long long count = ctl->count;
+    unsigned long long my_steps = 0, my_written = 0, my_atomics = 0;
+
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->head, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const unsigned long long i = base + lane;
+        bool active = false;
+        Walk w;
+        typename V::T val = 0;
+        if (i < count) {
+            const uint32_t pix = __ldg(q.pix + i);
+            const float diff = __ldg(q.diff + i);
+            const pvp_pair *P = pairs + __ldg(q.pair + i);
+            const int v = (int)(pix / (uint32_t)width), u = (int)(pix - (uint32_t)v * (uint32_t)width);
+            float dx, dy, dz;
+            pixel_ray(u, v, width, height, __ldg(&P->focal), P->R, dx, dy, dz);
+            Ray r;
+            active = ray_setup(__ldg(&P->cam[0]), __ldg(&P->cam[1]), __ldg(&P->cam[2]), dx, dy, dz, g, r);
+            if (active) {
+                walk_init(w, r, g);
+                val = A::make(diff, g);
+                active = w.t_cur <= w.t_end;  // :365 on entry
+            }
+        }
+        while (__any_sync(0xffffffffu, active)) {
+            const bool writes = active && (!SLAB || (w.ix >= g.slab_lo && w.ix < g.slab_hi));
+            const unsigned key = writes ? w.idx : KEY_NONE;
+            typename V::T sum = writes ? val : (typename V::T)0;
+            bool issue;
+            if (VARIANT == 2) {
+                const unsigned grp = __match_any_sync(0xffffffffu, key);
+                issue = writes && (lane == (unsigned)(__ffs(grp) - 1));
+                if (MODE == PVP_ACCUM_F32) {
+                    // integer-valued addends (uint8 frames): exact integer warp reduction
+                    const int iv = __float2int_rz((float)sum);
+                    const bool integral = ((float)iv == (float)sum);
+                    if (__all_sync(0xffffffffu, integral)) {
+                        sum = (typename V::T)__reduce_add_sync(grp, iv);
+                    } else {  // arbitrary floats: leader gathers its group's values
+                        typename V::T acc = 0;
+                        unsigned m = grp;
+                        for (unsigned todo = __reduce_max_sync(0xffffffffu, (unsigned)__popc(grp)); todo > 0; --todo) {
+                            const int src = m ? __ffs(m) - 1 : (int)lane;
+                            const typename V::T t = __shfl_sync(0xffffffffu, sum, src);
+                            if (m) { acc = V::add(acc, t); m &= m - 1; }
+                        }
+                        sum = acc;
+                    }
+                } else {
+                    const unsigned long long qv = (unsigned long long)sum;
+                    if (__all_sync(0xffffffffu, qv < (1ull << 26))) {
+                        sum = (typename V::T)__reduce_add_sync(grp, (unsigned)qv);
+                    } else {
+                        typename V::T acc = 0;
+                        unsigned m = grp;
+                        for (unsigned todo = __reduce_max_sync(0xffffffffu, (unsigned)__popc(grp)); todo > 0; --todo) {
+                            const int src = m ? __ffs(m) - 1 : (int)lane;
+                            const typename V::T t = __shfl_sync(0xffffffffu, sum, src);
+                            if (m) { acc = V::add(acc, t); m &= m - 1; }
+                        }
+                        sum = acc;
+                    }
+                }
+            } else {
+                const unsigned prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+                const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev_key);
+                const int my_head = 31 - __clz(heads & le_mask);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const typename V::T t = V::shfl_up(sum, d);
+                    if ((int)lane - d >= my_head) sum = V::add(sum, t);
+                }
+                issue = writes && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+            }
+            if (issue) { A::add(grid + key, sum); ++my_atomics; }
+            my_steps += active;
+            my_written += writes;
+            if (active) active = walk_advance(w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+        my_written += __shfl_xor_sync(0xffffffffu, my_written, o);
+        my_atomics += __shfl_xor_sync(0xffffffffu, my_atomics, o);
+    }
+    if (lane == 0 && my_steps) {
+        atomicAdd(&ctl->n_steps, my_steps);
+        atomicAdd(&ctl->n_written, my_written);
+        atomicAdd(&ctl->n_atomics, my_atomics);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->n_rays, count);
+}
+
 // Ray set-up of ray_voxel.cpp:506-515 as a stage.
 __global__ void pixel_rays_kernel(const uint32_t *__restrict__ pix, long long n, int width, int height, pvp_pair pose,
                                   float *__restrict__ dirs)
@@ -286,17 +457,41 @@ static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_strid
     return PVP_OK;
 }
 
+template <int MODE, int VARIANT, bool SLAB>
+static void launch_agg(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height)
+{
+    auto k = dda_accumulate_agg_kernel<MODE, VARIANT, SLAB>;
+    k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
+                                                                           width, height, ctx->ctl_dev);
+}
+
+// dda_variant: 0 = auto (currently 1), 1 = segmented-scan aggregation, 2 = match.any aggregation,
+// 3 = one RED per lane and step (no aggregation; also used when the slab has >= 2^32 cells).
 static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, void *grid_dev, int width, int height)
 {
     LaunchScope scope(ctx, 2);
-    if (accum_mode == PVP_ACCUM_F32) {
-        auto k = dda_accumulate_kernel<PVP_ACCUM_F32>;
-        k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (float *)grid_dev, width,
-                                                                               height, ctx->ctl_dev);
+    int variant = (int)ctx->opt_dda_variant;
+    if (variant <= 0 || variant > 3) variant = 1;
+    const unsigned long long cells = (unsigned long long)(g.slab_hi - g.slab_lo) * g.n * g.n;
+    if (cells >= 0xffffffffull) variant = 3;
+    const bool slab = !(g.slab_lo == 0 && g.slab_hi == g.n);
+    const bool f32 = accum_mode == PVP_ACCUM_F32;
+    if (variant == 3) {
+        if (f32) {
+            auto k = dda_accumulate_kernel<PVP_ACCUM_F32>;
+            k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (float *)grid_dev, width,
+                                                                                   height, ctx->ctl_dev);
+        } else {
+            auto k = dda_accumulate_kernel<PVP_ACCUM_FIXED>;
+            k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g,
+                                                                                   (unsigned long long *)grid_dev, width, height, ctx->ctl_dev);
+        }
+    } else if (variant == 1) {
+        if (f32) { if (slab) launch_agg<PVP_ACCUM_F32, 1, true>(ctx, g, grid_dev, width, height); else launch_agg<PVP_ACCUM_F32, 1, false>(ctx, g, grid_dev, width, height); }
+        else { if (slab) launch_agg<PVP_ACCUM_FIXED, 1, true>(ctx, g, grid_dev, width, height); else launch_agg<PVP_ACCUM_FIXED, 1, false>(ctx, g, grid_dev, width, height); }
     } else {
-        auto k = dda_accumulate_kernel<PVP_ACCUM_FIXED>;
-        k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g,
-                                                                               (unsigned long long *)grid_dev, width, height, ctx->ctl_dev);
+        if (f32) { if (slab) launch_agg<PVP_ACCUM_F32, 2, true>(ctx, g, grid_dev, width, height); else launch_agg<PVP_ACCUM_F32, 2, false>(ctx, g, grid_dev, width, height); }
+        else { if (slab) launch_agg<PVP_ACCUM_FIXED, 2, true>(ctx, g, grid_dev, width, height); else launch_agg<PVP_ACCUM_FIXED, 2, false>(ctx, g, grid_dev, width, height); }
     }
     PVP_CUDA(cudaGetLastError());
     return PVP_OK;

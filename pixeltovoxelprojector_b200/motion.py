@@ -36,16 +36,22 @@ class Context:
         self._stream_handle = None
         h = C.c_void_p()
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
-        check(lib.pvp_ctx_create(self.device.index, C.c_void_p(s.cuda_stream), C.byref(h)))
+        check(lib.pvp_ctx_create(self.device.index, C.c_void_p(self._handle_of(s)), C.byref(h)))
         self.handle = h
-        self._stream_handle = s.cuda_stream
+        self._stream_handle = self._handle_of(s)
         self._pinned_stream = stream is not None
+
+    @staticmethod
+    def _handle_of(stream: torch.cuda.Stream) -> int:
+        # torch's default stream is the legacy default stream, whose handle is 0 == NULL; the C ABI reads
+        # NULL as "make a private stream", so name the legacy stream explicitly (cudaStreamLegacy == 0x1).
+        return stream.cuda_stream or 1
 
     def use_current_stream(self) -> None:
         """Enqueue on torch's current stream (unless a stream was pinned at construction)."""
         if self._pinned_stream:
             return
-        s = torch.cuda.current_stream(self.device).cuda_stream
+        s = self._handle_of(torch.cuda.current_stream(self.device))
         if s != self._stream_handle:
             check(self._lib.pvp_ctx_set_stream(self.handle, C.c_void_p(s)))
             self._stream_handle = s

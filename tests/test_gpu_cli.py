@@ -42,10 +42,10 @@ def test_cli_binary_matches_reference_cli(tmp_path):
     out = str(tmp_path / "voxel_grid.bin")
     res = subprocess.run([EXE, meta, str(tmp_path), out], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
-    assert res.stdout == str(g["stdout"]).replace(str(g["stdout"]).split("Saved voxel grid to ")[1].strip(), out)
+    assert res.stdout == f"Saved voxel grid to {out}\n"
     # same diagnostics as the reference: one failed load (+ skip notice) and one size mismatch
     assert res.stderr.count("Skipping frame due to load error.") == str(g["stderr"]).count("Skipping frame due to load error.") == 1
-    assert res.stderr.count("Images differ in size") == str(g["stderr"]).count("Images differ in size") == 1
+    assert res.stderr.count("Images differ in size") == str(g["stderr"]).count("Images differ in size") == 2
     check_bin(out, g)
     # fixed-point mode writes the same float32 payload for integer frames
     out2 = str(tmp_path / "fx.bin")
@@ -81,7 +81,7 @@ def test_python_pipeline_sharded_equals_whole(tmp_path):
             total += grid.data
             pairs += rep["n_pairs"]
             del grid
-        assert pairs == 5     # cam0: (0,1),(1,3),(3,4); cam3: (0,1) + the mismatched pair is not counted, (2,3) mismatched too
+        assert pairs == 4     # cam0: (0,1),(1,3),(3,4); cam3: (0,1); the two size-mismatched pairs cast no rays
         if whole is None:
             whole = total
             flat = pvp.VoxelGrid(accum="fixed", frac_bits=8, data=total).to_float32().cpu().numpy().reshape(-1)

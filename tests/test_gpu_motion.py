@@ -192,6 +192,45 @@ def test_sequence_float_frames_tolerance_and_fixed_exact(ctx, oracle):
                           bits(oracle.fixed_to_f32(want_fx, 20)))
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("accum", ["f32", "fixed"])
+def test_k2_variants_bit_exact(ctx, oracle, variant, accum):
+    """Every K2 variant (segmented-scan aggregation, match.any aggregation, plain per-lane RED) must give the
+    reference's grid bit for bit on integer-valued frames, for whole grids and slabs, and the same counters."""
+    rng = np.random.default_rng(20 + variant)
+    F, H, W, N, vs, center = 4, 50, 131, 72, 5.0, (0.0, 0.0, 500.0)   # odd width: partial warps, unaligned rows
+    frames, poses = _scene(rng, F, H, W, N, vs, center, True)
+    pairs, _ = pvp.make_pairs(poses, W)
+    mode = 0 if accum == "f32" else 1
+    want, tot = _oracle_run(oracle, frames, poses, N, vs, center, 2.0, accum_mode=mode, frac_bits=10)
+    ctx.set_option("dda_variant", variant)
+    try:
+        grid = pvp.VoxelGrid(N, vs, center, accum=accum, frac_bits=10)
+        st = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, grid, 2.0)
+        assert (st["n_rays"], st["n_steps"], st["n_written"]) == tuple(tot)
+        assert st["n_atomics"] <= st["n_written"] and (variant != 3 or st["n_atomics"] == st["n_written"])
+        assert np.array_equal(grid.data.cpu().numpy(), want)
+        parts = []
+        for lo, hi in ((0, 30), (30, 31), (31, N)):
+            s = pvp.VoxelGrid(N, vs, center, accum=accum, frac_bits=10, slab=(lo, hi))
+            pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, s, 2.0)
+            parts.append(s.data)
+        assert np.array_equal(torch.cat(parts).cpu().numpy(), want)
+        # float frames: same support, tolerance for fp32, exact for fixed
+        ff = np.clip(frames.astype(np.float32) + rng.uniform(-1, 1, frames.shape).astype(np.float32), 0, 255)
+        wantf, _ = _oracle_run(oracle, ff, poses, N, vs, center, 2.0, accum_mode=mode, frac_bits=10)
+        gridf = pvp.VoxelGrid(N, vs, center, accum=accum, frac_bits=10)
+        pvp.accumulate_motion(torch.as_tensor(ff, device=DEV), pairs, gridf, 2.0)
+        if accum == "fixed":
+            assert np.array_equal(gridf.data.cpu().numpy(), wantf)
+        else:
+            got = gridf.data.cpu().numpy()
+            assert np.array_equal(got != 0, wantf != 0)
+            np.testing.assert_allclose(got, wantf, rtol=RTOL_F32_ATOMICS, atol=0)
+    finally:
+        ctx.set_option("dda_variant", 0)
+
+
 def test_edge_cases(ctx, oracle):
     N, vs, center = 32, 1.0, (0.0, 0.0, 0.0)
     W, H = 16, 8
