@@ -275,6 +275,8 @@ int pvp_process_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, voi
     if (rc) return rc;
     if (!grid_dev) p.grid_provided = 0;
     DeviceGuard guard(ctx->device);
+    // the counters describe THIS call: clear whatever earlier calls without `stats` left behind
+    if (stats) PVP_CUDA(cudaMemsetAsync(&ctx->ctl_dev->img_rays, 0, 2 * sizeof(unsigned long long), ctx->stream));
     if ((rc = launch_image(ctx, image_dev, grid_dev, tex_dev, p, args->accum_mode))) return rc;
     return fetch_image_stats(ctx, stats);
 }
@@ -304,6 +306,7 @@ int pvp_process_image_host(pvp_ctx *ctx, const double *image, double *grid, doub
     PVP_TRY(cudaMemcpyAsync(d_img, image, sizeof(double) * n_img, cudaMemcpyHostToDevice, ctx->stream));
     PVP_TRY(cudaMemcpyAsync(d_tex, tex, sizeof(double) * n_tex, cudaMemcpyHostToDevice, ctx->stream));
     if (n_grid) PVP_TRY(cudaMemcpyAsync(d_grid, grid, sizeof(double) * n_grid, cudaMemcpyHostToDevice, ctx->stream));
+    if (stats) PVP_TRY(cudaMemsetAsync(&ctx->ctl_dev->img_rays, 0, 2 * sizeof(unsigned long long), ctx->stream));
     rc = pvp_process_image(ctx, d_img, d_grid, d_tex, args, nullptr);
     if (rc) { cleanup(); return rc; }
     PVP_TRY(cudaMemcpyAsync(tex, d_tex, sizeof(double) * n_tex, cudaMemcpyDeviceToHost, ctx->stream));

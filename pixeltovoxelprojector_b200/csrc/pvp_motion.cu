@@ -546,7 +546,6 @@ static int check_common(pvp_ctx *ctx, const void *frames, int frame_dtype, long 
     PVP_REQUIRE(ctx != nullptr, "ctx is NULL");
     PVP_REQUIRE(n_pairs >= 0, "n_pairs < 0");
     PVP_REQUIRE(n_pairs == 0 || (frames && pairs), "frames / pairs is NULL");
-    PVP_REQUIRE(grid_dev != nullptr, "grid_dev is NULL");
     PVP_REQUIRE(frame_dtype == PVP_FRAME_U8 || frame_dtype == PVP_FRAME_F32, "bad frame_dtype %d", frame_dtype);
     PVP_REQUIRE(width > 0 && height > 0 && (long long)width * height < (1ll << 32), "bad frame size %dx%d", width, height);
     PVP_REQUIRE(frame_stride >= (long long)width * height, "frame_stride smaller than a frame");
@@ -615,6 +614,7 @@ int pvp_motion_accumulate(pvp_ctx *ctx, const void *frames_dev, int frame_dtype,
     if (rc) return rc;
     GridP g;
     if ((rc = make_gridp(grid, &g))) return rc;
+    PVP_REQUIRE(grid_dev != nullptr || g.slab_lo == g.slab_hi, "grid_dev is NULL");  // an empty slab stores nothing
     if ((rc = validate_pairs(pairs, n_pairs, -1))) return rc;
     DeviceGuard guard(ctx->device);
     if (n_pairs > 0) {
@@ -632,6 +632,7 @@ int pvp_motion_accumulate_host(pvp_ctx *ctx, const void *frames_host, int frame_
     if (rc) return rc;
     GridP g;
     if ((rc = make_gridp(grid, &g))) return rc;
+    PVP_REQUIRE(grid_dev != nullptr || g.slab_lo == g.slab_hi, "grid_dev is NULL");
     if ((rc = validate_pairs(pairs, n_pairs, n_frames))) return rc;
     if (n_pairs == 0) return fetch_stats(ctx, stats);
     DeviceGuard guard(ctx->device);
