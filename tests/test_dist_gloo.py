@@ -1,0 +1,91 @@
+"""The N>1 host logic on CPU: world_size-2 gloo process group (127.0.0.1).  Covers the shard arithmetic, the
+single grid sum-reduce (int64 fixed point: bit-exact; fp32), and slab-wise .bin assembly.  The kernels
+themselves need a GPU and are covered by `-m gpu` (test_python_pipeline_sharded_equals_whole)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT  # noqa: F401  (puts the repo on sys.path)
+
+from pixeltovoxelprojector_b200 import distributed as pd
+from pixeltovoxelprojector_b200.motion import read_bin, write_bin
+
+
+def test_shard_ranges_partition():
+    for total in (0, 1, 7, 500, 1001):
+        for world in (1, 2, 3, 8):
+            blocks = [pd.shard_range(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            assert max(h - l for l, h in blocks) - min(h - l for l, h in blocks) <= 1
+    pairs = [(i, i + 1) for i in range(11)]
+    got = sum((pd.split_pairs(pairs, r, 4) for r in range(4)), [])
+    assert got == pairs
+    with pytest.raises(ValueError):
+        pd.shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 12
+        rng = np.random.default_rng(100 + rank)
+        # frame sharding: private grids, one sum-reduce to rank 0
+        fixed = torch.from_numpy(rng.integers(0, 1 << 40, (n, n, n), dtype=np.int64))
+        f32 = torch.from_numpy(rng.integers(0, 255, (n, n, n)).astype(np.float32))
+        mine_fixed, mine_f32 = fixed.clone(), f32.clone()
+        pd.reduce_grid(fixed, dst=0)
+        pd.reduce_grid(f32, dst=0)
+        everyone = mine_fixed.clone()
+        pd.reduce_grid(everyone, all_ranks=True)
+        parts = [torch.zeros_like(mine_fixed) for _ in range(world)]
+        dist.all_gather(parts, mine_fixed)
+        want = sum(parts)
+        assert torch.equal(everyone, want)
+        if rank == 0:
+            assert torch.equal(fixed, want)
+            parts32 = [torch.from_numpy(np.random.default_rng(100 + r).integers(0, 1 << 40, (n, n, n), dtype=np.int64)) for r in range(world)]
+            assert torch.equal(want, sum(parts32))
+            assert torch.equal(f32, sum(torch.from_numpy(_f32_of(r, n)) for r in range(world)))
+        # slab sharding: every rank writes its byte range of the shared .bin
+        whole = np.random.default_rng(7).random((n, n, n)).astype(np.float32)
+        lo, hi = pd.slab_range(n, rank, world)
+        path = os.path.join(tmp, "slabs.bin")
+        if rank == 0:
+            pd.write_bin_header(path, n, 6.0)
+        dist.barrier()
+        pd.write_bin_slab(path, n, (lo, hi), whole[lo:hi])
+        dist.barrier()
+        if rank == 0:
+            ref = os.path.join(tmp, "whole.bin")
+            write_bin(ref, whole, 6.0)
+            assert open(path, "rb").read() == open(ref, "rb").read()
+            back, vs = read_bin(path)
+            assert np.array_equal(back, whole) and vs == 6.0
+    finally:
+        dist.destroy_process_group()
+
+
+def _f32_of(rank, n):
+    rng = np.random.default_rng(100 + rank)
+    rng.integers(0, 1 << 40, (n, n, n), dtype=np.int64)
+    return rng.integers(0, 255, (n, n, n)).astype(np.float32)
+
+
+def test_world2_gloo_reduce_and_slab_assembly(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)

@@ -1,0 +1,59 @@
+"""Multi-GPU parity check, run under torchrun (one rank per GPU, NCCL):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+Frame-sharded and slab-sharded runs of the ray_voxel pipeline must write the same .bin as one GPU alone
+(fixed point: byte-identical; fp32 with uint8 frames: byte-identical too, the sums are exact)."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pixeltovoxelprojector_b200 as pvp  # noqa: E402
+from pixeltovoxelprojector_b200 import synth  # noqa: E402
+from pixeltovoxelprojector_b200.distributed import ray_voxel_distributed  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n, vs, center = 192, 5.0, (0.0, 0.0, 500.0)
+    folder = os.path.join(tempfile.gettempdir(), "pvp_dist_check")
+    if rank == 0:
+        frames = {c: synth.dense_frames(7, 120, 160, seed=c) for c in (0, 1, 2)}
+        poses = {c: synth.orbit_poses(7, n, vs, center, seed=10 + c, camera_index=c) for c in (0, 1, 2)}
+        synth.write_sequence(folder, frames, poses, shuffle_seed=3)
+        os.remove(os.path.join(folder, poses[1][3].image_file))  # a skipped frame inside a shard
+    dist.barrier()
+    meta = os.path.join(folder, "metadata.json")
+    ok = True
+    for accum in ("fixed", "f32"):
+        outs = {}
+        for mode in ("frames", "slabs"):
+            outs[mode] = os.path.join(folder, f"{mode}_{accum}.bin")
+            rep = ray_voxel_distributed(meta, folder, outs[mode], mode=mode, n=n, voxel_size=vs, center=center, accum=accum, frac_bits=12)
+            dist.barrier()
+            if rank == 0:
+                print(f"[{accum}/{mode}] world={world} pairs={rep['n_pairs']} rays={rep['n_rays']} steps={rep['n_steps']} written={rep['n_written']}")
+        if rank == 0:
+            grid = pvp.VoxelGrid(n, vs, center, accum=accum, frac_bits=12)
+            one = pvp.ray_voxel_accumulate(meta, folder, grid)
+            single = os.path.join(folder, f"single_{accum}.bin")
+            grid.save(single)
+            ref = open(single, "rb").read()
+            for mode, path in outs.items():
+                same = open(path, "rb").read() == ref
+                ok &= same
+                print(f"[{accum}/{mode}] identical to 1-GPU .bin: {same} (1-GPU steps={one['n_steps']})")
+    flag = torch.tensor([int(ok)], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
