@@ -19,6 +19,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION; the contract is ONE JSON line on stdout
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 WORKLOADS = {
     # the configuration BASELINE.json's metric is quoted on: 1080p frames into a 512^3 fp32 grid, one camera whose
