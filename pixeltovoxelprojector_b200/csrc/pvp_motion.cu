@@ -363,6 +363,203 @@ dda_accumulate_agg_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, 
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->n_rays, count);
 }
 
+// ---- variant 4: "lean" lock-step kernel ---------------------------------------------------------
+// Same algorithm as variant 1 (per-lane DDA in lock-step, runs of equal voxels among consecutive lanes
+// summed by a segmented warp scan, one RED per run) with the inner loop cut from 78 to ~45 SASS
+// instructions and re-balanced between the ALU and FMA pipes (ncu on variant 1: ALU pipe 84 %, FMA 16 %):
+//   * axis choice through one FMNMX3: m = min(tmx,tmy,tmz); z iff tmz == m, else y iff tmy == m, else x.
+//     For NaN-free t values this is exactly the reference's strict-< chain with ties to the later axis
+//     (ray_voxel.cpp:375-387).  The only way t_max += t_delta can make a NaN is a -inf t_max, i.e. an overflow
+//     of (boundary - camera) / dir with |dir| >= 1e-12: the host only selects this kernel when every camera and
+//     grid coordinate of the batch is below 1e25 in magnitude (lean_geometry_ok); anything else runs variant 3,
+//     which keeps the reference's compare structure.
+//   * per-axis "steps left inside [0,N)" counters are floats decremented by predicated FADDs (FMA pipe);
+//     the ray's step count is recovered from them when it ends -- no per-iteration counter.
+//   * no per-iteration select of key/value: a lane whose ray ended is parked in a state that keeps it
+//     harmless (key NONE, value 0, zero strides, t frozen) by a warp-uniform slow path that runs only in
+//     iterations where some ray ends (~5 %), which also decides the loop exit.
+//   * scan predicates are single LOP3s of the run-head ballot against lane-constant window masks.
+struct LaneMasks {
+    unsigned w1, w2, w4, w8, w16, next;
+};
+
+__device__ __forceinline__ LaneMasks lane_masks(unsigned lane)
+{
+    LaneMasks m;
+    // window_d = lanes (lane-d+1 .. lane); a head inside it means lane-d belongs to another run.  For
+    // lane < d the window reaches bit 0, which is always a head, so the predicate is false as required.
+    auto win = [lane](unsigned d) { return lane + 1 >= d ? (((1u << d) - 1u) << (lane + 1 - d)) : ((2u << lane) - 1u); };
+    m.w1 = 1u << lane; m.w2 = win(2); m.w4 = win(4); m.w8 = win(8);
+    m.w16 = lane + 1 >= 16 ? (0xffffu << (lane - 15)) : ((2u << lane) - 1u);
+    m.next = lane == 31 ? 1u : (1u << (lane + 1));  // lane 31 always ends a run: bit 0 is always set
+    return m;
+}
+
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+template <int MODE, bool NARROW> struct LeanVal;
+template <bool NARROW> struct LeanVal<PVP_ACCUM_F32, NARROW> {
+    using T = float;
+    __device__ static __forceinline__ T make(float diff, const GridP &) { return diff; }
+    __device__ static __forceinline__ T add(T a, T b) { return fadd(a, b); }
+    __device__ static __forceinline__ void red(float *p, T v) { atomicAdd(p, v); }
+};
+template <> struct LeanVal<PVP_ACCUM_FIXED, false> {
+    using T = unsigned long long;
+    __device__ static __forceinline__ T make(float diff, const GridP &g) { return (unsigned long long)quantize_fixed(diff, g.fixed_scale); }
+    __device__ static __forceinline__ T add(T a, T b) { return a + b; }
+    __device__ static __forceinline__ void red(unsigned long long *p, T v) { atomicAdd(p, v); }
+};
+// NARROW: the host guarantees 32 * max(value) * 2^frac_bits < 2^32 (uint8 frames, frac_bits <= 19), so run
+// sums fit 32 bits and the scan costs one shuffle per step; the RED is still a 64-bit add.
+template <> struct LeanVal<PVP_ACCUM_FIXED, true> {
+    using T = unsigned;
+    __device__ static __forceinline__ T make(float diff, const GridP &g) { return (unsigned)quantize_fixed(diff, g.fixed_scale); }
+    __device__ static __forceinline__ T add(T a, T b) { return a + b; }
+    __device__ static __forceinline__ void red(unsigned long long *p, T v) { atomicAdd(p, (unsigned long long)v); }
+};
+
+constexpr float REM_PARKED = 1.0e9f;  // 1e9f - 1 == 1e9f: a parked lane's counters never run out
+
+// red.global.add with the issue decision as a PTX predicate (the address is formed outside the predicate)
+__device__ __forceinline__ void red_if(bool p, float *addr, float v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q red.global.add.f32 [%1], %2;\n\t}" ::"r"((unsigned)p), "l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_if(bool p, unsigned long long *addr, unsigned long long v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q red.global.add.u64 [%1], %2;\n\t}" ::"r"((unsigned)p), "l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_if(bool p, unsigned long long *addr, unsigned v) { red_if(p, addr, (unsigned long long)v); }
+
+// key of the lane below (lane 0: none) and whether this lane starts a run, from one SHFL.UP and its range predicate
+__device__ __forceinline__ bool run_head(unsigned key)
+{
+    unsigned prev, inrange;
+    asm volatile("{\n\t.reg .pred q;\n\tshfl.sync.up.b32 %0|q, %2, 1, 0, 0xffffffff;\n\tselp.u32 %1, 1, 0, q;\n\t}" : "=r"(prev), "=r"(inrange) : "r"(key));
+    return !inrange || key != prev;
+}
+
+template <int MODE, bool SLAB, bool NARROW>
+__global__ void __launch_bounds__(K2_THREADS)
+dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
+                           int width, int height, Ctl *__restrict__ ctl)
+{
+    using A = Accum<MODE>;
+    using V = LeanVal<MODE, NARROW>;
+    using T = typename V::T;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const LaneMasks lm = lane_masks(lane);
+    const unsigned long long count = ctl->count;
+    const int N = g.n;
+    const unsigned slab_cells = (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)N * (unsigned)N;
+    unsigned long long my_steps = 0, my_written = 0, my_atomics = 0;
+
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->head, 32ull);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= count) break;
+        const unsigned long long i = base + lane;
+
+        // parked state (also the state of lanes past the end of the queue and of rays that miss the grid)
+        float t_end = CUDART_INF_F, tmx = 0.f, tmy = 0.f, tmz = 0.f, tdx = 0.f, tdy = 0.f, tdz = 0.f;
+        float remx = REM_PARKED, remy = REM_PARKED, remz = REM_PARKED, rem0 = 0.f;
+        unsigned idx = KEY_NONE;
+        int dix = 0, diy = 0, diz = 0;
+        T val = 0;
+        float n_issued = 0.f, n_inslab = 0.f;
+
+        if (i < count) {
+            const uint32_t pix = __ldg(q.pix + i);
+            const float diff = __ldg(q.diff + i);
+            const pvp_pair *P = pairs + __ldg(q.pair + i);
+            const int v = (int)(pix / (uint32_t)width), u = (int)(pix - (uint32_t)v * (uint32_t)width);
+            float dx, dy, dz;
+            pixel_ray(u, v, width, height, __ldg(&P->focal), P->R, dx, dy, dz);
+            Ray r;
+            if (ray_setup(__ldg(&P->cam[0]), __ldg(&P->cam[1]), __ldg(&P->cam[2]), dx, dy, dz, g, r) && r.t_cur <= r.t_end) {
+                t_end = r.t_end;
+                tmx = r.tmx; tmy = r.tmy; tmz = r.tmz; tdx = r.tdx; tdy = r.tdy; tdz = r.tdz;
+                idx = (unsigned)((r.ix - g.slab_lo) * N + r.iy) * (unsigned)N + (unsigned)r.iz;  // negative x offsets wrap past slab_cells
+                dix = r.sx * N * N; diy = r.sy * N; diz = r.sz;
+                remx = (float)(r.sx > 0 ? N - 1 - r.ix : r.ix);
+                remy = (float)(r.sy > 0 ? N - 1 - r.iy : r.iy);
+                remz = (float)(r.sz > 0 ? N - 1 - r.iz : r.iz);
+                rem0 = remx + remy + remz;
+                val = V::make(diff, g);
+            }
+        }
+        if (__all_sync(FULL, idx == KEY_NONE)) continue;
+
+        for (;;) {
+            // ---- accumulate the current voxel: one RED per run of equal keys --------------------------
+            unsigned key = idx;
+            T sum = val;
+            if (SLAB) {
+                const bool in = idx < slab_cells;  // parked lanes (KEY_NONE) are outside every slab
+                key = in ? idx : KEY_NONE;
+                sum = in ? val : (T)0;
+                n_inslab += in ? 1.f : 0.f;
+            }
+            const unsigned heads = __ballot_sync(FULL, run_head(key));  // bit 0 is always set
+            T t;
+            t = __shfl_up_sync(FULL, sum, 1);  if (!(heads & lm.w1))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 2);  if (!(heads & lm.w2))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 4);  if (!(heads & lm.w4))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t);
+            const bool issue = (heads & lm.next) && key != KEY_NONE;
+            red_if(issue, grid + key, sum);
+            if (issue) n_issued += 1.f;
+            // ---- one DDA step (ray_voxel.cpp:375-391) -------------------------------------------------
+            const float m = fmin3(tmx, tmy, tmz);
+            const bool cz = (tmz == m);
+            const bool cy = !cz && (tmy == m);
+            const bool cx = !cz && (tmy != m);
+            if (cx) { tmx = fadd(tmx, tdx); remx -= 1.f; }
+            if (cy) { tmy = fadd(tmy, tdy); remy -= 1.f; }
+            if (cz) { tmz = fadd(tmz, tdz); remz -= 1.f; }
+            idx += (unsigned)(cz ? diz : (cy ? diy : dix));
+            const bool still = (fmin3(remx, remy, remz) >= 0.f) && (m <= t_end);
+            // ---- rays that ended: park the lane; leave when the whole warp is parked ---------------------
+            if (__any_sync(FULL, !still)) {
+                const bool park = !still && idx != KEY_NONE;
+                my_steps += park ? (unsigned long long)(unsigned)(int)(rem0 - (remx + remy + remz)) : 0ull;  // advances performed == voxels emitted
+                idx = park ? KEY_NONE : idx; val = park ? (T)0 : val;
+                dix = park ? 0 : dix; diy = park ? 0 : diy; diz = park ? 0 : diz;
+                tmx = park ? 0.f : tmx; tmy = park ? 0.f : tmy; tmz = park ? 0.f : tmz;
+                tdx = park ? 0.f : tdx; tdy = park ? 0.f : tdy; tdz = park ? 0.f : tdz;
+                t_end = park ? CUDART_INF_F : t_end;
+                remx = park ? REM_PARKED : remx; remy = park ? REM_PARKED : remy; remz = park ? REM_PARKED : remz;
+                if (__all_sync(FULL, idx == KEY_NONE)) break;
+            }
+        }
+        my_atomics += (unsigned long long)n_issued;
+        if (SLAB) my_written += (unsigned long long)n_inslab;
+
+    }
+    if (!SLAB) my_written = my_steps;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_steps += __shfl_xor_sync(FULL, my_steps, o);
+        my_written += __shfl_xor_sync(FULL, my_written, o);
+        my_atomics += __shfl_xor_sync(FULL, my_atomics, o);
+    }
+    if (lane == 0 && my_steps) {
+        atomicAdd(&ctl->n_steps, my_steps);
+        atomicAdd(&ctl->n_written, my_written);
+        atomicAdd(&ctl->n_atomics, my_atomics);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->n_rays, count);
+}
+
 // Ray set-up of ray_voxel.cpp:506-515 as a stage.
 __global__ void pixel_rays_kernel(const uint32_t *__restrict__ pix, long long n, int width, int height, pvp_pair pose,
                                   float *__restrict__ dirs)
@@ -465,18 +662,47 @@ static void launch_agg(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, 
                                                                            width, height, ctx->ctl_dev);
 }
 
-// dda_variant: 0 = auto (currently 1), 1 = segmented-scan aggregation, 2 = match.any aggregation,
-// 3 = one RED per lane and step (no aggregation; also used when the slab has >= 2^32 cells).
-static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, void *grid_dev, int width, int height)
+template <int MODE, bool SLAB, bool NARROW>
+static void launch_lean(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height)
+{
+    auto k = dda_accumulate_lean_kernel<MODE, SLAB, NARROW>;
+    k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
+                                                                           width, height, ctx->ctl_dev);
+}
+
+// See the lean kernel's header: no t value of the batch can overflow to -inf.
+static bool lean_geometry_ok(const GridP &g, const pvp_pair *pairs, int n_pairs)
+{
+    const float lim = 1e25f;
+    if (!(g.vs > 0.f && g.vs < lim)) return false;
+    for (int a = 0; a < 3; ++a)
+        if (!(fabsf(g.gmin[a]) < lim && fabsf(g.gmax[a]) < lim)) return false;
+    for (int i = 0; i < n_pairs; ++i)
+        for (int a = 0; a < 3; ++a)
+            if (!(fabsf(pairs[i].cam[a]) < lim)) return false;  // NaN fails too
+    return true;
+}
+
+// dda_variant: 0 = auto (4 where its 32-bit voxel keys allow, else 3), 1 = segmented-scan aggregation (round-1
+// baseline), 2 = match.any aggregation, 3 = one RED per lane and step (no aggregation, any grid size),
+// 4 = lean lock-step kernel.  narrow_ok: every value * 2^frac_bits * 32 fits 32 bits (uint8 frames).
+static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_ok, bool lean_ok, void *grid_dev, int width, int height)
 {
     LaunchScope scope(ctx, 2);
     int variant = (int)ctx->opt_dda_variant;
-    if (variant <= 0 || variant > 3) variant = 1;
-    const unsigned long long cells = (unsigned long long)(g.slab_hi - g.slab_lo) * g.n * g.n;
-    if (cells >= 0xffffffffull) variant = 3;
+    if (variant <= 0 || variant > 4) variant = 4;
     const bool slab = !(g.slab_lo == 0 && g.slab_hi == g.n);
+    const unsigned long long cells = (unsigned long long)(g.slab_hi - g.slab_lo) * g.n * g.n;
+    const unsigned long long full = (unsigned long long)g.n * g.n * g.n;
+    if (cells >= 0xffffffffull) variant = 3;
+    if (variant == 4 && (slab ? full > (1ull << 31) : full >= 0xffffffffull)) variant = 3;  // slab test relies on wrapped offsets
+    if (variant == 4 && !lean_ok) variant = 3;
     const bool f32 = accum_mode == PVP_ACCUM_F32;
-    if (variant == 3) {
+    if (variant == 4) {
+        if (f32) { if (slab) launch_lean<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height); else launch_lean<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height); }
+        else if (narrow_ok) { if (slab) launch_lean<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height); else launch_lean<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height); }
+        else { if (slab) launch_lean<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height); else launch_lean<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height); }
+    } else if (variant == 3) {
         if (f32) {
             auto k = dda_accumulate_kernel<PVP_ACCUM_F32>;
             k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (float *)grid_dev, width,
@@ -534,7 +760,9 @@ static int run_batches(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, lo
         rc = frame_dtype == PVP_FRAME_U8 ? launch_k1<uint8_t>(ctx, frames_dev, frame_stride, n_pix, np, threshold)
                                          : launch_k1<float>(ctx, frames_dev, frame_stride, n_pix, np, threshold);
         if (rc) return rc;
-        rc = launch_k2(ctx, g, accum_mode, grid_dev, width, height);
+        // narrow fixed-point sums: |diff| <= 255 for uint8 frames, so 32 lanes * 255 * 2^frac_bits < 2^32 iff frac_bits <= 19
+        const bool narrow_ok = frame_dtype == PVP_FRAME_U8 && g.fixed_scale <= 524288.f;
+        rc = launch_k2(ctx, g, accum_mode, narrow_ok, lean_geometry_ok(g, pairs + p0, np), grid_dev, width, height);
         if (rc) return rc;
     }
     return PVP_OK;

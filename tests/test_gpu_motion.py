@@ -192,10 +192,10 @@ def test_sequence_float_frames_tolerance_and_fixed_exact(ctx, oracle):
                           bits(oracle.fixed_to_f32(want_fx, 20)))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("accum", ["f32", "fixed"])
 def test_k2_variants_bit_exact(ctx, oracle, variant, accum):
-    """Every K2 variant (segmented-scan aggregation, match.any aggregation, plain per-lane RED) must give the
+    """Every K2 variant (segmented-scan aggregation, match.any aggregation, plain per-lane RED, lean lock-step) must give the
     reference's grid bit for bit on integer-valued frames, for whole grids and slabs, and the same counters."""
     rng = np.random.default_rng(20 + variant)
     F, H, W, N, vs, center = 4, 50, 131, 72, 5.0, (0.0, 0.0, 500.0)   # odd width: partial warps, unaligned rows
