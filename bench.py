@@ -187,6 +187,9 @@ def run_ours(args, wl):
     ctx = pvp.default_context(dev)
     if args.variant:
         ctx.set_option("dda_variant", args.variant)
+    for kv in args.opt or []:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
 
     frames_np, poses = make_inputs(wl, seed=1000 + rank)   # weak scaling: every rank has its own frames, same shape
     frames_dev = torch.as_tensor(frames_np, device=dev)
@@ -342,6 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p_dense_512", choices=sorted(WORKLOADS))
+    ap.add_argument("--opt", action="append", help="context option key=value (pvp_ctx_set_option), repeatable; kernel experiments")
     ap.add_argument("--variant", type=int, default=0, help="K2 variant (0 = library default; see pvp_motion.cu launch_k2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments only)")
     args = ap.parse_args()

@@ -365,8 +365,9 @@ dda_accumulate_agg_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, 
 
 // ---- variant 4: "lean" lock-step kernel ---------------------------------------------------------
 // Same algorithm as variant 1 (per-lane DDA in lock-step, runs of equal voxels among consecutive lanes
-// summed by a segmented warp scan, one RED per run) with the inner loop cut from 78 to ~45 SASS
-// instructions and re-balanced between the ALU and FMA pipes (ncu on variant 1: ALU pipe 84 %, FMA 16 %):
+// summed by a segmented warp scan, one RED per run) with the inner loop cut from 78 to 48 SASS
+// instructions, 5 instead of 6 shuffles, and re-balanced between the ALU and FMA pipes (ncu on variant 1:
+// ALU pipe 84 %, FMA 16 %).  Measured 1080p -> 512^3: 514 G voxel-steps/s against 361 (profiles/):
 //   * axis choice through one FMNMX3: m = min(tmx,tmy,tmz); z iff tmz == m, else y iff tmy == m, else x.
 //     For NaN-free t values this is exactly the reference's strict-< chain with ties to the later axis
 //     (ray_voxel.cpp:375-387).  The only way t_max += t_delta can make a NaN is a -inf t_max, i.e. an overflow
@@ -379,6 +380,9 @@ dda_accumulate_agg_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, 
 //     harmless (key NONE, value 0, zero strides, t frozen) by a warp-uniform slow path that runs only in
 //     iterations where some ray ends (~5 %), which also decides the loop exit.
 //   * scan predicates are single LOP3s of the run-head ballot against lane-constant window masks.
+//   * software pipelining: the DDA step runs first and the shuffle of the NEW keys (next iteration's run
+//     heads) is issued before the scan of the current voxel, off the scan's dependent chain; the first scan
+//     step needs no shuffle at all because the value of the lane below is constant while no lane parks.
 struct LaneMasks {
     unsigned w1, w2, w4, w8, w16, next;
 };
@@ -445,8 +449,8 @@ __device__ __forceinline__ bool run_head(unsigned key)
     return !inrange || key != prev;
 }
 
-template <int MODE, bool SLAB, bool NARROW>
-__global__ void __launch_bounds__(K2_THREADS)
+template <int MODE, bool SLAB, bool NARROW, int MINB>
+__global__ void __launch_bounds__(K2_THREADS, MINB)
 dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
                            int width, int height, Ctl *__restrict__ ctl)
 {
@@ -498,27 +502,19 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
         }
         if (__all_sync(FULL, idx == KEY_NONE)) continue;
 
+        // Loop-carried across iterations so that they are off the scan's critical path: the run heads of the
+        // CURRENT voxel keys (computed right after the previous DDA step) and, for whole-grid kernels, the value
+        // of the lane below (constant while no lane parks).
+        unsigned heads = 0;
+        T pval = 0;
+        if (!SLAB) {
+            heads = __ballot_sync(FULL, run_head(idx));  // bit 0 is always set
+            pval = __shfl_up_sync(FULL, val, 1);
+        }
+
         for (;;) {
-            // ---- accumulate the current voxel: one RED per run of equal keys --------------------------
-            unsigned key = idx;
-            T sum = val;
-            if (SLAB) {
-                const bool in = idx < slab_cells;  // parked lanes (KEY_NONE) are outside every slab
-                key = in ? idx : KEY_NONE;
-                sum = in ? val : (T)0;
-                n_inslab += in ? 1.f : 0.f;
-            }
-            const unsigned heads = __ballot_sync(FULL, run_head(key));  // bit 0 is always set
-            T t;
-            t = __shfl_up_sync(FULL, sum, 1);  if (!(heads & lm.w1))  sum = V::add(sum, t);
-            t = __shfl_up_sync(FULL, sum, 2);  if (!(heads & lm.w2))  sum = V::add(sum, t);
-            t = __shfl_up_sync(FULL, sum, 4);  if (!(heads & lm.w4))  sum = V::add(sum, t);
-            t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t);
-            t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t);
-            const bool issue = (heads & lm.next) && key != KEY_NONE;
-            red_if(issue, grid + key, sum);
-            if (issue) n_issued += 1.f;
-            // ---- one DDA step (ray_voxel.cpp:375-391) -------------------------------------------------
+            // ---- one DDA step (ray_voxel.cpp:375-391), first: the new keys' shuffle overlaps the scan below ----
+            const unsigned cur = idx;
             const float m = fmin3(tmx, tmy, tmz);
             const bool cz = (tmz == m);
             const bool cy = !cz && (tmy == m);
@@ -528,6 +524,30 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
             if (cz) { tmz = fadd(tmz, tdz); remz -= 1.f; }
             idx += (unsigned)(cz ? diz : (cy ? diy : dix));
             const bool still = (fmin3(remx, remy, remz) >= 0.f) && (m <= t_end);
+            bool next_head = false;
+            if (!SLAB) next_head = run_head(idx);
+            // ---- accumulate the voxel the step left: one RED per run of equal keys -------------------------
+            unsigned key = cur;
+            T sum, t;
+            if (SLAB) {
+                const bool in = cur < slab_cells;  // parked lanes (KEY_NONE) are outside every slab
+                key = in ? cur : KEY_NONE;
+                sum = in ? val : (T)0;
+                if (in) n_inslab += 1.f;
+                heads = __ballot_sync(FULL, run_head(key));
+                t = __shfl_up_sync(FULL, sum, 1);
+                if (!(heads & lm.w1)) sum = V::add(sum, t);
+            } else {
+                sum = (heads & lm.w1) ? val : V::add(val, pval);
+            }
+            t = __shfl_up_sync(FULL, sum, 2);  if (!(heads & lm.w2))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 4);  if (!(heads & lm.w4))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t);
+            const bool issue = (heads & lm.next) && key != KEY_NONE;
+            red_if(issue, grid + key, sum);
+            if (issue) n_issued += 1.f;
+            if (!SLAB) heads = __ballot_sync(FULL, next_head);
             // ---- rays that ended: park the lane; leave when the whole warp is parked ---------------------
             if (__any_sync(FULL, !still)) {
                 const bool park = !still && idx != KEY_NONE;
@@ -539,6 +559,10 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
                 t_end = park ? CUDART_INF_F : t_end;
                 remx = park ? REM_PARKED : remx; remy = park ? REM_PARKED : remy; remz = park ? REM_PARKED : remz;
                 if (__all_sync(FULL, idx == KEY_NONE)) break;
+                if (!SLAB) {
+                    heads = __ballot_sync(FULL, run_head(idx));
+                    pval = __shfl_up_sync(FULL, val, 1);
+                }
             }
         }
         my_atomics += (unsigned long long)n_issued;
@@ -662,10 +686,11 @@ static void launch_agg(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, 
                                                                            width, height, ctx->ctl_dev);
 }
 
+// lean_regs: 0/80 = compiled for 3 resident CTAs per SM (<= 80 registers; measured best), 64 = for 4 (<= 64 registers)
 template <int MODE, bool SLAB, bool NARROW>
 static void launch_lean(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height)
 {
-    auto k = dda_accumulate_lean_kernel<MODE, SLAB, NARROW>;
+    auto k = ctx->opt_lean_regs == 64 ? dda_accumulate_lean_kernel<MODE, SLAB, NARROW, 4> : dda_accumulate_lean_kernel<MODE, SLAB, NARROW, 3>;
     k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
                                                                            width, height, ctx->ctl_dev);
 }
