@@ -32,6 +32,12 @@ WORKLOADS = {
     # sparse motion (moving blobs, ~1 % of the pixels): frames/s matters, many pairs per step
     "1080p_sparse_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=72, motion="sparse", accum="f32"),
     "1080p_dense_512_fixed": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=72, motion="dense", accum="fixed"),
+    # BASELINE config[4]: process_image_cpp path (fp64 fixed-step march) on a 4096x4096 image into a 512^3 grid,
+    # fixed-point deterministic accumulation; ~1 sample per voxel pitch
+    "image_4096_512_fixed": dict(path="B", H=4096, W=4096, N=512, accum="fixed", frac_bits=20, pool=3),
+    "image_4096_512_f64": dict(path="B", H=4096, W=4096, N=512, accum="f64", frac_bits=0, pool=3),
+    "image_1024_256_f64": dict(path="B", H=1024, W=1024, N=256, accum="f64", frac_bits=0, pool=3),
+    "image_tiny": dict(path="B", H=96, W=96, N=32, accum="f64", frac_bits=0, pool=2),
     # small smoke-sized case for CPU-side checks of this script
     "tiny": dict(H=120, W=160, N=64, voxel_size=16.0, center=(0.0, 0.0, 500.0), pairs_per_step=2, pool=8, motion="dense", accum="f32"),
 }
@@ -161,6 +167,206 @@ def run_reference(args, wl):
         "e2e": {"value": v, "unit": "voxel-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s": (args.steps / bands) / tot_s if tot_s > 0 else 0.0,
     }))
+
+
+# ---- path B (process_image_cpp) ---------------------------------------------------------------------------------
+def image_scene(wl, seed):
+    """Synthetic C5 scene: rng.random() images, observer at the origin looking at a cube in front of it,
+    one march sample per voxel pitch."""
+    rng = np.random.default_rng(seed)
+    n = wl["N"]
+    images = rng.random((wl["pool"], wl["H"], wl["W"]))
+    half = n / 2.0
+    ext = [(-half, half), (-half, half), (100.0, 100.0 + n)]
+    geom = dict(earth_position=[0.0, 0.0, 0.0], pointing_direction=[0.02, 0.01, 1.0], fov=0.8, extent=ext,
+                max_distance=float(100 + n + 88), num_steps=int(100 + n + 88), sky=(0.0, 0.0, 1.0, 1.0))
+    return images, geom
+
+
+def image_config(args, wl):
+    return {"workload": args.workload, "path": "process_image_cpp (fp64 fixed-step march)", "image": f"{wl['W']}x{wl['H']} float64",
+            "grid": f"{wl['N']}^3 {'int64 fixed point, frac_bits %d' % wl['frac_bits'] if wl['accum'] == 'fixed' else 'float64'}",
+            "images_per_step": 1, "parallelism": f"images sharded over {args.gpus} GPU(s), private grids, one NCCL reduce per run" if args.gpus > 1 else "1 GPU",
+            "l2": "grid (1 GiB) and image (134 MB) exceed L2; 256 MiB buffer written between timed steps"}
+
+
+def run_reference_image(args, wl):
+    """--impl reference for path B: the unmodified process_image.cpp (oracle/_ref, -O2 -fopenmp) on all host cores,
+    each step a band of image rows (bounded sample)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle
+    images, geom = image_scene(wl, seed=2000)
+    n = wl["N"]
+    use_ref = oracle.have_ref()
+    mod = oracle.ref_process_image_module() if use_ref else None
+    port = None if use_ref else oracle.Oracle()
+    cores = os.cpu_count() or 1
+    rows = max(8, wl["H"] // 128)                 # 32 rows of 4096 px: ~60 M samples per step
+    stride = wl["H"] // rows                      # spread over the image so that every OpenMP thread (static row blocks) gets work
+    grid = np.zeros((n, n, n), np.float64)
+    tex = np.zeros((8, 8), np.float64)
+
+    def band(step):
+        img = np.zeros((wl["H"], wl["W"]))
+        sel = (np.arange(rows) * stride + (step * 7) % stride) % wl["H"]
+        img[sel] = images[0][sel]
+        return img
+
+    def one(step):
+        img = band(step)
+        t0 = time.perf_counter()
+        if use_ref:
+            mod.process_image_cpp(img, geom["earth_position"], geom["pointing_direction"], geom["fov"], wl["W"], wl["H"], grid, geom["extent"],
+                                  geom["max_distance"], geom["num_steps"], tex, *geom["sky"], False, False)
+        else:
+            port.process_image(img, geom["earth_position"], geom["pointing_direction"], geom["fov"], wl["W"], wl["H"], grid, geom["extent"],
+                               geom["max_distance"], geom["num_steps"], tex, *geom["sky"], False, False)
+        dt = time.perf_counter() - t0
+        return dt
+
+    import pixeltovoxelprojector_b200.synth  # noqa: F401  (keeps import order identical to the path-A arm)
+    for s in range(args.warmup):
+        one(s)
+    tot_s = sum(one(args.warmup + s) for s in range(args.steps))
+    # samples are counted by the C port on the same bands (the reference module has no counter)
+    o = oracle.Oracle()
+    samples = 0
+    for s in range(args.steps):
+        img = band(args.warmup + s)
+        samples += o.process_image(img, geom["earth_position"], geom["pointing_direction"], geom["fov"], wl["W"], wl["H"], np.zeros((n, n, n)), geom["extent"],
+                                   geom["max_distance"], geom["num_steps"], np.zeros((8, 8)), *geom["sky"], False, False)[1]
+    v = samples / tot_s if tot_s > 0 else 0.0
+    kind = "reference" if use_ref else "port"
+    sample = f"per step: {rows} rows (every {stride}th) of one {wl['W']}x{wl['H']} image ({samples // max(1, args.steps)} samples), {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": "voxel_steps_per_sec", "value": v, "unit": "voxel-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": image_config(args, wl),
+        "cpu_baseline": {"value": v, "unit": "voxel-steps/s", "cores": cores if use_ref else 1, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "voxel-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours_image(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import pixeltovoxelprojector_b200 as pvp
+    from pixeltovoxelprojector_b200 import process_image as pi
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = pvp.default_context(dev)
+    for kv in args.opt or []:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
+    images_np, geom = image_scene(wl, seed=2000 + rank)
+    n, H, W = wl["N"], wl["H"], wl["W"]
+    cell = torch.int64 if wl["accum"] == "fixed" else torch.float64
+    images_dev = torch.as_tensor(images_np, device=dev)
+    images_pin = torch.as_tensor(images_np).pin_memory()
+    stage = torch.empty((H, W), dtype=torch.float64, device=dev)
+    grid = torch.zeros((n, n, n), dtype=cell, device=dev)
+    tex = torch.zeros((8, 8), dtype=cell, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    kw = dict(accum_mode=wl["accum"], frac_bits=wl["frac_bits"], ctx=ctx)
+
+    def call(img, want_stats):
+        pvp.process_image_cpp(img, geom["earth_position"], geom["pointing_direction"], geom["fov"], W, H, grid, geom["extent"], geom["max_distance"],
+                              geom["num_steps"], tex, *geom["sky"], False, False, want_stats=want_stats, **kw)
+        return pi.last_stats if want_stats else None
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for s in range(args.warmup):
+        call(images_dev[s % wl["pool"]], False)
+    samples_per_image = [call(images_dev[i], True)["n_samples"] for i in range(wl["pool"])]
+    grid.zero_()
+    ctx.get_profile(reset=True)
+    ctx.profile(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
+    barrier()
+    my_samples = 0
+    with ClockSampler(local) as clocks:
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)
+            ev[s][0].record()
+            call(images_dev[s % wl["pool"]], False)
+            ev[s][1].record()
+            my_samples += samples_per_image[s % wl["pool"]]
+        ev[-1][0].record()
+        if world > 1:
+            dist.reduce(grid, dst=0)
+        ev[-1][1].record()
+        barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    prof = ctx.get_profile(reset=True)
+    ctx.profile(False)
+    # e2e: the image of every step comes from pinned HOST memory (H2D inside), the step's counters go back (D2H)
+    grid.zero_()
+    e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_samples = 0
+    barrier()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        e_ev[s][0].record()
+        stage.copy_(images_pin[s % wl["pool"]], non_blocking=True)
+        e_samples += call(stage, True)["n_samples"]
+        e_ev[s][1].record()
+    barrier()
+    t = torch.tensor([ms, sum(a.elapsed_time(b) for a, b in e_ev)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(my_samples), float(e_samples)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    k3_s = prof["ms_k3"] * 1e-3
+    achieved = 16 * my_samples / k3_s / 1e9 if k3_s > 0 else 0.0     # one 8-byte atomic RMW per sample (SURVEY 8d)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                "kernel": "process_image_kernel (K3)", "peak_source": peak_src, "algorithmic_bytes_per_voxel_step": 16,
+                "voxel_steps_per_launch": my_samples / max(1, prof["launches_k3"]), "avg_launch_ms": prof["ms_k3"] / max(1, prof["launches_k3"]),
+                "k3_share_of_step": prof["ms_k3"] / ms if ms > 0 else None}
+    if args.no_cpu:
+        cpu = {"value": 0.0, "unit": "voxel-steps/s", "cores": 0, "kind": "skipped", "sample": ""}
+    else:
+        import io, contextlib
+        buf = io.StringIO()
+        a2 = argparse.Namespace(**{**vars(args), "steps": 3, "warmup": 1})
+        with contextlib.redirect_stdout(buf):
+            run_reference_image(a2, wl)
+        cpu = json.loads(buf.getvalue().strip().splitlines()[-1])["cpu_baseline"]
+    value = float(tot[0].item()) / (float(t[0].item()) * 1e-3)
+    e_value = float(tot[1].item()) / (float(t[1].item()) * 1e-3)
+    print(json.dumps({
+        "metric": "voxel_steps_per_sec", "value": value, "unit": "voxel-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(t[0].item()) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": image_config(args, wl), "frames_per_s": args.steps * world / (float(t[0].item()) * 1e-3),
+        "e2e": {"value": e_value, "unit": "voxel-steps/s", "h2d_bytes_per_step": H * W * 8, "d2h_bytes_per_step": 16,
+                "frames_per_s": args.steps * world / (float(t[1].item()) * 1e-3),
+                "api": "pixeltovoxelprojector_b200.process_image_cpp(CUDA tensors; image staged from pinned host memory) -> pvp_process_image"},
+        "gpu_launches": int(prof["launches_k3"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+    }))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def workload_config(args, wl):
@@ -350,7 +556,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments only)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if wl.get("path") == "B":
+        (run_reference_image if args.impl == "reference" else run_ours_image)(args, wl)
+    elif args.impl == "reference":
         run_reference(args, wl)
     else:
         run_ours(args, wl)

@@ -244,6 +244,16 @@ int pvp_process_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, voi
 int pvp_process_image_host(pvp_ctx *ctx, const double *image, double *grid, double *tex, const pvp_image_args *args,
                            pvp_image_stats *stats);
 
+/*
+ * Self-test of the lock-step path-B kernel's division by the grid extent (a reciprocal-based sequence that must equal
+ * the reference's IEEE division, process_image.cpp:94-96, bit for bit): compares both on n_random numerators drawn
+ * uniformly in [0, extent] and on +-64 ulps around every k*extent/n_grid voxel boundary (quotient bit-identical for
+ * numerators >= 2^-960, voxel index identical always).  *eligible = 0 means the
+ * library would use the generic kernel (plain division) for this extent and nothing is compared.
+ */
+int pvp_selftest_div_by_extent(pvp_ctx *ctx, double extent, int64_t n_random, int32_t n_grid, uint64_t seed, uint64_t *mismatches,
+                               int32_t *eligible);
+
 /* ---- roofline micro-benchmark (measured L2-atomic peak) ---------- */
 /*
  * Issues n_ops independent atomic adds into a buffer of buf_bytes with the given address

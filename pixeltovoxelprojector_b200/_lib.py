@@ -123,6 +123,7 @@ SIGNATURES = {
     "pvp_read_bin": (C.c_int, [C.c_char_p, C.c_int32, _P]),
     "pvp_process_image": (C.c_int, [_P, _P, _P, _P, C.POINTER(ImageArgs), C.POINTER(ImageStats)]),
     "pvp_process_image_host": (C.c_int, [_P, _P, _P, _P, C.POINTER(ImageArgs), C.POINTER(ImageStats)]),
+    "pvp_selftest_div_by_extent": (C.c_int, [_P, C.c_double, C.c_int64, C.c_int32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "pvp_atomic_microbench": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_float)]),
     "pvp_atomic_microbench_ops": (C.c_int64, [_P, C.c_int64]),
 }

@@ -233,6 +233,7 @@ int pvp_ctx_set_option(pvp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "max_queue")) { PVP_REQUIRE(value >= 1024, "max_queue must be >= 1024"); ctx->opt_max_queue = value; }
     else if (!strcmp(key, "ctas_per_sm")) ctx->opt_ctas_per_sm = value;
     else if (!strcmp(key, "lean_regs")) ctx->opt_lean_regs = value;
+    else if (!strcmp(key, "image_variant")) ctx->opt_image_variant = value;
     else { set_error("pvp_ctx_set_option: unknown key '%s'", key); return PVP_ERR_INVALID; }
     return PVP_OK;
 }

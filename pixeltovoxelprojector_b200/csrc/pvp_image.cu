@@ -71,6 +71,81 @@ template <> struct Cell<PVP_ACCUM_FIXED> {
 
 constexpr int K3_THREADS = 128;
 
+// One pixel up to the march bounds (process_image.cpp:236-340): brightness filter, fp64 camera ray, RA/Dec, sky-texture
+// lookup / background subtraction / accumulate, AABB clip.  Returns true when the pixel marches samples
+// s_entry..s_exit; `counted` tells whether it reached the ray stage (statistics).
+template <int MODE>
+__device__ __forceinline__ bool pixel_setup(const double *__restrict__ image, typename Cell<MODE>::T *__restrict__ tex, const ImageP &p,
+                                            long long px, double &w0, double &w1, double &w2, typename Cell<MODE>::V &val,
+                                            int &s_entry, int &s_exit, bool &counted)
+{
+    using C = Cell<MODE>;
+    counted = false;
+    const long long i = px / p.W, j = px - i * p.W;
+    double brightness = image[i * p.is0 + j * p.is1];  // :236
+    if (!(brightness > 0)) return false;               // :238
+
+    const double x_cam = dsub((double)j, p.cx), y_cam = dsub((double)i, p.cy), z_cam = p.focal;  // :241-243
+    const double norm = __dsqrt_rn(dadd(dadd(dmul(x_cam, x_cam), dmul(y_cam, y_cam)), dmul(z_cam, z_cam)));
+    const double c0 = ddiv(x_cam, norm), c1 = ddiv(y_cam, norm), c2 = ddiv(z_cam, norm);
+    w0 = dadd(dadd(dmul(p.xa[0], c0), dmul(p.ya[0], c1)), dmul(p.za[0], c2));  // :250-252
+    w1 = dadd(dadd(dmul(p.xa[1], c0), dmul(p.ya[1], c1)), dmul(p.za[1], c2));
+    w2 = dadd(dadd(dmul(p.xa[2], c0), dmul(p.ya[2], c1)), dmul(p.za[2], c2));
+    const double dn = __dsqrt_rn(dadd(dadd(dmul(w0, w0), dmul(w1, w1)), dmul(w2, w2)));  // :255-260
+    w0 = ddiv(w0, dn); w1 = ddiv(w1, dn); w2 = ddiv(w2, dn);
+
+    const double r = __dsqrt_rn(dadd(dadd(dmul(w0, w0), dmul(w1, w1)), dmul(w2, w2)));   // :267
+    const double dec = asin(ddiv(w2, r));
+    double ra = atan2(w1, w0);
+    if (ra < 0) ra = dadd(ra, 2 * M_PI);  // :270
+    double ra_off = dsub(ra, p.c_ra), dec_off = dsub(dec, p.c_dec);
+    if (ra_off > M_PI) ra_off = dsub(ra_off, 2 * M_PI);  // :277-278
+    if (ra_off < -M_PI) ra_off = dadd(ra_off, 2 * M_PI);
+    const bool within = (fabs(ra_off) <= p.half_w) && (fabs(dec_off) <= p.half_h);  // :281-282
+    const double u = dmul(ddiv(dadd(ra_off, p.half_w), p.ang_w), (double)p.tw);      // :285-286
+    const double v = dmul(ddiv(dadd(dec_off, p.half_h), p.ang_h), (double)p.th);
+    long long u_idx = trunc64_like_x86(u), v_idx = trunc64_like_x86(v);              // :288-293
+    u_idx = min(max(u_idx, 0ll), p.tw - 1);
+    v_idx = min(max(v_idx, 0ll), p.th - 1);
+    typename C::T *texel = tex + (v_idx * p.ts0 + u_idx * p.ts1);
+
+    if (p.bg_sub) {  // :296-307 (the reference also loads the texel when it is not used)
+        const double background = within ? C::read(texel, p.scale) : 0.0;
+        brightness = dsub(brightness, background);
+        if (brightness <= 0) return false;
+    }
+    val = C::make(brightness, p.scale);
+    if (p.update_tex && within) C::add(texel, val);  // :310-314
+    counted = true;
+    if (!p.grid_provided) return false;  // :317
+
+    // ray_aabb_intersection, :24-61
+    double tmin = -CUDART_INF, tmax = CUDART_INF;
+    bool hit = true;
+    const double dir[3] = {w0, w1, w2};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (fabs(dir[a]) > 1e-8) {
+            double t1 = ddiv(dsub(p.ext[2 * a], p.o[a]), dir[a]);
+            double t2 = ddiv(dsub(p.ext[2 * a + 1], p.o[a]), dir[a]);
+            if (t1 > t2) { double sw = t1; t1 = t2; t2 = sw; }
+            tmin = (tmin < t1) ? t1 : tmin;  // std::max(tmin, t1)
+            tmax = (t2 < tmax) ? t2 : tmax;  // std::min(tmax, t2)
+            if (tmin > tmax) hit = false;
+        } else if (p.o[a] < p.ext[2 * a] || p.o[a] > p.ext[2 * a + 1]) {
+            hit = false;
+        }
+    }
+    if (!hit) return false;
+    const double t_entry = (tmin < 0.0) ? 0.0 : tmin;                      // :334
+    const double t_exit = (p.max_distance < tmax) ? p.max_distance : tmax;  // :335
+    if (!(t_entry <= t_exit)) return false;                                 // :337
+    s_entry = trunc32_like_x86(ddiv(t_entry, p.step_size));                 // :339-340
+    s_exit = trunc32_like_x86(ddiv(t_exit, p.step_size));
+    return true;
+}
+
+// Generic kernel: one thread per pixel, any grid size / strides / extent; one RED per sample.
 template <int MODE>
 __global__ void __launch_bounds__(K3_THREADS)
 process_image_kernel(const double *__restrict__ image, typename Cell<MODE>::T *__restrict__ grid,
@@ -80,67 +155,13 @@ process_image_kernel(const double *__restrict__ image, typename Cell<MODE>::T *_
     unsigned long long my_rays = 0, my_samples = 0;
     const long long n_px = p.W * p.H;
     for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < n_px; px += (long long)gridDim.x * blockDim.x) {
-        const long long i = px / p.W, j = px - i * p.W;
-        double brightness = image[i * p.is0 + j * p.is1];  // :236
-        if (!(brightness > 0)) continue;                   // :238
-
-        const double x_cam = dsub((double)j, p.cx), y_cam = dsub((double)i, p.cy), z_cam = p.focal;  // :241-243
-        const double norm = __dsqrt_rn(dadd(dadd(dmul(x_cam, x_cam), dmul(y_cam, y_cam)), dmul(z_cam, z_cam)));
-        const double c0 = ddiv(x_cam, norm), c1 = ddiv(y_cam, norm), c2 = ddiv(z_cam, norm);
-        double w0 = dadd(dadd(dmul(p.xa[0], c0), dmul(p.ya[0], c1)), dmul(p.za[0], c2));  // :250-252
-        double w1 = dadd(dadd(dmul(p.xa[1], c0), dmul(p.ya[1], c1)), dmul(p.za[1], c2));
-        double w2 = dadd(dadd(dmul(p.xa[2], c0), dmul(p.ya[2], c1)), dmul(p.za[2], c2));
-        const double dn = __dsqrt_rn(dadd(dadd(dmul(w0, w0), dmul(w1, w1)), dmul(w2, w2)));  // :255-260
-        w0 = ddiv(w0, dn); w1 = ddiv(w1, dn); w2 = ddiv(w2, dn);
-
-        const double r = __dsqrt_rn(dadd(dadd(dmul(w0, w0), dmul(w1, w1)), dmul(w2, w2)));   // :267
-        const double dec = asin(ddiv(w2, r));
-        double ra = atan2(w1, w0);
-        if (ra < 0) ra = dadd(ra, 2 * M_PI);  // :270
-        double ra_off = dsub(ra, p.c_ra), dec_off = dsub(dec, p.c_dec);
-        if (ra_off > M_PI) ra_off = dsub(ra_off, 2 * M_PI);  // :277-278
-        if (ra_off < -M_PI) ra_off = dadd(ra_off, 2 * M_PI);
-        const bool within = (fabs(ra_off) <= p.half_w) && (fabs(dec_off) <= p.half_h);  // :281-282
-        const double u = dmul(ddiv(dadd(ra_off, p.half_w), p.ang_w), (double)p.tw);      // :285-286
-        const double v = dmul(ddiv(dadd(dec_off, p.half_h), p.ang_h), (double)p.th);
-        long long u_idx = trunc64_like_x86(u), v_idx = trunc64_like_x86(v);              // :288-293
-        u_idx = min(max(u_idx, 0ll), p.tw - 1);
-        v_idx = min(max(v_idx, 0ll), p.th - 1);
-        typename C::T *texel = tex + (v_idx * p.ts0 + u_idx * p.ts1);
-
-        if (p.bg_sub) {  // :296-307 (the reference also loads the texel when it is not used)
-            const double background = within ? C::read(texel, p.scale) : 0.0;
-            brightness = dsub(brightness, background);
-            if (brightness <= 0) continue;
-        }
-        const typename C::V val = C::make(brightness, p.scale);
-        if (p.update_tex && within) C::add(texel, val);  // :310-314
-        ++my_rays;
-        if (!p.grid_provided) continue;  // :317
-
-        // ray_aabb_intersection, :24-61
-        double tmin = -CUDART_INF, tmax = CUDART_INF;
-        bool hit = true;
-        const double dir[3] = {w0, w1, w2};
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (fabs(dir[a]) > 1e-8) {
-                double t1 = ddiv(dsub(p.ext[2 * a], p.o[a]), dir[a]);
-                double t2 = ddiv(dsub(p.ext[2 * a + 1], p.o[a]), dir[a]);
-                if (t1 > t2) { double s = t1; t1 = t2; t2 = s; }
-                tmin = (tmin < t1) ? t1 : tmin;  // std::max(tmin, t1)
-                tmax = (t2 < tmax) ? t2 : tmax;  // std::min(tmax, t2)
-                if (tmin > tmax) hit = false;
-            } else if (p.o[a] < p.ext[2 * a] || p.o[a] > p.ext[2 * a + 1]) {
-                hit = false;
-            }
-        }
-        if (!hit) continue;
-        const double t_entry = (tmin < 0.0) ? 0.0 : tmin;                      // :334
-        const double t_exit = (p.max_distance < tmax) ? p.max_distance : tmax;  // :335
-        if (!(t_entry <= t_exit)) continue;                                     // :337
-        const int s_entry = trunc32_like_x86(ddiv(t_entry, p.step_size));       // :339-340
-        const int s_exit = trunc32_like_x86(ddiv(t_exit, p.step_size));
+        double w0, w1, w2;
+        typename C::V val;
+        int s_entry, s_exit;
+        bool counted;
+        const bool marches = pixel_setup<MODE>(image, tex, p, px, w0, w1, w2, val, s_entry, s_exit, counted);
+        my_rays += counted;
+        if (!marches) continue;
 
         const double ex0 = dsub(p.ext[1], p.ext[0]), ex1 = dsub(p.ext[3], p.ext[2]), ex2 = dsub(p.ext[5], p.ext[4]);
         for (long long s = s_entry; s <= s_exit; ++s) {  // :342
@@ -164,6 +185,181 @@ process_image_kernel(const double *__restrict__ image, typename Cell<MODE>::T *_
         my_samples += __shfl_xor_sync(0xffffffffu, my_samples, o);
     }
     if ((threadIdx.x & 31) == 0 && (my_rays | my_samples)) {
+        atomicAdd(&ctl->img_rays, my_rays);
+        atomicAdd(&ctl->img_samples, my_samples);
+    }
+}
+
+// ---- lock-step kernel ----------------------------------------------------------------------------------------------
+// The 32 lanes of a warp hold 32 consecutive pixels and march the SAME sample index s together, so neighbouring
+// rays sit at the same depth and mostly in the same voxel: runs of equal voxel offsets among consecutive lanes are
+// summed with a segmented warp scan and one RED is issued per run (the mechanism of K2).  Per sample the index
+// arithmetic is 32 bit and the three divisions by the grid extent use a reciprocal prepared on the host:
+//   q0 = RN(a*y); r = a - q0*b (exact, FMA); q1 = RN(q0 + r*y); r = a - q1*b; q = RN(q1 + r*y)   with y = RN(1/b)
+// which is the correctly rounded a/b (Markstein's theorem; q1 is already faithful) unless b's significand is all
+// ones -- the host checks that, and the exponent range, before choosing this kernel (fast_ok), so the voxel index
+// is the reference's bit for bit.  FMA appears only inside this division, never in the reference's own expressions.
+struct ImageFastP {
+    double b[3], y[3], nd[3];  // extent, RN(1/extent), (double)n
+    int n1[3];                 // n - 1
+    unsigned gs[3];            // element strides
+};
+
+__device__ __forceinline__ double div_by_extent(double a, double b, double y)
+{
+    double q = dmul(a, y);
+    double r = __fma_rn(-q, b, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-q, b, a);
+    return __fma_rn(r, y, q);
+}
+
+// Self-test of div_by_extent against the IEEE division it replaces (pvp_selftest_div_by_extent): numerators are drawn
+// where the march draws them -- uniformly in [0, b], and within a few ulps of every k*b/n boundary.  The quotient must be
+// bit-identical for a >= 2^-960 (below that the exact remainder underflows and the quotient, < 2^-460, can only select
+// voxel 0); the voxel index must be identical always.
+__device__ __forceinline__ bool div_differs(double a, double b, double y, double nd, int n1)
+{
+    const double q1 = div_by_extent(a, b, y), q2 = ddiv(a, b);
+    const bool idx_differs = min(__double2int_rz(dmul(q1, nd)), n1) != min(__double2int_rz(dmul(q2, nd)), n1);
+    return idx_differs || (a >= 0x1p-960 && __double_as_longlong(q1) != __double_as_longlong(q2));
+}
+
+__global__ void div_selftest_kernel(double b, double y, long long n_random, int n_grid, unsigned long long seed,
+                                    unsigned long long *__restrict__ mismatches)
+{
+    unsigned long long bad = 0;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i < n_random; i += nth) {
+        unsigned long long x = (unsigned long long)i * 0x9e3779b97f4a7c15ull + seed;
+        x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+        const double a = dmul((double)(x >> 11) * 0x1p-53, b);
+        bad += div_differs(a, b, y, (double)n_grid, n_grid - 1);
+    }
+    for (long long i = tid; i < (long long)(n_grid + 1) * 129; i += nth) {
+        const long long k = i / 129;
+        const int d = (int)(i % 129) - 64;
+        double a = dmul(ddiv((double)k, (double)n_grid), b);
+        a = __longlong_as_double(__double_as_longlong(a) + d);  // +-64 ulps around the boundary
+        if (!(a >= 0.0 && a <= b)) continue;
+        bad += div_differs(a, b, y, (double)n_grid, n_grid - 1);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+constexpr unsigned IMG_NONE = 0xffffffffu;
+constexpr int K3L_THREADS = 256;
+
+struct ScanMasks { unsigned w1, w2, w4, w8, w16, next; };
+__device__ __forceinline__ ScanMasks scan_masks(unsigned lane)
+{
+    ScanMasks m;
+    auto win = [lane](unsigned d) { return lane + 1 >= d ? (((1u << d) - 1u) << (lane + 1 - d)) : ((2u << lane) - 1u); };
+    m.w1 = 1u << lane; m.w2 = win(2); m.w4 = win(4); m.w8 = win(8);
+    m.w16 = lane + 1 >= 16 ? (0xffffu << (lane - 15)) : ((2u << lane) - 1u);
+    m.next = lane == 31 ? 1u : (1u << (lane + 1));
+    return m;
+}
+
+__device__ __forceinline__ bool img_run_head(unsigned key)
+{
+    unsigned prev, inrange;
+    asm volatile("{\n\t.reg .pred q;\n\tshfl.sync.up.b32 %0|q, %2, 1, 0, 0xffffffff;\n\tselp.u32 %1, 1, 0, q;\n\t}" : "=r"(prev), "=r"(inrange) : "r"(key));
+    return !inrange || key != prev;
+}
+
+__device__ __forceinline__ void img_red(double *p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void img_red(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
+__device__ __forceinline__ void img_red(unsigned long long *p, unsigned v) { atomicAdd(p, (unsigned long long)v); }
+
+// One warp, one group of 32 pixels: samples wlo..whi in lock-step.  S is the type the run sums are formed in.
+template <typename S, typename CellT>
+__device__ __forceinline__ unsigned march_lockstep(CellT *__restrict__ grid, const ImageP &p, const ImageFastP &f, const ScanMasks &lm,
+                                                   double w0, double w1, double w2, S val, int lo, int hi, int wlo, int whi)
+{
+    const unsigned FULL = 0xffffffffu;
+    unsigned n_in = 0;
+    // voxel offset of sample s, or IMG_NONE (outside [lo,hi], or outside the extent: process_image.cpp:85, :349-352)
+    auto key_of = [&](int s) -> unsigned {
+        const double d = dmul((double)s, p.step_size);  // :344
+        const double qx = dadd(p.o[0], dmul(d, w0)), qy = dadd(p.o[1], dmul(d, w1)), qz = dadd(p.o[2], dmul(d, w2));
+        const bool in = (s >= lo) & (s <= hi) & (p.ext[0] <= qx) & (qx <= p.ext[1]) & (p.ext[2] <= qy) & (qy <= p.ext[3]) &
+                        (p.ext[4] <= qz) & (qz <= p.ext[5]);
+        // inside the extent the scaled coordinate lies in [0, n]: int truncation + upper clamp == :94-104
+        const int xi = min(__double2int_rz(dmul(div_by_extent(dsub(qx, p.ext[0]), f.b[0], f.y[0]), f.nd[0])), f.n1[0]);
+        const int yi = min(__double2int_rz(dmul(div_by_extent(dsub(qy, p.ext[2]), f.b[1], f.y[1]), f.nd[1])), f.n1[1]);
+        const int zi = min(__double2int_rz(dmul(div_by_extent(dsub(qz, p.ext[4]), f.b[2], f.y[2]), f.nd[2])), f.n1[2]);
+        const unsigned off = (unsigned)xi * f.gs[0] + (unsigned)yi * f.gs[1] + (unsigned)zi * f.gs[2];
+        return in ? off : IMG_NONE;
+    };
+    unsigned key = key_of(wlo);
+    unsigned heads = __ballot_sync(FULL, img_run_head(key));
+    for (int s = wlo;; ++s) {
+        // next sample's key first: its arithmetic and shuffle overlap the scan of the current one
+        unsigned key_n = IMG_NONE;
+        if (s != whi) key_n = key_of(s + 1);
+        const bool head_n = img_run_head(key_n);
+        const bool live = key != IMG_NONE;
+        n_in += live;
+        S sum = live ? val : (S)0, t;
+        t = __shfl_up_sync(FULL, sum, 1);  if (!(heads & lm.w1))  sum += t;
+        t = __shfl_up_sync(FULL, sum, 2);  if (!(heads & lm.w2))  sum += t;
+        t = __shfl_up_sync(FULL, sum, 4);  if (!(heads & lm.w4))  sum += t;
+        t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum += t;
+        t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum += t;
+        if ((heads & lm.next) && live) img_red(grid + key, sum);  // :356-357, once per run
+        if (s == whi) break;
+        heads = __ballot_sync(FULL, head_n);
+        key = key_n;
+    }
+    return n_in;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(K3L_THREADS)
+process_image_lockstep_kernel(const double *__restrict__ image, typename Cell<MODE>::T *__restrict__ grid,
+                              typename Cell<MODE>::T *__restrict__ tex, ImageP p, ImageFastP f, Ctl *__restrict__ ctl)
+{
+    using C = Cell<MODE>;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const ScanMasks lm = scan_masks(lane);
+    const long long n_px = p.W * p.H;
+    const unsigned long long n_groups = (unsigned long long)((n_px + 31) / 32);
+    unsigned long long my_rays = 0, my_samples = 0;
+    for (;;) {
+        unsigned long long group = 0;
+        if (lane == 0) group = atomicAdd(&ctl->head, 1ull);
+        group = __shfl_sync(FULL, group, 0);
+        if (group >= n_groups) break;
+        const long long px = (long long)group * 32 + lane;
+        double w0 = 0, w1 = 0, w2 = 0;
+        typename C::V val = 0;
+        int lo = INT32_MAX, hi = INT32_MIN;  // empty range
+        if (px < n_px) {
+            int s_entry, s_exit;
+            bool counted;
+            if (pixel_setup<MODE>(image, tex, p, px, w0, w1, w2, val, s_entry, s_exit, counted) && s_entry <= s_exit) { lo = s_entry; hi = s_exit; }
+            my_rays += counted;
+        }
+        const int wlo = __reduce_min_sync(FULL, lo), whi = __reduce_max_sync(FULL, hi);
+        if (wlo > whi) continue;
+        if (MODE == PVP_ACCUM_FIXED) {
+            // run sums of 32 lanes fit 32 bits when every value is below 2^27 (brightness <= 1 at frac_bits <= 27)
+            if (__all_sync(FULL, (unsigned long long)val < (1ull << 27)))
+                my_samples += march_lockstep<unsigned>((unsigned long long *)grid, p, f, lm, w0, w1, w2, (unsigned)val, lo, hi, wlo, whi);
+            else
+                my_samples += march_lockstep<unsigned long long>((unsigned long long *)grid, p, f, lm, w0, w1, w2, (unsigned long long)val, lo, hi, wlo, whi);
+        } else {
+            my_samples += march_lockstep<double>((double *)grid, p, f, lm, w0, w1, w2, (double)val, lo, hi, wlo, whi);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_rays += __shfl_xor_sync(FULL, my_rays, o);
+        my_samples += __shfl_xor_sync(FULL, my_samples, o);
+    }
+    if (lane == 0 && (my_rays | my_samples)) {
         atomicAdd(&ctl->img_rays, my_rays);
         atomicAdd(&ctl->img_samples, my_samples);
     }
@@ -223,11 +419,53 @@ static int make_imagep(const pvp_image_args *a, ImageP *p)
     return PVP_OK;
 }
 
+// Conditions under which the lock-step kernel reproduces the reference's voxel index bit for bit (see its header).
+static bool make_fastp(const ImageP &p, ImageFastP *f)
+{
+    if (!p.grid_provided) return false;
+    unsigned long long span = 0;
+    for (int k = 0; k < 3; ++k) {
+        volatile double b = p.ext[2 * k + 1] - p.ext[2 * k];  // :94-96, the divisor
+        int e = 0;
+        const double m = frexp(b, &e);  // b = m * 2^e, m in [0.5, 1)
+        if (!(b > 0.0) || !std::isfinite(b) || e < -500 || e > 500) return false;
+        if (m == 1.0 - 0x1p-53) return false;  // significand all ones: the one case Markstein's theorem excludes
+        if (!(fabs(p.ext[2 * k]) < 0x1p500 && fabs(p.ext[2 * k + 1]) < 0x1p500)) return false;
+        if (p.gn[k] < 1 || p.gn[k] > (1ll << 30) || p.gs[k] < 0 || p.gs[k] > 0xffffffffll) return false;
+        f->b[k] = b;
+        volatile double y = 1.0 / b;  // correctly rounded (IEEE division, x86-64 SSE2)
+        f->y[k] = y;
+        f->nd[k] = (double)p.gn[k];
+        f->n1[k] = (int)(p.gn[k] - 1);
+        f->gs[k] = (unsigned)p.gs[k];
+        span += (unsigned long long)(p.gn[k] - 1) * (unsigned long long)p.gs[k];
+    }
+    return span < 0xffffffffull;  // voxel offsets are 32-bit keys, 0xffffffff is reserved
+}
+
+// image_variant: 0 = auto (lock-step where fast_ok), 1 = generic per-pixel kernel, 2 = lock-step (falls back if !fast_ok)
 static int launch_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, void *tex_dev, const ImageP &p, int accum_mode)
 {
     const long long n_px = p.W * p.H;
-    int blocks = (int)std::min<long long>((n_px + K3_THREADS - 1) / K3_THREADS, (long long)ctx->sm_count * 16);
     LaunchScope scope(ctx, 3);
+    ImageFastP f;
+    if (ctx->opt_image_variant != 1 && make_fastp(p, &f)) {
+        PVP_CUDA(cudaMemsetAsync(&ctx->ctl_dev->head, 0, sizeof(unsigned long long), ctx->stream));
+        int per_sm = 0;
+        const void *k = accum_mode == PVP_ACCUM_F64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64>
+                                                    : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED>;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, K3L_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        const long long groups = (n_px + 31) / 32;
+        const int blocks = (int)std::min<long long>((groups + K3L_THREADS / 32 - 1) / (K3L_THREADS / 32), (long long)ctx->sm_count * per_sm);
+        if (accum_mode == PVP_ACCUM_F64)
+            process_image_lockstep_kernel<PVP_ACCUM_F64><<<blocks, K3L_THREADS, 0, ctx->stream>>>(image_dev, (double *)grid_dev, (double *)tex_dev, p, f, ctx->ctl_dev);
+        else
+            process_image_lockstep_kernel<PVP_ACCUM_FIXED><<<blocks, K3L_THREADS, 0, ctx->stream>>>(image_dev, (unsigned long long *)grid_dev,
+                                                                                                    (unsigned long long *)tex_dev, p, f, ctx->ctl_dev);
+        PVP_CUDA(cudaGetLastError());
+        return PVP_OK;
+    }
+    int blocks = (int)std::min<long long>((n_px + K3_THREADS - 1) / K3_THREADS, (long long)ctx->sm_count * 16);
     if (accum_mode == PVP_ACCUM_F64)
         process_image_kernel<PVP_ACCUM_F64><<<blocks, K3_THREADS, 0, ctx->stream>>>(image_dev, (double *)grid_dev, (double *)tex_dev, p, ctx->ctl_dev);
     else
@@ -279,6 +517,31 @@ int pvp_process_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, voi
     if (stats) PVP_CUDA(cudaMemsetAsync(&ctx->ctl_dev->img_rays, 0, 2 * sizeof(unsigned long long), ctx->stream));
     if ((rc = launch_image(ctx, image_dev, grid_dev, tex_dev, p, args->accum_mode))) return rc;
     return fetch_image_stats(ctx, stats);
+}
+
+int pvp_selftest_div_by_extent(pvp_ctx *ctx, double extent, int64_t n_random, int32_t n_grid, uint64_t seed, uint64_t *mismatches,
+                               int32_t *eligible)
+{
+    PVP_REQUIRE(ctx && mismatches && eligible && n_random >= 0 && n_grid >= 1, "pvp_selftest_div_by_extent: bad argument");
+    ImageP p = {};
+    p.grid_provided = 1;
+    for (int k = 0; k < 3; ++k) { p.ext[2 * k] = 0.0; p.ext[2 * k + 1] = extent; p.gn[k] = n_grid; }
+    p.gs[0] = (long long)n_grid * n_grid; p.gs[1] = n_grid; p.gs[2] = 1;
+    ImageFastP f;
+    *eligible = make_fastp(p, &f) ? 1 : 0;
+    *mismatches = 0;
+    if (!*eligible) return PVP_OK;  // the lock-step kernel would not be used for this extent
+    DeviceGuard guard(ctx->device);
+    unsigned long long *d_bad = nullptr;
+    PVP_CUDA(cudaMalloc(&d_bad, sizeof(*d_bad)));
+    cudaMemsetAsync(d_bad, 0, sizeof(*d_bad), ctx->stream);
+    ++ctx->prof.launches_other;
+    div_selftest_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(f.b[0], f.y[0], n_random, n_grid, seed, d_bad);
+    cudaError_t e = cudaMemcpyAsync(mismatches, d_bad, sizeof(*d_bad), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_bad);
+    PVP_CUDA(e);
+    return PVP_OK;
 }
 
 int pvp_process_image_host(pvp_ctx *ctx, const double *image, double *grid, double *tex, const pvp_image_args *args,

@@ -83,7 +83,55 @@ def test_strides_empty_grid_and_errors(ctx):
     assert not g32.any()
 
 
-def test_random_scenes_vs_oracle(ctx, oracle):
+def test_division_by_extent_equals_ieee_division(ctx):
+    """The lock-step kernel divides by the grid extent with a host-prepared reciprocal (Markstein sequence); it must
+    equal IEEE division bit for bit wherever the library chooses that kernel.  4e8 numerators per extent, plus +-64 ulps
+    around every voxel boundary; extents the sequence is not proven for must be declared ineligible."""
+    import ctypes as C
+    from pixeltovoxelprojector_b200._lib import check
+    rng = np.random.default_rng(77)
+    extents = [20.0, 17.0, 512.0, 0.3, 1e-3, 123456.789, 3.0, 2.0 / 3.0, float(np.nextafter(2.0, 0)) / 4, 1e200, 7e-190]
+    extents += [float(x) for x in np.exp(rng.uniform(-40, 40, 12))]
+    for b in extents:
+        bad, ok = C.c_uint64(0), C.c_int32(0)
+        check(ctx._lib.pvp_selftest_div_by_extent(ctx.handle, b, 40_000_000, 512, int(rng.integers(1 << 62)), C.byref(bad), C.byref(ok)))
+        all_ones = np.frexp(b)[0] == 1.0 - 2.0 ** -53
+        too_big = not (2.0 ** -500 < b < 2.0 ** 499)
+        assert bool(ok.value) == (not all_ones and not too_big), b
+        assert bad.value == 0, (b, bad.value)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_random_scenes_vs_oracle(ctx, oracle, variant):
+    """variant 1 = generic per-pixel kernel, 2 = lock-step kernel with warp-aggregated REDs (the default where eligible)."""
+    ctx.set_option("image_variant", variant)
+    try:
+        _random_scenes(oracle)
+    finally:
+        ctx.set_option("image_variant", 0)
+
+
+def test_lockstep_fixed_point_wide_and_ineligible_extent(ctx, oracle):
+    """Fixed point with values >= 2^27 takes the 64-bit run sums; an extent whose significand is all ones falls back to
+    the generic kernel; both must match the oracle exactly."""
+    rng = np.random.default_rng(31)
+    H, W = 40, 52
+    img = rng.random((H, W)) * 1000.0          # * 2^24 >> 2^27: wide sums
+    pos, pointing = [0.1, -0.2, 0.3], [0.05, 0.02, 1.0]
+    odd = float(np.nextafter(32.0, 0))          # 31.999...: significand all ones
+    for ext in ([(-8.0, 9.0), (-7.0, 6.5), (10.0, 28.0)], [(0.0, odd), (-7.0, 6.5), (10.0, 28.0)]):
+        og, ot = np.zeros((20, 24, 28), np.int64), np.zeros((8, 8), np.int64)
+        nr, ns = oracle.process_image(img, pos, pointing, 0.9, W, H, og, ext, 60.0, 240, ot, 0.0, 0.0, 1.0, 1.0, True, False, accum_mode=1, frac_bits=24)
+        gi = torch.zeros(og.shape, dtype=torch.int64, device="cuda")
+        ti = torch.zeros(ot.shape, dtype=torch.int64, device="cuda")
+        pvp.process_image_cpp(torch.as_tensor(img, device="cuda"), pos, pointing, 0.9, W, H, gi, ext, 60.0, 240, ti, 0.0, 0.0, 1.0, 1.0, True, False,
+                              accum_mode="fixed", frac_bits=24, want_stats=True)
+        from pixeltovoxelprojector_b200 import process_image as pi
+        assert pi.last_stats == {"n_rays": nr, "n_samples": ns} and ns > 1000
+        assert np.array_equal(gi.cpu().numpy(), og) and np.array_equal(ti.cpu().numpy(), ot)
+
+
+def _random_scenes(oracle):
     rng = np.random.default_rng(9)
     for trial in range(6):
         H, W = int(rng.integers(8, 70)), int(rng.integers(8, 70))
