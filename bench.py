@@ -41,6 +41,14 @@ WORKLOADS = {
     # small smoke-sized case for CPU-side checks of this script
     "tiny": dict(H=120, W=160, N=64, voxel_size=16.0, center=(0.0, 0.0, 500.0), pairs_per_step=2, pool=8, motion="dense", accum="f32"),
 }
+def measured_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]["bytes_per_launch"]
+    except Exception:
+        return None
+
+
 ALGO_BYTES_PER_STEP = {"f32": 8, "fixed": 16}   # one atomic RMW: 4 B read + 4 B write (fp32), 8 + 8 (int64) -- SURVEY 8d
 
 
@@ -341,8 +349,8 @@ def run_ours_image(args, wl):
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     k3_s = prof["ms_k3"] * 1e-3
     achieved = 16 * my_samples / k3_s / 1e9 if k3_s > 0 else 0.0     # one 8-byte atomic RMW per sample
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
-                "kernel": "process_image_kernel (K3)", "peak_source": peak_src, "algorithmic_bytes_per_voxel_step": 16,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": measured_traffic(args.workload), "kernel": "process_image_lockstep_kernel (K3)", "peak_source": peak_src, "algorithmic_bytes_per_voxel_step": 16,
                 "voxel_steps_per_launch": my_samples / max(1, prof["launches_k3"]), "avg_launch_ms": prof["ms_k3"] / max(1, prof["launches_k3"]),
                 "k3_share_of_step": prof["ms_k3"] / ms if ms > 0 else None}
     if args.no_cpu:
@@ -495,8 +503,8 @@ def run_ours(args, wl):
     k2_s = prof["ms_k2"] * 1e-3
     per_rank_steps = stats["n_steps"]
     achieved = ALGO_BYTES_PER_STEP[wl["accum"]] * per_rank_steps / k2_s / 1e9 if k2_s > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
-                "kernel": "dda_accumulate_kernel (K2)", "peak_source": peak_src,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": measured_traffic(args.workload), "kernel": "dda_accumulate_lean_kernel (K2)", "peak_source": peak_src,
                 "algorithmic_bytes_per_voxel_step": ALGO_BYTES_PER_STEP[wl["accum"]],
                 "voxel_steps_per_launch": per_rank_steps / max(1, prof["launches_k2"]), "avg_launch_ms": prof["ms_k2"] / max(1, prof["launches_k2"]),
                 "k2_share_of_step": prof["ms_k2"] / ms if ms > 0 else None, "k1_ms_total": prof["ms_k1"]}
