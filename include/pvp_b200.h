@@ -205,6 +205,24 @@ int pvp_write_bin(const char *path, int32_t n, float voxel_size, const float *gr
 int pvp_read_bin_header(const char *path, int32_t *n, float *voxel_size);
 int pvp_read_bin(const char *path, int32_t n, float *grid_host);
 
+/* ---- consumer side of the .bin: voxelmotionviewer.py:56-96 with the grid in HBM ---- */
+/*
+ * The two order statistics np.percentile(flat, q) interpolates between (voxelmotionviewer.py:72): *v_k = the k-th
+ * smallest of the n float32 cells (k counted from 0), *v_k1 = the (k+1)-th (== *v_k when k = n-1).  Radix select, 4-5
+ * passes over the grid.  The interpolation itself (numpy's "linear" method) is host arithmetic on these two values.
+ */
+int pvp_grid_order_stats(pvp_ctx *ctx, const float *grid_dev, int64_t n, int64_t k, float *v_k, float *v_k1);
+/*
+ * replaces np.argwhere(voxel_grid > thresh) and the index -> world conversion of voxelmotionviewer.py:77-95, in the
+ * same (C) order.  Any of the outputs may be NULL: coords_dev [cap][3] int32 = (i0,i1,i2) of voxel_grid[i0,i1,i2];
+ * points_dev [cap][3] float64 = (x,y,z) with x from i2, y from i1, z from i0 (the viewer's "z up" reading, :85-93):
+ * grid_min[a] + (idx + 0.5) * voxel_size; intens_dev [cap] float32.  *count = number of cells above thresh (may
+ * exceed cap: nothing past cap is written; call with cap 0 to size the outputs).  The comparison is done in float64,
+ * which is exact for a float32 or a float64 threshold.
+ */
+int pvp_grid_extract_above(pvp_ctx *ctx, const float *grid_dev, int32_t n_side, double thresh, double voxel_size, const double grid_min[3],
+                           int64_t cap, double *points_dev, float *intens_dev, int32_t *coords_dev, int64_t *count);
+
 /* ---- path B: process_image_cpp --------------------------------------------- */
 /*
  * replaces process_image_cpp, process_image.cpp:125-366.  Arrays are addressed by element

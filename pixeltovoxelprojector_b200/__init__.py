@@ -9,5 +9,6 @@ from .motion import (Context, FramePose, VoxelGrid, accumulate_motion, cast_rays
                      focal_length, load_image_gray, load_metadata, make_pairs, pixel_rays, ray_voxel_accumulate, ray_voxel_main,
                      read_bin, rotation_matrix, write_bin)
 from .process_image import process_image_cpp  # noqa: F401
+from .analysis import extract_top_percentile_z_up, grid_percentile, load_voxel_grid  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,91 @@
+"""BASELINE.json's multi-GPU configurations at their full shapes, on one GPU with the ranks run one after another
+(the collective itself is covered by tests/test_dist_gloo.py on CPU and tools/dist_check.py under torchrun):
+
+* config 3: 4 cameras x 3840x2160 frames into a 512^3 grid, frame pairs sharded over 2 / 4 / 8 ranks, private grids,
+  one sum-reduce.  Property: the sum of the shard grids equals the whole run (fixed point: bit for bit; fp32 with
+  uint8 frames: bit for bit too, every addend is an integer and the sums stay below 2^24).
+* config 4: a 1024^3 grid (4 GiB fp32) sharded into 8 x-slabs.  Property: every slab walks every ray with full-grid
+  arithmetic, writes partition the voxel steps, and the concatenated slabs equal the whole grid.
+
+No CPU oracle at these sizes; the small-size bit-exact parity against the oracle is in test_gpu_motion.py."""
+import numpy as np
+import pytest
+import torch
+
+import pixeltovoxelprojector_b200 as pvp
+from pixeltovoxelprojector_b200 import synth
+from pixeltovoxelprojector_b200.distributed import shard_range, slab_range
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _four_camera_scene(frames_per_cam, H, W, N, vs, center):
+    frames, poses, pairs = [], [], []
+    for cam in range(4):
+        f = synth.sparse_frames(frames_per_cam, H, W, seed=40 + cam, blob=160, blobs=5)
+        p = synth.orbit_poses(frames_per_cam, N, vs, center, seed=50 + cam, camera_index=cam)
+        base = len(poses)
+        frames.append(f)
+        poses += p
+        pairs += [(base + i - 1, base + i) for i in range(1, frames_per_cam)]   # consecutive frames of ONE camera
+    return np.concatenate(frames), poses, pairs
+
+
+def test_config3_four_4k_cameras_frame_sharded_512(ctx):
+    H, W, N, vs, center = 2160, 3840, 512, 2.0, (0.0, 0.0, 500.0)
+    frames_np, poses, pairs = _four_camera_scene(3, H, W, N, vs, center)
+    frames = torch.as_tensor(frames_np, device=DEV)
+    whole_fx = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=8)
+    tab, n = pvp.make_pairs(poses, W, pairs=pairs)
+    st = pvp.accumulate_motion(frames, tab, whole_fx, 2.0)
+    assert n == 8 and st["n_rays"] > 20000 and st["n_steps"] > 100 * st["n_rays"]   # moving blobs: only their edges change
+    whole_f32 = pvp.VoxelGrid(N, vs, center)
+    pvp.accumulate_motion(frames, tab, whole_f32, 2.0)
+    assert float(whole_f32.data.max()) < 2 ** 24
+    assert torch.equal(whole_f32.data, whole_fx.to_float32())           # exact integer sums in both modes
+    for world in (2, 4, 8):
+        total_fx = torch.zeros_like(whole_fx.data)
+        total_f32 = torch.zeros_like(whole_f32.data)
+        steps = 0
+        for rank in range(world):
+            lo, hi = shard_range(len(pairs), rank, world)
+            if lo == hi:
+                continue
+            t, _ = pvp.make_pairs(poses, W, pairs=pairs[lo:hi])
+            g = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=8)
+            steps += pvp.accumulate_motion(frames, t, g, 2.0)["n_steps"]
+            total_fx += g.data                                            # the rank-0 side of the sum-reduce
+            g32 = pvp.VoxelGrid(N, vs, center)
+            pvp.accumulate_motion(frames, t, g32, 2.0)
+            total_f32 += g32.data
+            del g, g32
+        assert steps == st["n_steps"]
+        assert torch.equal(total_fx, whole_fx.data), world
+        assert torch.equal(total_f32, whole_f32.data), world
+
+
+def test_config4_1024_grid_eight_x_slabs(ctx):
+    H, W, N, vs, center = 1080, 1920, 1024, 1.0, (0.0, 0.0, 500.0)
+    frames = torch.as_tensor(synth.sparse_frames(3, H, W, seed=60, blob=120, blobs=4), device=DEV)
+    poses = synth.orbit_poses(3, N, vs, center, seed=61)
+    tab, _ = pvp.make_pairs(poses, W)
+    whole = pvp.VoxelGrid(N, vs, center)                                   # 4 GiB
+    st = pvp.accumulate_motion(frames, tab, whole, 2.0)
+    assert st["n_steps"] > 200 * st["n_rays"] > 0 and st["n_written"] == st["n_steps"]
+    written, world = 0, 8
+    for rank in range(world):
+        lo, hi = slab_range(N, rank, world)
+        assert hi - lo == 128
+        slab = pvp.VoxelGrid(N, vs, center, slab=(lo, hi))                 # 512 MiB: x-planes [lo, hi) only
+        s = pvp.accumulate_motion(frames, tab, slab, 2.0)
+        assert (s["n_rays"], s["n_steps"]) == (st["n_rays"], st["n_steps"])   # every rank walks every ray in full
+        written += s["n_written"]
+        assert torch.equal(slab.data, whole.data[lo:hi]), rank             # a contiguous byte range of the .bin
+        del slab
+    assert written == st["n_steps"]
+    # the fixed-point slab path (64-bit cells) on one slab
+    lo, hi = slab_range(N, 3, world)
+    fx = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=6, slab=(lo, hi))
+    pvp.accumulate_motion(frames, tab, fx, 2.0)
+    assert torch.equal(fx.to_float32(), whole.data[lo:hi])
