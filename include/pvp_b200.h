@@ -174,6 +174,7 @@ typedef struct pvp_run_options {
     int32_t shard_count;
     int32_t chunk_frames; /* frames staged per H2D chunk (0 = 32) */
     int32_t verbose;      /* print the reference's per-frame diagnostics to stderr */
+    int32_t decode_threads; /* host threads decoding image files ahead of the GPU (0 = $PVP_DECODE_THREADS or min(16, cores)) */
 } pvp_run_options;
 
 typedef struct pvp_run_report {

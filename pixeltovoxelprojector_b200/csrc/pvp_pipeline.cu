@@ -11,8 +11,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pvp_internal.h"
@@ -225,6 +229,7 @@ void pvp_run_options_default(pvp_run_options *o)
     o->shard_rank = 0; o->shard_count = 1;
     o->chunk_frames = 0;
     o->verbose = 1;
+    o->decode_threads = 0;
 }
 
 }  // extern "C"
@@ -237,6 +242,85 @@ struct PinnedChunk {
     uint8_t *buf = nullptr;
     size_t cap = 0;
     cudaEvent_t done = nullptr;
+};
+
+// Decode prefetcher: once K2 is fast, decoding 1080p/4K files is what limits frames/s through the CLI.
+// The frames a run will visit are known up front (metadata order), so a pool of host threads decodes them ahead of
+// the consumer into a bounded ring; the consumer sees them strictly in order, so skip-on-error / size-mismatch /
+// prev<-curr semantics (ray_voxel.cpp:464-481, :534) are untouched.
+class DecodePool {
+public:
+    struct Item { bool ok = false; int w = 0, h = 0; std::vector<uint8_t> px; };
+
+    DecodePool(std::vector<std::string> paths, int threads) : paths_(std::move(paths))
+    {
+        const int n = (int)paths_.size();
+        threads = std::max(1, std::min(threads, std::max(1, n)));
+        ring_.resize((size_t)std::min(n, 2 * threads + 2));
+        state_.assign(ring_.size(), -1);
+        for (int t = 0; t < threads && n > 0; ++t) workers_.emplace_back([this] { work(); });
+    }
+    ~DecodePool()
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    // frame `idx` (consumed in increasing order); valid until release(idx)
+    const Item &get(int idx)
+    {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return state_[(size_t)idx % ring_.size()] == idx; });
+        return ring_[(size_t)idx % ring_.size()];
+    }
+    void release(int idx)
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            state_[(size_t)idx % ring_.size()] = -1;
+            consumed_ = idx + 1;
+        }
+        cv_.notify_all();
+    }
+
+private:
+    void work()
+    {
+        for (;;) {
+            const int idx = next_.fetch_add(1);
+            if (idx >= (int)paths_.size()) return;
+            const size_t slot = (size_t)idx % ring_.size();
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return stop_ || (idx < consumed_ + (int)ring_.size() && state_[slot] == -1); });
+                if (stop_) return;
+                state_[slot] = -2;  // being filled
+            }
+            Item &it = ring_[slot];
+            it.ok = pvp_load_image_gray(paths_[(size_t)idx].c_str(), nullptr, 0, &it.w, &it.h) == PVP_OK;
+            if (it.ok) {
+                it.px.resize((size_t)it.w * it.h);
+                it.ok = pvp_load_image_gray(paths_[(size_t)idx].c_str(), it.px.data(), (int64_t)it.px.size(), &it.w, &it.h) == PVP_OK;
+            }
+            {
+                std::lock_guard<std::mutex> g(m_);
+                state_[slot] = idx;
+            }
+            cv_.notify_all();
+        }
+    }
+    std::vector<std::string> paths_;
+    std::vector<Item> ring_;
+    std::vector<int> state_;  // -1 free, -2 being filled, else the frame index it holds
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::atomic<int> next_{0};
+    int consumed_ = 0;
+    bool stop_ = false;
 };
 
 struct Runner {
@@ -338,11 +422,39 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
     std::vector<uint8_t> tmp;
     uint64_t skipped = 0, mismatched = 0;
 
-    auto load = [&](const pvp_frame_info &fi, int *w, int *h) -> bool {
+    auto load = [&](const pvp_frame_info &fi, int *w, int *h) -> bool {  // serial load (shard look-back only)
         std::string path = R.folder + "/" + fi.image_file;  // :467
         if (pvp_load_image_gray(path.c_str(), nullptr, 0, w, h) != PVP_OK) return false;
         tmp.resize((size_t)*w * *h);
         return pvp_load_image_gray(path.c_str(), tmp.data(), (int64_t)tmp.size(), w, h) == PVP_OK;
+    };
+    // every frame of this rank's block, in visiting order, goes through the decode pool
+    std::vector<std::string> visit;
+    {
+        long long s0 = 0;
+        for (auto &kv : by_cam) {
+            auto &cf = kv.second;
+            if (cf.size() < 2) continue;
+            const long long cam_lo = s0, cam_hi = s0 + (long long)cf.size();
+            s0 = cam_hi;
+            const long long a = std::max(lo, cam_lo) - cam_lo, b = std::min(hi, cam_hi) - cam_lo;
+            for (long long k = a; k < b; ++k) visit.push_back(R.folder + "/" + cf[(size_t)k].image_file);
+        }
+    }
+    int decode_threads = opt->decode_threads;
+    if (decode_threads <= 0) {
+        const char *env = getenv("PVP_DECODE_THREADS");
+        decode_threads = env ? atoi(env) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    }
+    DecodePool pool(std::move(visit), decode_threads);
+    int visit_idx = 0;
+    auto load_next = [&](int *w, int *h) -> bool {  // next frame of the visiting order -> tmp
+        const int idx = visit_idx++;
+        const DecodePool::Item &it = pool.get(idx);
+        const bool ok = it.ok;
+        if (ok) { *w = it.w; *h = it.h; tmp = it.px; }
+        pool.release(idx);
+        return ok;
     };
     auto push_frame = [&](int w, int h) -> int {  // append tmp as a new frame of the open chunk
         const size_t fbytes = (size_t)w * h;
@@ -376,7 +488,7 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
         for (long long k = a; k < b; ++k) {
             const pvp_frame_info &ci = cf[(size_t)k];
             int w, h;
-            if (!load(ci, &w, &h)) {  // :470-473
+            if (!load_next(&w, &h)) {  // :470-473
                 if (opt->verbose) fprintf(stderr, "Failed to load image: %s/%s\nSkipping frame due to load error.\n", R.folder.c_str(), ci.image_file);
                 ++skipped;
                 continue;
@@ -425,7 +537,7 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
 // The CLI of ray_voxel.cpp:400-558: `ray_voxel <metadata.json> <image_folder> <output_voxel_bin>`
 // with the reference's constants as defaults and its messages / exit codes, plus optional flags
 // after the three positionals:
-//   --n N --voxel-size S --center X Y Z --threshold T --fixed-point [BITS] --device D --quiet --stats
+//   --n N --voxel-size S --center X Y Z --threshold T --fixed-point [BITS] --device D --decode-threads T --quiet --stats
 int pvp_ray_voxel_main(int argc, char **argv)
 {
     if (argc < 4) {
@@ -443,6 +555,7 @@ int pvp_ray_voxel_main(int argc, char **argv)
         else if (!strcmp(argv[i], "--threshold") && need(1)) opt.threshold = strtof(argv[++i], nullptr);
         else if (!strcmp(argv[i], "--fixed-point")) { opt.grid.accum_mode = PVP_ACCUM_FIXED; if (need(1) && argv[i + 1][0] != '-') opt.grid.frac_bits = atoi(argv[++i]); }
         else if (!strcmp(argv[i], "--device") && need(1)) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--decode-threads") && need(1)) opt.decode_threads = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--quiet")) opt.verbose = 0;
         else if (!strcmp(argv[i], "--stats")) want_stats = 1;
         else { fprintf(stderr, "ray_voxel: unknown or incomplete option '%s'\n", argv[i]); return 1; }

@@ -89,3 +89,20 @@ def test_python_pipeline_sharded_equals_whole(tmp_path):
             assert np.array_equal(nz, g["nz_index"]) and np.array_equal(bits(flat[nz]), bits(g["nz_value"]))
         else:
             assert torch.equal(whole, total)
+
+
+def test_decode_pool_does_not_change_results(tmp_path):
+    """frames are decoded ahead by a pool of host threads; skip / size-mismatch / pairing semantics and the
+    grid must not depend on the number of threads (1 = the old serial loader)."""
+    g, meta = materialise(tmp_path)
+    ref = None
+    for threads in (1, 2, 7):
+        grid = pvp.VoxelGrid(accum="fixed", frac_bits=8)
+        rep = pvp.ray_voxel_accumulate(meta, str(tmp_path), grid, decode_threads=threads)
+        key = (rep["n_pairs"], rep["n_frames_loaded"], rep["n_frames_skipped"], rep["n_size_mismatch"], rep["n_rays"], rep["n_steps"])
+        if ref is None:
+            ref = (key, grid.data.clone())
+            assert rep["n_pairs"] == 4 and rep["n_frames_skipped"] == 1
+        else:
+            assert key == ref[0] and torch.equal(grid.data, ref[1])
+        del grid

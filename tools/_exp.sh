@@ -1,7 +1,3 @@
-source tools/gpu_exp.sh
-run sparse --workload 1080p_sparse_512
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/exp_sparse.json").read().strip().splitlines()[-1])
-print({k:d[k] for k in ("frames_per_s","rays_per_s","ms_per_step","gpu_launches")}, d["e2e"], d["roofline"]["k1_ms_total"], d["roofline"]["avg_launch_ms"], d["roofline"]["k2_share_of_step"])
-PY
+python -m pytest tests/test_gpu_cli.py -m gpu -x -q 2>&1 | tail -3
+python tools/cli_throughput.py --frames 120 --format png
+python tools/cli_throughput.py --frames 120 --format pgm
