@@ -500,7 +500,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
                 val = V::make(diff, g);
             }
         }
-        if (__all_sync(FULL, idx == KEY_NONE)) continue;
+        if (__all_sync(FULL, remx == REM_PARKED)) continue;  // (parked is tested on remx: in slab kernels a live voxel offset can wrap to KEY_NONE)
 
         // Loop-carried across iterations so that they are off the scan's critical path: the run heads of the
         // CURRENT voxel keys (computed right after the previous DDA step) and, for whole-grid kernels, the value
@@ -550,7 +550,9 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
             if (!SLAB) heads = __ballot_sync(FULL, next_head);
             // ---- rays that ended: park the lane; leave when the whole warp is parked ---------------------
             if (__any_sync(FULL, !still)) {
-                const bool park = !still && idx != KEY_NONE;
+                // (not "idx != KEY_NONE": a ray that leaves the grid downwards from linear offset N^2-1 / N-1 / 0 wraps to
+                // exactly 0xffffffff and would then never be parked nor counted)
+                const bool park = !still && remx != REM_PARKED;
                 my_steps += park ? (unsigned long long)(unsigned)(int)(rem0 - (remx + remy + remz)) : 0ull;  // advances performed == voxels emitted
                 idx = park ? KEY_NONE : idx; val = park ? (T)0 : val;
                 dix = park ? 0 : dix; diy = park ? 0 : diy; diz = park ? 0 : diz;
@@ -558,7 +560,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
                 tdx = park ? 0.f : tdx; tdy = park ? 0.f : tdy; tdz = park ? 0.f : tdz;
                 t_end = park ? CUDART_INF_F : t_end;
                 remx = park ? REM_PARKED : remx; remy = park ? REM_PARKED : remy; remz = park ? REM_PARKED : remz;
-                if (__all_sync(FULL, idx == KEY_NONE)) break;
+                if (__all_sync(FULL, remx == REM_PARKED)) break;
                 if (!SLAB) {
                     heads = __ballot_sync(FULL, run_head(idx));
                     pval = __shfl_up_sync(FULL, val, 1);

@@ -299,3 +299,42 @@ def test_full_size_properties_1080p_256(ctx):
     gf = pvp.VoxelGrid(N, vs, center)
     pvp.accumulate_motion(frames, pairs, gf, 2.0)
     torch.testing.assert_close(gf.data, gfx.to_float32(), rtol=RTOL_F32_ATOMICS, atol=0)
+
+
+def test_rays_leaving_through_low_corners_and_tiny_grids(ctx, oracle):
+    """Regression: the lock-step kernel keys voxels by their 32-bit linear offset and reserves 0xffffffff.  A ray that steps
+    out of the grid downwards from offset 0 / N-1 / N^2-1 wraps to exactly that value, and in a slab kernel a LIVE voxel
+    (lo-1, N-1, N-1) has that relative offset.  Counters and grids must still equal the reference: camera near the low corner
+    looking at it, tiny grids, every slab split."""
+    rng = np.random.default_rng(77)
+    H, W = 24, 40
+    for N, vs in ((2, 8.0), (3, 4.0), (5, 3.0), (8, 2.0)):
+        center = (0.0, 0.0, 0.0)
+        half = N * vs / 2
+        frames = synth.dense_frames(4, H, W, seed=N)
+        # inside the grid, looking (mostly) towards the (-,-,-) corner / the -z face, wide field of view
+        poses = [pvp.FramePose((float(np.float32(-half + vs * 0.6 + 0.3 * i)), float(np.float32(-half + vs * 0.7)), float(np.float32(-half + vs * 1.1 + 0.2 * i))),
+                               yaw=float(rng.uniform(-40, 40)), pitch=float(rng.uniform(-40, 40)), roll=float(rng.uniform(-20, 20)), fov_degrees=100.0)
+                 for i in range(4)]
+        pairs, _ = pvp.make_pairs(poses, W)
+        want, tot = _oracle_run(oracle, frames, poses, N, vs, center, 2.0)
+        assert tot[1] > 500
+        for variant in (0, 1, 3):
+            ctx.set_option("dda_variant", variant)
+            try:
+                grid = pvp.VoxelGrid(N, vs, center)
+                st = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, grid, 2.0)
+                assert (st["n_rays"], st["n_steps"], st["n_written"]) == tuple(tot), (N, variant)
+                assert np.array_equal(grid.data.cpu().numpy(), want)
+                planes_written = 0
+                for lo in range(N + 1):
+                    for hi in sorted({lo, min(N, lo + 1), N}):
+                        s = pvp.VoxelGrid(N, vs, center, slab=(lo, hi))
+                        ss = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, s, 2.0)
+                        assert (ss["n_rays"], ss["n_steps"]) == (tot[0], tot[1]), (N, variant, lo, hi)
+                        assert np.array_equal(s.data.cpu().numpy(), want[lo:hi]), (N, variant, lo, hi)
+                        if hi == lo + 1:
+                            planes_written += ss["n_written"]
+                assert planes_written == tot[1]     # the single-plane slabs partition the voxel steps
+            finally:
+                ctx.set_option("dda_variant", 0)

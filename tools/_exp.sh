@@ -1,3 +1,4 @@
-python -m pytest tests/test_gpu_cli.py -m gpu -x -q 2>&1 | tail -3
-python tools/cli_throughput.py --frames 120 --format png
-python tools/cli_throughput.py --frames 120 --format pgm
+L=pixeltovoxelprojector_b200/libpvp_b200.so
+cp $L /tmp/real.so; cp exp_build/oldpark.so $L
+python -m pytest tests/test_gpu_motion.py -m gpu -x -q -k "low_corners" 2>&1 | tail -6
+cp /tmp/real.so $L
