@@ -338,3 +338,41 @@ def test_rays_leaving_through_low_corners_and_tiny_grids(ctx, oracle):
                 assert planes_written == tot[1]     # the single-plane slabs partition the voxel steps
             finally:
                 ctx.set_option("dda_variant", 0)
+
+
+def test_random_geometry_sweep_vs_oracle(ctx, oracle):
+    """Broad randomised parity sweep of the default (lean lock-step) kernel: cameras inside and outside the grid (outside ones
+    look in through min or max faces -- the latter cast no steps, ray_voxel.cpp:329-334), full-range yaw / pitch / roll, fov
+    20..140 degrees, odd and even N, frame sizes that leave partial warps, both accumulation modes and a random slab."""
+    rng = np.random.default_rng(4242)
+    total_steps = 0
+    for trial in range(60):
+        N = int(rng.choice([1, 2, 3, 7, 16, 31, 40]))
+        vs = float(rng.choice([0.5, 1.0, 2.5, 6.0]))
+        center = tuple(float(np.float32(c)) for c in rng.uniform(-50, 50, 3))
+        half = N * vs / 2
+        H, W = int(rng.integers(1, 40)), int(rng.integers(1, 70))
+        F = 3
+        frames = synth.dense_frames(F, H, W, seed=1000 + trial)
+        poses = []
+        for f in range(F):
+            where = rng.choice(["inside", "outside", "far"])
+            scale = {"inside": 0.95, "outside": 2.0, "far": 6.0}[where]
+            pos = np.array(center) + rng.uniform(-1, 1, 3) * half * scale
+            poses.append(pvp.FramePose(tuple(float(np.float32(p)) for p in pos), yaw=float(np.float32(rng.uniform(-180, 180))),
+                                       pitch=float(np.float32(rng.uniform(-90, 90))), roll=float(np.float32(rng.uniform(-180, 180))),
+                                       fov_degrees=float(np.float32(rng.uniform(20, 140)))))
+        pairs, _ = pvp.make_pairs(poses, W)
+        for accum, mode in (("f32", 0), ("fixed", 1)):
+            want, tot = _oracle_run(oracle, frames, poses, N, vs, center, 2.0, accum_mode=mode, frac_bits=9)
+            grid = pvp.VoxelGrid(N, vs, center, accum=accum, frac_bits=9)
+            st = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, grid, 2.0)
+            assert (st["n_rays"], st["n_steps"], st["n_written"]) == tuple(tot), (trial, accum)
+            assert np.array_equal(grid.data.cpu().numpy(), want), (trial, accum)
+            lo = int(rng.integers(0, N + 1))
+            hi = int(rng.integers(lo, N + 1))
+            s = pvp.VoxelGrid(N, vs, center, accum=accum, frac_bits=9, slab=(lo, hi))
+            ss = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, s, 2.0)
+            assert (ss["n_rays"], ss["n_steps"]) == (tot[0], tot[1]) and np.array_equal(s.data.cpu().numpy(), want[lo:hi]), (trial, accum, lo, hi)
+        total_steps += tot[1]
+    assert total_steps > 150000
