@@ -172,3 +172,53 @@ def test_full_size_properties_4096_512_fixed(ctx):
         assert int(gi.sum()) == pi.last_stats["n_samples"] * int(0.5 * scale * (1 << 20))
     assert pi.last_stats["n_rays"] == H * W and pi.last_stats["n_samples"] > 50 * H * W
     assert torch.equal(grids[0], grids[1]) and torch.equal(grids[2], grids[0] * 2)
+
+
+def test_lockstep_random_sweep_fixed_point_exact(ctx, oracle):
+    """Broad randomised sweep of the lock-step kernel in fixed-point mode (bit-exact against the oracle): observer inside
+    and outside the grid, non-cubic and strided grids, steps longer and shorter than a voxel, max_distance clipping inside
+    the grid, pointing along +-z (the up-vector switch, process_image.cpp:203-211), widths that leave partial warps, zero
+    pixels, texture updates."""
+    from pixeltovoxelprojector_b200 import process_image as pi
+    rng = np.random.default_rng(515)
+    total = 0
+    for trial in range(36):
+        H, W = int(rng.integers(1, 50)), int(rng.integers(1, 90))
+        img = rng.random((H, W))
+        img[rng.random((H, W)) < 0.25] = 0.0
+        shape = tuple(int(x) for x in rng.integers(1, 36, 3))
+        lo = rng.uniform(-20, 5, 3)
+        ext = [(float(lo[k]), float(lo[k] + rng.uniform(0.5, 40))) for k in range(3)]
+        mid = np.array([(a + b) / 2 for a, b in ext])
+        size = np.array([b - a for a, b in ext])
+        kind = trial % 4
+        pos = mid + rng.uniform(-0.45, 0.45, 3) * size if kind == 0 else mid + rng.normal(size=3) * size * 1.5
+        if kind == 2:
+            pointing = np.array([0.0, 0.0, float(rng.choice([-2.0, 3.0]))])       # parallel to z: up switches to y
+        else:
+            pointing = (mid - pos) + rng.normal(size=3) * size * 0.3
+            if not np.any(pointing):
+                pointing = np.array([0.3, 0.2, 1.0])
+        max_distance = float(rng.uniform(0.3, 3.0) * np.linalg.norm(size))
+        num_steps = int(rng.choice([7, 40, 300, 1500]))
+        fov = float(rng.uniform(0.2, 2.2))
+        sky = [float(rng.uniform(0, 6.28)), float(rng.uniform(-1.5, 1.5)), float(rng.uniform(0.5, 6.0)), float(rng.uniform(0.5, 3.0))]
+        upd = bool(trial % 3 == 0)
+        og, ot = np.zeros(shape, np.int64), np.zeros((6, 9), np.int64)
+        nr, ns = oracle.process_image(img, pos, pointing, fov, W, H, og, ext, max_distance, num_steps, ot, *sky, upd, False, accum_mode=1, frac_bits=22)
+        # a strided device grid: every other plane of a larger tensor along a random axis
+        ax = int(rng.integers(0, 3))
+        big_shape = list(shape)
+        big_shape[ax] *= 2
+        big = torch.zeros(big_shape, dtype=torch.int64, device="cuda")
+        view = big[tuple(slice(None, None, 2) if k == ax else slice(None) for k in range(3))]
+        ti = torch.zeros(ot.shape, dtype=torch.int64, device="cuda")
+        pvp.process_image_cpp(torch.as_tensor(img, device="cuda"), list(pos), list(pointing), fov, W, H, view, ext, max_distance, num_steps, ti, *sky, upd, False,
+                              accum_mode="fixed", frac_bits=22, want_stats=True)
+        assert pi.last_stats == {"n_rays": nr, "n_samples": ns}, trial
+        assert np.array_equal(view.cpu().numpy(), og), trial
+        assert int(big.sum()) == int(og.sum())                                   # nothing written between the planes of the view
+        if upd:
+            assert np.array_equal(ti.cpu().numpy(), ot), trial
+        total += ns
+    assert total > 300000

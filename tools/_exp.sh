@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_motion.py -m gpu -x -q -k "sweep or corners" 2>&1 | tail -12
+python -m pytest tests/test_gpu_process_image.py -m gpu -x -q -k "sweep" 2>&1 | tail -12
