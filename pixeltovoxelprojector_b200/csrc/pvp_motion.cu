@@ -449,8 +449,14 @@ __device__ __forceinline__ bool run_head(unsigned key)
     return !inrange || key != prev;
 }
 
+#ifndef PVP_LEAN_THREADS
+#define PVP_LEAN_THREADS 256  // measured at 1080p -> 512^3: 256-thread CTAs 503 G steps/s, 128 and 64 threads 489 G (same resident warps)
+#endif
+constexpr int LEAN_THREADS = PVP_LEAN_THREADS;  // warps are independent; the CTA size only sets how registers divide an SM
+constexpr int LEAN_CTAS_A = 7 * 128 / LEAN_THREADS > 0 ? 7 * 128 / LEAN_THREADS : 1, LEAN_CTAS_B = 6 * 128 / LEAN_THREADS, LEAN_CTAS_C = 8 * 128 / LEAN_THREADS;
+
 template <int MODE, bool SLAB, bool NARROW, int MINB>
-__global__ void __launch_bounds__(K2_THREADS, MINB)
+__global__ void __launch_bounds__(LEAN_THREADS, MINB)
 dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
                            int width, int height, Ctl *__restrict__ ctl)
 {
@@ -659,11 +665,11 @@ static int make_gridp(const pvp_grid_desc *d, GridP *g)
     return PVP_OK;
 }
 
-static int k2_grid_size(pvp_ctx *ctx, const void *kernel)
+static int k2_grid_size(pvp_ctx *ctx, const void *kernel, int threads = K2_THREADS)
 {
     int per_sm = 0;
     if (ctx->opt_ctas_per_sm > 0) per_sm = (int)ctx->opt_ctas_per_sm;
-    else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, K2_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     return ctx->sm_count * per_sm;  // persistent: every CTA resident, a multiple of the SM count
 }
 
@@ -688,13 +694,14 @@ static void launch_agg(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, 
                                                                            width, height, ctx->ctl_dev);
 }
 
-// lean_regs: 0/80 = compiled for 3 resident CTAs per SM (<= 80 registers; measured best), 64 = for 4 (<= 64 registers)
+// lean_regs: register budget = resident warps per SM: 0/72 -> 28 warps at 128-thread CTAs (24 at 256), 80 -> 24 warps, 64 -> 32 warps
 template <int MODE, bool SLAB, bool NARROW>
 static void launch_lean(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height)
 {
-    auto k = ctx->opt_lean_regs == 64 ? dda_accumulate_lean_kernel<MODE, SLAB, NARROW, 4> : dda_accumulate_lean_kernel<MODE, SLAB, NARROW, 3>;
-    k<<<k2_grid_size(ctx, (const void *)k), K2_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
-                                                                           width, height, ctx->ctl_dev);
+    auto k = ctx->opt_lean_regs == 64 ? dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_C>
+           : ctx->opt_lean_regs == 80 ? dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_B> : dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_A>;
+    k<<<k2_grid_size(ctx, (const void *)k, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
+                                                                                           width, height, ctx->ctl_dev);
 }
 
 // See the lean kernel's header: no t value of the batch can overflow to -inf.
