@@ -280,7 +280,18 @@ def run_ours_image(args, wl):
     images_dev = torch.as_tensor(images_np, device=dev)
     images_pin = torch.as_tensor(images_np).pin_memory()
     stage = torch.empty((H, W), dtype=torch.float64, device=dev)
-    grid = torch.zeros((n, n, n), dtype=cell, device=dev)
+    symm = None
+    if world > 1 and args.reduce == "peers":
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            grid = symm_mem.empty((n, n, n), dtype=cell, device=dev)
+            grid.zero_()
+            symm = symm_mem.rendezvous(grid, dist.group.WORLD)
+        except Exception as e:
+            print(f"bench.py: symmetric memory unavailable ({e!r}); using the NCCL reduce", file=sys.stderr)
+            symm = None
+    if symm is None:
+        grid = torch.zeros((n, n, n), dtype=cell, device=dev)
     tex = torch.zeros((8, 8), dtype=cell, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     kw = dict(accum_mode=wl["accum"], frac_bits=wl["frac_bits"], ctx=ctx)
@@ -314,7 +325,15 @@ def run_ours_image(args, wl):
             my_samples += samples_per_image[s % wl["pool"]]
         ev[-1][0].record()
         if world > 1:
-            dist.reduce(grid, dst=0)
+            if symm is not None and wl["accum"] == "fixed":
+                import ctypes as C
+                from pixeltovoxelprojector_b200._lib import check
+                ptrs = (C.c_void_p * world)(*[int(p) for p in symm.buffer_ptrs])
+                symm.barrier(channel=0)
+                check(ctx._lib.pvp_grid_reduce_peers(ctx.handle, ptrs, world, rank, 0, int(symm.multicast_ptr) or None, grid.numel(), 1))
+                symm.barrier(channel=1)
+            else:
+                dist.reduce(grid, dst=0)
         ev[-1][1].record()
         barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -380,7 +399,7 @@ def run_ours_image(args, wl):
 def workload_config(args, wl):
     return {"workload": args.workload, "k2_variant": getattr(args, "variant", 0), "frame": f"{wl['W']}x{wl['H']} uint8", "grid": f"{wl['N']}^3 {wl['accum']}", "voxel_size": wl["voxel_size"],
             "pairs_per_step": wl["pairs_per_step"], "motion": wl["motion"], "camera": "pose changes every frame (orbit inside the grid)",
-            "parallelism": f"frames sharded over {args.gpus} GPU(s), private grids, one NCCL reduce per run" if args.gpus > 1 else "1 GPU",
+            "parallelism": f"frames sharded over {args.gpus} GPU(s), private grids, one grid merge per run inside the timed region: {getattr(args, 'reduce_how', 'NCCL reduce')}" if args.gpus > 1 else "1 GPU",
             "l2": "256 MiB buffer written between timed steps (L2 flush); frame pool 149 MB and grid > L2" if wl["N"] >= 512 else
                   "256 MiB buffer written between timed steps (L2 flush)"}
 
@@ -408,7 +427,20 @@ def run_ours(args, wl):
     frames_np, poses = make_inputs(wl, seed=1000 + rank)   # weak scaling: every rank has its own frames, same shape
     frames_dev = torch.as_tensor(frames_np, device=dev)
     frames_pin = torch.as_tensor(frames_np).pin_memory()
-    grid = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev)
+    grid, reduce_how = None, "none (1 GPU)"
+    if world > 1:
+        from pixeltovoxelprojector_b200 import distributed as pd
+        if args.reduce == "peers":
+            try:   # private grid in NVLink symmetric memory: the merge is our own kernel (multimem.ld_reduce over NVSwitch)
+                grid = pd.symmetric_grid(wl["N"], wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev)
+                reduce_how = "pvp_grid_reduce_peers (own kernel, %s)" % ("NVSwitch multicast ld_reduce" if (grid.symm.multicast_ptr and world > 2) else "NVLink peer loads")
+            except Exception as e:
+                print(f"bench.py: symmetric memory unavailable ({e!r}); using the NCCL reduce", file=sys.stderr)
+        if grid is None:
+            reduce_how = "NCCL reduce"
+    if grid is None:
+        grid = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev)
+    args.reduce_how = reduce_how
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     B, H, W = wl["pairs_per_step"], wl["H"], wl["W"]
     pair_tabs = {}
@@ -457,10 +489,14 @@ def run_ours(args, wl):
             ev[s][1].record()
         ev[-1][0].record()
         if world > 1:                        # the run's single grid merge over NVLink (SURVEY 8e mode 1)
-            dist.reduce(grid.data, dst=0)
+            if getattr(grid, "symm", None) is not None:
+                pd.reduce_grid_peers(grid, dst=0, ctx=ctx)
+            else:
+                dist.reduce(grid.data, dst=0)
         ev[-1][1].record()
         barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
+    reduce_ms = ev[-1][0].elapsed_time(ev[-1][1])
     prof = ctx.get_profile(reset=True)
     ctx.profile(False)
     stats = pvp.accumulate_motion(frames_dev, pairs_for(0)[1], grid, 2.0, ctx=ctx, n_pairs=0, want_stats=True)
@@ -546,6 +582,7 @@ def run_ours(args, wl):
         "gpu_launches": int(prof["launches_k1"] + prof["launches_k2"]),
         "roofline": roofline, "l2_atomic_roofline": l2, "cpu_baseline": cpu, "clocks": clocks.summary(),
         "atomics_per_voxel_step": float(tot[2].item()) / max(1.0, all_steps),
+        "grid_merge_ms": reduce_ms if world > 1 else None,
     }
     print(json.dumps(line))
     if world > 1:
@@ -561,6 +598,7 @@ def main():
     ap.add_argument("--workload", default="1080p_dense_512", choices=sorted(WORKLOADS))
     ap.add_argument("--opt", action="append", help="context option key=value (pvp_ctx_set_option), repeatable; kernel experiments")
     ap.add_argument("--variant", type=int, default=0, help="K2 variant (0 = library default; see pvp_motion.cu launch_k2)")
+    ap.add_argument("--reduce", default="peers", choices=["peers", "nccl"], help="N>1: grid merge by our peer-memory kernel (default) or by NCCL")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments only)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

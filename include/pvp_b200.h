@@ -206,6 +206,19 @@ int pvp_write_bin(const char *path, int32_t n, float voxel_size, const float *gr
 int pvp_read_bin_header(const char *path, int32_t *n, float *voxel_size);
 int pvp_read_bin(const char *path, int32_t n, float *grid_host);
 
+/* ---- multi-GPU: the run's single grid merge (SURVEY 8e mode 1) over NVLink peer memory ---- */
+/*
+ * This rank sums its 1/world slice of the cells over ALL ranks' private grids and stores the result into rank dst_rank's
+ * grid (dst_rank < 0: into every rank's grid).  peers[r] = the address through which THIS process reaches rank r's grid
+ * (symmetric / peer-mapped memory, peers[rank] = the local grid); multicast = the NVSwitch multicast address of the same
+ * allocation (then one multimem.ld_reduce per 16 bytes returns the sum of all GPUs) or NULL (plain peer loads, added in
+ * rank order).  The call only enqueues a kernel on the context stream and contains no inter-GPU wait: every rank must
+ * have finished accumulating before any rank's kernel starts, and finished this kernel before any grid is touched again
+ * (barriers in the caller).  accum_mode: PVP_ACCUM_F32 (float32 cells) or PVP_ACCUM_FIXED (int64 cells).
+ */
+int pvp_grid_reduce_peers(pvp_ctx *ctx, void *const *peers, int world, int rank, int dst_rank, void *multicast, int64_t n_cells,
+                          int accum_mode);
+
 /* ---- consumer side of the .bin: voxelmotionviewer.py:56-96 with the grid in HBM ---- */
 /*
  * The two order statistics np.percentile(flat, q) interpolates between (voxelmotionviewer.py:72): *v_k = the k-th

@@ -121,6 +121,7 @@ SIGNATURES = {
     "pvp_write_bin": (C.c_int, [C.c_char_p, C.c_int32, C.c_float, _P]),
     "pvp_read_bin_header": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "pvp_read_bin": (C.c_int, [C.c_char_p, C.c_int32, _P]),
+    "pvp_grid_reduce_peers": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, C.c_int, _P, C.c_int64, C.c_int]),
     "pvp_grid_order_stats": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pvp_grid_extract_above": (C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, C.POINTER(C.c_int64)]),
     "pvp_process_image": (C.c_int, [_P, _P, _P, _P, C.POINTER(ImageArgs), C.POINTER(ImageStats)]),

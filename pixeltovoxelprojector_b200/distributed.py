@@ -39,7 +39,9 @@ def split_pairs(pairs: list[tuple[int, int]], rank: int, world: int) -> list[tup
 
 
 def reduce_grid(cells: torch.Tensor, dst: int = 0, group=None, all_ranks: bool = False) -> torch.Tensor:
-    """The run's single grid merge: in-place sum over ranks (to `dst`, or to everyone with all_ranks)."""
+    """The run's single grid merge through the process group's collective (NCCL on GPUs, gloo in CPU tests): in-place sum
+    over ranks (to `dst`, or to everyone with all_ranks).  Grids made by :func:`symmetric_grid` use
+    :func:`reduce_grid_peers` instead (our own kernel over NVLink peer memory / NVSwitch multicast)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return cells
     if all_ranks:
@@ -47,6 +49,52 @@ def reduce_grid(cells: torch.Tensor, dst: int = 0, group=None, all_ranks: bool =
     else:
         dist.reduce(cells, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return cells
+
+
+def symmetric_grid(n: int, voxel_size: float, center, accum: str = "f32", frac_bits: int = 16, device=None, group=None):
+    """A private full grid allocated in NVLink symmetric memory (torch.distributed._symmetric_memory: every rank can
+    address every rank's copy, plus the NVSwitch multicast address), so that the run's grid merge can be done by
+    pvp_grid_reduce_peers instead of a library collective.  Collective: every rank of the group must call it."""
+    import torch.distributed._symmetric_memory as symm_mem
+    from . import motion
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    dtype = torch.float32 if accum == "f32" else torch.int64
+    cells = symm_mem.empty((n, n, n), dtype=dtype, device=dev)
+    cells.zero_()
+    handle = symm_mem.rendezvous(cells, group if group is not None else dist.group.WORLD)
+    grid = motion.VoxelGrid(n, voxel_size, center, accum=accum, frac_bits=frac_bits, device=dev, data=cells)
+    grid.symm = handle
+    return grid
+
+
+def reduce_grid_peers(grid, dst: int | None = 0, ctx=None, multicast: bool | None = None) -> None:
+    """The run's single grid merge with our own kernel over NVLink peer memory (SURVEY 8e mode 1): every rank sums 1/world
+    of the cells over all ranks' grids -- one multimem.ld_reduce per 16 bytes when the NVSwitch multicast address exists --
+    and stores them into rank `dst`'s grid (None: into every rank's).  Stream-ordered; the two symmetric-memory barriers
+    keep every rank's accumulate kernels before, and every later use of the grids after, all ranks' reduce kernels.
+    multicast=None picks by world size: plain peer loads for 2 GPUs (a multicast load would also pull the local copy through
+    the switch: 1.19 ms vs 0.85 ms for 512 MiB), the switch reduction from 4 GPUs up (8 GPUs: 1.44 ms vs 1.52 ms to one rank,
+    1.22 ms to all ranks; NCCL reduce / all_reduce on the same box: 1.05 / 1.34 ms -- tools/reduce_bench.py)."""
+    import ctypes as C
+
+    from . import motion
+    from ._lib import check
+
+    h = grid.symm
+    world, rank = h.world_size, h.rank
+    if world == 1:
+        return
+    ctx = ctx or motion.default_context(grid.data.device)
+    ctx.use_current_stream()
+    ptrs = (C.c_void_p * world)(*[int(p) for p in h.buffer_ptrs])
+    if multicast is None:
+        multicast = world > 2
+    mc = int(h.multicast_ptr) if (multicast and h.multicast_ptr) else None
+    h.barrier(channel=0)
+    check(ctx._lib.pvp_grid_reduce_peers(ctx.handle, ptrs, world, rank, -1 if dst is None else int(dst), mc, grid.data.numel(),
+                                         0 if grid.accum == "f32" else 1))
+    h.barrier(channel=1)
 
 
 def write_bin_header(path: str, n: int, voxel_size: float) -> None:
@@ -71,7 +119,7 @@ def write_bin_slab(path: str, n: int, slab: tuple[int, int], cells_f32: np.ndarr
 
 def ray_voxel_distributed(metadata_json: str, image_folder: str, output_bin: str | None, mode: str = "frames", n: int = 500,
                           voxel_size: float = 6.0, center=(0.0, 0.0, 500.0), threshold: float = 2.0, accum: str = "f32",
-                          frac_bits: int = 16, group=None) -> dict:
+                          frac_bits: int = 16, group=None, peer_reduce: bool = True) -> dict:
     """The ray_voxel pipeline (ray_voxel.cpp:400-558) over all ranks of the process group.  Returns this rank's counters
     summed over ranks (n_steps, n_rays ...).  Rank 0 (frames) / every rank (slabs) writes `output_bin`."""
     from . import motion
@@ -80,9 +128,19 @@ def ray_voxel_distributed(metadata_json: str, image_folder: str, output_bin: str
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = torch.device("cuda", torch.cuda.current_device())
     if mode == "frames":
-        grid = motion.VoxelGrid(n, voxel_size, center, accum=accum, frac_bits=frac_bits, device=dev)
+        grid = None
+        if world > 1 and peer_reduce:
+            try:
+                grid = symmetric_grid(n, voxel_size, center, accum=accum, frac_bits=frac_bits, device=dev, group=group)
+            except Exception:  # no symmetric memory on this system: library collective
+                grid = None
+        if grid is None:
+            grid = motion.VoxelGrid(n, voxel_size, center, accum=accum, frac_bits=frac_bits, device=dev)
         rep = motion.ray_voxel_accumulate(metadata_json, image_folder, grid, threshold, shard=(rank, world))
-        reduce_grid(grid.data, dst=0, group=group)
+        if getattr(grid, "symm", None) is not None:
+            reduce_grid_peers(grid, dst=0)
+        else:
+            reduce_grid(grid.data, dst=0, group=group)
         if rank == 0 and output_bin:
             grid.save(output_bin)
     elif mode == "slabs":

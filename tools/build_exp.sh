@@ -5,7 +5,7 @@
 set -e
 cd "$(dirname "$0")/../pixeltovoxelprojector_b200/csrc"
 mkdir -p ../../exp_build/obj_$1
-for f in pvp_context pvp_motion pvp_image pvp_microbench pvp_pipeline pvp_analysis; do
+for f in pvp_context pvp_motion pvp_image pvp_microbench pvp_pipeline pvp_analysis pvp_collective; do
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -Xcompiler -fPIC,-O2,-ffp-contract=off $2 -c -o ../../exp_build/obj_$1/$f.o $f.cu &
 done
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O2 -x cu -c -o ../../exp_build/obj_$1/pvp_imageio.o pvp_imageio.cpp &

@@ -49,6 +49,26 @@ def main():
                 same = open(path, "rb").read() == ref
                 ok &= same
                 print(f"[{accum}/{mode}] identical to 1-GPU .bin: {same} (1-GPU steps={one['n_steps']})")
+    # the peer-memory reduce kernel against the NCCL collective on random grids: multicast and plain peer loads, to one rank
+    # and to all ranks, float32 (integer-valued => exact in any order) and int64, sizes that do / do not fill 16-byte vectors
+    from pixeltovoxelprojector_b200.distributed import reduce_grid, reduce_grid_peers, symmetric_grid
+    for accum, nn in (("f32", 96), ("fixed", 96), ("f32", 3), ("fixed", 5)):
+        for dst in (0, None):
+            for mc in (True, False):
+                g = symmetric_grid(nn, vs, center, accum=accum, frac_bits=12)
+                gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+                vals = torch.randint(0, 1 << 16, g.data.shape, device="cuda", generator=gen)
+                g.data.copy_(vals.to(g.data.dtype))
+                want = vals.to(torch.int64).clone()
+                dist.all_reduce(want)
+                reduce_grid_peers(g, dst=dst, multicast=mc)
+                torch.cuda.synchronize()
+                if dst is None or rank == dst:
+                    same = bool(torch.equal(g.data.to(torch.int64), want))
+                    ok &= same
+                    if rank == 0:
+                        print(f"[peer reduce {accum} n={nn} dst={dst} multicast={mc and bool(g.symm.multicast_ptr)}] equals NCCL all_reduce: {same}")
+                dist.barrier()
     flag = torch.tensor([int(ok)], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
