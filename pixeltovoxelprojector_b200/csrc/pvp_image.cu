@@ -283,14 +283,28 @@ __device__ __forceinline__ unsigned march_lockstep(CellT *__restrict__ grid, con
     auto key_of = [&](int s) -> unsigned {
         const double d = dmul((double)s, p.step_size);  // :344
         const double qx = dadd(p.o[0], dmul(d, w0)), qy = dadd(p.o[1], dmul(d, w1)), qz = dadd(p.o[2], dmul(d, w2));
-        const bool in = (s >= lo) & (s <= hi) & (p.ext[0] <= qx) & (qx <= p.ext[1]) & (p.ext[2] <= qy) & (qy <= p.ext[3]) &
-                        (p.ext[4] <= qz) & (qz <= p.ext[5]);
         // inside the extent the scaled coordinate lies in [0, n]: int truncation + upper clamp == :94-104
         const int xi = min(__double2int_rz(dmul(div_by_extent(dsub(qx, p.ext[0]), f.b[0], f.y[0]), f.nd[0])), f.n1[0]);
         const int yi = min(__double2int_rz(dmul(div_by_extent(dsub(qy, p.ext[2]), f.b[1], f.y[1]), f.nd[1])), f.n1[1]);
         const int zi = min(__double2int_rz(dmul(div_by_extent(dsub(qz, p.ext[4]), f.b[2], f.y[2]), f.nd[2])), f.n1[2]);
         const unsigned off = (unsigned)xi * f.gs[0] + (unsigned)yi * f.gs[1] + (unsigned)zi * f.gs[2];
-        return in ? off : IMG_NONE;
+        // in = lo <= s <= hi and the inclusive bounds test of :85 -- one chained predicate (the compiler's own form is a
+        // chain of eight selects), then key = in ? off : IMG_NONE
+        unsigned key;
+        asm("{\n\t.reg .pred q;\n\t"
+            "setp.ge.s32 q, %1, %2;\n\t"
+            "setp.le.and.s32 q, %1, %3, q;\n\t"
+            "setp.le.and.f64 q, %4, %5, q;\n\t"
+            "setp.le.and.f64 q, %5, %6, q;\n\t"
+            "setp.le.and.f64 q, %7, %8, q;\n\t"
+            "setp.le.and.f64 q, %8, %9, q;\n\t"
+            "setp.le.and.f64 q, %10, %11, q;\n\t"
+            "setp.le.and.f64 q, %11, %12, q;\n\t"
+            "selp.u32 %0, %13, 0xffffffff, q;\n\t}"
+            : "=r"(key)
+            : "r"(s), "r"(lo), "r"(hi), "d"(p.ext[0]), "d"(qx), "d"(p.ext[1]), "d"(p.ext[2]), "d"(qy), "d"(p.ext[3]), "d"(p.ext[4]), "d"(qz),
+              "d"(p.ext[5]), "r"(off));
+        return key;
     };
     unsigned key = key_of(wlo);
     unsigned heads = __ballot_sync(FULL, img_run_head(key));
