@@ -175,6 +175,11 @@ typedef struct pvp_run_options {
     int32_t chunk_frames; /* frames staged per H2D chunk (0 = 32) */
     int32_t verbose;      /* print the reference's per-frame diagnostics to stderr */
     int32_t decode_threads; /* host threads decoding image files ahead of the GPU (0 = $PVP_DECODE_THREADS or min(16, cores)) */
+    int32_t loader_noise; /* 1: add the reference loader's per-pixel uniform noise in [-1,1) (ray_voxel.cpp:203-218): the same
+                             std::mt19937 / uniform_real_distribution<float> stream over all frames in load order, clamped to
+                             [0,255]; frames are then float32.  The reference seeds it from std::random_device (not
+                             reproducible); here the seed is noise_seed.  Default 0 = exact 8-bit values.  Not shardable. */
+    uint32_t noise_seed;
 } pvp_run_options;
 
 typedef struct pvp_run_report {

@@ -13,10 +13,15 @@
  *     distribution that always returns 0, which removes the unseeded per-pixel noise of
  *     load_image_gray (ray_voxel.cpp:206-215) and makes the reference CLI reproducible.
  *     All standard headers are included BEFORE the macro so only the reference's use is hit.
+ *   - with -DPVP_REF_NOISE_SEEDED the token `random_device` is re-pointed at a device that returns the value of
+ *     $PVP_REF_NOISE_SEED, so the reference's own noise code (static mt19937 seeded once, one
+ *     uniform_real_distribution<float>(-1,1) draw per pixel in load order) runs unchanged but reproducibly: the golden
+ *     for the product's --loader-noise mode.
  */
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -36,6 +41,16 @@ template <class T> struct zero_distribution {
 }  // namespace pvp_ref_shim
 namespace std { using pvp_ref_shim::zero_distribution; }
 #define uniform_real_distribution zero_distribution
+#endif
+
+#ifdef PVP_REF_NOISE_SEEDED
+namespace pvp_ref_shim {
+struct env_seed_device {
+    unsigned operator()() const { const char *e = std::getenv("PVP_REF_NOISE_SEED"); return e ? (unsigned)std::strtoul(e, nullptr, 10) : 0u; }
+};
+}  // namespace pvp_ref_shim
+namespace std { using pvp_ref_shim::env_seed_device; }
+#define random_device env_seed_device
 #endif
 
 #define main ref_main

@@ -46,7 +46,8 @@ class FrameInfo(C.Structure):
 
 class RunOptions(C.Structure):
     _fields_ = [("grid", GridDesc), ("threshold", C.c_float), ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
-                ("chunk_frames", C.c_int32), ("verbose", C.c_int32), ("decode_threads", C.c_int32)]
+                ("chunk_frames", C.c_int32), ("verbose", C.c_int32), ("decode_threads", C.c_int32),
+                ("loader_noise", C.c_int32), ("noise_seed", C.c_uint32)]
 
 
 class RunReport(C.Structure):

@@ -15,6 +15,7 @@
 #include <condition_variable>
 #include <map>
 #include <mutex>
+#include <random>
 #include <string>
 #include <thread>
 #include <vector>
@@ -230,6 +231,8 @@ void pvp_run_options_default(pvp_run_options *o)
     o->chunk_frames = 0;
     o->verbose = 1;
     o->decode_threads = 0;
+    o->loader_noise = 0;
+    o->noise_seed = 0;
 }
 
 }  // extern "C"
@@ -335,6 +338,10 @@ struct Runner {
     std::vector<pvp_pair> pairs;
     int max_frames = 32;
     uint64_t frames_loaded = 0, pairs_done = 0;
+    // loader noise (ray_voxel.cpp:203-218): frames become float32, one generator for the whole run, seeded once
+    bool noise = false;
+    size_t elem = 1;
+    std::mt19937 gen;
 
     int ensure(PinnedChunk &c, size_t bytes)
     {
@@ -360,10 +367,10 @@ struct Runner {
     int flush(bool carry)
     {
         PinnedChunk &c = chunk[cur];
-        const size_t fbytes = (size_t)W * H;
+        const size_t fbytes = (size_t)W * H * elem;
         if (!pairs.empty()) {
-            int rc = pvp_motion_accumulate_host(ctx, c.buf, PVP_FRAME_U8, (int64_t)fbytes, W, H, n_frames, pairs.data(), (int)pairs.size(),
-                                                opt->threshold, grid_dev, &opt->grid, nullptr);
+            int rc = pvp_motion_accumulate_host(ctx, c.buf, noise ? PVP_FRAME_F32 : PVP_FRAME_U8, (int64_t)W * H, W, H, n_frames, pairs.data(),
+                                                (int)pairs.size(), opt->threshold, grid_dev, &opt->grid, nullptr);
             if (rc) return rc;
             PVP_CUDA(cudaEventRecord(c.done, ctx->stream));
             pairs_done += pairs.size();
@@ -398,6 +405,8 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
     PVP_REQUIRE(ctx && metadata_json && image_folder && grid_dev && opt, "pvp_ray_voxel_accumulate: NULL argument");
     PVP_REQUIRE(opt->shard_count >= 1 && opt->shard_rank >= 0 && opt->shard_rank < opt->shard_count, "bad shard %d/%d",
                 opt->shard_rank, opt->shard_count);
+    PVP_REQUIRE(!(opt->loader_noise && opt->shard_count > 1),
+                "loader_noise draws one pseudo-random stream over all frames in load order (ray_voxel.cpp:203-209); it cannot be frame-sharded");
     pvp_frame_info *frames = nullptr;
     int n = 0;
     int rc = pvp_load_metadata(metadata_json, &frames, &n);
@@ -418,6 +427,10 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
     DeviceGuard guard(ctx->device);
     Runner R{ctx, opt, grid_dev, image_folder};
     R.max_frames = opt->chunk_frames > 1 ? opt->chunk_frames : 32;
+    if (opt->loader_noise) {
+        R.noise = true; R.elem = sizeof(float);
+        R.gen.seed(opt->noise_seed);  // the reference: static std::mt19937 gen(rd()) -- here rd() is the caller's seed
+    }
     if ((rc = R.init())) return rc;
     std::vector<uint8_t> tmp;
     uint64_t skipped = 0, mismatched = 0;
@@ -457,12 +470,25 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
         return ok;
     };
     auto push_frame = [&](int w, int h) -> int {  // append tmp as a new frame of the open chunk
-        const size_t fbytes = (size_t)w * h;
+        const size_t fbytes = (size_t)w * h * R.elem;
         PinnedChunk &c = R.chunk[R.cur];
         int rc2 = R.ensure(c, (size_t)R.max_frames * fbytes);
         if (rc2) return rc2;
         if (R.n_frames == 0) PVP_CUDA(cudaEventSynchronize(c.done));
-        memcpy(c.buf + (size_t)R.n_frames * fbytes, tmp.data(), fbytes);
+        if (R.noise) {  // load_image_gray, ray_voxel.cpp:203-218: same generator, same distribution, same draw order
+            std::uniform_real_distribution<float> noise_dist(-1.0f, 1.0f);
+            float *dst = reinterpret_cast<float *>(c.buf + (size_t)R.n_frames * fbytes);
+            const size_t n_px = (size_t)w * h;
+            for (size_t i = 0; i < n_px; ++i) {
+                float val = static_cast<float>(tmp[i]);
+                val += noise_dist(R.gen);
+                if (val < 0.0f) val = 0.0f;
+                if (val > 255.0f) val = 255.0f;
+                dst[i] = val;
+            }
+        } else {
+            memcpy(c.buf + (size_t)R.n_frames * fbytes, tmp.data(), fbytes);
+        }
         R.W = w; R.H = h; R.n_frames++;
         R.frames_loaded++;
         return PVP_OK;
@@ -537,7 +563,7 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
 // The CLI of ray_voxel.cpp:400-558: `ray_voxel <metadata.json> <image_folder> <output_voxel_bin>`
 // with the reference's constants as defaults and its messages / exit codes, plus optional flags
 // after the three positionals:
-//   --n N --voxel-size S --center X Y Z --threshold T --fixed-point [BITS] --device D --decode-threads T --quiet --stats
+//   --n N --voxel-size S --center X Y Z --threshold T --fixed-point [BITS] --device D --decode-threads T --loader-noise SEED --quiet --stats
 int pvp_ray_voxel_main(int argc, char **argv)
 {
     if (argc < 4) {
@@ -556,6 +582,7 @@ int pvp_ray_voxel_main(int argc, char **argv)
         else if (!strcmp(argv[i], "--fixed-point")) { opt.grid.accum_mode = PVP_ACCUM_FIXED; if (need(1) && argv[i + 1][0] != '-') opt.grid.frac_bits = atoi(argv[++i]); }
         else if (!strcmp(argv[i], "--device") && need(1)) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--decode-threads") && need(1)) opt.decode_threads = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--loader-noise") && need(1)) { opt.loader_noise = 1; opt.noise_seed = (uint32_t)strtoul(argv[++i], nullptr, 10); }
         else if (!strcmp(argv[i], "--quiet")) opt.verbose = 0;
         else if (!strcmp(argv[i], "--stats")) want_stats = 1;
         else { fprintf(stderr, "ray_voxel: unknown or incomplete option '%s'\n", argv[i]); return 1; }

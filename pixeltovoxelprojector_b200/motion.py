@@ -342,10 +342,12 @@ def load_image_gray(path: str) -> np.ndarray:
 
 
 def ray_voxel_accumulate(metadata_json: str, image_folder: str, grid: VoxelGrid, threshold: float = 2.0, shard: tuple[int, int] = (0, 1),
-                         chunk_frames: int = 0, verbose: bool = False, ctx: Context | None = None, decode_threads: int = 0) -> dict:
+                         chunk_frames: int = 0, verbose: bool = False, ctx: Context | None = None, decode_threads: int = 0,
+                         loader_noise_seed: int | None = None) -> dict:
     """main's frame loop (ray_voxel.cpp:450-537) into ``grid``.  ``shard=(rank, count)`` makes this
     process handle one contiguous block of the frames (frame sharding, SURVEY 8e mode 1).  ``decode_threads`` host
-    threads decode the image files ahead of the GPU (0 = $PVP_DECODE_THREADS or min(16, cores)); results do not depend on it."""
+    threads decode the image files ahead of the GPU (0 = $PVP_DECODE_THREADS or min(16, cores)); results do not depend on it.
+    ``loader_noise_seed``: add the reference loader's per-pixel noise (ray_voxel.cpp:203-218) from std::mt19937(seed)."""
     ctx = ctx or default_context(grid.data.device)
     ctx.use_current_stream()
     opt = _lib.RunOptions()
@@ -355,6 +357,8 @@ def ray_voxel_accumulate(metadata_json: str, image_folder: str, grid: VoxelGrid,
     opt.shard_rank, opt.shard_count = int(shard[0]), int(shard[1])
     opt.chunk_frames, opt.verbose = int(chunk_frames), int(bool(verbose))
     opt.decode_threads = int(decode_threads)
+    if loader_noise_seed is not None:
+        opt.loader_noise, opt.noise_seed = 1, int(loader_noise_seed) & 0xffffffff
     st, rep = Stats(), _lib.RunReport()
     check(ctx._lib.pvp_ray_voxel_accumulate(ctx.handle, os.fsencode(metadata_json), os.fsencode(image_folder), grid.data.data_ptr(),
                                             C.byref(opt), C.byref(st), C.byref(rep)))

@@ -106,3 +106,34 @@ def test_decode_pool_does_not_change_results(tmp_path):
         else:
             assert key == ref[0] and torch.equal(grid.data, ref[1])
         del grid
+
+
+def test_cli_loader_noise_matches_seeded_reference(tmp_path):
+    """--loader-noise SEED reproduces the reference's own load_image_gray noise (ray_voxel.cpp:203-218: one mt19937 for the
+    whole run, one uniform [-1,1) draw per pixel in load order, clamp to [0,255]) when the reference's random_device is
+    pinned to the same seed (tests/golden/make_golden_noise.py).  Same visited voxels; float frames with fp32 atomics differ
+    from the reference's serial sum only by summation order (rtol 1e-5); fixed point agrees to the quantisation step."""
+    g, meta = materialise(tmp_path)
+    gn = golden("cli_noise_golden.npz")
+    out = str(tmp_path / "noisy.bin")
+    res = subprocess.run([EXE, meta, str(tmp_path), out, "--loader-noise", str(int(gn["seed"])), "--quiet"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    grid, _ = pvp.read_bin(out)
+    flat = grid.reshape(-1)
+    nz = np.flatnonzero(flat)
+    assert not np.allclose(gn["nz_value"], g["nz_value"], rtol=1e-4)     # the noise really changes the accumulated values
+    assert np.array_equal(nz, gn["nz_index"])                             # identical support
+    np.testing.assert_allclose(flat[nz], gn["nz_value"], rtol=1e-5, atol=0)
+    # python entry, other seed => different grid; same seed twice => identical (fixed point: bit for bit)
+    a = pvp.VoxelGrid(accum="fixed", frac_bits=16)
+    b = pvp.VoxelGrid(accum="fixed", frac_bits=16)
+    c = pvp.VoxelGrid(accum="fixed", frac_bits=16)
+    pvp.ray_voxel_accumulate(meta, str(tmp_path), a, loader_noise_seed=int(gn["seed"]))
+    pvp.ray_voxel_accumulate(meta, str(tmp_path), b, loader_noise_seed=int(gn["seed"]), decode_threads=3, chunk_frames=2)
+    pvp.ray_voxel_accumulate(meta, str(tmp_path), c, loader_noise_seed=7)
+    assert torch.equal(a.data, b.data) and not torch.equal(a.data, c.data)
+    fa = a.to_float32().cpu().numpy().reshape(-1)
+    assert np.array_equal(np.flatnonzero(fa), gn["nz_index"])
+    np.testing.assert_allclose(fa[gn["nz_index"]], gn["nz_value"], rtol=1e-5, atol=2.0 ** -16 * 64)
+    with pytest.raises(pvp.PvpError, match="cannot be frame-sharded"):
+        pvp.ray_voxel_accumulate(meta, str(tmp_path), c, loader_noise_seed=1, shard=(0, 2))
