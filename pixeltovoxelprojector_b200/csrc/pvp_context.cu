@@ -106,6 +106,8 @@ int pvp_version(void) { return PVP_VERSION; }
 
 const char *pvp_last_error(void) { return g_err; }
 
+int pvp_ctx_destroy(pvp_ctx *ctx);
+
 int pvp_ctx_create(int device, void *stream, pvp_ctx **out)
 {
     PVP_REQUIRE(out != nullptr, "pvp_ctx_create: out is NULL");
@@ -130,22 +132,30 @@ int pvp_ctx_create(int device, void *stream, pvp_ctx **out)
     if (!ctx) { set_error("pvp_ctx_create: out of host memory"); return PVP_ERR_NOMEM; }
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (stream) {
-        ctx->stream = (cudaStream_t)stream;
-    } else {
-        PVP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->own_stream = true;
+    auto init = [&]() -> int {
+        if (stream) {
+            ctx->stream = (cudaStream_t)stream;
+        } else {
+            PVP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            ctx->own_stream = true;
+        }
+        PVP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        PVP_CUDA(cudaEventCreate(&ctx->ev_a));
+        PVP_CUDA(cudaEventCreate(&ctx->ev_b));
+        for (int i = 0; i < 2; ++i) {
+            PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+            PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+        }
+        PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_pairs, cudaEventDisableTiming));
+        PVP_CUDA(cudaMalloc(&ctx->ctl_dev, sizeof(Ctl)));
+        PVP_CUDA(cudaMemset(ctx->ctl_dev, 0, sizeof(Ctl)));
+        return PVP_OK;
+    };
+    const int rc = init();
+    if (rc != PVP_OK) {  // release whatever was created (the error text is already set)
+        pvp_ctx_destroy(ctx);
+        return rc;
     }
-    PVP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    PVP_CUDA(cudaEventCreate(&ctx->ev_a));
-    PVP_CUDA(cudaEventCreate(&ctx->ev_b));
-    for (int i = 0; i < 2; ++i) {
-        PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
-        PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
-    }
-    PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_pairs, cudaEventDisableTiming));
-    PVP_CUDA(cudaMalloc(&ctx->ctl_dev, sizeof(Ctl)));
-    PVP_CUDA(cudaMemset(ctx->ctl_dev, 0, sizeof(Ctl)));
     *out = ctx;
     return PVP_OK;
 }
@@ -154,8 +164,8 @@ int pvp_ctx_destroy(pvp_ctx *ctx)
 {
     if (!ctx) return PVP_OK;
     DeviceGuard guard(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->stream || ctx->own_stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->queue.pix) cudaFree(ctx->queue.pix);
     if (ctx->queue.diff) cudaFree(ctx->queue.diff);
     if (ctx->queue.pair) cudaFree(ctx->queue.pair);
@@ -163,17 +173,17 @@ int pvp_ctx_destroy(pvp_ctx *ctx)
     if (ctx->pairs_pinned) cudaFreeHost(ctx->pairs_pinned);
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
-        cudaEventDestroy(ctx->ev_copy[i]);
-        cudaEventDestroy(ctx->ev_done[i]);
+        if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
     }
     if (ctx->ctl_dev) cudaFree(ctx->ctl_dev);
     for (auto &t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
-    cudaEventDestroy(ctx->ev_a);
-    cudaEventDestroy(ctx->ev_b);
-    cudaEventDestroy(ctx->ev_pairs);
-    cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->ev_pairs) cudaEventDestroy(ctx->ev_pairs);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PVP_OK;
 }

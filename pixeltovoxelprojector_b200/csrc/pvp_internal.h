@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -59,6 +60,8 @@ struct pvp_ctx {
     struct Timed { cudaEvent_t a, b; int kind; };
     std::vector<Timed> timed;          // event pairs recorded since the last get_profile
     std::vector<cudaEvent_t> ev_pool;  // recycled events
+
+    std::map<const void *, int> occupancy;  // resident CTAs per SM of the persistent kernels (cached occupancy query)
 
     // options (pvp_ctx_set_option)
     int64_t opt_dda_variant = 0;       // 0 = default

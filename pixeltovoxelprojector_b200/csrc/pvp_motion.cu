@@ -668,8 +668,17 @@ static int make_gridp(const pvp_grid_desc *d, GridP *g)
 static int k2_grid_size(pvp_ctx *ctx, const void *kernel, int threads = K2_THREADS)
 {
     int per_sm = 0;
-    if (ctx->opt_ctas_per_sm > 0) per_sm = (int)ctx->opt_ctas_per_sm;
-    else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    if (ctx->opt_ctas_per_sm > 0) {
+        per_sm = (int)ctx->opt_ctas_per_sm;
+    } else {
+        auto hit = ctx->occupancy.find(kernel);  // the query costs microseconds per launch: keep the answer per kernel
+        if (hit != ctx->occupancy.end()) {
+            per_sm = hit->second;
+        } else {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+            ctx->occupancy[kernel] = per_sm;
+        }
+    }
     return ctx->sm_count * per_sm;  // persistent: every CTA resident, a multiple of the SM count
 }
 
