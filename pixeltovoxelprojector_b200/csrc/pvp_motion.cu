@@ -106,6 +106,83 @@ motion_compact_kernel(const T *__restrict__ frames, long long frame_stride, cons
     }
 }
 
+// Row-group ordering: a thread handles the same PX columns of R consecutive rows and writes its entries column by
+// column, top pixel first, so that 32 (or 64) consecutive queue entries form a compact 2-D tile of the image
+// (32/R columns x R rows) instead of a 32 x 1 strip.  The rays of a tile diverge less -- fewer distinct voxels per
+// lock-step iteration, more even ray lengths -- and for lean2 entries 2i / 2i+1 are vertical neighbours.  Same filters,
+// same entries as motion_compact_kernel; only the order differs.
+template <typename T, int R>
+__global__ void __launch_bounds__(K1_THREADS)
+motion_compact_rowgroup_kernel(const T *__restrict__ frames, long long frame_stride, const pvp_pair *__restrict__ pairs,
+                               int width, int height, float threshold, bool vec_ok, Queue q, Ctl *__restrict__ ctl)
+{
+    constexpr int PX = FrameVec<T>::PX;
+    const int pair = blockIdx.y;
+    const T *prev = frames + (long long)pairs[pair].prev * frame_stride;
+    const T *curr = frames + (long long)pairs[pair].curr * frame_stride;
+    const int segs = (width + PX - 1) / PX, row_groups = (height + R - 1) / R;
+    const unsigned seg_id = blockIdx.x * K1_THREADS + threadIdx.x;  // < 2^28: the host bounds width * height below 2^32
+    const int rg = (int)(seg_id / (unsigned)segs), u0 = (int)(seg_id - (unsigned)rg * (unsigned)segs) * PX;
+    const long long n_pix = (long long)width * height;
+
+    float d[R][PX];
+    unsigned mask[R];
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        mask[r] = 0;
+        const int v = R * rg + r;
+        if (rg < row_groups && v < height) {
+            const long long first = (long long)v * width + u0;
+            T a[PX], b[PX];
+            const bool whole = u0 + PX <= width;   // a partial segment at the row end must not read into the next row
+            load_px<T>(prev, first, whole ? n_pix : first + (width - u0), vec_ok && whole, a);
+            load_px<T>(curr, first, whole ? n_pix : first + (width - u0), vec_ok && whole, b);
+#pragma unroll
+            for (int k = 0; k < PX; ++k) {
+                d[r][k] = motion_diff(a[k], b[k]);
+                if (u0 + k < width && motion_casts_ray(d[r][k], threshold)) mask[r] |= 1u << k;
+            }
+        }
+        cnt += __popc(mask[r]);
+    }
+
+    __shared__ unsigned warp_tot[K1_THREADS / 32];
+    __shared__ unsigned long long cta_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = cnt;
+    if (__ballot_sync(0xffffffffu, cnt != 0) != 0) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int w = 0; w < K1_THREADS / 32; ++w) { unsigned c = warp_tot[w]; warp_tot[w] = tot; tot += c; }
+        cta_base = tot ? atomicAdd(&ctl->count, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (cnt == 0) return;
+    unsigned long long pos = cta_base + warp_tot[warp] + (unsigned)(incl - cnt);
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (mask[r] & (1u << k)) {
+                q.pix[pos] = (uint32_t)((R * rg + r) * width + u0 + k);
+                q.diff[pos] = d[r][k];
+                q.pair[pos] = (uint16_t)pair;
+                ++pos;
+            }
+        }
+    }
+}
+
 // detect_motion as a stand-alone stage (ray_voxel.cpp:236-255): mask + diff image.
 template <typename T>
 __global__ void detect_motion_kernel(const T *__restrict__ prev, const T *__restrict__ next, long long n, float threshold,
@@ -458,7 +535,7 @@ constexpr int LEAN_CTAS_A = 7 * 128 / LEAN_THREADS > 0 ? 7 * 128 / LEAN_THREADS 
 template <int MODE, bool SLAB, bool NARROW, int MINB>
 __global__ void __launch_bounds__(LEAN_THREADS, MINB)
 dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
-                           int width, int height, Ctl *__restrict__ ctl)
+                           int width, int height, Ctl *__restrict__ ctl, unsigned long long count_lo, unsigned long long count_hi)
 {
     using A = Accum<MODE>;
     using V = LeanVal<MODE, NARROW>;
@@ -467,6 +544,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
     const unsigned lane = threadIdx.x & 31;
     const LaneMasks lm = lane_masks(lane);
     const unsigned long long count = ctl->count;
+    if (count < count_lo || count >= count_hi) return;  // auto mode launches both lock-step kernels; the ray count picks one
     const int N = g.n;
     const unsigned slab_cells = (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)N * (unsigned)N;
     unsigned long long my_steps = 0, my_written = 0, my_atomics = 0;
@@ -592,6 +670,152 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->n_rays, count);
 }
 
+// ---- variant 5: "lean2", two rays per lane -------------------------------------------------------------------------
+// A warp takes 64 consecutive queue entries; lane l walks entries 2l (ray A) and 2l+1 (ray B), which the row-pair
+// ordering of K1 makes vertical neighbours (u,v) / (u,v+1).  Both rays advance one DDA step per iteration.  B's voxel
+// is A's voxel ~89 % of the time: then B's value simply joins A's before the run scan, so ONE scan and ONE set of run
+// REDs serve 64 voxel steps instead of 32 -- the warp's rays form a 32 x 2 tile, and a tile touches fewer distinct
+// voxels than a 64 x 1 strip.  Where B sits in another voxel it issues its own RED.  Per ray the arithmetic, the step
+// order and the counters are those of variant 4 (same bit-exact visited sets).
+struct RayS {
+    float t_end, tmx, tmy, tmz, tdx, tdy, tdz, remx, remy, remz, rem0;
+    unsigned idx;
+    int dix, diy, diz;
+};
+
+__device__ __forceinline__ void rays_park(RayS &r)
+{
+    r.t_end = CUDART_INF_F; r.tmx = r.tmy = r.tmz = 0.f; r.tdx = r.tdy = r.tdz = 0.f;
+    r.remx = r.remy = r.remz = REM_PARKED; r.rem0 = 0.f;
+    r.idx = KEY_NONE; r.dix = r.diy = r.diz = 0;
+}
+
+// queue entry -> walking state; returns the value to accumulate (0 when the ray casts no step)
+template <typename V>
+__device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, unsigned long long i, unsigned long long count,
+                                                    const pvp_pair *__restrict__ pairs, const GridP &g, int width, int height)
+{
+    rays_park(s);
+    if (i >= count) return 0;
+    const uint32_t pix = __ldg(q.pix + i);
+    const float diff = __ldg(q.diff + i);
+    const pvp_pair *P = pairs + __ldg(q.pair + i);
+    const int v = (int)(pix / (uint32_t)width), u = (int)(pix - (uint32_t)v * (uint32_t)width);
+    float dx, dy, dz;
+    pixel_ray(u, v, width, height, __ldg(&P->focal), P->R, dx, dy, dz);
+    Ray r;
+    if (!(ray_setup(__ldg(&P->cam[0]), __ldg(&P->cam[1]), __ldg(&P->cam[2]), dx, dy, dz, g, r) && r.t_cur <= r.t_end)) return 0;
+    const int N = g.n;
+    s.t_end = r.t_end;
+    s.tmx = r.tmx; s.tmy = r.tmy; s.tmz = r.tmz; s.tdx = r.tdx; s.tdy = r.tdy; s.tdz = r.tdz;
+    s.idx = (unsigned)((r.ix - g.slab_lo) * N + r.iy) * (unsigned)N + (unsigned)r.iz;
+    s.dix = r.sx * N * N; s.diy = r.sy * N; s.diz = r.sz;
+    s.remx = (float)(r.sx > 0 ? N - 1 - r.ix : r.ix);
+    s.remy = (float)(r.sy > 0 ? N - 1 - r.iy : r.iy);
+    s.remz = (float)(r.sz > 0 ? N - 1 - r.iz : r.iz);
+    s.rem0 = s.remx + s.remy + s.remz;
+    return V::make(diff, g);
+}
+
+// one DDA step (ray_voxel.cpp:375-391); false when the ray ended with this step
+__device__ __forceinline__ bool rays_step(RayS &s)
+{
+    const float m = fmin3(s.tmx, s.tmy, s.tmz);
+    const bool cz = (s.tmz == m);
+    const bool cy = !cz && (s.tmy == m);
+    const bool cx = !cz && (s.tmy != m);
+    if (cx) { s.tmx = fadd(s.tmx, s.tdx); s.remx -= 1.f; }
+    if (cy) { s.tmy = fadd(s.tmy, s.tdy); s.remy -= 1.f; }
+    if (cz) { s.tmz = fadd(s.tmz, s.tdz); s.remz -= 1.f; }
+    s.idx += (unsigned)(cz ? s.diz : (cy ? s.diy : s.dix));
+    return (fmin3(s.remx, s.remy, s.remz) >= 0.f) && (m <= s.t_end);
+}
+
+template <int MODE, bool SLAB, bool NARROW, int MINB>
+__global__ void __launch_bounds__(LEAN_THREADS, MINB)
+dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
+                            int width, int height, Ctl *__restrict__ ctl, unsigned long long count_lo, unsigned long long count_hi)
+{
+    using V = LeanVal<MODE, NARROW>;
+    using T = typename V::T;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const LaneMasks lm = lane_masks(lane);
+    const unsigned long long count = ctl->count;
+    if (count < count_lo || count >= count_hi) return;  // auto mode launches both lock-step kernels; the ray count picks one
+    const unsigned slab_cells = (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)g.n * (unsigned)g.n;
+    unsigned long long my_steps = 0, my_written = 0, my_atomics = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->head, 64ull);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= count) break;
+        RayS a, b;
+        T va = rays_setup<V>(a, q, base + 2 * lane, count, pairs, g, width, height);
+        T vb = rays_setup<V>(b, q, base + 2 * lane + 1, count, pairs, g, width, height);
+        float n_issued = 0.f, n_inslab = 0.f;
+        if (__all_sync(FULL, a.remx == REM_PARKED && b.remx == REM_PARKED)) continue;
+
+        unsigned heads = __ballot_sync(FULL, run_head(SLAB ? (a.idx < slab_cells ? a.idx : KEY_NONE) : a.idx));
+        for (;;) {
+            // ---- one DDA step of both rays first: the shuffle of A's new key overlaps the scan below ----------------
+            unsigned ka = a.idx, kb = b.idx;
+            const bool still_a = rays_step(a), still_b = rays_step(b);
+            T sa = va, sb = vb;
+            if (SLAB) {  // writes outside the slab are suppressed; parked rays (KEY_NONE) are outside every slab
+                const bool ina = ka < slab_cells, inb = kb < slab_cells;
+                ka = ina ? ka : KEY_NONE; kb = inb ? kb : KEY_NONE;
+                sa = ina ? va : (T)0; sb = inb ? vb : (T)0;
+                n_inslab += (ina ? 1.f : 0.f) + (inb ? 1.f : 0.f);
+            }
+            const bool next_head = run_head(SLAB ? (a.idx < slab_cells ? a.idx : KEY_NONE) : a.idx);
+            // ---- B joins A where both sit in the same voxel; otherwise B issues its own RED ------------------------
+            const bool same = (kb == ka);
+            const bool b_alone = !same && kb != KEY_NONE;
+            T sum = same ? V::add(sa, sb) : sa, t;
+            t = __shfl_up_sync(FULL, sum, 1);  if (!(heads & lm.w1))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 2);  if (!(heads & lm.w2))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 4);  if (!(heads & lm.w4))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t);
+            const bool issue = (heads & lm.next) && ka != KEY_NONE;
+            red_if(issue, grid + ka, sum);
+            red_if(b_alone, grid + kb, sb);
+            if (issue) n_issued += 1.f;
+            if (b_alone) n_issued += 1.f;
+            heads = __ballot_sync(FULL, next_head);
+            // ---- rays that ended: park them; leave when every ray of the warp is parked ----------------------------
+            if (__any_sync(FULL, !(still_a && still_b))) {
+                if (!still_a && a.remx != REM_PARKED) {
+                    my_steps += (unsigned long long)(unsigned)(int)(a.rem0 - (a.remx + a.remy + a.remz));
+                    rays_park(a); va = 0;
+                }
+                if (!still_b && b.remx != REM_PARKED) {
+                    my_steps += (unsigned long long)(unsigned)(int)(b.rem0 - (b.remx + b.remy + b.remz));
+                    rays_park(b); vb = 0;
+                }
+                if (__all_sync(FULL, a.remx == REM_PARKED && b.remx == REM_PARKED)) break;
+                heads = __ballot_sync(FULL, run_head(SLAB ? (a.idx < slab_cells ? a.idx : KEY_NONE) : a.idx));
+            }
+        }
+        my_atomics += (unsigned long long)n_issued;
+        if (SLAB) my_written += (unsigned long long)n_inslab;
+    }
+    if (!SLAB) my_written = my_steps;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_steps += __shfl_xor_sync(FULL, my_steps, o);
+        my_written += __shfl_xor_sync(FULL, my_written, o);
+        my_atomics += __shfl_xor_sync(FULL, my_atomics, o);
+    }
+    if (lane == 0 && my_steps) {
+        atomicAdd(&ctl->n_steps, my_steps);
+        atomicAdd(&ctl->n_written, my_written);
+        atomicAdd(&ctl->n_atomics, my_atomics);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->n_rays, count);
+}
+
 // Ray set-up of ray_voxel.cpp:506-515 as a stage.
 __global__ void pixel_rays_kernel(const uint32_t *__restrict__ pix, long long n, int width, int height, pvp_pair pose,
                                   float *__restrict__ dirs)
@@ -683,9 +907,21 @@ static int k2_grid_size(pvp_ctx *ctx, const void *kernel, int threads = K2_THREA
 }
 
 template <typename T>
-static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_stride, long long n_pix, int n_pairs, float threshold)
+static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_stride, long long n_pix, int n_pairs, float threshold,
+                     int width = 0, int height = 0, int row_group = 1)
 {
     constexpr int PX = FrameVec<T>::PX;
+    if (row_group > 1) {
+        const bool vec = ((uintptr_t)frames_dev % sizeof(typename FrameVec<T>::V) == 0) && (frame_stride % PX == 0) && (width % PX == 0);
+        const int R = row_group >= 8 ? 8 : row_group >= 4 ? 4 : 2;
+        const long long segs = (long long)((width + PX - 1) / PX) * ((height + R - 1) / R);
+        dim3 grid((unsigned)((segs + K1_THREADS - 1) / K1_THREADS), (unsigned)n_pairs);
+        LaunchScope scope(ctx, 1);
+        auto k = R == 8 ? motion_compact_rowgroup_kernel<T, 8> : R == 4 ? motion_compact_rowgroup_kernel<T, 4> : motion_compact_rowgroup_kernel<T, 2>;
+        k<<<grid, K1_THREADS, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, width, height, threshold, vec, ctx->queue, ctx->ctl_dev);
+        PVP_CUDA(cudaGetLastError());
+        return PVP_OK;
+    }
     const bool vec_ok = ((uintptr_t)frames_dev % sizeof(typename FrameVec<T>::V) == 0) && (frame_stride % PX == 0);
     dim3 grid((unsigned)((n_pix + (long long)K1_THREADS * PX - 1) / ((long long)K1_THREADS * PX)), (unsigned)n_pairs);
     LaunchScope scope(ctx, 1);
@@ -705,12 +941,24 @@ static void launch_agg(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, 
 
 // lean_regs: register budget = resident warps per SM: 0/72 -> 28 warps at 128-thread CTAs (24 at 256), 80 -> 24 warps, 64 -> 32 warps
 template <int MODE, bool SLAB, bool NARROW>
-static void launch_lean(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height)
+static void launch_lean(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height, unsigned long long count_lo = 0,
+                        unsigned long long count_hi = ~0ull)
 {
     auto k = ctx->opt_lean_regs == 64 ? dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_C>
            : ctx->opt_lean_regs == 80 ? dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_B> : dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_A>;
     k<<<k2_grid_size(ctx, (const void *)k, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
-                                                                                           width, height, ctx->ctl_dev);
+                                                                                           width, height, ctx->ctl_dev, count_lo, count_hi);
+}
+
+template <int MODE, bool SLAB, bool NARROW>
+static void launch_lean2(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height, unsigned long long count_lo = 0,
+                         unsigned long long count_hi = ~0ull)
+{
+    // lean_regs: 0/80 -> 3 resident CTAs (24 warps; measured best: 670 G voxel-steps/s at 512^3), 128 -> 2 CTAs (622 G), 64 -> 4 CTAs
+    auto k = ctx->opt_lean_regs == 128 ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 2>
+           : ctx->opt_lean_regs == 64  ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 4> : dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 3>;
+    k<<<k2_grid_size(ctx, (const void *)k, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
+                                                                                           width, height, ctx->ctl_dev, count_lo, count_hi);
 }
 
 // See the lean kernel's header: no t value of the batch can overflow to -inf.
@@ -726,22 +974,47 @@ static bool lean_geometry_ok(const GridP &g, const pvp_pair *pairs, int n_pairs)
     return true;
 }
 
-// dda_variant: 0 = auto (4 where its 32-bit voxel keys allow, else 3), 1 = segmented-scan aggregation (round-1
+// 0 = auto: both lock-step kernels are launched and the ray count of the batch picks one on the device (lean2 from
+// LEAN2_MIN_RAYS_PER_WARP rays per resident warp up: with fewer rays its 64-ray chunks leave SMs idle)
+static int effective_variant(const pvp_ctx *ctx)
+{
+    const int v = (int)ctx->opt_dda_variant;
+    return (v < 0 || v > 5) ? 0 : v;
+}
+constexpr unsigned long long LEAN2_MIN_RAYS_PER_WARP = 256;
+
+// dda_variant: 0 = auto (lean2 / lean by ray count where their 32-bit voxel keys allow, else 3), 1 = segmented-scan aggregation (round-1
 // baseline), 2 = match.any aggregation, 3 = one RED per lane and step (no aggregation, any grid size),
-// 4 = lean lock-step kernel.  narrow_ok: every value * 2^frac_bits * 32 fits 32 bits (uint8 frames).
+// 4 = lean lock-step kernel (one ray per lane), 5 = lean2 (two rays per lane, K1 in row-pair order).  narrow_ok: every value * 2^frac_bits * 32 fits 32 bits (uint8 frames).
 static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_ok, bool lean_ok, void *grid_dev, int width, int height)
 {
     LaunchScope scope(ctx, 2);
-    int variant = (int)ctx->opt_dda_variant;
-    if (variant <= 0 || variant > 4) variant = 4;
+    int variant = effective_variant(ctx);
     const bool slab = !(g.slab_lo == 0 && g.slab_hi == g.n);
     const unsigned long long cells = (unsigned long long)(g.slab_hi - g.slab_lo) * g.n * g.n;
     const unsigned long long full = (unsigned long long)g.n * g.n * g.n;
     if (cells >= 0xffffffffull) variant = 3;
-    if (variant == 4 && (slab ? full > (1ull << 31) : full >= 0xffffffffull)) variant = 3;  // slab test relies on wrapped offsets
-    if (variant == 4 && !lean_ok) variant = 3;
+    const bool lockstep = variant == 0 || variant >= 4;
+    if (lockstep && (slab ? full > (1ull << 31) : full >= 0xffffffffull)) variant = 3;  // slab test relies on wrapped offsets
+    if (lockstep && !lean_ok) variant = 3;
     const bool f32 = accum_mode == PVP_ACCUM_F32;
-    if (variant == 4) {
+    if (variant == 0) {
+        const unsigned long long T = (unsigned long long)ctx->sm_count * 3 * (LEAN_THREADS / 32) * LEAN2_MIN_RAYS_PER_WARP;
+        if (f32) {
+            if (slab) { launch_lean<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height, T); }
+            else { launch_lean<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height, T); }
+        } else if (narrow_ok) {
+            if (slab) { launch_lean<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height, T); }
+            else { launch_lean<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height, T); }
+        } else {
+            if (slab) { launch_lean<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height, T); }
+            else { launch_lean<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height, T); }
+        }
+    } else if (variant == 5) {
+        if (f32) { if (slab) launch_lean2<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height); else launch_lean2<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height); }
+        else if (narrow_ok) { if (slab) launch_lean2<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height); else launch_lean2<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height); }
+        else { if (slab) launch_lean2<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height); else launch_lean2<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height); }
+    } else if (variant == 4) {
         if (f32) { if (slab) launch_lean<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height); else launch_lean<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height); }
         else if (narrow_ok) { if (slab) launch_lean<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height); else launch_lean<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height); }
         else { if (slab) launch_lean<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height); else launch_lean<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height); }
@@ -800,8 +1073,11 @@ static int run_batches(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, lo
         rc = upload_pairs(ctx, pairs + p0, np);
         if (rc) return rc;
         PVP_CUDA(cudaMemsetAsync(ctx->ctl_dev, 0, 2 * sizeof(unsigned long long), ctx->stream));  // count, head
-        rc = frame_dtype == PVP_FRAME_U8 ? launch_k1<uint8_t>(ctx, frames_dev, frame_stride, n_pix, np, threshold)
-                                         : launch_k1<float>(ctx, frames_dev, frame_stride, n_pix, np, threshold);
+        // queue order: tiles of R image rows (lean2 walks two vertically adjacent pixels per lane); 1 = plain row-major
+        const int ev = effective_variant(ctx);
+        const int row_group = ctx->opt_k1_row_group > 0 ? (int)ctx->opt_k1_row_group : ((ev == 0 || ev >= 4) ? 2 : 1);
+        rc = frame_dtype == PVP_FRAME_U8 ? launch_k1<uint8_t>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group)
+                                         : launch_k1<float>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group);
         if (rc) return rc;
         // narrow fixed-point sums: |diff| <= 255 for uint8 frames, so 32 lanes * 255 * 2^frac_bits < 2^32 iff frac_bits <= 19
         const bool narrow_ok = frame_dtype == PVP_FRAME_U8 && g.fixed_scale <= 524288.f;

@@ -192,7 +192,7 @@ def test_sequence_float_frames_tolerance_and_fixed_exact(ctx, oracle):
                           bits(oracle.fixed_to_f32(want_fx, 20)))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("accum", ["f32", "fixed"])
 def test_k2_variants_bit_exact(ctx, oracle, variant, accum):
     """Every K2 variant (segmented-scan aggregation, match.any aggregation, plain per-lane RED, lean lock-step) must give the
@@ -319,7 +319,7 @@ def test_rays_leaving_through_low_corners_and_tiny_grids(ctx, oracle):
         pairs, _ = pvp.make_pairs(poses, W)
         want, tot = _oracle_run(oracle, frames, poses, N, vs, center, 2.0)
         assert tot[1] > 500
-        for variant in (0, 1, 3):
+        for variant in (0, 1, 3, 5):
             ctx.set_option("dda_variant", variant)
             try:
                 grid = pvp.VoxelGrid(N, vs, center)
@@ -340,11 +340,22 @@ def test_rays_leaving_through_low_corners_and_tiny_grids(ctx, oracle):
                 ctx.set_option("dda_variant", 0)
 
 
-def test_random_geometry_sweep_vs_oracle(ctx, oracle):
+@pytest.mark.parametrize("variant", [0, 5])
+def test_random_geometry_sweep_vs_oracle(ctx, oracle, variant):
     """Broad randomised parity sweep of the default (lean lock-step) kernel: cameras inside and outside the grid (outside ones
     look in through min or max faces -- the latter cast no steps, ray_voxel.cpp:329-334), full-range yaw / pitch / roll, fov
     20..140 degrees, odd and even N, frame sizes that leave partial warps, both accumulation modes and a random slab."""
     rng = np.random.default_rng(4242)
+    total_steps = 0
+    ctx.set_option("dda_variant", variant)
+    try:
+        total_steps = _geometry_sweep(ctx, oracle, rng)
+    finally:
+        ctx.set_option("dda_variant", 0)
+    assert total_steps > 150000
+
+
+def _geometry_sweep(ctx, oracle, rng):
     total_steps = 0
     for trial in range(60):
         N = int(rng.choice([1, 2, 3, 7, 16, 31, 40]))
@@ -375,4 +386,4 @@ def test_random_geometry_sweep_vs_oracle(ctx, oracle):
             ss = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, s, 2.0)
             assert (ss["n_rays"], ss["n_steps"]) == (tot[0], tot[1]) and np.array_equal(s.data.cpu().numpy(), want[lo:hi]), (trial, accum, lo, hi)
         total_steps += tot[1]
-    assert total_steps > 150000
+    return total_steps
