@@ -329,7 +329,7 @@ __device__ __forceinline__ unsigned march_lockstep(CellT *__restrict__ grid, con
     return n_in;
 }
 
-template <int MODE>
+template <int MODE, int TILE_H>
 __global__ void __launch_bounds__(K3L_THREADS)
 process_image_lockstep_kernel(const double *__restrict__ image, typename Cell<MODE>::T *__restrict__ grid,
                               typename Cell<MODE>::T *__restrict__ tex, ImageP p, ImageFastP f, Ctl *__restrict__ ctl)
@@ -338,19 +338,25 @@ process_image_lockstep_kernel(const double *__restrict__ image, typename Cell<MO
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
     const ScanMasks lm = scan_masks(lane);
-    const long long n_px = p.W * p.H;
-    const unsigned long long n_groups = (unsigned long long)((n_px + 31) / 32);
+    constexpr int TILE_W = 32 / TILE_H;
+    // a warp's 32 pixels form a compact tile of the image, TILE_H rows x 32/TILE_H columns, consecutive lanes being
+    // vertical neighbours (the row-group order of K1): the rays of a tile diverge less than those of a 32 x 1 strip
+    const long long tiles_x = (p.W + TILE_W - 1) / TILE_W, tiles_y = (p.H + TILE_H - 1) / TILE_H;
+    const unsigned long long n_groups = (unsigned long long)(tiles_x * tiles_y);
     unsigned long long my_rays = 0, my_samples = 0;
     for (;;) {
         unsigned long long group = 0;
         if (lane == 0) group = atomicAdd(&ctl->head, 1ull);
         group = __shfl_sync(FULL, group, 0);
         if (group >= n_groups) break;
-        const long long px = (long long)group * 32 + lane;
+        const long long ty = (long long)(group / (unsigned long long)tiles_x), tx = (long long)group - ty * tiles_x;
+        const long long pi = ty * TILE_H + (lane % TILE_H), pj = tx * TILE_W + (lane / TILE_H);
+        const bool in_image = pi < p.H && pj < p.W;
+        const long long px = pi * p.W + pj;
         double w0 = 0, w1 = 0, w2 = 0;
         typename C::V val = 0;
         int lo = INT32_MAX, hi = INT32_MIN;  // empty range
-        if (px < n_px) {
+        if (in_image) {
             int s_entry, s_exit;
             bool counted;
             if (pixel_setup<MODE>(image, tex, p, px, w0, w1, w2, val, s_entry, s_exit, counted) && s_entry <= s_exit) { lo = s_entry; hi = s_exit; }
@@ -466,16 +472,17 @@ static int launch_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, v
     if (ctx->opt_image_variant != 1 && make_fastp(p, &f)) {
         PVP_CUDA(cudaMemsetAsync(&ctx->ctl_dev->head, 0, sizeof(unsigned long long), ctx->stream));
         int per_sm = 0;
-        const void *k = accum_mode == PVP_ACCUM_F64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64>
-                                                    : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED>;
+        const int th = ctx->opt_image_tile_h == 1 ? 1 : ctx->opt_image_tile_h == 4 ? 4 : ctx->opt_image_tile_h == 8 ? 8 : 2;
+        const bool f64 = accum_mode == PVP_ACCUM_F64;
+        const void *k = th == 1 ? (f64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64, 1> : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED, 1>)
+                      : th == 4 ? (f64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64, 4> : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED, 4>)
+                      : th == 8 ? (f64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64, 8> : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED, 8>)
+                                : (f64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64, 2> : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED, 2>);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, K3L_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
-        const long long groups = (n_px + 31) / 32;
+        const long long groups = ((p.W + 32 / th - 1) / (32 / th)) * ((p.H + th - 1) / th);
         const int blocks = (int)std::min<long long>((groups + K3L_THREADS / 32 - 1) / (K3L_THREADS / 32), (long long)ctx->sm_count * per_sm);
-        if (accum_mode == PVP_ACCUM_F64)
-            process_image_lockstep_kernel<PVP_ACCUM_F64><<<blocks, K3L_THREADS, 0, ctx->stream>>>(image_dev, (double *)grid_dev, (double *)tex_dev, p, f, ctx->ctl_dev);
-        else
-            process_image_lockstep_kernel<PVP_ACCUM_FIXED><<<blocks, K3L_THREADS, 0, ctx->stream>>>(image_dev, (unsigned long long *)grid_dev,
-                                                                                                    (unsigned long long *)tex_dev, p, f, ctx->ctl_dev);
+        void *args[] = {(void *)&image_dev, (void *)&grid_dev, (void *)&tex_dev, (void *)&p, (void *)&f, (void *)&ctx->ctl_dev};
+        PVP_CUDA(cudaLaunchKernel(k, dim3((unsigned)blocks), dim3(K3L_THREADS), args, 0, ctx->stream));
         PVP_CUDA(cudaGetLastError());
         return PVP_OK;
     }
