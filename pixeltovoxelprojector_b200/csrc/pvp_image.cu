@@ -272,6 +272,35 @@ __device__ __forceinline__ void img_red(double *p, double v) { atomicAdd(p, v); 
 __device__ __forceinline__ void img_red(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 __device__ __forceinline__ void img_red(unsigned long long *p, unsigned v) { atomicAdd(p, (unsigned long long)v); }
 
+// voxel offset of sample s of one ray, or IMG_NONE (outside [lo,hi], or outside the extent: process_image.cpp:85, :349-352)
+__device__ __forceinline__ unsigned sample_key(const ImageP &p, const ImageFastP &f, int s, double w0, double w1, double w2, int lo, int hi)
+{
+    const double d = dmul((double)s, p.step_size);  // :344
+    const double qx = dadd(p.o[0], dmul(d, w0)), qy = dadd(p.o[1], dmul(d, w1)), qz = dadd(p.o[2], dmul(d, w2));
+    // inside the extent the scaled coordinate lies in [0, n]: int truncation + upper clamp == :94-104
+    const int xi = min(__double2int_rz(dmul(div_by_extent(dsub(qx, p.ext[0]), f.b[0], f.y[0]), f.nd[0])), f.n1[0]);
+    const int yi = min(__double2int_rz(dmul(div_by_extent(dsub(qy, p.ext[2]), f.b[1], f.y[1]), f.nd[1])), f.n1[1]);
+    const int zi = min(__double2int_rz(dmul(div_by_extent(dsub(qz, p.ext[4]), f.b[2], f.y[2]), f.nd[2])), f.n1[2]);
+    const unsigned off = (unsigned)xi * f.gs[0] + (unsigned)yi * f.gs[1] + (unsigned)zi * f.gs[2];
+    // in = lo <= s <= hi and the inclusive bounds test of :85 -- one chained predicate (the compiler's own form is a
+    // chain of eight selects), then key = in ? off : IMG_NONE
+    unsigned key;
+    asm("{\n\t.reg .pred q;\n\t"
+        "setp.ge.s32 q, %1, %2;\n\t"
+        "setp.le.and.s32 q, %1, %3, q;\n\t"
+        "setp.le.and.f64 q, %4, %5, q;\n\t"
+        "setp.le.and.f64 q, %5, %6, q;\n\t"
+        "setp.le.and.f64 q, %7, %8, q;\n\t"
+        "setp.le.and.f64 q, %8, %9, q;\n\t"
+        "setp.le.and.f64 q, %10, %11, q;\n\t"
+        "setp.le.and.f64 q, %11, %12, q;\n\t"
+        "selp.u32 %0, %13, 0xffffffff, q;\n\t}"
+        : "=r"(key)
+        : "r"(s), "r"(lo), "r"(hi), "d"(p.ext[0]), "d"(qx), "d"(p.ext[1]), "d"(p.ext[2]), "d"(qy), "d"(p.ext[3]), "d"(p.ext[4]), "d"(qz),
+          "d"(p.ext[5]), "r"(off));
+    return key;
+}
+
 // One warp, one group of 32 pixels: samples wlo..whi in lock-step.  S is the type the run sums are formed in.
 template <typename S, typename CellT>
 __device__ __forceinline__ unsigned march_lockstep(CellT *__restrict__ grid, const ImageP &p, const ImageFastP &f, const ScanMasks &lm,
@@ -279,33 +308,7 @@ __device__ __forceinline__ unsigned march_lockstep(CellT *__restrict__ grid, con
 {
     const unsigned FULL = 0xffffffffu;
     unsigned n_in = 0;
-    // voxel offset of sample s, or IMG_NONE (outside [lo,hi], or outside the extent: process_image.cpp:85, :349-352)
-    auto key_of = [&](int s) -> unsigned {
-        const double d = dmul((double)s, p.step_size);  // :344
-        const double qx = dadd(p.o[0], dmul(d, w0)), qy = dadd(p.o[1], dmul(d, w1)), qz = dadd(p.o[2], dmul(d, w2));
-        // inside the extent the scaled coordinate lies in [0, n]: int truncation + upper clamp == :94-104
-        const int xi = min(__double2int_rz(dmul(div_by_extent(dsub(qx, p.ext[0]), f.b[0], f.y[0]), f.nd[0])), f.n1[0]);
-        const int yi = min(__double2int_rz(dmul(div_by_extent(dsub(qy, p.ext[2]), f.b[1], f.y[1]), f.nd[1])), f.n1[1]);
-        const int zi = min(__double2int_rz(dmul(div_by_extent(dsub(qz, p.ext[4]), f.b[2], f.y[2]), f.nd[2])), f.n1[2]);
-        const unsigned off = (unsigned)xi * f.gs[0] + (unsigned)yi * f.gs[1] + (unsigned)zi * f.gs[2];
-        // in = lo <= s <= hi and the inclusive bounds test of :85 -- one chained predicate (the compiler's own form is a
-        // chain of eight selects), then key = in ? off : IMG_NONE
-        unsigned key;
-        asm("{\n\t.reg .pred q;\n\t"
-            "setp.ge.s32 q, %1, %2;\n\t"
-            "setp.le.and.s32 q, %1, %3, q;\n\t"
-            "setp.le.and.f64 q, %4, %5, q;\n\t"
-            "setp.le.and.f64 q, %5, %6, q;\n\t"
-            "setp.le.and.f64 q, %7, %8, q;\n\t"
-            "setp.le.and.f64 q, %8, %9, q;\n\t"
-            "setp.le.and.f64 q, %10, %11, q;\n\t"
-            "setp.le.and.f64 q, %11, %12, q;\n\t"
-            "selp.u32 %0, %13, 0xffffffff, q;\n\t}"
-            : "=r"(key)
-            : "r"(s), "r"(lo), "r"(hi), "d"(p.ext[0]), "d"(qx), "d"(p.ext[1]), "d"(p.ext[2]), "d"(qy), "d"(p.ext[3]), "d"(p.ext[4]), "d"(qz),
-              "d"(p.ext[5]), "r"(off));
-        return key;
-    };
+    auto key_of = [&](int s) -> unsigned { return sample_key(p, f, s, w0, w1, w2, lo, hi); };
     unsigned key = key_of(wlo);
     unsigned heads = __ballot_sync(FULL, img_run_head(key));
     for (int s = wlo;; ++s) {
@@ -327,6 +330,101 @@ __device__ __forceinline__ unsigned march_lockstep(CellT *__restrict__ grid, con
         key = key_n;
     }
     return n_in;
+}
+
+// Two pixels per lane (vertical neighbours, the lean2 idea of path A): pixel B's sample sits in pixel A's voxel most of the
+// time and then joins A's value before the scan, so one scan serves 64 samples; otherwise B issues its own RED.
+template <typename S, typename CellT>
+__device__ __forceinline__ unsigned march_lockstep2(CellT *__restrict__ grid, const ImageP &p, const ImageFastP &f, const ScanMasks &lm,
+                                                    double a0, double a1, double a2, S val_a, int lo_a, int hi_a,
+                                                    double b0, double b1, double b2, S val_b, int lo_b, int hi_b, int wlo, int whi)
+{
+    const unsigned FULL = 0xffffffffu;
+    unsigned n_in = 0;
+    unsigned ka = sample_key(p, f, wlo, a0, a1, a2, lo_a, hi_a), kb = sample_key(p, f, wlo, b0, b1, b2, lo_b, hi_b);
+    unsigned heads = __ballot_sync(FULL, img_run_head(ka));
+    for (int s = wlo;; ++s) {
+        unsigned ka_n = IMG_NONE, kb_n = IMG_NONE;
+        if (s != whi) {
+            ka_n = sample_key(p, f, s + 1, a0, a1, a2, lo_a, hi_a);
+            kb_n = sample_key(p, f, s + 1, b0, b1, b2, lo_b, hi_b);
+        }
+        const bool head_n = img_run_head(ka_n);
+        const bool live_a = ka != IMG_NONE, live_b = kb != IMG_NONE;
+        n_in += (unsigned)live_a + (unsigned)live_b;
+        const bool same = live_b && kb == ka;
+        const bool b_alone = live_b && !same;
+        S sum = (live_a ? val_a : (S)0) + (same ? val_b : (S)0), t;
+        t = __shfl_up_sync(FULL, sum, 1);  if (!(heads & lm.w1))  sum += t;
+        t = __shfl_up_sync(FULL, sum, 2);  if (!(heads & lm.w2))  sum += t;
+        t = __shfl_up_sync(FULL, sum, 4);  if (!(heads & lm.w4))  sum += t;
+        t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum += t;
+        t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum += t;
+        if ((heads & lm.next) && live_a) img_red(grid + ka, sum);
+        if (b_alone) img_red(grid + kb, val_b);
+        if (s == whi) break;
+        heads = __ballot_sync(FULL, head_n);
+        ka = ka_n; kb = kb_n;
+    }
+    return n_in;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(K3L_THREADS)
+process_image_lockstep2_kernel(const double *__restrict__ image, typename Cell<MODE>::T *__restrict__ grid,
+                               typename Cell<MODE>::T *__restrict__ tex, ImageP p, ImageFastP f, Ctl *__restrict__ ctl)
+{
+    using C = Cell<MODE>;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const ScanMasks lm = scan_masks(lane);
+    // a warp's tile: 32 columns x 2 rows; lane l holds the two pixels of column l
+    const long long tiles_x = (p.W + 31) / 32, tiles_y = (p.H + 1) / 2;
+    const unsigned long long n_groups = (unsigned long long)(tiles_x * tiles_y);
+    unsigned long long my_rays = 0, my_samples = 0;
+    for (;;) {
+        unsigned long long group = 0;
+        if (lane == 0) group = atomicAdd(&ctl->head, 1ull);
+        group = __shfl_sync(FULL, group, 0);
+        if (group >= n_groups) break;
+        const long long ty = (long long)(group / (unsigned long long)tiles_x), tx = (long long)group - ty * tiles_x;
+        const long long pj = tx * 32 + lane, pi = ty * 2;
+        double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+        typename C::V val_a = 0, val_b = 0;
+        int lo_a = INT32_MAX, hi_a = INT32_MIN, lo_b = INT32_MAX, hi_b = INT32_MIN;  // empty ranges
+        if (pj < p.W) {
+            int s_entry, s_exit;
+            bool counted;
+            if (pixel_setup<MODE>(image, tex, p, pi * p.W + pj, a0, a1, a2, val_a, s_entry, s_exit, counted) && s_entry <= s_exit) { lo_a = s_entry; hi_a = s_exit; }
+            my_rays += counted;
+            if (pi + 1 < p.H) {
+                if (pixel_setup<MODE>(image, tex, p, (pi + 1) * p.W + pj, b0, b1, b2, val_b, s_entry, s_exit, counted) && s_entry <= s_exit) { lo_b = s_entry; hi_b = s_exit; }
+                my_rays += counted;
+            }
+        }
+        const int wlo = __reduce_min_sync(FULL, min(lo_a, lo_b)), whi = __reduce_max_sync(FULL, max(hi_a, hi_b));
+        if (wlo > whi) continue;
+        if (MODE == PVP_ACCUM_FIXED) {
+            // run sums of 64 values fit 32 bits when every value is below 2^26
+            if (__all_sync(FULL, (unsigned long long)val_a < (1ull << 26) && (unsigned long long)val_b < (1ull << 26)))
+                my_samples += march_lockstep2<unsigned>((unsigned long long *)grid, p, f, lm, a0, a1, a2, (unsigned)val_a, lo_a, hi_a, b0, b1, b2, (unsigned)val_b,
+                                                        lo_b, hi_b, wlo, whi);
+            else
+                my_samples += march_lockstep2<unsigned long long>((unsigned long long *)grid, p, f, lm, a0, a1, a2, (unsigned long long)val_a, lo_a, hi_a, b0, b1,
+                                                                  b2, (unsigned long long)val_b, lo_b, hi_b, wlo, whi);
+        } else {
+            my_samples += march_lockstep2<double>((double *)grid, p, f, lm, a0, a1, a2, (double)val_a, lo_a, hi_a, b0, b1, b2, (double)val_b, lo_b, hi_b, wlo, whi);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_rays += __shfl_xor_sync(FULL, my_rays, o);
+        my_samples += __shfl_xor_sync(FULL, my_samples, o);
+    }
+    if (lane == 0 && (my_rays | my_samples)) {
+        atomicAdd(&ctl->img_rays, my_rays);
+        atomicAdd(&ctl->img_samples, my_samples);
+    }
 }
 
 template <int MODE, int TILE_H>
@@ -463,7 +561,8 @@ static bool make_fastp(const ImageP &p, ImageFastP *f)
     return span < 0xffffffffull;  // voxel offsets are 32-bit keys, 0xffffffff is reserved
 }
 
-// image_variant: 0 = auto (lock-step where fast_ok), 1 = generic per-pixel kernel, 2 = lock-step (falls back if !fast_ok)
+// image_variant: 0 = auto (two-pixel lock-step where fast_ok), 1 = generic per-pixel kernel, 2 = one-pixel lock-step, 3 = two-pixel lock-step
+// (the lock-step kernels fall back to the generic one if !fast_ok)
 static int launch_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, void *tex_dev, const ImageP &p, int accum_mode)
 {
     const long long n_px = p.W * p.H;
@@ -474,6 +573,16 @@ static int launch_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, v
         int per_sm = 0;
         const int th = ctx->opt_image_tile_h == 1 ? 1 : ctx->opt_image_tile_h == 4 ? 4 : ctx->opt_image_tile_h == 8 ? 8 : 2;
         const bool f64 = accum_mode == PVP_ACCUM_F64;
+        if (ctx->opt_image_variant != 2) {  // default: two pixels per lane
+            const void *k2 = f64 ? (const void *)process_image_lockstep2_kernel<PVP_ACCUM_F64> : (const void *)process_image_lockstep2_kernel<PVP_ACCUM_FIXED>;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, K3L_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+            const long long groups2 = ((p.W + 31) / 32) * ((p.H + 1) / 2);
+            const int blocks2 = (int)std::min<long long>((groups2 + K3L_THREADS / 32 - 1) / (K3L_THREADS / 32), (long long)ctx->sm_count * per_sm);
+            void *args2[] = {(void *)&image_dev, (void *)&grid_dev, (void *)&tex_dev, (void *)&p, (void *)&f, (void *)&ctx->ctl_dev};
+            PVP_CUDA(cudaLaunchKernel(k2, dim3((unsigned)blocks2), dim3(K3L_THREADS), args2, 0, ctx->stream));
+            PVP_CUDA(cudaGetLastError());
+            return PVP_OK;
+        }
         const void *k = th == 1 ? (f64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64, 1> : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED, 1>)
                       : th == 4 ? (f64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64, 4> : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED, 4>)
                       : th == 8 ? (f64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64, 8> : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED, 8>)

@@ -101,9 +101,10 @@ def test_division_by_extent_equals_ieee_division(ctx):
         assert bad.value == 0, (b, bad.value)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_random_scenes_vs_oracle(ctx, oracle, variant):
-    """variant 1 = generic per-pixel kernel, 2 = lock-step kernel with warp-aggregated REDs (the default where eligible)."""
+    """variant 1 = generic per-pixel kernel, 2 = lock-step kernel with warp-aggregated REDs, one pixel per lane, 3 = two pixels
+    per lane (the default where eligible)."""
     ctx.set_option("image_variant", variant)
     try:
         _random_scenes(oracle)
@@ -174,13 +175,23 @@ def test_full_size_properties_4096_512_fixed(ctx):
     assert torch.equal(grids[0], grids[1]) and torch.equal(grids[2], grids[0] * 2)
 
 
-def test_lockstep_random_sweep_fixed_point_exact(ctx, oracle):
+@pytest.mark.parametrize("variant", [2, 3])
+def test_lockstep_random_sweep_fixed_point_exact(ctx, oracle, variant):
     """Broad randomised sweep of the lock-step kernel in fixed-point mode (bit-exact against the oracle): observer inside
     and outside the grid, non-cubic and strided grids, steps longer and shorter than a voxel, max_distance clipping inside
     the grid, pointing along +-z (the up-vector switch, process_image.cpp:203-211), widths that leave partial warps, zero
     pixels, texture updates."""
     from pixeltovoxelprojector_b200 import process_image as pi
     rng = np.random.default_rng(515)
+    ctx.set_option("image_variant", variant)
+    try:
+        total = _lockstep_sweep(oracle, pi, rng)
+    finally:
+        ctx.set_option("image_variant", 0)
+    assert total > 300000
+
+
+def _lockstep_sweep(oracle, pi, rng):
     total = 0
     for trial in range(36):
         H, W = int(rng.integers(1, 50)), int(rng.integers(1, 90))
@@ -221,4 +232,4 @@ def test_lockstep_random_sweep_fixed_point_exact(ctx, oracle):
         if upd:
             assert np.array_equal(ti.cpu().numpy(), ot), trial
         total += ns
-    assert total > 300000
+    return total
