@@ -999,6 +999,7 @@ static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_o
     if (lockstep && !lean_ok) variant = 3;
     const bool f32 = accum_mode == PVP_ACCUM_F32;
     if (variant == 0) {
+        ++ctx->prof.launches_k2;  // two kernels are launched (the scope above counted one); the one not chosen exits at once
         const unsigned long long T = (unsigned long long)ctx->sm_count * 3 * (LEAN_THREADS / 32) * LEAN2_MIN_RAYS_PER_WARP;
         if (f32) {
             if (slab) { launch_lean<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height, T); }
