@@ -24,6 +24,7 @@ struct GridP {
     float gmin[3];
     float gmax[3];
     float fixed_scale;  // 2^frac_bits
+    int frac_shift;     // frac_bits (0 for float32 grids)
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }

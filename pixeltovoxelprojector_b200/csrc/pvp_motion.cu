@@ -488,21 +488,22 @@ template <bool NARROW> struct LeanVal<PVP_ACCUM_F32, NARROW> {
     using T = float;
     __device__ static __forceinline__ T make(float diff, const GridP &) { return diff; }
     __device__ static __forceinline__ T add(T a, T b) { return fadd(a, b); }
-    __device__ static __forceinline__ void red(float *p, T v) { atomicAdd(p, v); }
+    __device__ static __forceinline__ float cell_value(T v, const GridP &) { return v; }
 };
 template <> struct LeanVal<PVP_ACCUM_FIXED, false> {
     using T = unsigned long long;
     __device__ static __forceinline__ T make(float diff, const GridP &g) { return (unsigned long long)quantize_fixed(diff, g.fixed_scale); }
     __device__ static __forceinline__ T add(T a, T b) { return a + b; }
-    __device__ static __forceinline__ void red(unsigned long long *p, T v) { atomicAdd(p, v); }
+    __device__ static __forceinline__ unsigned long long cell_value(T v, const GridP &) { return v; }
 };
-// NARROW: the host guarantees 32 * max(value) * 2^frac_bits < 2^32 (uint8 frames, frac_bits <= 19), so run
-// sums fit 32 bits and the scan costs one shuffle per step; the RED is still a 64-bit add.
+// NARROW ("integral"): uint8 frames -- every |prev - curr| is an integer <= 255, so its fixed-point image is diff << frac_bits
+// exactly and a run sum of up to 64 of them (< 2^14) is exact in fp32.  The scan then runs on the plain diffs with FADDs
+// (FMA pipe, like the float32 mode) and only the lane that issues the RED converts: (u64)sum << frac_bits.
 template <> struct LeanVal<PVP_ACCUM_FIXED, true> {
-    using T = unsigned;
-    __device__ static __forceinline__ T make(float diff, const GridP &g) { return (unsigned)quantize_fixed(diff, g.fixed_scale); }
-    __device__ static __forceinline__ T add(T a, T b) { return a + b; }
-    __device__ static __forceinline__ void red(unsigned long long *p, T v) { atomicAdd(p, (unsigned long long)v); }
+    using T = float;
+    __device__ static __forceinline__ T make(float diff, const GridP &) { return diff; }
+    __device__ static __forceinline__ T add(T a, T b) { return fadd(a, b); }
+    __device__ static __forceinline__ unsigned long long cell_value(T v, const GridP &g) { return (unsigned long long)__float2uint_rz(v) << g.frac_shift; }
 };
 
 constexpr float REM_PARKED = 1.0e9f;  // 1e9f - 1 == 1e9f: a parked lane's counters never run out
@@ -516,7 +517,6 @@ __device__ __forceinline__ void red_if(bool p, unsigned long long *addr, unsigne
 {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q red.global.add.u64 [%1], %2;\n\t}" ::"r"((unsigned)p), "l"(addr), "l"(v) : "memory");
 }
-__device__ __forceinline__ void red_if(bool p, unsigned long long *addr, unsigned v) { red_if(p, addr, (unsigned long long)v); }
 
 // key of the lane below (lane 0: none) and whether this lane starts a run, from one SHFL.UP and its range predicate
 __device__ __forceinline__ bool run_head(unsigned key)
@@ -629,7 +629,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
             t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t);
             t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t);
             const bool issue = (heads & lm.next) && key != KEY_NONE;
-            red_if(issue, grid + key, sum);
+            red_if(issue, grid + key, V::cell_value(sum, g));
             if (issue) n_issued += 1.f;
             if (!SLAB) heads = __ballot_sync(FULL, next_head);
             // ---- rays that ended: park the lane; leave when the whole warp is parked ---------------------
@@ -779,8 +779,8 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
             t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t);
             t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t);
             const bool issue = (heads & lm.next) && ka != KEY_NONE;
-            red_if(issue, grid + ka, sum);
-            red_if(b_alone, grid + kb, sb);
+            red_if(issue, grid + ka, V::cell_value(sum, g));
+            red_if(b_alone, grid + kb, V::cell_value(sb, g));
             if (issue) n_issued += 1.f;
             if (b_alone) n_issued += 1.f;
             heads = __ballot_sync(FULL, next_head);
@@ -886,6 +886,7 @@ static int make_gridp(const pvp_grid_desc *d, GridP *g)
         g->gmin[a] = lo; g->gmax[a] = hi;
     }
     g->fixed_scale = (float)((long long)1 << (d->accum_mode == PVP_ACCUM_FIXED ? d->frac_bits : 0));
+    g->frac_shift = d->accum_mode == PVP_ACCUM_FIXED ? d->frac_bits : 0;
     return PVP_OK;
 }
 
@@ -985,7 +986,7 @@ constexpr unsigned long long LEAN2_MIN_RAYS_PER_WARP = 256;
 
 // dda_variant: 0 = auto (lean2 / lean by ray count where their 32-bit voxel keys allow, else 3), 1 = segmented-scan aggregation (round-1
 // baseline), 2 = match.any aggregation, 3 = one RED per lane and step (no aggregation, any grid size),
-// 4 = lean lock-step kernel (one ray per lane), 5 = lean2 (two rays per lane, K1 in row-pair order).  narrow_ok: every value * 2^frac_bits * 32 fits 32 bits (uint8 frames).
+// 4 = lean lock-step kernel (one ray per lane), 5 = lean2 (two rays per lane, K1 in row-pair order).  narrow_ok: uint8 frames, i.e. integer addends (LeanVal<FIXED, true>).
 static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_ok, bool lean_ok, void *grid_dev, int width, int height)
 {
     LaunchScope scope(ctx, 2);
@@ -1080,8 +1081,8 @@ static int run_batches(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, lo
         rc = frame_dtype == PVP_FRAME_U8 ? launch_k1<uint8_t>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group)
                                          : launch_k1<float>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group);
         if (rc) return rc;
-        // narrow fixed-point sums: |diff| <= 255 for uint8 frames, so 32 lanes * 255 * 2^frac_bits < 2^32 iff frac_bits <= 19
-        const bool narrow_ok = frame_dtype == PVP_FRAME_U8 && g.fixed_scale <= 524288.f;
+        // "integral" fixed-point sums: uint8 frames have integer diffs <= 255 (see LeanVal<FIXED, true>)
+        const bool narrow_ok = frame_dtype == PVP_FRAME_U8;
         rc = launch_k2(ctx, g, accum_mode, narrow_ok, lean_geometry_ok(g, pairs + p0, np), grid_dev, width, height);
         if (rc) return rc;
     }
