@@ -60,6 +60,9 @@ typedef struct pvp_grid_desc {
     int32_t frac_bits;    /* fixed-point fractional bits (0..40), ignored for F32 */
     int32_t slab_lo;      /* first x-plane stored at grid_dev */
     int32_t slab_hi;      /* one past the last x-plane stored (n for a whole grid) */
+    float attenuation_alpha; /* 0 (default) = reference behaviour: the distance attenuation of ray_voxel.cpp:524-525 is computed and
+                                discarded (:526).  > 0 = opt-in extension: every voxel step adds
+                                pix_val * 1/(1 + alpha * distance), distance = RayStep::distance, all in IEEE fp32 */
 } pvp_grid_desc;
 
 /*

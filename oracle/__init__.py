@@ -110,6 +110,9 @@ class Oracle(_PathA):
         L.pvpo_accumulate_pair.restype = C.c_int
         L.pvpo_accumulate_pair_u8.argtypes = [_u8p, _u8p] + common
         L.pvpo_accumulate_pair_u8.restype = C.c_int
+        L.pvpo_accumulate_pair_att.argtypes = [_f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_float, _f32p, C.c_float, C.c_float,
+                                               C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u64ref, _u64ref, _u64ref]
+        L.pvpo_accumulate_pair_att.restype = C.c_int
         L.pvpo_fixed_to_f32.argtypes = [_i64p, _f32p, C.c_int64, C.c_int]
         L.pvpo_fixed_to_f32.restype = None
         L.pvpo_quantize_f64.argtypes = [C.c_double, C.c_int]
@@ -135,14 +138,22 @@ class Oracle(_PathA):
         return changed, diff
 
     def accumulate_pair(self, prev, curr, cam, R, focal, grid, N, voxel_size, center, threshold,
-                        accum_mode=0, frac_bits=16, slab=None):
+                        accum_mode=0, frac_bits=16, slab=None, attenuation_alpha=0.0):
         """ray_voxel.cpp:484-531 on one frame pair; ``grid`` (f32 or i64, C order, shape
-        [slab_hi-slab_lo, N, N]) is updated in place.  Returns (n_rays, n_steps, n_written)."""
+        [slab_hi-slab_lo, N, N]) is updated in place.  Returns (n_rays, n_steps, n_written).
+        attenuation_alpha > 0: the opt-in extension that applies the factor of :524-525 (unpinned, see pvp_oracle.c)."""
         H, W = prev.shape
         lo, hi = (0, N) if slab is None else slab
         assert grid.flags.c_contiguous and grid.size == (hi - lo) * N * N
         assert grid.dtype == (np.float32 if accum_mode == 0 else np.int64)
         nr, ns, nw = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        if attenuation_alpha:
+            a, b = np.ascontiguousarray(prev, np.float32), np.ascontiguousarray(curr, np.float32)
+            rc = self._lib.pvpo_accumulate_pair_att(a, b, W, H, _f3(cam), np.ascontiguousarray(R, np.float32), C.c_float(focal), int(N),
+                                                    C.c_float(voxel_size), _f3(center), C.c_float(threshold), C.c_float(attenuation_alpha),
+                                                    grid.ctypes.data, int(accum_mode), int(frac_bits), int(lo), int(hi), C.byref(nr), C.byref(ns), C.byref(nw))
+            assert rc == 0
+            return nr.value, ns.value, nw.value
         if prev.dtype == np.uint8:
             fn, a, b = self._lib.pvpo_accumulate_pair_u8, np.ascontiguousarray(prev), np.ascontiguousarray(curr, np.uint8)
         else:

@@ -237,6 +237,26 @@ static void o_emit_acc(void *c, int ix, int iy, int iz, float t)
     a->written++;
 }
 
+/* SURVEY 8f N4 (opt-in extension, NOT reference behaviour): the distance attenuation the reference computes at
+ * ray_voxel.cpp:524-525 and then discards (:526 multiplies by 1.f instead).  Here it is applied:
+ *   float dist = rs.distance; float attenuation = 1.f/(1.f + alpha*dist); float val = pix_val * attenuation;
+ * Parity for this mode is UNPINNED: no build of the unmodified reference executes it. */
+struct o_att_ctx {
+    struct o_acc_ctx acc;
+    float pix_val, alpha;
+    int accum_mode, frac_bits;
+};
+static inline int64_t o_quantize(float val, int frac_bits);
+static void o_emit_acc_att(void *c, int ix, int iy, int iz, float t)
+{
+    struct o_att_ctx *a = (struct o_att_ctx *)c;
+    float dist = t;                                         /* :524 */
+    float attenuation = 1.f / (1.f + a->alpha * dist);      /* :525 */
+    a->acc.val = a->pix_val * attenuation;                  /* :526 with the factor applied */
+    if (a->accum_mode != 0) a->acc.qval = o_quantize(a->acc.val, a->frac_bits);
+    o_emit_acc(&a->acc, ix, iy, iz, t);
+}
+
 /* Fixed-point quantisation shared by oracle and kernels: q = rint(val * 2^frac_bits),
  * round-to-nearest-even; the scaling is exact in fp32 (power of two). */
 static inline int64_t o_quantize(float val, int frac_bits)
@@ -275,6 +295,39 @@ PVPO_API int pvpo_accumulate_pair(const float *prev, const float *curr, int widt
             a.written = 0;
             steps += (uint64_t)o_cast_ray(cam, dir, N, voxel_size, center, o_emit_acc, &a);
             written += (uint64_t)a.written;
+            rays++;
+        }
+    }
+    if (n_rays) *n_rays += rays;
+    if (n_steps) *n_steps += steps;
+    if (n_written) *n_written += written;
+    return 0;
+}
+
+/* pvpo_accumulate_pair with the opt-in distance attenuation (see o_emit_acc_att); alpha == 0 is NOT routed here. */
+PVPO_API int pvpo_accumulate_pair_att(const float *prev, const float *curr, int width, int height,
+                                      const float cam[3], const float R[9], float focal_len,
+                                      int N, float voxel_size, const float center[3], float threshold, float alpha,
+                                      void *grid, int accum_mode, int frac_bits, int slab_lo, int slab_hi,
+                                      uint64_t *n_rays, uint64_t *n_steps, uint64_t *n_written)
+{
+    uint64_t rays = 0, steps = 0, written = 0;
+    for (int v = 0; v < height; ++v) {
+        for (int u = 0; u < width; ++u) {
+            float d = fabsf(prev[(int64_t)v * width + u] - curr[(int64_t)v * width + u]);   /* :250 */
+            if (!(d > threshold)) continue;                        /* :252, :496 */
+            float pix_val = d;                                     /* :500 */
+            if (pix_val < 1e-3f) continue;                         /* :501 */
+            float dir[3];
+            pvpo_pixel_ray(u, v, width, height, focal_len, R, dir);   /* :506-515 */
+            struct o_att_ctx a;
+            a.acc.grid_f32 = accum_mode == 0 ? (float *)grid : NULL;
+            a.acc.grid_i64 = accum_mode == 0 ? NULL : (int64_t *)grid;
+            a.acc.N = N; a.acc.slab_lo = slab_lo; a.acc.slab_hi = slab_hi;
+            a.acc.val = 0.f; a.acc.qval = 0; a.acc.written = 0;
+            a.pix_val = pix_val; a.alpha = alpha; a.accum_mode = accum_mode; a.frac_bits = frac_bits;
+            steps += (uint64_t)o_cast_ray(cam, dir, N, voxel_size, center, o_emit_acc_att, &a);
+            written += (uint64_t)a.acc.written;
             rays++;
         }
     }

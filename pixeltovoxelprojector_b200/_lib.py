@@ -24,7 +24,8 @@ class PvpError(RuntimeError):
 
 class GridDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("voxel_size", C.c_float), ("center", C.c_float * 3), ("accum_mode", C.c_int32),
-                ("frac_bits", C.c_int32), ("slab_lo", C.c_int32), ("slab_hi", C.c_int32)]
+                ("frac_bits", C.c_int32), ("slab_lo", C.c_int32), ("slab_hi", C.c_int32),
+                ("attenuation_alpha", C.c_float)]
 
 
 class Pair(C.Structure):

@@ -25,6 +25,7 @@ struct GridP {
     float gmax[3];
     float fixed_scale;  // 2^frac_bits
     int frac_shift;     // frac_bits (0 for float32 grids)
+    float alpha;        // opt-in distance attenuation (0 = off, the reference's behaviour)
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -153,6 +154,12 @@ __device__ __forceinline__ float motion_diff(float a, float b) { return fabsf(fs
 
 // The two filters between a pixel and a ray: changed (:252, :496) and pix_val >= 1e-3 (:501).
 __device__ __forceinline__ bool motion_casts_ray(float d, float threshold) { return (d > threshold) && !(d < 1e-3f); }
+
+// The factor the reference computes and discards (ray_voxel.cpp:524-526), applied only when alpha > 0.
+__device__ __forceinline__ float attenuate(float pix_val, float alpha, float dist)
+{
+    return fmul(pix_val, fdiv(1.f, fadd(1.f, fmul(alpha, dist))));
+}
 
 // Fixed-point quantisation: rint(val * 2^frac_bits), nearest-even.
 __device__ __forceinline__ long long quantize_fixed(float val, float scale) { return __float2ll_rn(fmul(val, scale)); }

@@ -247,7 +247,8 @@ dda_accumulate_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, type
                 while (r.t_cur <= r.t_end) {
                     ++my_steps;
                     if (r.ix >= g.slab_lo && r.ix < g.slab_hi) {
-                        A::add(grid + ((long long)(r.ix - g.slab_lo) * sx_stride + (long long)r.iy * N + r.iz), val);
+                        A::add(grid + ((long long)(r.ix - g.slab_lo) * sx_stride + (long long)r.iy * N + r.iz),
+                               g.alpha > 0.f ? A::make(attenuate(diff, g.alpha, r.t_cur), g) : val);
                         ++my_written;
                     }
                     if (!ray_advance(r, N)) break;
@@ -679,6 +680,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
 // order and the counters are those of variant 4 (same bit-exact visited sets).
 struct RayS {
     float t_end, tmx, tmy, tmz, tdx, tdy, tdz, remx, remy, remz, rem0;
+    float t_cur;  // RayStep::distance of the current voxel (only read by the attenuating kernels)
     unsigned idx;
     int dix, diy, diz;
 };
@@ -686,16 +688,17 @@ struct RayS {
 __device__ __forceinline__ void rays_park(RayS &r)
 {
     r.t_end = CUDART_INF_F; r.tmx = r.tmy = r.tmz = 0.f; r.tdx = r.tdy = r.tdz = 0.f;
-    r.remx = r.remy = r.remz = REM_PARKED; r.rem0 = 0.f;
+    r.remx = r.remy = r.remz = REM_PARKED; r.rem0 = 0.f; r.t_cur = 0.f;
     r.idx = KEY_NONE; r.dix = r.diy = r.diz = 0;
 }
 
 // queue entry -> walking state; returns the value to accumulate (0 when the ray casts no step)
 template <typename V>
 __device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, unsigned long long i, unsigned long long count,
-                                                    const pvp_pair *__restrict__ pairs, const GridP &g, int width, int height)
+                                                    const pvp_pair *__restrict__ pairs, const GridP &g, int width, int height, float &raw_diff)
 {
     rays_park(s);
+    raw_diff = 0.f;
     if (i >= count) return 0;
     const uint32_t pix = __ldg(q.pix + i);
     const float diff = __ldg(q.diff + i);
@@ -706,7 +709,8 @@ __device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, uns
     Ray r;
     if (!(ray_setup(__ldg(&P->cam[0]), __ldg(&P->cam[1]), __ldg(&P->cam[2]), dx, dy, dz, g, r) && r.t_cur <= r.t_end)) return 0;
     const int N = g.n;
-    s.t_end = r.t_end;
+    s.t_end = r.t_end; s.t_cur = r.t_cur;
+    raw_diff = diff;
     s.tmx = r.tmx; s.tmy = r.tmy; s.tmz = r.tmz; s.tdx = r.tdx; s.tdy = r.tdy; s.tdz = r.tdz;
     s.idx = (unsigned)((r.ix - g.slab_lo) * N + r.iy) * (unsigned)N + (unsigned)r.iz;
     s.dix = r.sx * N * N; s.diy = r.sy * N; s.diz = r.sz;
@@ -728,10 +732,11 @@ __device__ __forceinline__ bool rays_step(RayS &s)
     if (cy) { s.tmy = fadd(s.tmy, s.tdy); s.remy -= 1.f; }
     if (cz) { s.tmz = fadd(s.tmz, s.tdz); s.remz -= 1.f; }
     s.idx += (unsigned)(cz ? s.diz : (cy ? s.diy : s.dix));
+    s.t_cur = m;  // :376-386 (dead in the kernels that do not attenuate)
     return (fmin3(s.remx, s.remy, s.remz) >= 0.f) && (m <= s.t_end);
 }
 
-template <int MODE, bool SLAB, bool NARROW, int MINB>
+template <int MODE, bool SLAB, bool NARROW, int MINB, bool ATT = false>
 __global__ void __launch_bounds__(LEAN_THREADS, MINB)
 dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
                             int width, int height, Ctl *__restrict__ ctl, unsigned long long count_lo, unsigned long long count_hi)
@@ -751,8 +756,9 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
         base = __shfl_sync(FULL, base, 0);
         if (base >= count) break;
         RayS a, b;
-        T va = rays_setup<V>(a, q, base + 2 * lane, count, pairs, g, width, height);
-        T vb = rays_setup<V>(b, q, base + 2 * lane + 1, count, pairs, g, width, height);
+        float da, db;  // the rays' pix_val (ray_voxel.cpp:500); the attenuating kernel derives every step's value from it
+        T va = rays_setup<V>(a, q, base + 2 * lane, count, pairs, g, width, height, da);
+        T vb = rays_setup<V>(b, q, base + 2 * lane + 1, count, pairs, g, width, height, db);
         float n_issued = 0.f, n_inslab = 0.f;
         if (__all_sync(FULL, a.remx == REM_PARKED && b.remx == REM_PARKED)) continue;
 
@@ -760,6 +766,10 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
         for (;;) {
             // ---- one DDA step of both rays first: the shuffle of A's new key overlaps the scan below ----------------
             unsigned ka = a.idx, kb = b.idx;
+            if (ATT) {  // value of THIS voxel step: pix_val / (1 + alpha * distance), before the step moves t_cur on
+                va = V::make(attenuate(da, g.alpha, a.t_cur), g);
+                vb = V::make(attenuate(db, g.alpha, b.t_cur), g);
+            }
             const bool still_a = rays_step(a), still_b = rays_step(b);
             T sa = va, sb = vb;
             if (SLAB) {  // writes outside the slab are suppressed; parked rays (KEY_NONE) are outside every slab
@@ -788,11 +798,11 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
             if (__any_sync(FULL, !(still_a && still_b))) {
                 if (!still_a && a.remx != REM_PARKED) {
                     my_steps += (unsigned long long)(unsigned)(int)(a.rem0 - (a.remx + a.remy + a.remz));
-                    rays_park(a); va = 0;
+                    rays_park(a); va = 0; da = 0.f;
                 }
                 if (!still_b && b.remx != REM_PARKED) {
                     my_steps += (unsigned long long)(unsigned)(int)(b.rem0 - (b.remx + b.remy + b.remz));
-                    rays_park(b); vb = 0;
+                    rays_park(b); vb = 0; db = 0.f;
                 }
                 if (__all_sync(FULL, a.remx == REM_PARKED && b.remx == REM_PARKED)) break;
                 heads = __ballot_sync(FULL, run_head(SLAB ? (a.idx < slab_cells ? a.idx : KEY_NONE) : a.idx));
@@ -887,6 +897,8 @@ static int make_gridp(const pvp_grid_desc *d, GridP *g)
     }
     g->fixed_scale = (float)((long long)1 << (d->accum_mode == PVP_ACCUM_FIXED ? d->frac_bits : 0));
     g->frac_shift = d->accum_mode == PVP_ACCUM_FIXED ? d->frac_bits : 0;
+    PVP_REQUIRE(d->attenuation_alpha >= 0.f && d->attenuation_alpha < 1e30f, "attenuation_alpha must be finite and >= 0");
+    g->alpha = d->attenuation_alpha;
     return PVP_OK;
 }
 
@@ -955,6 +967,12 @@ template <int MODE, bool SLAB, bool NARROW>
 static void launch_lean2(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height, unsigned long long count_lo = 0,
                          unsigned long long count_hi = ~0ull)
 {
+    if (g.alpha > 0.f) {  // opt-in distance attenuation: values change every step, so no integral shortcut (NARROW is false here)
+        auto ka = dda_accumulate_lean2_kernel<MODE, SLAB, false, 3, true>;
+        ka<<<k2_grid_size(ctx, (const void *)ka, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
+                                                                                                 width, height, ctx->ctl_dev, count_lo, count_hi);
+        return;
+    }
     // lean_regs: 0/80 -> 3 resident CTAs (24 warps; measured best: 670 G voxel-steps/s at 512^3), 128 -> 2 CTAs (622 G), 64 -> 4 CTAs
     auto k = ctx->opt_lean_regs == 128 ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 2>
            : ctx->opt_lean_regs == 64  ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 4> : dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 3>;
@@ -987,7 +1005,7 @@ constexpr unsigned long long LEAN2_MIN_RAYS_PER_WARP = 256;
 // dda_variant: 0 = auto (lean2 / lean by ray count where their 32-bit voxel keys allow, else 3), 1 = segmented-scan aggregation (round-1
 // baseline), 2 = match.any aggregation, 3 = one RED per lane and step (no aggregation, any grid size),
 // 4 = lean lock-step kernel (one ray per lane), 5 = lean2 (two rays per lane, K1 in row-pair order).  narrow_ok: uint8 frames, i.e. integer addends (LeanVal<FIXED, true>).
-static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_ok, bool lean_ok, void *grid_dev, int width, int height)
+static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_ok, bool lean_ok, void *grid_dev, int width, int height)  // NOLINT
 {
     LaunchScope scope(ctx, 2);
     int variant = effective_variant(ctx);
@@ -999,6 +1017,7 @@ static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_o
     if (lockstep && (slab ? full > (1ull << 31) : full >= 0xffffffffull)) variant = 3;  // slab test relies on wrapped offsets
     if (lockstep && !lean_ok) variant = 3;
     const bool f32 = accum_mode == PVP_ACCUM_F32;
+    if (g.alpha > 0.f && variant != 3) { variant = 5; narrow_ok = false; }  // only lean2 and variant 3 implement the attenuation
     if (variant == 0) {
         ++ctx->prof.launches_k2;  // two kernels are launched (the scope above counted one); the one not chosen exits at once
         const unsigned long long T = (unsigned long long)ctx->sm_count * 3 * (LEAN_THREADS / 32) * LEAN2_MIN_RAYS_PER_WARP;

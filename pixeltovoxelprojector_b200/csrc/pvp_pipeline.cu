@@ -226,6 +226,7 @@ void pvp_run_options_default(pvp_run_options *o)
     o->grid.accum_mode = PVP_ACCUM_F32;
     o->grid.frac_bits = 16;
     o->grid.slab_lo = 0; o->grid.slab_hi = 500;
+    o->grid.attenuation_alpha = 0.f;  // ray_voxel.cpp:526 multiplies by 1.f (alpha = 0.1 of :448 is dead in the reference)
     o->threshold = 2.0f;             // :447
     o->shard_rank = 0; o->shard_count = 1;
     o->chunk_frames = 0;
@@ -563,7 +564,7 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
 // The CLI of ray_voxel.cpp:400-558: `ray_voxel <metadata.json> <image_folder> <output_voxel_bin>`
 // with the reference's constants as defaults and its messages / exit codes, plus optional flags
 // after the three positionals:
-//   --n N --voxel-size S --center X Y Z --threshold T --fixed-point [BITS] --device D --decode-threads T --loader-noise SEED --quiet --stats
+//   --n N --voxel-size S --center X Y Z --threshold T --fixed-point [BITS] --device D --decode-threads T --loader-noise SEED --attenuation ALPHA --quiet --stats
 int pvp_ray_voxel_main(int argc, char **argv)
 {
     if (argc < 4) {
@@ -582,6 +583,7 @@ int pvp_ray_voxel_main(int argc, char **argv)
         else if (!strcmp(argv[i], "--fixed-point")) { opt.grid.accum_mode = PVP_ACCUM_FIXED; if (need(1) && argv[i + 1][0] != '-') opt.grid.frac_bits = atoi(argv[++i]); }
         else if (!strcmp(argv[i], "--device") && need(1)) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--decode-threads") && need(1)) opt.decode_threads = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--attenuation") && need(1)) opt.grid.attenuation_alpha = strtof(argv[++i], nullptr);
         else if (!strcmp(argv[i], "--loader-noise") && need(1)) { opt.loader_noise = 1; opt.noise_seed = (uint32_t)strtoul(argv[++i], nullptr, 10); }
         else if (!strcmp(argv[i], "--quiet")) opt.verbose = 0;
         else if (!strcmp(argv[i], "--stats")) want_stats = 1;

@@ -149,11 +149,12 @@ class VoxelGrid:
 
     def __init__(self, n: int = 500, voxel_size: float = 6.0, center: Sequence[float] = (0.0, 0.0, 500.0), accum: str = "f32",
                  frac_bits: int = 16, slab: tuple[int, int] | None = None, device: torch.device | str | int | None = None,
-                 data: torch.Tensor | None = None):
+                 data: torch.Tensor | None = None, attenuation_alpha: float = 0.0):
         if accum not in ("f32", "fixed"):
             raise ValueError("accum must be 'f32' or 'fixed'")
         self.n, self.voxel_size, self.center = int(n), float(voxel_size), tuple(float(c) for c in center)
         self.accum, self.frac_bits = accum, int(frac_bits)
+        self.attenuation_alpha = float(attenuation_alpha)   # 0 = reference behaviour (ray_voxel.cpp:526 discards the factor)
         self.slab = (0, self.n) if slab is None else (int(slab[0]), int(slab[1]))
         if not (0 <= self.slab[0] <= self.slab[1] <= self.n):
             raise ValueError(f"bad slab {self.slab} for n={self.n}")
@@ -173,6 +174,7 @@ class VoxelGrid:
         d.center[:] = self.center
         d.accum_mode = ACCUM_F32 if self.accum == "f32" else ACCUM_FIXED
         d.frac_bits, d.slab_lo, d.slab_hi = self.frac_bits, self.slab[0], self.slab[1]
+        d.attenuation_alpha = self.attenuation_alpha
         return d
 
     def zero_(self) -> "VoxelGrid":

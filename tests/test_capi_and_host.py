@@ -36,13 +36,14 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header_sizes():
-    assert C.sizeof(_lib.Pair) == 60 and C.sizeof(_lib.GridDesc) == 36 and C.sizeof(_lib.Stats) == 32
+    assert C.sizeof(_lib.Pair) == 60 and C.sizeof(_lib.GridDesc) == 40 and C.sizeof(_lib.Stats) == 32
     assert C.sizeof(_lib.FrameInfo) == 4 * 10 + 512
     opt = _lib.RunOptions()
     _lib.load().pvp_run_options_default(C.byref(opt))
     # the hard-coded constants of ray_voxel.cpp:434-447
     assert (opt.grid.n, opt.grid.voxel_size, tuple(opt.grid.center), opt.threshold) == (500, 6.0, (0.0, 0.0, 500.0), 2.0)
     assert (opt.grid.slab_lo, opt.grid.slab_hi, opt.shard_rank, opt.shard_count) == (0, 500, 0, 1)
+    assert opt.grid.attenuation_alpha == 0.0 and opt.loader_noise == 0      # reference behaviour by default (:526, no seeded noise)
 
 
 def test_no_gpu_fails_loudly():

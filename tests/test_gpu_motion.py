@@ -387,3 +387,54 @@ def _geometry_sweep(ctx, oracle, rng):
             assert (ss["n_rays"], ss["n_steps"]) == (tot[0], tot[1]) and np.array_equal(s.data.cpu().numpy(), want[lo:hi]), (trial, accum, lo, hi)
         total_steps += tot[1]
     return total_steps
+
+
+def test_opt_in_distance_attenuation(ctx, oracle):
+    """attenuation_alpha > 0 applies the factor the reference computes and discards (ray_voxel.cpp:524-526),
+    val = pix_val / (1 + alpha * distance) per voxel step.  Opt-in extension: checked against the oracle's restatement of those
+    lines with the factor applied (fixed point: bit for bit -- every addend is quantised from the same IEEE fp32 product;
+    float32: same support, rtol 1e-5); alpha = 0 stays the reference's behaviour bit for bit."""
+    rng = np.random.default_rng(88)
+    F, H, W, N, vs, center = 4, 33, 52, 40, 5.0, (0.0, 0.0, 500.0)
+    frames, poses = _scene(rng, F, H, W, N, vs, center, True)
+    pairs, _ = pvp.make_pairs(poses, W)
+    alpha = 0.1
+
+    def oracle_att(mode, slab=None):
+        lo, hi = (0, N) if slab is None else slab
+        grid = np.zeros((hi - lo, N, N), np.float32 if mode == 0 else np.int64)
+        tot = np.zeros(3, np.int64)
+        for c in range(1, F):
+            R = oracle.rotation_matrix(poses[c].yaw, poses[c].pitch, poses[c].roll)
+            f = oracle.focal_length(poses[c].fov_degrees, W)
+            tot += oracle.accumulate_pair(frames[c - 1], frames[c], np.array(poses[c].camera_position, np.float32), R, f, grid, N, vs,
+                                          np.array(center, np.float32), 2.0, accum_mode=mode, frac_bits=14, slab=slab, attenuation_alpha=alpha)
+        return grid, tot
+
+    plain, _ = _oracle_run(oracle, frames, poses, N, vs, center, 2.0)
+    for variant in (0, 3, 5):
+        ctx.set_option("dda_variant", variant)
+        try:
+            want_fx, tot = oracle_att(1)
+            g = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=14, attenuation_alpha=alpha)
+            st = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, g, 2.0)
+            assert (st["n_rays"], st["n_steps"], st["n_written"]) == tuple(tot)
+            assert np.array_equal(g.data.cpu().numpy(), want_fx), variant
+            want_f, _ = oracle_att(0)
+            gf = pvp.VoxelGrid(N, vs, center, attenuation_alpha=alpha)
+            pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, gf, 2.0)
+            got = gf.data.cpu().numpy()
+            assert np.array_equal(got != 0, want_f != 0)
+            np.testing.assert_allclose(got, want_f, rtol=RTOL_F32_ATOMICS, atol=0)
+            assert (got < plain).any() and (got <= plain + 1e-3).all()      # the factor is < 1 for distance > 0
+            want_s, _ = oracle_att(1, slab=(7, 29))
+            gs = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=14, slab=(7, 29), attenuation_alpha=alpha)
+            pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, gs, 2.0)
+            assert np.array_equal(gs.data.cpu().numpy(), want_s), variant
+            g0 = pvp.VoxelGrid(N, vs, center, attenuation_alpha=0.0)
+            pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, g0, 2.0)
+            assert np.array_equal(bits(g0.data.cpu().numpy()), bits(plain))
+        finally:
+            ctx.set_option("dda_variant", 0)
+    with pytest.raises(pvp.PvpError, match="attenuation_alpha"):
+        pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, pvp.VoxelGrid(N, vs, center, attenuation_alpha=-1.0), 2.0)
