@@ -116,6 +116,7 @@ using namespace pvp;
 extern "C" int pvp_grid_reduce_peers(pvp_ctx *ctx, void *const *peers, int world, int rank, int dst_rank, void *multicast, int64_t n_cells,
                                      int accum_mode)
 {
+    const bool pull_mode = ctx && ctx->opt_reduce_pull != 0;
     PVP_REQUIRE(ctx && peers, "pvp_grid_reduce_peers: NULL argument");
     PVP_REQUIRE(world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world && dst_rank < world, "pvp_grid_reduce_peers: bad rank/world (%d/%d -> %d)",
                 rank, world, dst_rank);
@@ -130,7 +131,14 @@ extern "C" int pvp_grid_reduce_peers(pvp_ctx *ctx, void *const *peers, int world
     }
     if (world == 1 || n_cells == 0) return PVP_OK;
     DeviceGuard guard(ctx->device);
-    auto slice = [&](long long n, long long *lo, long long *hi) { *lo = n * rank / world; *hi = n * (rank + 1) / world; };
+    // Slice of this rank.  With the multicast address and ONE destination the destination pulls the whole grid through the
+    // switch by itself (slice = everything on dst_rank, nothing elsewhere): the reduced cells cross NVLink once, into the
+    // rank that wants them, instead of once into the reducing rank and once more into the destination.
+    const bool dst_pulls = multicast != nullptr && dst_rank >= 0 && pull_mode;
+    auto slice = [&](long long n, long long *lo, long long *hi) {
+        if (dst_pulls) { *lo = 0; *hi = rank == dst_rank ? n : 0; }
+        else { *lo = n * rank / world; *hi = n * (rank + 1) / world; }
+    };
     long long lo, hi;
     if (accum_mode == PVP_ACCUM_F32) {
         if (aligned16 && n_cells % 4 == 0) {

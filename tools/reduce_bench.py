@@ -36,7 +36,9 @@ def main():
     res = {
         "nccl reduce -> rank 0": timed(lambda: dist.reduce(plain, dst=0)),
         "nccl all_reduce": timed(lambda: dist.all_reduce(plain)),
-        "peers multicast -> rank 0": timed(lambda: pd.reduce_grid_peers(g, dst=0, ctx=ctx, multicast=True)),
+        "peers multicast -> rank 0 (every rank reduces a slice)": timed(lambda: pd.reduce_grid_peers(g, dst=0, ctx=ctx, multicast=True)),
+        "peers multicast -> rank 0 (rank 0 pulls everything)": (ctx.set_option("reduce_pull", 1), timed(lambda: pd.reduce_grid_peers(g, dst=0, ctx=ctx, multicast=True)),
+                                                                 ctx.set_option("reduce_pull", 0))[1],
         "peers multicast -> all": timed(lambda: pd.reduce_grid_peers(g, dst=None, ctx=ctx, multicast=True)),
         "peers plain loads -> rank 0": timed(lambda: pd.reduce_grid_peers(g, dst=0, ctx=ctx, multicast=False)),
         "two symmetric-memory barriers alone": timed(lambda: (g.symm.barrier(channel=0), g.symm.barrier(channel=1))),
