@@ -330,7 +330,8 @@ def run_ours_image(args, wl):
                 from pixeltovoxelprojector_b200._lib import check
                 ptrs = (C.c_void_p * world)(*[int(p) for p in symm.buffer_ptrs])
                 symm.barrier(channel=0)
-                check(ctx._lib.pvp_grid_reduce_peers(ctx.handle, ptrs, world, rank, 0, int(symm.multicast_ptr) or None, grid.numel(), 1))
+                mc = int(symm.multicast_ptr) if (symm.multicast_ptr and world > 2) else None
+                check(ctx._lib.pvp_grid_reduce_peers(ctx.handle, ptrs, world, rank, 0 if world == 2 else -1, mc, grid.numel(), 1))
                 symm.barrier(channel=1)
             else:
                 dist.reduce(grid, dst=0)
@@ -433,7 +434,7 @@ def run_ours(args, wl):
         if args.reduce == "peers":
             try:   # private grid in NVLink symmetric memory: the merge is our own kernel (multimem.ld_reduce over NVSwitch)
                 grid = pd.symmetric_grid(wl["N"], wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev)
-                reduce_how = "pvp_grid_reduce_peers (own kernel, %s)" % ("NVSwitch multicast ld_reduce" if (grid.symm.multicast_ptr and world > 2) else "NVLink peer loads")
+                reduce_how = "pvp_grid_reduce_peers (own kernel, %s)" % ("NVSwitch multicast ld_reduce + multicast store, sum on every rank" if (grid.symm.multicast_ptr and world > 2) else "NVLink peer loads into rank 0")
             except Exception as e:
                 print(f"bench.py: symmetric memory unavailable ({e!r}); using the NCCL reduce", file=sys.stderr)
         if grid is None:
@@ -490,7 +491,7 @@ def run_ours(args, wl):
         ev[-1][0].record()
         if world > 1:                        # the run's single grid merge over NVLink (SURVEY 8e mode 1)
             if getattr(grid, "symm", None) is not None:
-                pd.reduce_grid_peers(grid, dst=0, ctx=ctx)
+                pd.reduce_grid_peers(grid, dst=0 if world == 2 else None, ctx=ctx)   # see distributed.ray_voxel_distributed
             else:
                 dist.reduce(grid.data, dst=0)
         ev[-1][1].record()

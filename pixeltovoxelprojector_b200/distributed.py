@@ -138,7 +138,9 @@ def ray_voxel_distributed(metadata_json: str, image_folder: str, output_bin: str
             grid = motion.VoxelGrid(n, voxel_size, center, accum=accum, frac_bits=frac_bits, device=dev)
         rep = motion.ray_voxel_accumulate(metadata_json, image_folder, grid, threshold, shard=(rank, world))
         if getattr(grid, "symm", None) is not None:
-            reduce_grid_peers(grid, dst=0)
+            # measured (tools/reduce_bench.py, 512 MiB): to every rank through multicast ld_reduce + multicast store is faster
+            # than to one rank from 4 GPUs up (8 GPUs: 1.22 ms vs 1.39 ms); with 2 GPUs plain peer loads into rank 0 win
+            reduce_grid_peers(grid, dst=0 if world == 2 else None)
         else:
             reduce_grid(grid.data, dst=0, group=group)
         if rank == 0 and output_bin:
