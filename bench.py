@@ -52,14 +52,16 @@ def measured_traffic(workload):
 ALGO_BYTES_PER_STEP = {"f32": 8, "fixed": 16}   # one atomic RMW: 4 B read + 4 B write (fp32), 8 + 8 (int64) -- SURVEY 8d
 
 
-def make_inputs(wl, seed):
+def make_inputs(wl, seed, pose_seed=1001):
+    """Frames differ per rank (seed); the pose table is the same on every rank, so that the per-GPU work of the weak-scaling
+    run is the same everywhere (ray lengths depend on the pose, not on the pixel values)."""
     from pixeltovoxelprojector_b200 import synth
     F = wl["pool"]
     if wl["motion"] == "dense":
         frames = synth.dense_frames(F, wl["H"], wl["W"], seed=seed)
     else:
         frames = synth.sparse_frames(F, wl["H"], wl["W"], seed=seed, blobs=6)
-    poses = synth.orbit_poses(F, wl["N"], wl["voxel_size"], wl["center"], seed=seed + 1)
+    poses = synth.orbit_poses(F, wl["N"], wl["voxel_size"], wl["center"], seed=pose_seed)
     return frames, poses
 
 
@@ -399,7 +401,7 @@ def run_ours_image(args, wl):
 
 def workload_config(args, wl):
     return {"workload": args.workload, "k2_variant": getattr(args, "variant", 0), "frame": f"{wl['W']}x{wl['H']} uint8", "grid": f"{wl['N']}^3 {wl['accum']}", "voxel_size": wl["voxel_size"],
-            "pairs_per_step": wl["pairs_per_step"], "motion": wl["motion"], "camera": "pose changes every frame (orbit inside the grid)",
+            "pairs_per_step": wl["pairs_per_step"], "motion": wl["motion"], "camera": "pose changes every frame (orbit inside the grid); N>1: same pose table, different frames on every rank",
             "parallelism": f"frames sharded over {args.gpus} GPU(s), private grids, one grid merge per run inside the timed region: {getattr(args, 'reduce_how', 'NCCL reduce')}" if args.gpus > 1 else "1 GPU",
             "l2": "256 MiB buffer written between timed steps (L2 flush); frame pool 149 MB and grid > L2" if wl["N"] >= 512 else
                   "256 MiB buffer written between timed steps (L2 flush)"}
