@@ -201,6 +201,7 @@ process_image_kernel(const double *__restrict__ image, typename Cell<MODE>::T *_
 // is the reference's bit for bit.  FMA appears only inside this division, never in the reference's own expressions.
 struct ImageFastP {
     double b[3], y[3], nd[3];  // extent, RN(1/extent), (double)n
+    double k20[3];             // RN(n / extent) * 2^20: the screening factor of voxel_index()
     int n1[3];                 // n - 1
     unsigned gs[3];            // element strides
 };
@@ -214,27 +215,43 @@ __device__ __forceinline__ double div_by_extent(double a, double b, double y)
     return __fma_rn(r, y, q);
 }
 
+// Voxel index of a coordinate offset a in [0, b] along axis k: min(trunc(RN(RN(a / b) * n)), n - 1), process_image.cpp:94-104.
+// Screening: s = a * K with K = RN(n/b) * 2^20 approximates (a*n/b) * 2^20 to a relative 2.3e-16, as does the reference's own value;
+// for n <= 2^24 both lie within 4e-9 of the real number a*n/b.  When the 20 fraction bits of s are not within 4 units (3.8e-6) of an
+// integer, trunc(s / 2^20) therefore IS the reference's index -- one DMUL and a conversion instead of the five-operation exact
+// division; otherwise (about 8 samples in a million, or a ray that runs exactly along voxel faces) the exact sequence decides.
+__device__ __forceinline__ int voxel_index(double a, const ImageFastP &f, int k)
+{
+    const long long t = __double2ll_rz(dmul(a, f.k20[k]));
+    int idx = (int)(t >> 20);
+    const unsigned fr = (unsigned)t & 0xFFFFFu;
+    if (fr < 4u || fr > 0xFFFFBu) idx = __double2int_rz(dmul(div_by_extent(a, f.b[k], f.y[k]), f.nd[k]));
+    return min(idx, f.n1[k]);
+}
+
 // Self-test of div_by_extent against the IEEE division it replaces (pvp_selftest_div_by_extent): numerators are drawn
 // where the march draws them -- uniformly in [0, b], and within a few ulps of every k*b/n boundary.  The quotient must be
 // bit-identical for a >= 2^-960 (below that the exact remainder underflows and the quotient, < 2^-460, can only select
 // voxel 0); the voxel index must be identical always.
-__device__ __forceinline__ bool div_differs(double a, double b, double y, double nd, int n1)
+__device__ __forceinline__ bool div_differs(double a, double b, double y, double nd, int n1, const ImageFastP &f)
 {
     const double q1 = div_by_extent(a, b, y), q2 = ddiv(a, b);
-    const bool idx_differs = min(__double2int_rz(dmul(q1, nd)), n1) != min(__double2int_rz(dmul(q2, nd)), n1);
+    const int want = min(__double2int_rz(dmul(q2, nd)), n1);
+    const bool idx_differs = min(__double2int_rz(dmul(q1, nd)), n1) != want || voxel_index(a, f, 0) != want;
     return idx_differs || (a >= 0x1p-960 && __double_as_longlong(q1) != __double_as_longlong(q2));
 }
 
-__global__ void div_selftest_kernel(double b, double y, long long n_random, int n_grid, unsigned long long seed,
+__global__ void div_selftest_kernel(ImageFastP f, long long n_random, int n_grid, unsigned long long seed,
                                     unsigned long long *__restrict__ mismatches)
 {
+    const double b = f.b[0], y = f.y[0];
     unsigned long long bad = 0;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
     for (long long i = tid; i < n_random; i += nth) {
         unsigned long long x = (unsigned long long)i * 0x9e3779b97f4a7c15ull + seed;
         x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
         const double a = dmul((double)(x >> 11) * 0x1p-53, b);
-        bad += div_differs(a, b, y, (double)n_grid, n_grid - 1);
+        bad += div_differs(a, b, y, (double)n_grid, n_grid - 1, f);
     }
     for (long long i = tid; i < (long long)(n_grid + 1) * 129; i += nth) {
         const long long k = i / 129;
@@ -242,7 +259,7 @@ __global__ void div_selftest_kernel(double b, double y, long long n_random, int 
         double a = dmul(ddiv((double)k, (double)n_grid), b);
         a = __longlong_as_double(__double_as_longlong(a) + d);  // +-64 ulps around the boundary
         if (!(a >= 0.0 && a <= b)) continue;
-        bad += div_differs(a, b, y, (double)n_grid, n_grid - 1);
+        bad += div_differs(a, b, y, (double)n_grid, n_grid - 1, f);
     }
     if (bad) atomicAdd(mismatches, bad);
 }
@@ -278,9 +295,9 @@ __device__ __forceinline__ unsigned sample_key(const ImageP &p, const ImageFastP
     const double d = dmul((double)s, p.step_size);  // :344
     const double qx = dadd(p.o[0], dmul(d, w0)), qy = dadd(p.o[1], dmul(d, w1)), qz = dadd(p.o[2], dmul(d, w2));
     // inside the extent the scaled coordinate lies in [0, n]: int truncation + upper clamp == :94-104
-    const int xi = min(__double2int_rz(dmul(div_by_extent(dsub(qx, p.ext[0]), f.b[0], f.y[0]), f.nd[0])), f.n1[0]);
-    const int yi = min(__double2int_rz(dmul(div_by_extent(dsub(qy, p.ext[2]), f.b[1], f.y[1]), f.nd[1])), f.n1[1]);
-    const int zi = min(__double2int_rz(dmul(div_by_extent(dsub(qz, p.ext[4]), f.b[2], f.y[2]), f.nd[2])), f.n1[2]);
+    const int xi = voxel_index(dsub(qx, p.ext[0]), f, 0);
+    const int yi = voxel_index(dsub(qy, p.ext[2]), f, 1);
+    const int zi = voxel_index(dsub(qz, p.ext[4]), f, 2);
     const unsigned off = (unsigned)xi * f.gs[0] + (unsigned)yi * f.gs[1] + (unsigned)zi * f.gs[2];
     // in = lo <= s <= hi and the inclusive bounds test of :85 -- one chained predicate (the compiler's own form is a
     // chain of eight selects), then key = in ? off : IMG_NONE
@@ -549,11 +566,13 @@ static bool make_fastp(const ImageP &p, ImageFastP *f)
         if (!(b > 0.0) || !std::isfinite(b) || e < -500 || e > 500) return false;
         if (m == 1.0 - 0x1p-53) return false;  // significand all ones: the one case Markstein's theorem excludes
         if (!(fabs(p.ext[2 * k]) < 0x1p500 && fabs(p.ext[2 * k + 1]) < 0x1p500)) return false;
-        if (p.gn[k] < 1 || p.gn[k] > (1ll << 30) || p.gs[k] < 0 || p.gs[k] > 0xffffffffll) return false;
+        if (p.gn[k] < 1 || p.gn[k] > (1ll << 24) || p.gs[k] < 0 || p.gs[k] > 0xffffffffll) return false;  // 2^24: voxel_index()
         f->b[k] = b;
         volatile double y = 1.0 / b;  // correctly rounded (IEEE division, x86-64 SSE2)
         f->y[k] = y;
         f->nd[k] = (double)p.gn[k];
+        volatile double kq = (double)p.gn[k] / b;  // RN(n / b); the scaling by 2^20 is exact
+        f->k20[k] = kq * 1048576.0;
         f->n1[k] = (int)(p.gn[k] - 1);
         f->gs[k] = (unsigned)p.gs[k];
         span += (unsigned long long)(p.gn[k] - 1) * (unsigned long long)p.gs[k];
@@ -666,7 +685,7 @@ int pvp_selftest_div_by_extent(pvp_ctx *ctx, double extent, int64_t n_random, in
     PVP_CUDA(cudaMalloc(&d_bad, sizeof(*d_bad)));
     cudaMemsetAsync(d_bad, 0, sizeof(*d_bad), ctx->stream);
     ++ctx->prof.launches_other;
-    div_selftest_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(f.b[0], f.y[0], n_random, n_grid, seed, d_bad);
+    div_selftest_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(f, n_random, n_grid, seed, d_bad);
     cudaError_t e = cudaMemcpyAsync(mismatches, d_bad, sizeof(*d_bad), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_bad);
