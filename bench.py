@@ -35,6 +35,7 @@ WORKLOADS = {
     "4k_dense_512": dict(H=2160, W=3840, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=2, pool=20, motion="dense", accum="f32"),
     # BASELINE config[3] shape on ONE GPU: the whole 1024^3 grid (4 GiB; slab sharding itself is covered by tests/test_gpu_configs.py)
     "1080p_dense_1024": dict(H=1080, W=1920, N=1024, voxel_size=1.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=24, motion="dense", accum="f32"),
+    "1080p_dense_768": dict(H=1080, W=1920, N=768, voxel_size=4.0 / 3.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=24, motion="dense", accum="f32"),
     "1080p_dense_512_fixed": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=72, motion="dense", accum="fixed"),
     # BASELINE config[4]: process_image_cpp path (fp64 fixed-step march) on a 4096x4096 image into a 512^3 grid,
     # fixed-point deterministic accumulation; ~1 sample per voxel pitch

@@ -1002,6 +1002,23 @@ static int effective_variant(const pvp_ctx *ctx)
 }
 constexpr unsigned long long LEAN2_MIN_RAYS_PER_WARP = 256;
 
+// Bytes of one x-plane of the grid (n * n cells).  Neighbouring image columns land in neighbouring x-planes, i.e. this
+// far apart in memory; once a plane outgrows a 2 MiB page the RED misses of a wide, flat ray tile dominate K2 (measured at
+// 768^3 / 1024^3 float32 and 512^3 int64: profiles/r1_summary.md, "large grids").  The auto settings follow it:
+//   <= 1 MiB: lean2, queue tiles of 2 image rows     (1080p -> 512^3 float32: 665 G voxel-steps/s)
+//   <= 2 MiB: lean2, tiles of 4 rows                 (512^3 int64: 570 -> 626 G)
+//   >  2 MiB: lean (32 rays per warp), tiles of 8 rows = 4 x 8 pixel chunks   (1024^3 float32: 294 -> 576 G)
+static size_t plane_bytes(const GridP &g, int accum_mode)
+{
+    return (size_t)g.n * g.n * (accum_mode == PVP_ACCUM_F32 ? sizeof(float) : sizeof(unsigned long long));
+}
+constexpr size_t PLANE_SMALL = 1u << 20, PLANE_LARGE = 2u << 20;
+static int auto_row_group(const GridP &g, int accum_mode)
+{
+    const size_t pb = plane_bytes(g, accum_mode);
+    return pb <= PLANE_SMALL ? 2 : pb <= PLANE_LARGE ? 4 : 8;
+}
+
 // dda_variant: 0 = auto (lean2 / lean by ray count where their 32-bit voxel keys allow, else 3), 1 = segmented-scan aggregation (round-1
 // baseline), 2 = match.any aggregation, 3 = one RED per lane and step (no aggregation, any grid size),
 // 4 = lean lock-step kernel (one ray per lane), 5 = lean2 (two rays per lane, K1 in row-pair order).  narrow_ok: uint8 frames, i.e. integer addends (LeanVal<FIXED, true>).
@@ -1018,6 +1035,7 @@ static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_o
     if (lockstep && !lean_ok) variant = 3;
     const bool f32 = accum_mode == PVP_ACCUM_F32;
     if (g.alpha > 0.f && variant != 3) { variant = 5; narrow_ok = false; }  // only lean2 and variant 3 implement the attenuation
+    if (variant == 0 && plane_bytes(g, accum_mode) > PLANE_LARGE) variant = 4;
     if (variant == 0) {
         ++ctx->prof.launches_k2;  // two kernels are launched (the scope above counted one); the one not chosen exits at once
         const unsigned long long T = (unsigned long long)ctx->sm_count * 3 * (LEAN_THREADS / 32) * LEAN2_MIN_RAYS_PER_WARP;
@@ -1096,7 +1114,7 @@ static int run_batches(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, lo
         PVP_CUDA(cudaMemsetAsync(ctx->ctl_dev, 0, 2 * sizeof(unsigned long long), ctx->stream));  // count, head
         // queue order: tiles of R image rows (lean2 walks two vertically adjacent pixels per lane); 1 = plain row-major
         const int ev = effective_variant(ctx);
-        const int row_group = ctx->opt_k1_row_group > 0 ? (int)ctx->opt_k1_row_group : ((ev == 0 || ev >= 4) ? 2 : 1);
+        const int row_group = ctx->opt_k1_row_group > 0 ? (int)ctx->opt_k1_row_group : ev == 0 ? auto_row_group(g, accum_mode) : ev >= 4 ? 2 : 1;
         rc = frame_dtype == PVP_FRAME_U8 ? launch_k1<uint8_t>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group)
                                          : launch_k1<float>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group);
         if (rc) return rc;
