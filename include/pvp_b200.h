@@ -271,6 +271,10 @@ typedef struct pvp_image_args {
     int32_t perform_background_subtraction; /* :142 */
     int32_t accum_mode;
     int32_t frac_bits;
+    /* rows [row_begin, row_end) of the image are processed -- a row shard of a multi-GPU run (the pixel loop of
+     * process_image.cpp:232-235 restricted in i; pixel coordinates stay those of the whole image).  0, 0 = all rows;
+     * row_begin == row_end > 0 = an empty shard. */
+    int64_t row_begin, row_end;
 } pvp_image_args;
 
 typedef struct pvp_image_stats {

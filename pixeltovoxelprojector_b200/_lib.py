@@ -67,7 +67,8 @@ class ImageArgs(C.Structure):
                 ("tex_stride", C.c_int64 * 2), ("center_ra_rad", C.c_double), ("center_dec_rad", C.c_double),
                 ("angular_width_rad", C.c_double), ("angular_height_rad", C.c_double),
                 ("update_celestial_sphere", C.c_int32), ("perform_background_subtraction", C.c_int32),
-                ("accum_mode", C.c_int32), ("frac_bits", C.c_int32)]
+                ("accum_mode", C.c_int32), ("frac_bits", C.c_int32),
+                ("row_begin", C.c_int64), ("row_end", C.c_int64)]
 
 
 class Profile(C.Structure):

@@ -27,6 +27,7 @@ struct ImageP {
     double xa[3], ya[3], za[3];  // camera basis (:214-228)
     double focal, cx, cy;  // :186-190
     long long W, H, is0, is1;
+    long long row0, row1;  // rows [row0, row1) of the image are processed (a row shard of a multi-GPU run; the whole image by default)
     long long gn[3], gs[3];
     double ext[6];
     double max_distance, step_size;
@@ -153,8 +154,8 @@ process_image_kernel(const double *__restrict__ image, typename Cell<MODE>::T *_
 {
     using C = Cell<MODE>;
     unsigned long long my_rays = 0, my_samples = 0;
-    const long long n_px = p.W * p.H;
-    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < n_px; px += (long long)gridDim.x * blockDim.x) {
+    const long long px_end = p.W * p.row1;
+    for (long long px = p.W * p.row0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; px < px_end; px += (long long)gridDim.x * blockDim.x) {
         double w0, w1, w2;
         typename C::V val;
         int s_entry, s_exit;
@@ -396,7 +397,7 @@ process_image_lockstep2_kernel(const double *__restrict__ image, typename Cell<M
     const unsigned lane = threadIdx.x & 31;
     const ScanMasks lm = scan_masks(lane);
     // a warp's tile: 32 columns x 2 rows; lane l holds the two pixels of column l
-    const long long tiles_x = (p.W + 31) / 32, tiles_y = (p.H + 1) / 2;
+    const long long tiles_x = (p.W + 31) / 32, tiles_y = (p.row1 - p.row0 + 1) / 2;
     const unsigned long long n_groups = (unsigned long long)(tiles_x * tiles_y);
     unsigned long long my_rays = 0, my_samples = 0;
     for (;;) {
@@ -405,7 +406,7 @@ process_image_lockstep2_kernel(const double *__restrict__ image, typename Cell<M
         group = __shfl_sync(FULL, group, 0);
         if (group >= n_groups) break;
         const long long ty = (long long)(group / (unsigned long long)tiles_x), tx = (long long)group - ty * tiles_x;
-        const long long pj = tx * 32 + lane, pi = ty * 2;
+        const long long pj = tx * 32 + lane, pi = p.row0 + ty * 2;
         double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
         typename C::V val_a = 0, val_b = 0;
         int lo_a = INT32_MAX, hi_a = INT32_MIN, lo_b = INT32_MAX, hi_b = INT32_MIN;  // empty ranges
@@ -414,7 +415,7 @@ process_image_lockstep2_kernel(const double *__restrict__ image, typename Cell<M
             bool counted;
             if (pixel_setup<MODE>(image, tex, p, pi * p.W + pj, a0, a1, a2, val_a, s_entry, s_exit, counted) && s_entry <= s_exit) { lo_a = s_entry; hi_a = s_exit; }
             my_rays += counted;
-            if (pi + 1 < p.H) {
+            if (pi + 1 < p.row1) {
                 if (pixel_setup<MODE>(image, tex, p, (pi + 1) * p.W + pj, b0, b1, b2, val_b, s_entry, s_exit, counted) && s_entry <= s_exit) { lo_b = s_entry; hi_b = s_exit; }
                 my_rays += counted;
             }
@@ -456,7 +457,7 @@ process_image_lockstep_kernel(const double *__restrict__ image, typename Cell<MO
     constexpr int TILE_W = 32 / TILE_H;
     // a warp's 32 pixels form a compact tile of the image, TILE_H rows x 32/TILE_H columns, consecutive lanes being
     // vertical neighbours (the row-group order of K1): the rays of a tile diverge less than those of a 32 x 1 strip
-    const long long tiles_x = (p.W + TILE_W - 1) / TILE_W, tiles_y = (p.H + TILE_H - 1) / TILE_H;
+    const long long tiles_x = (p.W + TILE_W - 1) / TILE_W, tiles_y = (p.row1 - p.row0 + TILE_H - 1) / TILE_H;
     const unsigned long long n_groups = (unsigned long long)(tiles_x * tiles_y);
     unsigned long long my_rays = 0, my_samples = 0;
     for (;;) {
@@ -465,8 +466,8 @@ process_image_lockstep_kernel(const double *__restrict__ image, typename Cell<MO
         group = __shfl_sync(FULL, group, 0);
         if (group >= n_groups) break;
         const long long ty = (long long)(group / (unsigned long long)tiles_x), tx = (long long)group - ty * tiles_x;
-        const long long pi = ty * TILE_H + (lane % TILE_H), pj = tx * TILE_W + (lane / TILE_H);
-        const bool in_image = pi < p.H && pj < p.W;
+        const long long pi = p.row0 + ty * TILE_H + (lane % TILE_H), pj = tx * TILE_W + (lane / TILE_H);
+        const bool in_image = pi < p.row1 && pj < p.W;
         const long long px = pi * p.W + pj;
         double w0 = 0, w1 = 0, w2 = 0;
         typename C::V val = 0;
@@ -539,6 +540,9 @@ static int make_imagep(const pvp_image_args *a, ImageP *p)
     m1 = z[0] * x[1]; m2 = z[1] * x[0]; y[2] = m1 - m2;
     for (int k = 0; k < 3; ++k) { p->o[k] = a->earth_position[k]; p->xa[k] = x[k]; p->ya[k] = y[k]; p->za[k] = z[k]; }
     p->W = a->image_width; p->H = a->image_height; p->is0 = a->image_stride[0]; p->is1 = a->image_stride[1];
+    PVP_REQUIRE(a->row_begin >= 0 && a->row_end >= 0 && a->row_end <= a->image_height && (a->row_end == 0 || a->row_begin <= a->row_end),
+                "pvp_process_image: bad row range [%lld, %lld) for %lld rows", (long long)a->row_begin, (long long)a->row_end, (long long)a->image_height);
+    p->row0 = a->row_begin; p->row1 = a->row_end == 0 && a->row_begin == 0 ? a->image_height : a->row_end;
     long long cells = 1;
     for (int k = 0; k < 3; ++k) { p->gn[k] = a->grid_shape[k]; p->gs[k] = a->grid_stride[k]; cells *= a->grid_shape[k]; }
     p->grid_provided = cells > 0;
@@ -584,7 +588,8 @@ static bool make_fastp(const ImageP &p, ImageFastP *f)
 // (the lock-step kernels fall back to the generic one if !fast_ok)
 static int launch_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, void *tex_dev, const ImageP &p, int accum_mode)
 {
-    const long long n_px = p.W * p.H;
+    const long long rows = p.row1 - p.row0, n_px = p.W * rows;
+    if (rows <= 0) return PVP_OK;  // an empty row shard
     LaunchScope scope(ctx, 3);
     ImageFastP f;
     if (ctx->opt_image_variant != 1 && make_fastp(p, &f)) {
@@ -595,7 +600,7 @@ static int launch_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, v
         if (ctx->opt_image_variant != 2) {  // default: two pixels per lane
             const void *k2 = f64 ? (const void *)process_image_lockstep2_kernel<PVP_ACCUM_F64> : (const void *)process_image_lockstep2_kernel<PVP_ACCUM_FIXED>;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, K3L_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
-            const long long groups2 = ((p.W + 31) / 32) * ((p.H + 1) / 2);
+            const long long groups2 = ((p.W + 31) / 32) * ((rows + 1) / 2);
             const int blocks2 = (int)std::min<long long>((groups2 + K3L_THREADS / 32 - 1) / (K3L_THREADS / 32), (long long)ctx->sm_count * per_sm);
             void *args2[] = {(void *)&image_dev, (void *)&grid_dev, (void *)&tex_dev, (void *)&p, (void *)&f, (void *)&ctx->ctl_dev};
             PVP_CUDA(cudaLaunchKernel(k2, dim3((unsigned)blocks2), dim3(K3L_THREADS), args2, 0, ctx->stream));
@@ -607,7 +612,7 @@ static int launch_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, v
                       : th == 8 ? (f64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64, 8> : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED, 8>)
                                 : (f64 ? (const void *)process_image_lockstep_kernel<PVP_ACCUM_F64, 2> : (const void *)process_image_lockstep_kernel<PVP_ACCUM_FIXED, 2>);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, K3L_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
-        const long long groups = ((p.W + 32 / th - 1) / (32 / th)) * ((p.H + th - 1) / th);
+        const long long groups = ((p.W + 32 / th - 1) / (32 / th)) * ((rows + th - 1) / th);
         const int blocks = (int)std::min<long long>((groups + K3L_THREADS / 32 - 1) / (K3L_THREADS / 32), (long long)ctx->sm_count * per_sm);
         void *args[] = {(void *)&image_dev, (void *)&grid_dev, (void *)&tex_dev, (void *)&p, (void *)&f, (void *)&ctx->ctl_dev};
         PVP_CUDA(cudaLaunchKernel(k, dim3((unsigned)blocks), dim3(K3L_THREADS), args, 0, ctx->stream));

@@ -168,3 +168,78 @@ def ray_voxel_distributed(metadata_json: str, image_folder: str, output_bin: str
         for k in ("n_rays", "n_steps", "n_pairs", "n_frames_loaded"):
             out[k] //= world
     return out
+
+
+# ---- path B (process_image_cpp) over several GPUs: SURVEY.md 8e, "B path" -------------------------------------------
+# Every pixel's ray is independent and the only shared state is additive (voxel grid, celestial-sphere texture:
+# process_image.cpp:309-313, :356-357), so a rank processes a block of image ROWS (one big image) or a block of the
+# IMAGES of the per-file loop (spacevoxelviewer.py:300-310) into PRIVATE grid + texture tensors, and the run ends with
+# one sum of both.  int64 fixed-point tensors merge bit-exactly in any order; float64 differs by summation order only.
+# Background subtraction reads the texture while it is being accumulated (:296-307): across ranks that read would see a
+# partial sum, so it is refused for world > 1 (the reference's only call site passes False, spacevoxelviewer.py:250).
+
+def _world_rank(group=None) -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def _check_shardable(perform_background_subtraction, world: int) -> None:
+    if perform_background_subtraction and world > 1:
+        raise ValueError("perform_background_subtraction=True reads the texture being accumulated (process_image.cpp:296-307): "
+                         "run it on one GPU (replicas only), not sharded")
+
+
+def process_image_sharded(image, earth_position, pointing_direction, fov, image_width, image_height, voxel_grid, voxel_grid_extent,
+                          max_distance, num_steps, celestial_sphere_texture, center_ra_rad, center_dec_rad, angular_width_rad,
+                          angular_height_rad, update_celestial_sphere, perform_background_subtraction, *, group=None,
+                          rank: int | None = None, world: int | None = None, **kw) -> tuple[int, int]:
+    """process_image_cpp (same 17 arguments) for ONE image shared by all ranks: this rank casts the rays of its block of
+    image rows into its private `voxel_grid` / `celestial_sphere_texture`.  Returns the row block.  Follow the last image
+    with :func:`reduce_sky`.  rank / world override the process group (tests run the ranks one after another)."""
+    from .process_image import process_image_cpp
+
+    w, r = _world_rank(group)
+    world, rank = (w if world is None else world), (r if rank is None else rank)
+    _check_shardable(perform_background_subtraction, world)
+    rows = shard_range(int(image_height), rank, world)
+    process_image_cpp(image, earth_position, pointing_direction, fov, image_width, image_height, voxel_grid, voxel_grid_extent,
+                      max_distance, num_steps, celestial_sphere_texture, center_ra_rad, center_dec_rad, angular_width_rad,
+                      angular_height_rad, update_celestial_sphere, perform_background_subtraction, row_range=rows, **kw)
+    return rows
+
+
+def process_images_sharded(observations, image_width, image_height, voxel_grid, voxel_grid_extent, max_distance, num_steps,
+                           celestial_sphere_texture, center_ra_rad, center_dec_rad, angular_width_rad, angular_height_rad,
+                           update_celestial_sphere=True, perform_background_subtraction=False, *, group=None,
+                           rank: int | None = None, world: int | None = None, **kw) -> tuple[int, int]:
+    """The per-file loop of spacevoxelviewer.py:300-310 with the FILES sharded: `observations` is the ordered list of
+    (image, earth_position, pointing_direction, fov) records (or a callable index -> record, so a rank only loads its own
+    files, with `n_observations=` in kw); this rank processes its contiguous block into its private tensors.  Returns the
+    block.  Follow with :func:`reduce_sky`."""
+    from .process_image import process_image_cpp
+
+    w, r = _world_rank(group)
+    world, rank = (w if world is None else world), (r if rank is None else rank)
+    _check_shardable(perform_background_subtraction, world)
+    n_obs = kw.pop("n_observations", None)
+    n_obs = len(observations) if n_obs is None else int(n_obs)
+    lo, hi = shard_range(n_obs, rank, world)
+    for k in range(lo, hi):
+        image, earth_position, pointing_direction, fov = observations(k) if callable(observations) else observations[k]
+        process_image_cpp(image, earth_position, pointing_direction, fov, image_width, image_height, voxel_grid, voxel_grid_extent,
+                          max_distance, num_steps, celestial_sphere_texture, center_ra_rad, center_dec_rad, angular_width_rad,
+                          angular_height_rad, update_celestial_sphere, perform_background_subtraction, **kw)
+    return lo, hi
+
+
+def reduce_sky(voxel_grid: torch.Tensor | None, celestial_sphere_texture: torch.Tensor | None, dst: int | None = 0, group=None) -> None:
+    """The single merge that ends a sharded path-B run: in-place sum over ranks of the private voxel grids and textures
+    (to rank `dst`, or to every rank with dst=None).  Tensors must be contiguous (strided views would be copied by the
+    collective and the sum lost)."""
+    for t in (voxel_grid, celestial_sphere_texture):
+        if t is None or t.numel() == 0:
+            continue
+        if not t.is_contiguous():
+            raise ValueError("reduce_sky needs contiguous tensors")
+        reduce_grid(t, dst=0 if dst is None else dst, group=group, all_ranks=dst is None)

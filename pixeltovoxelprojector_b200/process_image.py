@@ -62,12 +62,14 @@ def _fill_common(a: ImageArgs, earth_position, pointing_direction, fov, image_wi
 def process_image_cpp(image, earth_position, pointing_direction, fov, image_width, image_height, voxel_grid, voxel_grid_extent,
                       max_distance, num_steps, celestial_sphere_texture, center_ra_rad, center_dec_rad, angular_width_rad,
                       angular_height_rad, update_celestial_sphere, perform_background_subtraction, *, accum_mode: str = "f64",
-                      frac_bits: int = 32, ctx: Context | None = None, want_stats: bool = False) -> None:
+                      frac_bits: int = 32, ctx: Context | None = None, want_stats: bool = False,
+                      row_range: tuple[int, int] | None = None) -> None:
     """Process image and update voxel grid (process_image.cpp:125-366) on the B200.
 
     The 17 positional arguments are the reference's.  Keyword-only extras: ``accum_mode="fixed"``
     (int64 CUDA tensors holding value * 2**frac_bits; deterministic), ``ctx``, ``want_stats``
-    (fills ``process_image.last_stats``; forces a sync on the device path).
+    (fills ``process_image.last_stats``; forces a sync on the device path), ``row_range=(lo, hi)``
+    (only image rows lo <= i < hi cast rays -- a row shard of a multi-GPU run, see ``distributed.process_image_sharded``).
     """
     global last_stats
     on_device = isinstance(image, torch.Tensor) and image.is_cuda
@@ -79,6 +81,14 @@ def process_image_cpp(image, earth_position, pointing_direction, fov, image_widt
         raise ValueError("accum_mode must be 'f64' or 'fixed'")
     args.accum_mode = ACCUM_F64 if accum_mode == "f64" else ACCUM_FIXED
     args.frac_bits = int(frac_bits)
+    if row_range is not None:
+        lo, hi = int(row_range[0]), int(row_range[1])
+        if not 0 <= lo <= hi <= int(image_height):
+            raise ValueError(f"row_range {row_range} outside the image's {image_height} rows")
+        if lo == hi:      # an empty shard: nothing to do (the C ABI reads 0, 0 as "all rows")
+            last_stats = {"n_rays": 0, "n_samples": 0} if want_stats else last_stats
+            return None
+        args.row_begin, args.row_end = lo, hi
     st = ImageStats()
     st_ref = C.byref(st) if want_stats else None
 

@@ -76,8 +76,45 @@ def _worker(rank, world, port, tmp):
             assert open(path, "rb").read() == open(ref, "rb").read()
             back, vs = read_bin(path)
             assert np.array_equal(back, whole) and vs == 6.0
+        _path_b_host_logic(rank, world)
     finally:
         dist.destroy_process_group()
+
+
+def _path_b_host_logic(rank, world):
+    """SURVEY 8e "B path": file sharding + the merge of grid and texture, with the kernel call replaced by a CPU stand-in
+    (the real kernel is covered on the GPU by test_gpu_process_image.py::test_row_and_file_shards_sum_to_whole)."""
+    import pixeltovoxelprojector_b200.process_image as pi
+    calls = []
+
+    def fake(image, earth_position, pointing_direction, fov, w, h, grid, ext, md, ns, tex, *rest, row_range=None, **kw):
+        lo, hi = row_range if row_range is not None else (0, h)
+        calls.append((float(fov), lo, hi))
+        grid += int(image[lo:hi].sum())
+        tex += float(fov)
+    real, pi.process_image_cpp = pi.process_image_cpp, fake
+    try:
+        H, W, n_obs = 11, 6, 5
+        obs = [(torch.full((H, W), k + 1, dtype=torch.int64), [0, 0, 0], [0, 0, 1], float(k)) for k in range(n_obs)]
+        grid, tex = torch.zeros((3, 3, 3), dtype=torch.int64), torch.zeros((2, 2), dtype=torch.float64)
+        common = (W, H, grid, [(0, 1)] * 3, 10.0, 10, tex, 0.0, 0.0, 1.0, 1.0)
+        lo, hi = pd.process_images_sharded(obs, *common)
+        assert (lo, hi) == pd.shard_range(n_obs, rank, world) and [c[0] for c in calls] == [float(k) for k in range(lo, hi)]
+        loaded = []
+        pd.process_images_sharded(lambda k: (loaded.append(k), obs[k])[1], *common, n_observations=n_obs)   # lazy: only this rank's files
+        assert loaded == list(range(lo, hi))
+        rows = pd.process_image_sharded(obs[0][0], [0, 0, 0], [0, 0, 1], 0.5, *common, True, False)
+        assert rows == pd.shard_range(H, rank, world) and calls[-1] == (0.5, *rows)
+        pd.reduce_sky(grid, tex, dst=None)
+        per_image = [(k + 1) * H * W for k in range(n_obs)]
+        assert int(grid[0, 0, 0]) == 2 * sum(per_image) + H * W                 # both passes over the files + the row-sharded image
+        assert float(tex[0, 0]) == 2 * sum(range(n_obs)) + 0.5 * world
+        with pytest.raises(ValueError, match="background_subtraction"):
+            pd.process_image_sharded(obs[0][0], [0, 0, 0], [0, 0, 1], 0.5, *common, True, True)
+        with pytest.raises(ValueError, match="contiguous"):
+            pd.reduce_sky(grid[:, ::2], None)
+    finally:
+        pi.process_image_cpp = real
 
 
 def _f32_of(rank, n):

@@ -233,3 +233,75 @@ def _lockstep_sweep(oracle, pi, rng):
             assert np.array_equal(ti.cpu().numpy(), ot), trial
         total += ns
     return total
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_row_and_file_shards_sum_to_whole(ctx, oracle, variant):
+    """SURVEY 8e, path B over several GPUs (the ranks run one after another here): row shards of one image -- ragged,
+    odd boundaries that split the kernels' 2-row tiles, an empty shard -- and file shards of an observation list, each
+    into private int64 tensors, sum to exactly the single-GPU result, which equals the oracle; float64 mode agrees to
+    summation order.  A row range is part of the C ABI (pvp_image_args.row_begin / row_end)."""
+    from pixeltovoxelprojector_b200 import distributed as pd, process_image as pi
+    rng = np.random.default_rng(2024)
+    H, W = 37, 45
+    ext, shape = [(-8.0, 9.0), (-7.0, 6.5), (10.0, 28.0)], (20, 24, 28)
+    sky = (0.3, -0.2, 1.0, 1.5)
+    obs = []
+    for k in range(5):
+        img = rng.random((H, W))
+        img[rng.random((H, W)) < 0.2] = 0.0
+        obs.append((img, [0.1 * k, -0.2, 0.3], [0.05 - 0.02 * k, 0.02, 1.0], 0.9))
+    og, ot = np.zeros(shape, np.int64), np.zeros((16, 24), np.int64)
+    want_stats = [0, 0]
+    for img, pos, pointing, fov in obs:
+        nr, ns = oracle.process_image(img, pos, pointing, fov, W, H, og, ext, 60.0, 240, ot, *sky, True, False, accum_mode=1, frac_bits=24)
+        want_stats[0] += nr
+        want_stats[1] += ns
+    dev_obs = [(torch.as_tensor(img, device="cuda"), pos, pointing, fov) for img, pos, pointing, fov in obs]
+
+    def zeros(dtype=torch.int64):
+        return torch.zeros(shape, dtype=dtype, device="cuda"), torch.zeros((16, 24), dtype=dtype, device="cuda")
+    ctx.set_option("image_variant", variant)
+    try:
+        for world in (1, 2, 3, 5, 64):                              # 64 ranks for 37 rows / 5 files: most shards are empty
+            tg, tt = zeros()
+            tg_files, tt_files = zeros()
+            rays = samples = 0
+            for rank in range(world):
+                g, t = zeros()
+                for image, pos, pointing, fov in dev_obs:
+                    rows = pd.process_image_sharded(image, pos, pointing, fov, W, H, g, ext, 60.0, 240, t, *sky, True, False,
+                                                    rank=rank, world=world, accum_mode="fixed", frac_bits=24, want_stats=True)
+                    assert rows == pd.shard_range(H, rank, world)
+                    rays += pi.last_stats["n_rays"]
+                    samples += pi.last_stats["n_samples"]
+                tg += g
+                tt += t
+                g, t = zeros()
+                pd.process_images_sharded(dev_obs, W, H, g, ext, 60.0, 240, t, *sky, rank=rank, world=world, accum_mode="fixed", frac_bits=24)
+                tg_files += g
+                tt_files += t
+            assert [rays, samples] == want_stats, world
+            assert np.array_equal(tg.cpu().numpy(), og) and np.array_equal(tt.cpu().numpy(), ot), world
+            assert np.array_equal(tg_files.cpu().numpy(), og) and np.array_equal(tt_files.cpu().numpy(), ot), world
+        # float64 accumulation: 3 row shards against the whole image
+        wg, wt = zeros(torch.float64)
+        sg, st = zeros(torch.float64)
+        image, pos, pointing, fov = dev_obs[1]
+        pvp.process_image_cpp(image, pos, pointing, fov, W, H, wg, ext, 60.0, 240, wt, *sky, True, False)
+        for rank in range(3):
+            pd.process_image_sharded(image, pos, pointing, fov, W, H, sg, ext, 60.0, 240, st, *sky, True, False, rank=rank, world=3)
+        assert torch.equal(sg != 0, wg != 0)
+        torch.testing.assert_close(sg, wg, rtol=RTOL_F64_ATOMICS, atol=0)
+        torch.testing.assert_close(st, wt, rtol=RTOL_F64_ATOMICS, atol=0)
+        # numpy host path takes the row range too
+        hg, ht = np.zeros(shape), np.zeros((16, 24))
+        for lo, hi in ((0, 9), (9, 10), (10, H)):
+            dropin.process_image_cpp(obs[1][0], pos, pointing, fov, W, H, hg, ext, 60.0, 240, ht, *sky, True, False, row_range=(lo, hi))
+        np.testing.assert_allclose(hg, wg.cpu().numpy(), rtol=RTOL_F64_ATOMICS, atol=0)
+        with pytest.raises(ValueError, match="row_range"):
+            pvp.process_image_cpp(image, pos, pointing, fov, W, H, wg, ext, 60.0, 240, wt, *sky, True, False, row_range=(3, H + 1))
+        with pytest.raises(ValueError, match="background_subtraction"):
+            pd.process_image_sharded(image, pos, pointing, fov, W, H, wg, ext, 60.0, 240, wt, *sky, True, True, rank=0, world=2)
+    finally:
+        ctx.set_option("image_variant", 0)

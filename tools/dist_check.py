@@ -69,6 +69,32 @@ def main():
                     if rank == 0:
                         print(f"[peer reduce {accum} n={nn} dst={dst} multicast={mc and bool(g.symm.multicast_ptr)}] equals NCCL all_reduce: {same}")
                 dist.barrier()
+    # path B: row shards of one image and file shards of an observation list into private int64 tensors, one merge of grid +
+    # texture (NCCL), equal to one GPU alone bit for bit
+    from pixeltovoxelprojector_b200.distributed import process_image_sharded, process_images_sharded, reduce_sky
+    rng = np.random.default_rng(5)
+    H = W = 384
+    ext, shape, sky = [(-64.0, 64.0), (-64.0, 64.0), (40.0, 168.0)], (128, 128, 128), (0.3, -0.2, 1.0, 1.5)
+    obs = [(torch.as_tensor(rng.random((H, W)), device="cuda"), [0.5 * k, -0.2, 0.3], [0.05 - 0.02 * k, 0.02, 1.0], 0.9) for k in range(6)]
+    tail = (W, H)
+    for what in ("rows", "files"):
+        g = torch.zeros(shape, dtype=torch.int64, device="cuda")
+        t = torch.zeros((64, 96), dtype=torch.int64, device="cuda")
+        if what == "rows":
+            for image, pos, pointing, fov in obs:
+                process_image_sharded(image, pos, pointing, fov, W, H, g, ext, 200.0, 400, t, *sky, True, False, accum_mode="fixed", frac_bits=24)
+        else:
+            process_images_sharded(obs, W, H, g, ext, 200.0, 400, t, *sky, accum_mode="fixed", frac_bits=24)
+        reduce_sky(g, t, dst=0)
+        if rank == 0:
+            g1 = torch.zeros_like(g)
+            t1 = torch.zeros_like(t)
+            for image, pos, pointing, fov in obs:
+                pvp.process_image_cpp(image, pos, pointing, fov, W, H, g1, ext, 200.0, 400, t1, *sky, True, False, accum_mode="fixed", frac_bits=24)
+            same = bool(torch.equal(g, g1) and torch.equal(t, t1)) and int(g1.sum()) > 0
+            ok &= same
+            print(f"[path B {what}] world={world} merged grid + texture identical to 1 GPU: {same} (grid sum {int(g1.sum())})")
+        dist.barrier()
     flag = torch.tensor([int(ok)], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
