@@ -231,6 +231,32 @@ def test_k2_variants_bit_exact(ctx, oracle, variant, accum):
         ctx.set_option("dda_variant", 0)
 
 
+@pytest.mark.parametrize("rows", [1, 2, 4, 8])
+def test_queue_tile_heights_bit_exact(ctx, oracle, rows):
+    """K1 writes the ray queue in tiles of 1 / 2 / 4 / 8 image rows (the auto mode picks the height from the size of one
+    x-plane of the grid: 8 rows + the one-ray kernel for 1024^3); the order must not change anything: same grid as the
+    reference bit for bit with both lock-step kernels, uint8 and float frames, heights that leave a partial last tile."""
+    rng = np.random.default_rng(300 + rows)
+    F, H, W, N, vs, center = 3, 53, 131, 64, 5.0, (0.0, 0.0, 500.0)
+    frames, poses = _scene(rng, F, H, W, N, vs, center, True)
+    ff = np.clip(frames.astype(np.float32) + rng.uniform(-1, 1, frames.shape).astype(np.float32), 0, 255)
+    pairs, _ = pvp.make_pairs(poses, W)
+    want, tot = _oracle_run(oracle, frames, poses, N, vs, center, 2.0, accum_mode=1, frac_bits=10)
+    wantf, totf = _oracle_run(oracle, ff, poses, N, vs, center, 2.0, accum_mode=1, frac_bits=10)
+    ctx.set_option("k1_row_group", rows)
+    try:
+        for variant in (4, 5):
+            ctx.set_option("dda_variant", variant)
+            for fr, w, t in ((frames, want, tot), (ff, wantf, totf)):
+                grid = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=10)
+                st = pvp.accumulate_motion(torch.as_tensor(fr, device=DEV), pairs, grid, 2.0)
+                assert (st["n_rays"], st["n_steps"], st["n_written"]) == tuple(t), (variant, rows)
+                assert np.array_equal(grid.data.cpu().numpy(), w), (variant, rows)
+    finally:
+        ctx.set_option("k1_row_group", 0)
+        ctx.set_option("dda_variant", 0)
+
+
 def test_edge_cases(ctx, oracle):
     N, vs, center = 32, 1.0, (0.0, 0.0, 0.0)
     W, H = 16, 8
