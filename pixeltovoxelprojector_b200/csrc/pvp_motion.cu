@@ -507,7 +507,6 @@ template <> struct LeanVal<PVP_ACCUM_FIXED, true> {
     __device__ static __forceinline__ unsigned long long cell_value(T v, const GridP &g) { return (unsigned long long)__float2uint_rz(v) << g.frac_shift; }
 };
 
-constexpr float REM_PARKED = 1.0e9f;  // 1e9f - 1 == 1e9f: a parked lane's counters never run out
 
 // red.global.add with the issue decision as a PTX predicate (the address is formed outside the predicate)
 __device__ __forceinline__ void red_if(bool p, float *addr, float v)
@@ -532,6 +531,42 @@ __device__ __forceinline__ bool run_head(unsigned key)
 #endif
 constexpr int LEAN_THREADS = PVP_LEAN_THREADS;  // warps are independent; the CTA size only sets how registers divide an SM
 constexpr int LEAN_CTAS_A = 7 * 128 / LEAN_THREADS > 0 ? 7 * 128 / LEAN_THREADS : 1, LEAN_CTAS_B = 6 * 128 / LEAN_THREADS, LEAN_CTAS_C = 8 * 128 / LEAN_THREADS;
+
+// The step that takes an axis out of [0, N) is its (rem+1)-th, taken when t_max of that axis -- tm0 after `rem` rounded
+// additions of td -- is the minimum.  A rigorous LOWER bound of that value: each addition errs by at most 2^-24 of a
+// partial sum, all partial sums lie within |tm0| + rem*td, rem < 2^11, so the iterated sum is within 2^-13 (|tm0| + rem*td)
+// of tm0 + rem*td; the slack used is 2^-11 of it.  While the step's t (the minimum of the three t_max) is below the bound of
+// every axis and below t_end, the ray provably stays inside and alive -- no per-step bookkeeping; from the bound on (the
+// last step or two of a ray) the exact test runs in the warp-uniform slow path (step_leaves).
+__device__ __forceinline__ float axis_limit(float tm0, float td, int rem)
+{
+    if (!(td < CUDART_INF_F)) return CUDART_INF_F;  // parallel axis (safe_div, :266-272): never chosen before the others run out
+    const float span = fmul((float)rem, td);
+    return fsub(fadd(tm0, span), fmul(fadd(fabsf(tm0), span), 0x1p-11f));
+}
+
+// Does the step along the chosen axis (cz / cy / else x) leave [0, N)?  Decodes the voxel the step starts from.  Slab kernels
+// hold x relative to the slab, possibly negative (N^3 <= 2^31 there, so the offset is a valid int).
+template <bool SLAB>
+__device__ __forceinline__ bool step_leaves(unsigned cur, bool cz, bool cy, int dix, int diy, int diz, const GridP &g)
+{
+    const int N = g.n, NN = N * N;
+    int ix;
+    unsigned rest;
+    if (SLAB) {
+        const int rel = (int)cur;
+        const int q = rel >= 0 ? rel / NN : -((NN - 1 - rel) / NN);  // floor
+        ix = q + g.slab_lo;
+        rest = (unsigned)(rel - q * NN);
+    } else {
+        ix = (int)(cur / (unsigned)NN);
+        rest = cur - (unsigned)ix * (unsigned)NN;
+    }
+    const int iy = (int)(rest / (unsigned)N), iz = (int)(rest - (unsigned)iy * (unsigned)N);
+    if (cz) return diz > 0 ? iz == N - 1 : iz == 0;
+    if (cy) return diy > 0 ? iy == N - 1 : iy == 0;
+    return dix > 0 ? ix == N - 1 : ix == 0;
+}
 
 template <int MODE, bool SLAB, bool NARROW, int MINB>
 __global__ void __launch_bounds__(LEAN_THREADS, MINB)
@@ -558,8 +593,8 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
         const unsigned long long i = base + lane;
 
         // parked state (also the state of lanes past the end of the queue and of rays that miss the grid)
-        float t_end = CUDART_INF_F, tmx = 0.f, tmy = 0.f, tmz = 0.f, tdx = 0.f, tdy = 0.f, tdz = 0.f;
-        float remx = REM_PARKED, remy = REM_PARKED, remz = REM_PARKED, rem0 = 0.f;
+        float t_end = CUDART_INF_F, lim = CUDART_INF_F, tmx = 0.f, tmy = 0.f, tmz = 0.f, tdx = 0.f, tdy = 0.f, tdz = 0.f;
+        float walked = 0.f;  // iterations of this chunk so far == voxels emitted by every ray that is still alive
         unsigned idx = KEY_NONE;
         int dix = 0, diy = 0, diz = 0;
         T val = 0;
@@ -578,14 +613,12 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
                 tmx = r.tmx; tmy = r.tmy; tmz = r.tmz; tdx = r.tdx; tdy = r.tdy; tdz = r.tdz;
                 idx = (unsigned)((r.ix - g.slab_lo) * N + r.iy) * (unsigned)N + (unsigned)r.iz;  // negative x offsets wrap past slab_cells
                 dix = r.sx * N * N; diy = r.sy * N; diz = r.sz;
-                remx = (float)(r.sx > 0 ? N - 1 - r.ix : r.ix);
-                remy = (float)(r.sy > 0 ? N - 1 - r.iy : r.iy);
-                remz = (float)(r.sz > 0 ? N - 1 - r.iz : r.iz);
-                rem0 = remx + remy + remz;
+                lim = fminf(fminf(axis_limit(r.tmx, r.tdx, r.sx > 0 ? N - 1 - r.ix : r.ix), axis_limit(r.tmy, r.tdy, r.sy > 0 ? N - 1 - r.iy : r.iy)),
+                            fminf(axis_limit(r.tmz, r.tdz, r.sz > 0 ? N - 1 - r.iz : r.iz), r.t_end));
                 val = V::make(diff, g);
             }
         }
-        if (__all_sync(FULL, remx == REM_PARKED)) continue;  // (parked is tested on remx: in slab kernels a live voxel offset can wrap to KEY_NONE)
+        if (__all_sync(FULL, tdx == 0.f)) continue;  // (a live ray has t_delta > 0; not "idx == KEY_NONE": in slab kernels a live voxel offset can wrap to it)
 
         // Loop-carried across iterations so that they are off the scan's critical path: the run heads of the
         // CURRENT voxel keys (computed right after the previous DDA step) and, for whole-grid kernels, the value
@@ -604,11 +637,12 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
             const bool cz = (tmz == m);
             const bool cy = !cz && (tmy == m);
             const bool cx = !cz && (tmy != m);
-            if (cx) { tmx = fadd(tmx, tdx); remx -= 1.f; }
-            if (cy) { tmy = fadd(tmy, tdy); remy -= 1.f; }
-            if (cz) { tmz = fadd(tmz, tdz); remz -= 1.f; }
+            if (cx) tmx = fadd(tmx, tdx);
+            if (cy) tmy = fadd(tmy, tdy);
+            if (cz) tmz = fadd(tmz, tdz);
             idx += (unsigned)(cz ? diz : (cy ? diy : dix));
-            const bool still = (fmin3(remx, remy, remz) >= 0.f) && (m <= t_end);
+            walked += 1.f;
+            const bool sure = m < lim;  // below the ray's limit the step can neither leave the grid nor pass t_end (axis_limit)
             bool next_head = false;
             if (!SLAB) next_head = run_head(idx);
             // ---- accumulate the voxel the step left: one RED per run of equal keys -------------------------
@@ -634,18 +668,17 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
             if (issue) n_issued += 1.f;
             if (!SLAB) heads = __ballot_sync(FULL, next_head);
             // ---- rays that ended: park the lane; leave when the whole warp is parked ---------------------
-            if (__any_sync(FULL, !still)) {
-                // (not "idx != KEY_NONE": a ray that leaves the grid downwards from linear offset N^2-1 / N-1 / 0 wraps to
-                // exactly 0xffffffff and would then never be parked nor counted)
-                const bool park = !still && remx != REM_PARKED;
-                my_steps += park ? (unsigned long long)(unsigned)(int)(rem0 - (remx + remy + remz)) : 0ull;  // advances performed == voxels emitted
+            if (__any_sync(FULL, !sure)) {
+                // exact end-of-ray test (:388-391, :365) for the lanes at their limit.  (live is "tdx != 0", not "idx != KEY_NONE": a
+                // ray that leaves the grid downwards from linear offset N^2-1 / N-1 / 0 wraps to exactly 0xffffffff)
+                const bool park = !sure && tdx != 0.f && (step_leaves<SLAB>(cur, cz, cy, dix, diy, diz, g) || !(m <= t_end));
+                my_steps += park ? (unsigned long long)walked : 0ull;
                 idx = park ? KEY_NONE : idx; val = park ? (T)0 : val;
                 dix = park ? 0 : dix; diy = park ? 0 : diy; diz = park ? 0 : diz;
                 tmx = park ? 0.f : tmx; tmy = park ? 0.f : tmy; tmz = park ? 0.f : tmz;
                 tdx = park ? 0.f : tdx; tdy = park ? 0.f : tdy; tdz = park ? 0.f : tdz;
-                t_end = park ? CUDART_INF_F : t_end;
-                remx = park ? REM_PARKED : remx; remy = park ? REM_PARKED : remy; remz = park ? REM_PARKED : remz;
-                if (__all_sync(FULL, remx == REM_PARKED)) break;
+                t_end = park ? CUDART_INF_F : t_end; lim = park ? CUDART_INF_F : lim;
+                if (__all_sync(FULL, tdx == 0.f)) break;
                 if (!SLAB) {
                     heads = __ballot_sync(FULL, run_head(idx));
                     pval = __shfl_up_sync(FULL, val, 1);
@@ -679,16 +712,20 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
 // voxels than a 64 x 1 strip.  Where B sits in another voxel it issues its own RED.  Per ray the arithmetic, the step
 // order and the counters are those of variant 4 (same bit-exact visited sets).
 struct RayS {
-    float t_end, tmx, tmy, tmz, tdx, tdy, tdz, remx, remy, remz, rem0;
+    float t_end, lim;  // box exit t_max (:293); lim: below it a step can neither leave the grid nor pass t_end (see axis_limit)
+    float tmx, tmy, tmz, tdx, tdy, tdz;
     float t_cur;  // RayStep::distance of the current voxel (only read by the attenuating kernels)
     unsigned idx;
     int dix, diy, diz;
 };
 
+// A live ray has positive (or infinite) t_delta on every axis; a parked lane has zeros.
+__device__ __forceinline__ bool rays_live(const RayS &r) { return r.tdx != 0.f; }
+
 __device__ __forceinline__ void rays_park(RayS &r)
 {
-    r.t_end = CUDART_INF_F; r.tmx = r.tmy = r.tmz = 0.f; r.tdx = r.tdy = r.tdz = 0.f;
-    r.remx = r.remy = r.remz = REM_PARKED; r.rem0 = 0.f; r.t_cur = 0.f;
+    r.t_end = CUDART_INF_F; r.lim = CUDART_INF_F; r.tmx = r.tmy = r.tmz = 0.f; r.tdx = r.tdy = r.tdz = 0.f;
+    r.t_cur = 0.f;
     r.idx = KEY_NONE; r.dix = r.diy = r.diz = 0;
 }
 
@@ -714,26 +751,35 @@ __device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, uns
     s.tmx = r.tmx; s.tmy = r.tmy; s.tmz = r.tmz; s.tdx = r.tdx; s.tdy = r.tdy; s.tdz = r.tdz;
     s.idx = (unsigned)((r.ix - g.slab_lo) * N + r.iy) * (unsigned)N + (unsigned)r.iz;
     s.dix = r.sx * N * N; s.diy = r.sy * N; s.diz = r.sz;
-    s.remx = (float)(r.sx > 0 ? N - 1 - r.ix : r.ix);
-    s.remy = (float)(r.sy > 0 ? N - 1 - r.iy : r.iy);
-    s.remz = (float)(r.sz > 0 ? N - 1 - r.iz : r.iz);
-    s.rem0 = s.remx + s.remy + s.remz;
+    s.lim = fminf(fminf(axis_limit(r.tmx, r.tdx, r.sx > 0 ? N - 1 - r.ix : r.ix), axis_limit(r.tmy, r.tdy, r.sy > 0 ? N - 1 - r.iy : r.iy)),
+                  fminf(axis_limit(r.tmz, r.tdz, r.sz > 0 ? N - 1 - r.iz : r.iz), r.t_end));
     return V::make(diff, g);
 }
 
-// one DDA step (ray_voxel.cpp:375-391); false when the ray ended with this step
-__device__ __forceinline__ bool rays_step(RayS &s)
+// one DDA step (ray_voxel.cpp:375-391); returns the step's t (the minimum of the three t_max).  While it is below the ray's
+// limit the ray certainly goes on; otherwise rays_ended decides exactly.
+__device__ __forceinline__ float rays_step(RayS &s)
 {
     const float m = fmin3(s.tmx, s.tmy, s.tmz);
     const bool cz = (s.tmz == m);
     const bool cy = !cz && (s.tmy == m);
     const bool cx = !cz && (s.tmy != m);
-    if (cx) { s.tmx = fadd(s.tmx, s.tdx); s.remx -= 1.f; }
-    if (cy) { s.tmy = fadd(s.tmy, s.tdy); s.remy -= 1.f; }
-    if (cz) { s.tmz = fadd(s.tmz, s.tdz); s.remz -= 1.f; }
+    if (cx) s.tmx = fadd(s.tmx, s.tdx);
+    if (cy) s.tmy = fadd(s.tmy, s.tdy);
+    if (cz) s.tmz = fadd(s.tmz, s.tdz);
     s.idx += (unsigned)(cz ? s.diz : (cy ? s.diy : s.dix));
     s.t_cur = m;  // :376-386 (dead in the kernels that do not attenuate)
-    return (fmin3(s.remx, s.remy, s.remz) >= 0.f) && (m <= s.t_end);
+    return m;
+}
+
+// exact end-of-ray test of the step (t = m) just taken from voxel `cur` (:388-391 and the loop condition :365).  The axis of the
+// step is read back from the offset change (for N == 1 the strides coincide, and every step leaves whatever its axis).
+template <bool SLAB>
+__device__ __forceinline__ bool rays_ended(const RayS &s, unsigned cur, float m, const GridP &g)
+{
+    const int d = (int)(s.idx - cur);
+    const bool cz = d == s.diz, cy = !cz && d == s.diy;
+    return step_leaves<SLAB>(cur, cz, cy, s.dix, s.diy, s.diz, g) || !(m <= s.t_end);
 }
 
 template <int MODE, bool SLAB, bool NARROW, int MINB, bool ATT = false>
@@ -760,17 +806,21 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
         T va = rays_setup<V>(a, q, base + 2 * lane, count, pairs, g, width, height, da);
         T vb = rays_setup<V>(b, q, base + 2 * lane + 1, count, pairs, g, width, height, db);
         float n_issued = 0.f, n_inslab = 0.f;
-        if (__all_sync(FULL, a.remx == REM_PARKED && b.remx == REM_PARKED)) continue;
+        float walked = 0.f;  // iterations of this chunk so far == voxels emitted by every ray that is still alive
+        if (__all_sync(FULL, !rays_live(a) && !rays_live(b))) continue;
 
         unsigned heads = __ballot_sync(FULL, run_head(SLAB ? (a.idx < slab_cells ? a.idx : KEY_NONE) : a.idx));
         for (;;) {
             // ---- one DDA step of both rays first: the shuffle of A's new key overlaps the scan below ----------------
             unsigned ka = a.idx, kb = b.idx;
+            const unsigned ka0 = ka, kb0 = kb;
             if (ATT) {  // value of THIS voxel step: pix_val / (1 + alpha * distance), before the step moves t_cur on
                 va = V::make(attenuate(da, g.alpha, a.t_cur), g);
                 vb = V::make(attenuate(db, g.alpha, b.t_cur), g);
             }
-            const bool still_a = rays_step(a), still_b = rays_step(b);
+            const float ma = rays_step(a), mb = rays_step(b);
+            const bool any_unsure = __any_sync(FULL, !(ma < a.lim) || !(mb < b.lim));
+            walked += 1.f;
             T sa = va, sb = vb;
             if (SLAB) {  // writes outside the slab are suppressed; parked rays (KEY_NONE) are outside every slab
                 const bool ina = ka < slab_cells, inb = kb < slab_cells;
@@ -795,16 +845,17 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
             if (b_alone) n_issued += 1.f;
             heads = __ballot_sync(FULL, next_head);
             // ---- rays that ended: park them; leave when every ray of the warp is parked ----------------------------
-            if (__any_sync(FULL, !(still_a && still_b))) {
-                if (!still_a && a.remx != REM_PARKED) {
-                    my_steps += (unsigned long long)(unsigned)(int)(a.rem0 - (a.remx + a.remy + a.remz));
+            if (any_unsure) {
+                // (the original keys, not ka / kb: a slab kernel has replaced those outside its slab by KEY_NONE)
+                if (!(ma < a.lim) && rays_live(a) && rays_ended<SLAB>(a, ka0, ma, g)) {
+                    my_steps += (unsigned long long)walked;
                     rays_park(a); va = 0; da = 0.f;
                 }
-                if (!still_b && b.remx != REM_PARKED) {
-                    my_steps += (unsigned long long)(unsigned)(int)(b.rem0 - (b.remx + b.remy + b.remz));
+                if (!(mb < b.lim) && rays_live(b) && rays_ended<SLAB>(b, kb0, mb, g)) {
+                    my_steps += (unsigned long long)walked;
                     rays_park(b); vb = 0; db = 0.f;
                 }
-                if (__all_sync(FULL, a.remx == REM_PARKED && b.remx == REM_PARKED)) break;
+                if (__all_sync(FULL, !rays_live(a) && !rays_live(b))) break;
                 heads = __ballot_sync(FULL, run_head(SLAB ? (a.idx < slab_cells ? a.idx : KEY_NONE) : a.idx));
             }
         }
