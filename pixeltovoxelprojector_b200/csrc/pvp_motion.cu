@@ -472,6 +472,7 @@ __device__ __forceinline__ LaneMasks lane_masks(unsigned lane)
     // lane < d the window reaches bit 0, which is always a head, so the predicate is false as required.
     auto win = [lane](unsigned d) { return lane + 1 >= d ? (((1u << d) - 1u) << (lane + 1 - d)) : ((2u << lane) - 1u); };
     m.w1 = 1u << lane; m.w2 = win(2); m.w4 = win(4); m.w8 = win(8);
+    asm volatile("" : "+r"(m.w1));  // opaque: otherwise "heads & w1" is compiled as ((heads >> lane) & 1) != 1, three instructions instead of one LOP3
     m.w16 = lane + 1 >= 16 ? (0xffffu << (lane - 15)) : ((2u << lane) - 1u);
     m.next = lane == 31 ? 1u : (1u << (lane + 1));  // lane 31 always ends a run: bit 0 is always set
     return m;
