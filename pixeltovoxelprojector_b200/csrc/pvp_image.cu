@@ -217,17 +217,21 @@ __device__ __forceinline__ double div_by_extent(double a, double b, double y)
 }
 
 // Voxel index of a coordinate offset a in [0, b] along axis k: min(trunc(RN(RN(a / b) * n)), n - 1), process_image.cpp:94-104.
-// Screening: s = a * K with K = RN(n/b) * 2^20 approximates (a*n/b) * 2^20 to a relative 2.3e-16, as does the reference's own value;
-// for n <= 2^24 both lie within 4e-9 of the real number a*n/b.  When the 20 fraction bits of s are not within 4 units (3.8e-6) of an
-// integer, trunc(s / 2^20) therefore IS the reference's index -- one DMUL and a conversion instead of the five-operation exact
-// division; otherwise (about 8 samples in a million, or a ray that runs exactly along voxel faces) the exact sequence decides.
+// Screening: x = a * K with K = RN(n/b) * 2^20 approximates (a*n/b) * 2^20 to a relative 2.3e-16, as does the reference's own value;
+// for n <= 2^24 both lie within 4e-9 of the real number a*n/b, i.e. within 0.005 units of 2^-20.  y = x + (2^52 - 5) holds
+// r - 5 in its low mantissa bits, r = x rounded to an integer (within one unit of x).  When the 20 fraction bits of r are in
+// [5, 0xFFFFA], x is at least 4 units away from every multiple of 2^20, so r >> 20 == (r - 5) >> 20 IS the reference's index: one
+// DMUL, one DADD and a funnel shift instead of the five-operation exact division and a 64-bit conversion.  Otherwise (about 10
+// samples in a million, a ray that runs exactly along voxel faces, or x < 5, where y drops below 2^52 and its fraction field reads
+// >= 0xFFFF6) the exact sequence decides.  CLAMP = false: the caller knows a < b with a margin (safe_range), so the index is < n.
+template <bool CLAMP = true>
 __device__ __forceinline__ int voxel_index(double a, const ImageFastP &f, int k)
 {
-    const long long t = __double2ll_rz(dmul(a, f.k20[k]));
-    int idx = (int)(t >> 20);
-    const unsigned fr = (unsigned)t & 0xFFFFFu;
-    if (fr < 4u || fr > 0xFFFFBu) idx = __double2int_rz(dmul(div_by_extent(a, f.b[k], f.y[k]), f.nd[k]));
-    return min(idx, f.n1[k]);
+    const double y = dadd(dmul(a, f.k20[k]), 0x1p52 - 5.0);
+    const unsigned lo = (unsigned)__double2loint(y), hi = (unsigned)__double2hiint(y);
+    int idx = (int)__funnelshift_r(lo, hi, 20);
+    if ((lo & 0xFFFFFu) >= 0xFFFF6u) idx = __double2int_rz(dmul(div_by_extent(a, f.b[k], f.y[k]), f.nd[k]));
+    return CLAMP ? min(idx, f.n1[k]) : idx;
 }
 
 // Self-test of div_by_extent against the IEEE division it replaces (pvp_selftest_div_by_extent): numerators are drawn
@@ -350,41 +354,110 @@ __device__ __forceinline__ unsigned march_lockstep(CellT *__restrict__ grid, con
     return n_in;
 }
 
+// sample_key without the range and bounds tests, for samples where both are known to pass (safe_range)
+__device__ __forceinline__ unsigned sample_key_inside(const ImageP &p, const ImageFastP &f, int s, double w0, double w1, double w2, bool active)
+{
+    const double d = dmul((double)s, p.step_size);  // :344
+    const double qx = dadd(p.o[0], dmul(d, w0)), qy = dadd(p.o[1], dmul(d, w1)), qz = dadd(p.o[2], dmul(d, w2));
+    // (no upper clamp: safe_range keeps a margin to the faces that is far above the rounding of the index arithmetic)
+    const int xi = voxel_index<false>(dsub(qx, p.ext[0]), f, 0);
+    const int yi = voxel_index<false>(dsub(qy, p.ext[2]), f, 1);
+    const int zi = voxel_index<false>(dsub(qz, p.ext[4]), f, 2);
+    const unsigned off = (unsigned)xi * f.gs[0] + (unsigned)yi * f.gs[1] + (unsigned)zi * f.gs[2];
+    return active ? off : IMG_NONE;
+}
+
+// A sub-range [slo, shi] of a ray's samples [lo, hi] on which the inclusive bounds test of process_image.cpp:85 provably passes,
+// so that the march can skip its six fp64 compares there.  The computed sample position q = RN(o + RN(RN(s*step) * w)) is
+// within e = 2^-48 (|o| + |d_max w| + |ext|) of the exact x(s) = o + s*step*w per axis (three roundings, each below 2^-52 of
+// those magnitudes), and x(s) is linear in s: if at two samples the computed position keeps a margin of 2e to all six faces,
+// the exact position keeps e there and hence everywhere between them, and every computed position between them is inside.
+// The candidates are the first / last three samples of the ray; a ray that grazes a face gets an empty range (tests everywhere).
+__device__ __forceinline__ void safe_range(const ImageP &p, double w0, double w1, double w2, int lo, int hi, int &slo, int &shi)
+{
+    slo = INT32_MAX; shi = INT32_MIN;
+    if (lo > hi) return;
+    const double w[3] = {w0, w1, w2};
+    const double dmax = fabs((double)hi * p.step_size) + fabs((double)lo * p.step_size);
+    double e[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) e[k] = 0x1p-47 * (fabs(p.o[k]) + dmax * fabs(w[k]) + fabs(p.ext[2 * k]) + fabs(p.ext[2 * k + 1]));  // 2e
+    auto inside = [&](int s) {
+        const double d = (double)s * p.step_size;
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double q = p.o[k] + d * w[k];
+            ok = ok && (p.ext[2 * k] + e[k] <= q) && (q <= p.ext[2 * k + 1] - e[k]);
+        }
+        return ok;
+    };
+    int a = lo, b = hi;
+    for (int tries = 0; tries < 3 && a <= hi && !inside(a); ++tries) ++a;
+    for (int tries = 0; tries < 3 && b >= lo && !inside(b); ++tries) --b;
+    if (a <= b && inside(a) && inside(b)) { slo = a; shi = b; }
+}
+
 // Two pixels per lane (vertical neighbours, the lean2 idea of path A): pixel B's sample sits in pixel A's voxel most of the
 // time and then joins A's value before the scan, so one scan serves 64 samples; otherwise B issues its own RED.
+struct March2 {
+    unsigned ka, kb, heads, n_in;
+};
+
+template <typename S, typename CellT>
+__device__ __forceinline__ void march2_accumulate(CellT *__restrict__ grid, const ScanMasks &lm, const March2 &m, S val_a, S val_b, unsigned &n_in)
+{
+    const unsigned FULL = 0xffffffffu;
+    const bool live_a = m.ka != IMG_NONE, live_b = m.kb != IMG_NONE;
+    n_in += (unsigned)live_a + (unsigned)live_b;
+    const bool same = live_b && m.kb == m.ka;
+    const bool b_alone = live_b && !same;
+    S sum = (live_a ? val_a : (S)0) + (same ? val_b : (S)0), t;
+    t = __shfl_up_sync(FULL, sum, 1);  if (!(m.heads & lm.w1))  sum += t;
+    t = __shfl_up_sync(FULL, sum, 2);  if (!(m.heads & lm.w2))  sum += t;
+    t = __shfl_up_sync(FULL, sum, 4);  if (!(m.heads & lm.w4))  sum += t;
+    t = __shfl_up_sync(FULL, sum, 8);  if (!(m.heads & lm.w8))  sum += t;
+    t = __shfl_up_sync(FULL, sum, 16); if (!(m.heads & lm.w16)) sum += t;
+    if ((m.heads & lm.next) && live_a) img_red(grid + m.ka, sum);
+    if (b_alone) img_red(grid + m.kb, val_b);
+}
+
+// iterations s .. s_stop-1; each first computes the keys of sample s+1 (their arithmetic and shuffle overlap the scan of
+// sample s) -- with the full tests, or without them where s+1 lies in the warp's safe range
+template <bool TEST, typename S, typename CellT>
+__device__ __forceinline__ void march2_span(CellT *__restrict__ grid, const ImageP &p, const ImageFastP &f, const ScanMasks &lm, March2 &m, int &s, int s_stop,
+                                            double a0, double a1, double a2, S val_a, int lo_a, int hi_a,
+                                            double b0, double b1, double b2, S val_b, int lo_b, int hi_b)
+{
+    const unsigned FULL = 0xffffffffu;
+    for (; s < s_stop; ++s) {
+        const unsigned ka_n = TEST ? sample_key(p, f, s + 1, a0, a1, a2, lo_a, hi_a) : sample_key_inside(p, f, s + 1, a0, a1, a2, lo_a <= hi_a);
+        const unsigned kb_n = TEST ? sample_key(p, f, s + 1, b0, b1, b2, lo_b, hi_b) : sample_key_inside(p, f, s + 1, b0, b1, b2, lo_b <= hi_b);
+        const bool head_n = img_run_head(ka_n);
+        march2_accumulate<S>(grid, lm, m, val_a, val_b, m.n_in);
+        m.heads = __ballot_sync(FULL, head_n);
+        m.ka = ka_n; m.kb = kb_n;
+    }
+}
+
+// [mlo, mhi]: the samples inside every active ray's safe range (empty: mlo > mhi)
 template <typename S, typename CellT>
 __device__ __forceinline__ unsigned march_lockstep2(CellT *__restrict__ grid, const ImageP &p, const ImageFastP &f, const ScanMasks &lm,
                                                     double a0, double a1, double a2, S val_a, int lo_a, int hi_a,
-                                                    double b0, double b1, double b2, S val_b, int lo_b, int hi_b, int wlo, int whi)
+                                                    double b0, double b1, double b2, S val_b, int lo_b, int hi_b, int wlo, int whi, int mlo, int mhi)
 {
     const unsigned FULL = 0xffffffffu;
-    unsigned n_in = 0;
-    unsigned ka = sample_key(p, f, wlo, a0, a1, a2, lo_a, hi_a), kb = sample_key(p, f, wlo, b0, b1, b2, lo_b, hi_b);
-    unsigned heads = __ballot_sync(FULL, img_run_head(ka));
-    for (int s = wlo;; ++s) {
-        unsigned ka_n = IMG_NONE, kb_n = IMG_NONE;
-        if (s != whi) {
-            ka_n = sample_key(p, f, s + 1, a0, a1, a2, lo_a, hi_a);
-            kb_n = sample_key(p, f, s + 1, b0, b1, b2, lo_b, hi_b);
-        }
-        const bool head_n = img_run_head(ka_n);
-        const bool live_a = ka != IMG_NONE, live_b = kb != IMG_NONE;
-        n_in += (unsigned)live_a + (unsigned)live_b;
-        const bool same = live_b && kb == ka;
-        const bool b_alone = live_b && !same;
-        S sum = (live_a ? val_a : (S)0) + (same ? val_b : (S)0), t;
-        t = __shfl_up_sync(FULL, sum, 1);  if (!(heads & lm.w1))  sum += t;
-        t = __shfl_up_sync(FULL, sum, 2);  if (!(heads & lm.w2))  sum += t;
-        t = __shfl_up_sync(FULL, sum, 4);  if (!(heads & lm.w4))  sum += t;
-        t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum += t;
-        t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum += t;
-        if ((heads & lm.next) && live_a) img_red(grid + ka, sum);
-        if (b_alone) img_red(grid + kb, val_b);
-        if (s == whi) break;
-        heads = __ballot_sync(FULL, head_n);
-        ka = ka_n; kb = kb_n;
-    }
-    return n_in;
+    March2 m;
+    m.n_in = 0;
+    m.ka = sample_key(p, f, wlo, a0, a1, a2, lo_a, hi_a);
+    m.kb = sample_key(p, f, wlo, b0, b1, b2, lo_b, hi_b);
+    m.heads = __ballot_sync(FULL, img_run_head(m.ka));
+    int s = wlo;
+    march2_span<true, S>(grid, p, f, lm, m, s, min(whi, mlo - 1), a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);   // s+1 < mlo
+    march2_span<false, S>(grid, p, f, lm, m, s, min(whi, mhi), a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);      // mlo <= s+1 <= mhi
+    march2_span<true, S>(grid, p, f, lm, m, s, whi, a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);
+    march2_accumulate<S>(grid, lm, m, val_a, val_b, m.n_in);  // sample whi
+    return m.n_in;
 }
 
 template <int MODE>
@@ -422,16 +495,23 @@ process_image_lockstep2_kernel(const double *__restrict__ image, typename Cell<M
         }
         const int wlo = __reduce_min_sync(FULL, min(lo_a, lo_b)), whi = __reduce_max_sync(FULL, max(hi_a, hi_b));
         if (wlo > whi) continue;
+        // the samples on which every active ray of the warp provably passes its range and bounds tests
+        int slo_a, shi_a, slo_b, shi_b;
+        safe_range(p, a0, a1, a2, lo_a, hi_a, slo_a, shi_a);
+        safe_range(p, b0, b1, b2, lo_b, hi_b, slo_b, shi_b);
+        const int mlo = __reduce_max_sync(FULL, max(lo_a <= hi_a ? slo_a : INT32_MIN, lo_b <= hi_b ? slo_b : INT32_MIN));
+        const int mhi = __reduce_min_sync(FULL, min(lo_a <= hi_a ? shi_a : INT32_MAX, lo_b <= hi_b ? shi_b : INT32_MAX));
         if (MODE == PVP_ACCUM_FIXED) {
             // run sums of 64 values fit 32 bits when every value is below 2^26
             if (__all_sync(FULL, (unsigned long long)val_a < (1ull << 26) && (unsigned long long)val_b < (1ull << 26)))
                 my_samples += march_lockstep2<unsigned>((unsigned long long *)grid, p, f, lm, a0, a1, a2, (unsigned)val_a, lo_a, hi_a, b0, b1, b2, (unsigned)val_b,
-                                                        lo_b, hi_b, wlo, whi);
+                                                        lo_b, hi_b, wlo, whi, mlo, mhi);
             else
                 my_samples += march_lockstep2<unsigned long long>((unsigned long long *)grid, p, f, lm, a0, a1, a2, (unsigned long long)val_a, lo_a, hi_a, b0, b1,
-                                                                  b2, (unsigned long long)val_b, lo_b, hi_b, wlo, whi);
+                                                                  b2, (unsigned long long)val_b, lo_b, hi_b, wlo, whi, mlo, mhi);
         } else {
-            my_samples += march_lockstep2<double>((double *)grid, p, f, lm, a0, a1, a2, (double)val_a, lo_a, hi_a, b0, b1, b2, (double)val_b, lo_b, hi_b, wlo, whi);
+            my_samples += march_lockstep2<double>((double *)grid, p, f, lm, a0, a1, a2, (double)val_a, lo_a, hi_a, b0, b1, b2, (double)val_b, lo_b, hi_b, wlo, whi,
+                                                  mlo, mhi);
         }
     }
 #pragma unroll
