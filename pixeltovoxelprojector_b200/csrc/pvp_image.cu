@@ -224,13 +224,25 @@ __device__ __forceinline__ double div_by_extent(double a, double b, double y)
 // DMUL, one DADD and a funnel shift instead of the five-operation exact division and a 64-bit conversion.  Otherwise (about 10
 // samples in a million, a ray that runs exactly along voxel faces, or x < 5, where y drops below 2^52 and its fraction field reads
 // >= 0xFFFF6) the exact sequence decides.  CLAMP = false: the caller knows a < b with a margin (safe_range), so the index is < n.
-template <bool CLAMP = true>
-__device__ __forceinline__ int voxel_index(double a, const ImageFastP &f, int k)
+// the screened index of voxel_index(); `unsafe` collects "the exact sequence must decide" over several calls so that one
+// branch serves all the indices of a sample (six with two pixels per lane)
+__device__ __forceinline__ int voxel_index_screened(double a, const ImageFastP &f, int k, bool &unsafe)
 {
     const double y = dadd(dmul(a, f.k20[k]), 0x1p52 - 5.0);
     const unsigned lo = (unsigned)__double2loint(y), hi = (unsigned)__double2hiint(y);
-    int idx = (int)__funnelshift_r(lo, hi, 20);
-    if ((lo & 0xFFFFFu) >= 0xFFFF6u) idx = __double2int_rz(dmul(div_by_extent(a, f.b[k], f.y[k]), f.nd[k]));
+    unsafe = unsafe || (lo & 0xFFFFFu) >= 0xFFFF6u;
+    return (int)__funnelshift_r(lo, hi, 20);
+}
+__device__ __forceinline__ int voxel_index_exact(double a, const ImageFastP &f, int k)
+{
+    return __double2int_rz(dmul(div_by_extent(a, f.b[k], f.y[k]), f.nd[k]));
+}
+template <bool CLAMP = true>
+__device__ __forceinline__ int voxel_index(double a, const ImageFastP &f, int k)
+{
+    bool unsafe = false;
+    int idx = voxel_index_screened(a, f, k, unsafe);
+    if (unsafe) idx = voxel_index_exact(a, f, k);
     return CLAMP ? min(idx, f.n1[k]) : idx;
 }
 
@@ -280,6 +292,9 @@ __device__ __forceinline__ ScanMasks scan_masks(unsigned lane)
     m.w1 = 1u << lane; m.w2 = win(2); m.w4 = win(4); m.w8 = win(8);
     m.w16 = lane + 1 >= 16 ? (0xffffu << (lane - 15)) : ((2u << lane) - 1u);
     m.next = lane == 31 ? 1u : (1u << (lane + 1));
+    // opaque: otherwise the compiler rebuilds the masks from the lane number inside the march loop (~20 instructions per iteration
+    // in the float64 kernel) instead of keeping six registers
+    asm volatile("" : "+r"(m.w1), "+r"(m.w2), "+r"(m.w4), "+r"(m.w8), "+r"(m.w16), "+r"(m.next));
     return m;
 }
 
@@ -294,18 +309,20 @@ __device__ __forceinline__ void img_red(double *p, double v) { atomicAdd(p, v); 
 __device__ __forceinline__ void img_red(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 __device__ __forceinline__ void img_red(unsigned long long *p, unsigned v) { atomicAdd(p, (unsigned long long)v); }
 
-// voxel offset of sample s of one ray, or IMG_NONE (outside [lo,hi], or outside the extent: process_image.cpp:85, :349-352)
-__device__ __forceinline__ unsigned sample_key(const ImageP &p, const ImageFastP &f, int s, double w0, double w1, double w2, int lo, int hi)
+// position of the sample at distance d along one ray (process_image.cpp:345-347) and its offsets from the low faces
+struct SamplePos { double qx, qy, qz, ax, ay, az; };
+__device__ __forceinline__ SamplePos sample_pos(const ImageP &p, double d, double w0, double w1, double w2)
 {
-    const double d = dmul((double)s, p.step_size);  // :344
-    const double qx = dadd(p.o[0], dmul(d, w0)), qy = dadd(p.o[1], dmul(d, w1)), qz = dadd(p.o[2], dmul(d, w2));
-    // inside the extent the scaled coordinate lies in [0, n]: int truncation + upper clamp == :94-104
-    const int xi = voxel_index(dsub(qx, p.ext[0]), f, 0);
-    const int yi = voxel_index(dsub(qy, p.ext[2]), f, 1);
-    const int zi = voxel_index(dsub(qz, p.ext[4]), f, 2);
-    const unsigned off = (unsigned)xi * f.gs[0] + (unsigned)yi * f.gs[1] + (unsigned)zi * f.gs[2];
-    // in = lo <= s <= hi and the inclusive bounds test of :85 -- one chained predicate (the compiler's own form is a
-    // chain of eight selects), then key = in ? off : IMG_NONE
+    SamplePos r;
+    r.qx = dadd(p.o[0], dmul(d, w0)); r.qy = dadd(p.o[1], dmul(d, w1)); r.qz = dadd(p.o[2], dmul(d, w2));
+    r.ax = dsub(r.qx, p.ext[0]); r.ay = dsub(r.qy, p.ext[2]); r.az = dsub(r.qz, p.ext[4]);
+    return r;
+}
+
+// in = lo <= s <= hi and the inclusive bounds test of :85 -- one chained predicate (the compiler's own form is a chain of
+// eight selects) -- then key = in ? off : IMG_NONE
+__device__ __forceinline__ unsigned tested_key(const ImageP &p, int s, int lo, int hi, const SamplePos &q, unsigned off)
+{
     unsigned key;
     asm("{\n\t.reg .pred q;\n\t"
         "setp.ge.s32 q, %1, %2;\n\t"
@@ -318,9 +335,35 @@ __device__ __forceinline__ unsigned sample_key(const ImageP &p, const ImageFastP
         "setp.le.and.f64 q, %11, %12, q;\n\t"
         "selp.u32 %0, %13, 0xffffffff, q;\n\t}"
         : "=r"(key)
-        : "r"(s), "r"(lo), "r"(hi), "d"(p.ext[0]), "d"(qx), "d"(p.ext[1]), "d"(p.ext[2]), "d"(qy), "d"(p.ext[3]), "d"(p.ext[4]), "d"(qz),
+        : "r"(s), "r"(lo), "r"(hi), "d"(p.ext[0]), "d"(q.qx), "d"(p.ext[1]), "d"(p.ext[2]), "d"(q.qy), "d"(p.ext[3]), "d"(p.ext[4]), "d"(q.qz),
           "d"(p.ext[5]), "r"(off));
     return key;
+}
+
+// voxel offset of sample s of one ray, or IMG_NONE (outside [lo,hi], or outside the extent: process_image.cpp:85, :349-352)
+__device__ __forceinline__ unsigned sample_key(const ImageP &p, const ImageFastP &f, int s, double w0, double w1, double w2, int lo, int hi)
+{
+    const SamplePos q = sample_pos(p, dmul((double)s, p.step_size), w0, w1, w2);  // :344
+    // inside the extent the scaled coordinate lies in [0, n]: int truncation + upper clamp == :94-104
+    bool unsafe = false;
+    int xi = voxel_index_screened(q.ax, f, 0, unsafe), yi = voxel_index_screened(q.ay, f, 1, unsafe), zi = voxel_index_screened(q.az, f, 2, unsafe);
+    if (unsafe) { xi = voxel_index_exact(q.ax, f, 0); yi = voxel_index_exact(q.ay, f, 1); zi = voxel_index_exact(q.az, f, 2); }
+    xi = min(xi, f.n1[0]); yi = min(yi, f.n1[1]); zi = min(zi, f.n1[2]);
+    return tested_key(p, s, lo, hi, q, (unsigned)xi * f.gs[0] + (unsigned)yi * f.gs[1] + (unsigned)zi * f.gs[2]);
+}
+
+// run-sum update of one scan level as a predicated add (the compiler's own form for integers is a select and an add)
+__device__ __forceinline__ void scan_add(bool take, unsigned &sum, unsigned t)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q add.u32 %0, %0, %1;\n\t}" : "+r"(sum) : "r"(t), "r"((unsigned)take));
+}
+__device__ __forceinline__ void scan_add(bool take, unsigned long long &sum, unsigned long long t)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q add.u64 %0, %0, %1;\n\t}" : "+l"(sum) : "l"(t), "r"((unsigned)take));
+}
+__device__ __forceinline__ void scan_add(bool take, double &sum, double t)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q add.rn.f64 %0, %0, %1;\n\t}" : "+d"(sum) : "d"(t), "r"((unsigned)take));
 }
 
 // One warp, one group of 32 pixels: samples wlo..whi in lock-step.  S is the type the run sums are formed in.
@@ -352,19 +395,6 @@ __device__ __forceinline__ unsigned march_lockstep(CellT *__restrict__ grid, con
         key = key_n;
     }
     return n_in;
-}
-
-// sample_key without the range and bounds tests, for samples where both are known to pass (safe_range)
-__device__ __forceinline__ unsigned sample_key_inside(const ImageP &p, const ImageFastP &f, int s, double w0, double w1, double w2, bool active)
-{
-    const double d = dmul((double)s, p.step_size);  // :344
-    const double qx = dadd(p.o[0], dmul(d, w0)), qy = dadd(p.o[1], dmul(d, w1)), qz = dadd(p.o[2], dmul(d, w2));
-    // (no upper clamp: safe_range keeps a margin to the faces that is far above the rounding of the index arithmetic)
-    const int xi = voxel_index<false>(dsub(qx, p.ext[0]), f, 0);
-    const int yi = voxel_index<false>(dsub(qy, p.ext[2]), f, 1);
-    const int zi = voxel_index<false>(dsub(qz, p.ext[4]), f, 2);
-    const unsigned off = (unsigned)xi * f.gs[0] + (unsigned)yi * f.gs[1] + (unsigned)zi * f.gs[2];
-    return active ? off : IMG_NONE;
 }
 
 // A sub-range [slo, shi] of a ray's samples [lo, hi] on which the inclusive bounds test of process_image.cpp:85 provably passes,
@@ -404,20 +434,50 @@ struct March2 {
     unsigned ka, kb, heads, n_in;
 };
 
-template <typename S, typename CellT>
-__device__ __forceinline__ void march2_accumulate(CellT *__restrict__ grid, const ScanMasks &lm, const March2 &m, S val_a, S val_b, unsigned &n_in)
+// keys of sample s of both rays.  TEST: with the range and bounds tests; else for samples where both are known to pass
+// (safe_range: also a margin to the upper faces, so no clamp).  One distance, one "exact division needed" branch for all six indices.
+template <bool TEST>
+__device__ __forceinline__ void sample_keys2(const ImageP &p, const ImageFastP &f, int s, double a0, double a1, double a2, int lo_a, int hi_a,
+                                             double b0, double b1, double b2, int lo_b, int hi_b, unsigned &ka, unsigned &kb)
+{
+    const double d = dmul((double)s, p.step_size);  // :344
+    const SamplePos qa = sample_pos(p, d, a0, a1, a2), qb = sample_pos(p, d, b0, b1, b2);
+    bool unsafe = false;
+    int xa = voxel_index_screened(qa.ax, f, 0, unsafe), ya = voxel_index_screened(qa.ay, f, 1, unsafe), za = voxel_index_screened(qa.az, f, 2, unsafe);
+    int xb = voxel_index_screened(qb.ax, f, 0, unsafe), yb = voxel_index_screened(qb.ay, f, 1, unsafe), zb = voxel_index_screened(qb.az, f, 2, unsafe);
+    if (unsafe) {  // ~10 per million indices: the exact sequence is the reference's value for every one of them
+        xa = voxel_index_exact(qa.ax, f, 0); ya = voxel_index_exact(qa.ay, f, 1); za = voxel_index_exact(qa.az, f, 2);
+        xb = voxel_index_exact(qb.ax, f, 0); yb = voxel_index_exact(qb.ay, f, 1); zb = voxel_index_exact(qb.az, f, 2);
+    }
+    if (TEST) {
+        xa = min(xa, f.n1[0]); ya = min(ya, f.n1[1]); za = min(za, f.n1[2]);
+        xb = min(xb, f.n1[0]); yb = min(yb, f.n1[1]); zb = min(zb, f.n1[2]);
+    }
+    const unsigned off_a = (unsigned)xa * f.gs[0] + (unsigned)ya * f.gs[1] + (unsigned)za * f.gs[2];
+    const unsigned off_b = (unsigned)xb * f.gs[0] + (unsigned)yb * f.gs[1] + (unsigned)zb * f.gs[2];
+    if (TEST) {
+        ka = tested_key(p, s, lo_a, hi_a, qa, off_a);
+        kb = tested_key(p, s, lo_b, hi_b, qb, off_b);
+    } else {
+        ka = lo_a <= hi_a ? off_a : IMG_NONE;  // a lane without a ray stays silent
+        kb = lo_b <= hi_b ? off_b : IMG_NONE;
+    }
+}
+
+template <bool COUNT, typename S, typename CellT>
+__device__ __forceinline__ void march2_accumulate(CellT *__restrict__ grid, const ScanMasks &lm, March2 &m, S val_a, S val_b)
 {
     const unsigned FULL = 0xffffffffu;
     const bool live_a = m.ka != IMG_NONE, live_b = m.kb != IMG_NONE;
-    n_in += (unsigned)live_a + (unsigned)live_b;
+    if (COUNT) m.n_in += (unsigned)live_a + (unsigned)live_b;
     const bool same = live_b && m.kb == m.ka;
     const bool b_alone = live_b && !same;
     S sum = (live_a ? val_a : (S)0) + (same ? val_b : (S)0), t;
-    t = __shfl_up_sync(FULL, sum, 1);  if (!(m.heads & lm.w1))  sum += t;
-    t = __shfl_up_sync(FULL, sum, 2);  if (!(m.heads & lm.w2))  sum += t;
-    t = __shfl_up_sync(FULL, sum, 4);  if (!(m.heads & lm.w4))  sum += t;
-    t = __shfl_up_sync(FULL, sum, 8);  if (!(m.heads & lm.w8))  sum += t;
-    t = __shfl_up_sync(FULL, sum, 16); if (!(m.heads & lm.w16)) sum += t;
+    t = __shfl_up_sync(FULL, sum, 1);  scan_add(!(m.heads & lm.w1), sum, t);
+    t = __shfl_up_sync(FULL, sum, 2);  scan_add(!(m.heads & lm.w2), sum, t);
+    t = __shfl_up_sync(FULL, sum, 4);  scan_add(!(m.heads & lm.w4), sum, t);
+    t = __shfl_up_sync(FULL, sum, 8);  scan_add(!(m.heads & lm.w8), sum, t);
+    t = __shfl_up_sync(FULL, sum, 16); scan_add(!(m.heads & lm.w16), sum, t);
     if ((m.heads & lm.next) && live_a) img_red(grid + m.ka, sum);
     if (b_alone) img_red(grid + m.kb, val_b);
 }
@@ -430,11 +490,17 @@ __device__ __forceinline__ void march2_span(CellT *__restrict__ grid, const Imag
                                             double b0, double b1, double b2, S val_b, int lo_b, int hi_b)
 {
     const unsigned FULL = 0xffffffffu;
+    if (!TEST && s < s_stop) {
+        // not counted per iteration in the safe range: sample s (keys computed earlier) by its keys, samples s+1 .. s_stop-1 -- computed
+        // AND accumulated by this span -- are inside for every ray the lane has; sample s_stop is counted by whoever accumulates it
+        m.n_in += (unsigned)(m.ka != IMG_NONE) + (unsigned)(m.kb != IMG_NONE);
+        m.n_in += (unsigned)(s_stop - 1 - s) * ((unsigned)(lo_a <= hi_a) + (unsigned)(lo_b <= hi_b));
+    }
     for (; s < s_stop; ++s) {
-        const unsigned ka_n = TEST ? sample_key(p, f, s + 1, a0, a1, a2, lo_a, hi_a) : sample_key_inside(p, f, s + 1, a0, a1, a2, lo_a <= hi_a);
-        const unsigned kb_n = TEST ? sample_key(p, f, s + 1, b0, b1, b2, lo_b, hi_b) : sample_key_inside(p, f, s + 1, b0, b1, b2, lo_b <= hi_b);
+        unsigned ka_n, kb_n;
+        sample_keys2<TEST>(p, f, s + 1, a0, a1, a2, lo_a, hi_a, b0, b1, b2, lo_b, hi_b, ka_n, kb_n);
         const bool head_n = img_run_head(ka_n);
-        march2_accumulate<S>(grid, lm, m, val_a, val_b, m.n_in);
+        march2_accumulate<TEST, S>(grid, lm, m, val_a, val_b);
         m.heads = __ballot_sync(FULL, head_n);
         m.ka = ka_n; m.kb = kb_n;
     }
@@ -449,14 +515,13 @@ __device__ __forceinline__ unsigned march_lockstep2(CellT *__restrict__ grid, co
     const unsigned FULL = 0xffffffffu;
     March2 m;
     m.n_in = 0;
-    m.ka = sample_key(p, f, wlo, a0, a1, a2, lo_a, hi_a);
-    m.kb = sample_key(p, f, wlo, b0, b1, b2, lo_b, hi_b);
+    sample_keys2<true>(p, f, wlo, a0, a1, a2, lo_a, hi_a, b0, b1, b2, lo_b, hi_b, m.ka, m.kb);
     m.heads = __ballot_sync(FULL, img_run_head(m.ka));
     int s = wlo;
     march2_span<true, S>(grid, p, f, lm, m, s, min(whi, mlo - 1), a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);   // s+1 < mlo
     march2_span<false, S>(grid, p, f, lm, m, s, min(whi, mhi), a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);      // mlo <= s+1 <= mhi
     march2_span<true, S>(grid, p, f, lm, m, s, whi, a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);
-    march2_accumulate<S>(grid, lm, m, val_a, val_b, m.n_in);  // sample whi
+    march2_accumulate<true, S>(grid, lm, m, val_a, val_b);  // sample whi
     return m.n_in;
 }
 
