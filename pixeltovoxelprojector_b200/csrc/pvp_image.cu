@@ -205,6 +205,7 @@ struct ImageFastP {
     double k20[3];             // RN(n / extent) * 2^20: the screening factor of voxel_index()
     int n1[3];                 // n - 1
     unsigned gs[3];            // element strides
+    int affine_ok;             // the safe-range march may take the scaled coordinate from one FMA per axis (sample_keys2<2>)
 };
 
 __device__ __forceinline__ double div_by_extent(double a, double b, double y)
@@ -434,28 +435,74 @@ struct March2 {
     unsigned ka, kb, heads, n_in;
 };
 
-// keys of sample s of both rays.  TEST: with the range and bounds tests; else for samples where both are known to pass
-// (safe_range: also a margin to the upper faces, so no clamp).  One distance, one "exact division needed" branch for all six indices.
-template <bool TEST>
-__device__ __forceinline__ void sample_keys2(const ImageP &p, const ImageFastP &f, int s, double a0, double a1, double a2, int lo_a, int hi_a,
-                                             double b0, double b1, double b2, int lo_b, int hi_b, unsigned &ka, unsigned &kb)
+// Per-axis affine form of the scaled voxel coordinate of a ray's samples, x(s) = (o + s*step*w - ext_lo) * K + (2^52 - 5)
+// = s * dx + x0, for the safe range.
+struct Affine { double dx[3], x0[3]; };
+__device__ __forceinline__ Affine affine_of(const ImageP &p, const ImageFastP &f, double w0, double w1, double w2)
 {
+    const double w[3] = {w0, w1, w2};
+    Affine a;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        a.dx[k] = (p.step_size * w[k]) * f.k20[k];
+        a.x0[k] = (p.o[k] - p.ext[2 * k]) * f.k20[k] + (0x1p52 - 5.0);
+    }
+    return a;
+}
+
+// keys of sample s of both rays.  MODE 0: with the range and bounds tests.  MODE 1: for samples where both are known to pass
+// (safe_range: also a margin to the upper faces, so no clamp).  MODE 2: as 1, and the scaled coordinate of voxel_index_screened --
+// whose screening only needs it to within a few units of 2^-20 -- comes from ONE FMA per axis, y = RN(s * dx + x0), instead of
+// the reference's five roundings: with A = |o| + max_distance + |ext| and K = n/extent * 2^20, y is within 1 + 2^-51 A K units of
+// the real x(s) + 2^52 - 5 (rounding of dx, x0 and the FMA itself) and the reference's own RN(RN(a/b) n) within 2^-50 A K + 2^-8
+// units of x(s); the host allows this mode when A K <= 2^49 (make_fastp), so the two differ by less than 2.1 units and the window of
+// voxel_index_screened (5 units to either side of a multiple of 2^20) still proves trunc() equal.  Flagged samples take the exact
+// sequence on the reference's own operands.  One distance, one "exact division needed" branch for all six indices.
+template <int MODE>
+__device__ __forceinline__ void sample_keys2(const ImageP &p, const ImageFastP &f, int s, double a0, double a1, double a2, int lo_a, int hi_a,
+                                             double b0, double b1, double b2, int lo_b, int hi_b, const Affine &fa, const Affine &fb,
+                                             unsigned &ka, unsigned &kb)
+{
+    int xa, ya, za, xb, yb, zb;
+    if (MODE == 2) {
+        const double sd = (double)s;
+        const double y[6] = {__fma_rn(sd, fa.dx[0], fa.x0[0]), __fma_rn(sd, fa.dx[1], fa.x0[1]), __fma_rn(sd, fa.dx[2], fa.x0[2]),
+                             __fma_rn(sd, fb.dx[0], fb.x0[0]), __fma_rn(sd, fb.dx[1], fb.x0[1]), __fma_rn(sd, fb.dx[2], fb.x0[2])};
+        int idx[6];
+        bool unsafe = false;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const unsigned lo = (unsigned)__double2loint(y[k]), hi = (unsigned)__double2hiint(y[k]);
+            unsafe = unsafe || (lo & 0xFFFFFu) >= 0xFFFF6u;
+            idx[k] = (int)__funnelshift_r(lo, hi, 20);
+        }
+        xa = idx[0]; ya = idx[1]; za = idx[2]; xb = idx[3]; yb = idx[4]; zb = idx[5];
+        if (unsafe) {
+            const double d = dmul(sd, p.step_size);  // :344
+            const SamplePos qa = sample_pos(p, d, a0, a1, a2), qb = sample_pos(p, d, b0, b1, b2);
+            xa = voxel_index_exact(qa.ax, f, 0); ya = voxel_index_exact(qa.ay, f, 1); za = voxel_index_exact(qa.az, f, 2);
+            xb = voxel_index_exact(qb.ax, f, 0); yb = voxel_index_exact(qb.ay, f, 1); zb = voxel_index_exact(qb.az, f, 2);
+        }
+        ka = lo_a <= hi_a ? (unsigned)xa * f.gs[0] + (unsigned)ya * f.gs[1] + (unsigned)za * f.gs[2] : IMG_NONE;
+        kb = lo_b <= hi_b ? (unsigned)xb * f.gs[0] + (unsigned)yb * f.gs[1] + (unsigned)zb * f.gs[2] : IMG_NONE;
+        return;
+    }
     const double d = dmul((double)s, p.step_size);  // :344
     const SamplePos qa = sample_pos(p, d, a0, a1, a2), qb = sample_pos(p, d, b0, b1, b2);
     bool unsafe = false;
-    int xa = voxel_index_screened(qa.ax, f, 0, unsafe), ya = voxel_index_screened(qa.ay, f, 1, unsafe), za = voxel_index_screened(qa.az, f, 2, unsafe);
-    int xb = voxel_index_screened(qb.ax, f, 0, unsafe), yb = voxel_index_screened(qb.ay, f, 1, unsafe), zb = voxel_index_screened(qb.az, f, 2, unsafe);
+    xa = voxel_index_screened(qa.ax, f, 0, unsafe); ya = voxel_index_screened(qa.ay, f, 1, unsafe); za = voxel_index_screened(qa.az, f, 2, unsafe);
+    xb = voxel_index_screened(qb.ax, f, 0, unsafe); yb = voxel_index_screened(qb.ay, f, 1, unsafe); zb = voxel_index_screened(qb.az, f, 2, unsafe);
     if (unsafe) {  // ~10 per million indices: the exact sequence is the reference's value for every one of them
         xa = voxel_index_exact(qa.ax, f, 0); ya = voxel_index_exact(qa.ay, f, 1); za = voxel_index_exact(qa.az, f, 2);
         xb = voxel_index_exact(qb.ax, f, 0); yb = voxel_index_exact(qb.ay, f, 1); zb = voxel_index_exact(qb.az, f, 2);
     }
-    if (TEST) {
+    if (MODE == 0) {
         xa = min(xa, f.n1[0]); ya = min(ya, f.n1[1]); za = min(za, f.n1[2]);
         xb = min(xb, f.n1[0]); yb = min(yb, f.n1[1]); zb = min(zb, f.n1[2]);
     }
     const unsigned off_a = (unsigned)xa * f.gs[0] + (unsigned)ya * f.gs[1] + (unsigned)za * f.gs[2];
     const unsigned off_b = (unsigned)xb * f.gs[0] + (unsigned)yb * f.gs[1] + (unsigned)zb * f.gs[2];
-    if (TEST) {
+    if (MODE == 0) {
         ka = tested_key(p, s, lo_a, hi_a, qa, off_a);
         kb = tested_key(p, s, lo_b, hi_b, qb, off_b);
     } else {
@@ -483,14 +530,17 @@ __device__ __forceinline__ void march2_accumulate(CellT *__restrict__ grid, cons
 }
 
 // iterations s .. s_stop-1; each first computes the keys of sample s+1 (their arithmetic and shuffle overlap the scan of
-// sample s) -- with the full tests, or without them where s+1 lies in the warp's safe range
-template <bool TEST, typename S, typename CellT>
+// sample s) -- with the full tests (MODE 0), or without them where s+1 lies in the warp's safe range (MODE 1 / 2, sample_keys2)
+template <int MODE, typename S, typename CellT>
 __device__ __forceinline__ void march2_span(CellT *__restrict__ grid, const ImageP &p, const ImageFastP &f, const ScanMasks &lm, March2 &m, int &s, int s_stop,
                                             double a0, double a1, double a2, S val_a, int lo_a, int hi_a,
                                             double b0, double b1, double b2, S val_b, int lo_b, int hi_b)
 {
     const unsigned FULL = 0xffffffffu;
-    if (!TEST && s < s_stop) {
+    if (s >= s_stop) return;
+    Affine fa, fb;
+    if (MODE == 2) { fa = affine_of(p, f, a0, a1, a2); fb = affine_of(p, f, b0, b1, b2); }
+    if (MODE != 0) {
         // not counted per iteration in the safe range: sample s (keys computed earlier) by its keys, samples s+1 .. s_stop-1 -- computed
         // AND accumulated by this span -- are inside for every ray the lane has; sample s_stop is counted by whoever accumulates it
         m.n_in += (unsigned)(m.ka != IMG_NONE) + (unsigned)(m.kb != IMG_NONE);
@@ -498,9 +548,9 @@ __device__ __forceinline__ void march2_span(CellT *__restrict__ grid, const Imag
     }
     for (; s < s_stop; ++s) {
         unsigned ka_n, kb_n;
-        sample_keys2<TEST>(p, f, s + 1, a0, a1, a2, lo_a, hi_a, b0, b1, b2, lo_b, hi_b, ka_n, kb_n);
+        sample_keys2<MODE>(p, f, s + 1, a0, a1, a2, lo_a, hi_a, b0, b1, b2, lo_b, hi_b, fa, fb, ka_n, kb_n);
         const bool head_n = img_run_head(ka_n);
-        march2_accumulate<TEST, S>(grid, lm, m, val_a, val_b);
+        march2_accumulate<MODE == 0, S>(grid, lm, m, val_a, val_b);
         m.heads = __ballot_sync(FULL, head_n);
         m.ka = ka_n; m.kb = kb_n;
     }
@@ -515,18 +565,23 @@ __device__ __forceinline__ unsigned march_lockstep2(CellT *__restrict__ grid, co
     const unsigned FULL = 0xffffffffu;
     March2 m;
     m.n_in = 0;
-    sample_keys2<true>(p, f, wlo, a0, a1, a2, lo_a, hi_a, b0, b1, b2, lo_b, hi_b, m.ka, m.kb);
+    const Affine none = {};
+    sample_keys2<0>(p, f, wlo, a0, a1, a2, lo_a, hi_a, b0, b1, b2, lo_b, hi_b, none, none, m.ka, m.kb);
     m.heads = __ballot_sync(FULL, img_run_head(m.ka));
     int s = wlo;
-    march2_span<true, S>(grid, p, f, lm, m, s, min(whi, mlo - 1), a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);   // s+1 < mlo
-    march2_span<false, S>(grid, p, f, lm, m, s, min(whi, mhi), a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);      // mlo <= s+1 <= mhi
-    march2_span<true, S>(grid, p, f, lm, m, s, whi, a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);
+    march2_span<0, S>(grid, p, f, lm, m, s, min(whi, mlo - 1), a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);   // s+1 < mlo
+    if (f.affine_ok) march2_span<2, S>(grid, p, f, lm, m, s, min(whi, mhi), a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);  // mlo <= s+1 <= mhi
+    else march2_span<1, S>(grid, p, f, lm, m, s, min(whi, mhi), a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);
+    march2_span<0, S>(grid, p, f, lm, m, s, whi, a0, a1, a2, val_a, lo_a, hi_a, b0, b1, b2, val_b, lo_b, hi_b);
     march2_accumulate<true, S>(grid, lm, m, val_a, val_b);  // sample whi
     return m.n_in;
 }
 
+#ifndef PVP_K3_MINB
+#define PVP_K3_MINB 3  // 80 registers: measured 4096^2 -> 512^3 fixed point 624 G samples/s, against 517 G with ptxas' own choice (94 registers, 2 CTAs per SM)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(K3L_THREADS)
+__global__ void __launch_bounds__(K3L_THREADS, PVP_K3_MINB)
 process_image_lockstep2_kernel(const double *__restrict__ image, typename Cell<MODE>::T *__restrict__ grid,
                                typename Cell<MODE>::T *__restrict__ tex, ImageP p, ImageFastP f, Ctl *__restrict__ ctl)
 {
@@ -725,6 +780,12 @@ static bool make_fastp(const ImageP &p, ImageFastP *f)
         f->n1[k] = (int)(p.gn[k] - 1);
         f->gs[k] = (unsigned)p.gs[k];
         span += (unsigned long long)(p.gn[k] - 1) * (unsigned long long)p.gs[k];
+    }
+    // sample_keys2<2>: A K <= 2^49 with A = |o| + max_distance + |ext_lo| + |ext_hi| + extent (bounds every magnitude of the sample position)
+    f->affine_ok = std::isfinite(p.max_distance) && p.max_distance >= 0.0;
+    for (int k = 0; k < 3; ++k) {
+        const double A = fabs(p.o[k]) + p.max_distance + fabs(p.ext[2 * k]) + fabs(p.ext[2 * k + 1]) + f->b[k];
+        if (!(A * f->k20[k] <= 0x1p49)) f->affine_ok = 0;
     }
     return span < 0xffffffffull;  // voxel offsets are 32-bit keys, 0xffffffff is reserved
 }

@@ -305,3 +305,35 @@ def test_row_and_file_shards_sum_to_whole(ctx, oracle, variant):
             pd.process_image_sharded(image, pos, pointing, fov, W, H, wg, ext, 60.0, 240, wt, *sky, True, True, rank=0, world=2)
     finally:
         ctx.set_option("image_variant", 0)
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+def test_bench_geometry_and_samples_on_voxel_faces_exact(ctx, oracle, variant):
+    """The bench scene's geometry at a size the oracle finishes in seconds (512^2 image -> 128^3 grid, one sample per voxel
+    pitch, ~50 M samples), and an axis-aligned scene whose samples land EXACTLY on voxel faces (observer on the grid axis,
+    unit step, integer extent: the scaled coordinate of the lock-step kernels' screening is an exact integer there and the
+    exact division must decide) -- both bit for bit against the oracle in fixed-point mode, counters included."""
+    from pixeltovoxelprojector_b200 import process_image as pi
+    rng = np.random.default_rng(99)
+    ctx.set_option("image_variant", variant)
+    try:
+        n, H, W = 128, 512, 512
+        half = n / 2.0
+        scenes = [
+            (rng.random((H, W)), [0.0, 0.0, 0.0], [0.02, 0.01, 1.0], 0.8, [(-half, half), (-half, half), (100.0, 100.0 + n)], float(100 + n + 88), 100 + n + 88, (n, n, n)),
+            (rng.random((96, 96)), [0.0, 0.0, -10.0], [0.0, 0.0, 1.0], 0.5, [(-32.0, 32.0), (-32.0, 32.0), (0.0, 64.0)], 80.0, 80, (64, 64, 64)),
+            (rng.random((96, 96)), [0.5, 0.5, -10.0], [0.0, 0.0, 2.0], 0.5, [(-32.0, 32.0), (-32.0, 32.0), (0.0, 64.0)], 80.0, 160, (64, 32, 128)),
+            (rng.random((64, 80)), [-40.0, 0.0, 0.25], [1.0, 0.0, 0.0], 0.7, [(-32.0, 32.0), (-32.0, 32.0), (-32.0, 32.0)], 90.0, 360, (64, 64, 64)),
+        ]
+        for img, pos, pointing, fov, ext, md, ns, shape in scenes:
+            h, w = img.shape
+            og, ot = np.zeros(shape, np.int64), np.zeros((8, 8), np.int64)
+            nr, nsamp = oracle.process_image(img, pos, pointing, fov, w, h, og, ext, md, ns, ot, 0.0, 0.0, 1.0, 1.0, False, False, accum_mode=1, frac_bits=20)
+            gi = torch.zeros(shape, dtype=torch.int64, device="cuda")
+            ti = torch.zeros((8, 8), dtype=torch.int64, device="cuda")
+            pvp.process_image_cpp(torch.as_tensor(img, device="cuda"), pos, pointing, fov, w, h, gi, ext, md, ns, ti, 0.0, 0.0, 1.0, 1.0, False, False,
+                                  accum_mode="fixed", frac_bits=20, want_stats=True)
+            assert pi.last_stats == {"n_rays": nr, "n_samples": nsamp} and nsamp > 50 * nr > 0
+            assert np.array_equal(gi.cpu().numpy(), og)
+    finally:
+        ctx.set_option("image_variant", 0)
