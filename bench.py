@@ -398,7 +398,7 @@ def run_ours_image(args, wl):
     k3_s = prof["ms_k3"] * 1e-3
     achieved = 16 * my_samples / k3_s / 1e9 if k3_s > 0 else 0.0     # one 8-byte atomic RMW per sample
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": measured_traffic(args.workload), "kernel": "process_image_lockstep_kernel (K3)", "peak_source": peak_src, "algorithmic_bytes_per_voxel_step": 16,
+                "traffic": measured_traffic(args.workload), "kernel": "process_image_lockstep2_kernel (K3)", "peak_source": peak_src, "algorithmic_bytes_per_voxel_step": 16,
                 "voxel_steps_per_launch": my_samples / max(1, prof["launches_k3"]), "avg_launch_ms": prof["ms_k3"] / max(1, prof["launches_k3"]),
                 "k3_share_of_step": prof["ms_k3"] / ms if ms > 0 else None}
     if args.no_cpu:
