@@ -95,28 +95,32 @@ __device__ __forceinline__ bool pixel_setup(const double *__restrict__ image, ty
     const double dn = __dsqrt_rn(dadd(dadd(dmul(w0, w0), dmul(w1, w1)), dmul(w2, w2)));  // :255-260
     w0 = ddiv(w0, dn); w1 = ddiv(w1, dn); w2 = ddiv(w2, dn);
 
-    const double r = __dsqrt_rn(dadd(dadd(dmul(w0, w0), dmul(w1, w1)), dmul(w2, w2)));   // :267
-    const double dec = asin(ddiv(w2, r));
-    double ra = atan2(w1, w0);
-    if (ra < 0) ra = dadd(ra, 2 * M_PI);  // :270
-    double ra_off = dsub(ra, p.c_ra), dec_off = dsub(dec, p.c_dec);
-    if (ra_off > M_PI) ra_off = dsub(ra_off, 2 * M_PI);  // :277-278
-    if (ra_off < -M_PI) ra_off = dadd(ra_off, 2 * M_PI);
-    const bool within = (fabs(ra_off) <= p.half_w) && (fabs(dec_off) <= p.half_h);  // :281-282
-    const double u = dmul(ddiv(dadd(ra_off, p.half_w), p.ang_w), (double)p.tw);      // :285-286
-    const double v = dmul(ddiv(dadd(dec_off, p.half_h), p.ang_h), (double)p.th);
-    long long u_idx = trunc64_like_x86(u), v_idx = trunc64_like_x86(v);              // :288-293
-    u_idx = min(max(u_idx, 0ll), p.tw - 1);
-    v_idx = min(max(v_idx, 0ll), p.th - 1);
-    typename C::T *texel = tex + (v_idx * p.ts0 + u_idx * p.ts1);
+    if (p.update_tex || p.bg_sub) {  // RA/Dec and the texel have no other consumer (:267-314); warp-uniform
+        const double r = __dsqrt_rn(dadd(dadd(dmul(w0, w0), dmul(w1, w1)), dmul(w2, w2)));   // :267
+        const double dec = asin(ddiv(w2, r));
+        double ra = atan2(w1, w0);
+        if (ra < 0) ra = dadd(ra, 2 * M_PI);  // :270
+        double ra_off = dsub(ra, p.c_ra), dec_off = dsub(dec, p.c_dec);
+        if (ra_off > M_PI) ra_off = dsub(ra_off, 2 * M_PI);  // :277-278
+        if (ra_off < -M_PI) ra_off = dadd(ra_off, 2 * M_PI);
+        const bool within = (fabs(ra_off) <= p.half_w) && (fabs(dec_off) <= p.half_h);  // :281-282
+        const double u = dmul(ddiv(dadd(ra_off, p.half_w), p.ang_w), (double)p.tw);      // :285-286
+        const double v = dmul(ddiv(dadd(dec_off, p.half_h), p.ang_h), (double)p.th);
+        long long u_idx = trunc64_like_x86(u), v_idx = trunc64_like_x86(v);              // :288-293
+        u_idx = min(max(u_idx, 0ll), p.tw - 1);
+        v_idx = min(max(v_idx, 0ll), p.th - 1);
+        typename C::T *texel = tex + (v_idx * p.ts0 + u_idx * p.ts1);
 
-    if (p.bg_sub) {  // :296-307 (the reference also loads the texel when it is not used)
-        const double background = within ? C::read(texel, p.scale) : 0.0;
-        brightness = dsub(brightness, background);
-        if (brightness <= 0) return false;
+        if (p.bg_sub) {  // :296-307 (the reference also loads the texel when it is not used)
+            const double background = within ? C::read(texel, p.scale) : 0.0;
+            brightness = dsub(brightness, background);
+            if (brightness <= 0) return false;
+        }
+        val = C::make(brightness, p.scale);
+        if (p.update_tex && within) C::add(texel, val);  // :310-314
+    } else {
+        val = C::make(brightness, p.scale);
     }
-    val = C::make(brightness, p.scale);
-    if (p.update_tex && within) C::add(texel, val);  // :310-314
     counted = true;
     if (!p.grid_provided) return false;  // :317
 
@@ -205,6 +209,7 @@ struct ImageFastP {
     double k20[3];             // RN(n / extent) * 2^20: the screening factor of voxel_index()
     int n1[3];                 // n - 1
     unsigned gs[3];            // element strides
+    double margin[3];          // 32 units of 2^-20 voxel in world units (safe_range)
     int affine_ok;             // the safe-range march may take the scaled coordinate from one FMA per axis (sample_keys2<2>)
 };
 
@@ -404,7 +409,7 @@ __device__ __forceinline__ unsigned march_lockstep(CellT *__restrict__ grid, con
 // those magnitudes), and x(s) is linear in s: if at two samples the computed position keeps a margin of 2e to all six faces,
 // the exact position keeps e there and hence everywhere between them, and every computed position between them is inside.
 // The candidates are the first / last three samples of the ray; a ray that grazes a face gets an empty range (tests everywhere).
-__device__ __forceinline__ void safe_range(const ImageP &p, double w0, double w1, double w2, int lo, int hi, int &slo, int &shi)
+__device__ __forceinline__ void safe_range(const ImageP &p, const ImageFastP &f, double w0, double w1, double w2, int lo, int hi, int &slo, int &shi)
 {
     slo = INT32_MAX; shi = INT32_MIN;
     if (lo > hi) return;
@@ -412,7 +417,9 @@ __device__ __forceinline__ void safe_range(const ImageP &p, double w0, double w1
     const double dmax = fabs((double)hi * p.step_size) + fabs((double)lo * p.step_size);
     double e[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) e[k] = 0x1p-47 * (fabs(p.o[k]) + dmax * fabs(w[k]) + fabs(p.ext[2 * k]) + fabs(p.ext[2 * k + 1]));  // 2e
+    // 2e, plus 32 units of 2^-20 voxel: the scaled coordinate of a safe sample is then >= 32, so sample_keys2<2>'s y = RN(s dx + x0),
+    // within 1.6 units of x(s) + 2^52 - 5, cannot drop below 2^52 (where its mantissa would no longer hold r - 5)
+    for (int k = 0; k < 3; ++k) e[k] = 0x1p-47 * (fabs(p.o[k]) + dmax * fabs(w[k]) + fabs(p.ext[2 * k]) + fabs(p.ext[2 * k + 1])) + f.margin[k];
     auto inside = [&](int s) {
         const double d = (double)s * p.step_size;
         bool ok = true;
@@ -456,7 +463,7 @@ __device__ __forceinline__ Affine affine_of(const ImageP &p, const ImageFastP &f
 // the reference's five roundings: with A = |o| + max_distance + |ext| and K = n/extent * 2^20, y is within 1 + 2^-51 A K units of
 // the real x(s) + 2^52 - 5 (rounding of dx, x0 and the FMA itself) and the reference's own RN(RN(a/b) n) within 2^-50 A K + 2^-8
 // units of x(s); the host allows this mode when A K <= 2^49 (make_fastp), so the two differ by less than 2.1 units and the window of
-// voxel_index_screened (5 units to either side of a multiple of 2^20) still proves trunc() equal.  Flagged samples take the exact
+// voxel_index_screened (5 units to either side of a multiple of 2^20) still proves trunc() equal; safe_range keeps x(s) >= 32, so y >= 2^52.  Flagged samples take the exact
 // sequence on the reference's own operands.  One distance, one "exact division needed" branch for all six indices.
 template <int MODE>
 __device__ __forceinline__ void sample_keys2(const ImageP &p, const ImageFastP &f, int s, double a0, double a1, double a2, int lo_a, int hi_a,
@@ -617,8 +624,8 @@ process_image_lockstep2_kernel(const double *__restrict__ image, typename Cell<M
         if (wlo > whi) continue;
         // the samples on which every active ray of the warp provably passes its range and bounds tests
         int slo_a, shi_a, slo_b, shi_b;
-        safe_range(p, a0, a1, a2, lo_a, hi_a, slo_a, shi_a);
-        safe_range(p, b0, b1, b2, lo_b, hi_b, slo_b, shi_b);
+        safe_range(p, f, a0, a1, a2, lo_a, hi_a, slo_a, shi_a);
+        safe_range(p, f, b0, b1, b2, lo_b, hi_b, slo_b, shi_b);
         const int mlo = __reduce_max_sync(FULL, max(lo_a <= hi_a ? slo_a : INT32_MIN, lo_b <= hi_b ? slo_b : INT32_MIN));
         const int mhi = __reduce_min_sync(FULL, min(lo_a <= hi_a ? shi_a : INT32_MAX, lo_b <= hi_b ? shi_b : INT32_MAX));
         if (MODE == PVP_ACCUM_FIXED) {
@@ -777,6 +784,7 @@ static bool make_fastp(const ImageP &p, ImageFastP *f)
         f->nd[k] = (double)p.gn[k];
         volatile double kq = (double)p.gn[k] / b;  // RN(n / b); the scaling by 2^20 is exact
         f->k20[k] = kq * 1048576.0;
+        f->margin[k] = 32.0 / f->k20[k];
         f->n1[k] = (int)(p.gn[k] - 1);
         f->gs[k] = (unsigned)p.gs[k];
         span += (unsigned long long)(p.gn[k] - 1) * (unsigned long long)p.gs[k];

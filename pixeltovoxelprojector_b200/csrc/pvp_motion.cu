@@ -543,7 +543,8 @@ __device__ __forceinline__ float axis_limit(float tm0, float td, int rem)
 {
     if (!(td < CUDART_INF_F)) return CUDART_INF_F;  // parallel axis (safe_div, :266-272): never chosen before the others run out
     const float span = fmul((float)rem, td);
-    return fsub(fadd(tm0, span), fmul(fadd(fabsf(tm0), span), 0x1p-11f));
+    const float bound = fsub(fadd(tm0, span), fmul(fadd(fabsf(tm0), span), 0x1p-11f));
+    return bound == bound ? bound : -CUDART_INF_F;  // overflow (inf - inf): no proof, every step of this ray takes the exact test
 }
 
 // Does the step along the chosen axis (cz / cy / else x) leave [0, N)?  Decodes the voxel the step starts from.  Slab kernels
