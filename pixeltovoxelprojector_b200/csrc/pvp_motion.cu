@@ -106,79 +106,141 @@ motion_compact_kernel(const T *__restrict__ frames, long long frame_stride, cons
     }
 }
 
-// Row-group ordering: a thread handles the same PX columns of R consecutive rows and writes its entries column by
-// column, top pixel first, so that 32 (or 64) consecutive queue entries form a compact 2-D tile of the image
+// Row-group ordering: a thread handles 4 columns of R consecutive rows and emits its entries column by column, top pixel
+// first, threads in column order -- so 32 (or 64) consecutive queue entries form a compact 2-D tile of the image
 // (32/R columns x R rows) instead of a 32 x 1 strip.  The rays of a tile diverge less -- fewer distinct voxels per
 // lock-step iteration, more even ray lengths -- and for lean2 entries 2i / 2i+1 are vertical neighbours.  Same filters,
-// same entries as motion_compact_kernel; only the order differs.
+// same entries as motion_compact_kernel; only the order differs.  The CTA's entries are staged in shared memory in
+// that order and copied out with coalesced stores (a thread writing its own run of entries would scatter every store
+// instruction over 32 lines: 157 us per launch of four 1080p pairs, against 10 B x 8 M entries = 12 us of HBM time).
+constexpr int K1T_COLS = 4;                                   // columns per thread: one 32-bit (uint8) / 128-bit (float) load per row
+constexpr int K1T_MAX_ENTRIES = 4096;                          // per CTA: 32 KiB of staging
+template <int R> struct K1Tile {
+    static constexpr int THREADS = (K1T_MAX_ENTRIES / (K1T_COLS * R)) < 256 ? (K1T_MAX_ENTRIES / (K1T_COLS * R)) : 256;
+    static constexpr int ITER = R <= 2 ? 4 : R == 4 ? 2 : 1;  // blocks per CTA: 8 rows x 2 frames of loads in flight per thread
+};
+
+template <typename T> struct RowSeg;  // 4 pixels of a row as loaded: one 32-bit word (uint8) / one float4
+template <> struct RowSeg<uint8_t> { using V = unsigned; };
+template <> struct RowSeg<float> { using V = float4; };
+
+template <typename T>
+__device__ __forceinline__ typename RowSeg<T>::V load_cols(const T *__restrict__ row, int u0, int width, bool vec_ok)
+{
+    using V = typename RowSeg<T>::V;
+    if (vec_ok && u0 + K1T_COLS <= width) return __ldg(reinterpret_cast<const V *>(row + u0));
+    T px[K1T_COLS];
+#pragma unroll
+    for (int k = 0; k < K1T_COLS; ++k) px[k] = (u0 + k < width) ? __ldg(row + u0 + k) : T(0);
+    V v;
+    memcpy(&v, px, sizeof(v));
+    return v;
+}
+
+// A CTA handles ITER consecutive blocks of THREADS segments and issues all their loads first (sparse motion: most blocks are
+// still, the kernel is then a pure read of the frames and wants bytes in flight, not many small CTAs).
 template <typename T, int R>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1Tile<R>::THREADS)
 motion_compact_rowgroup_kernel(const T *__restrict__ frames, long long frame_stride, const pvp_pair *__restrict__ pairs,
                                int width, int height, float threshold, bool vec_ok, Queue q, Ctl *__restrict__ ctl)
 {
-    constexpr int PX = FrameVec<T>::PX;
+    constexpr int THREADS = K1Tile<R>::THREADS, C = K1T_COLS, ITER = K1Tile<R>::ITER;
     const int pair = blockIdx.y;
     const T *prev = frames + (long long)pairs[pair].prev * frame_stride;
     const T *curr = frames + (long long)pairs[pair].curr * frame_stride;
-    const int segs = (width + PX - 1) / PX, row_groups = (height + R - 1) / R;
-    const unsigned seg_id = blockIdx.x * K1_THREADS + threadIdx.x;  // < 2^28: the host bounds width * height below 2^32
-    const int rg = (int)(seg_id / (unsigned)segs), u0 = (int)(seg_id - (unsigned)rg * (unsigned)segs) * PX;
-    const long long n_pix = (long long)width * height;
+    const int segs = (width + C - 1) / C, row_groups = (height + R - 1) / R;
 
-    float d[R][PX];
-    unsigned mask[R];
-    int cnt = 0;
+    typename RowSeg<T>::V a[ITER][R] = {}, b[ITER][R] = {};
+    int rg[ITER], u0[ITER];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        mask[r] = 0;
-        const int v = R * rg + r;
-        if (rg < row_groups && v < height) {
-            const long long first = (long long)v * width + u0;
-            T a[PX], b[PX];
-            const bool whole = u0 + PX <= width;   // a partial segment at the row end must not read into the next row
-            load_px<T>(prev, first, whole ? n_pix : first + (width - u0), vec_ok && whole, a);
-            load_px<T>(curr, first, whole ? n_pix : first + (width - u0), vec_ok && whole, b);
-#pragma unroll
-            for (int k = 0; k < PX; ++k) {
-                d[r][k] = motion_diff(a[k], b[k]);
-                if (u0 + k < width && motion_casts_ray(d[r][k], threshold)) mask[r] |= 1u << k;
-            }
-        }
-        cnt += __popc(mask[r]);
-    }
-
-    __shared__ unsigned warp_tot[K1_THREADS / 32];
-    __shared__ unsigned long long cta_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int incl = cnt;
-    if (__ballot_sync(0xffffffffu, cnt != 0) != 0) {
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned tot = 0;
-#pragma unroll
-        for (int w = 0; w < K1_THREADS / 32; ++w) { unsigned c = warp_tot[w]; warp_tot[w] = tot; tot += c; }
-        cta_base = tot ? atomicAdd(&ctl->count, (unsigned long long)tot) : 0ull;
-    }
-    __syncthreads();
-    if (cnt == 0) return;
-    unsigned long long pos = cta_base + warp_tot[warp] + (unsigned)(incl - cnt);
-#pragma unroll
-    for (int k = 0; k < PX; ++k) {
+    for (int it = 0; it < ITER; ++it) {
+        const unsigned seg_id = (blockIdx.x * ITER + it) * THREADS + threadIdx.x;  // < 2^31: the host bounds width * height below 2^32
+        rg[it] = (int)(seg_id / (unsigned)segs);
+        u0[it] = (int)(seg_id - (unsigned)rg[it] * (unsigned)segs) * C;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (mask[r] & (1u << k)) {
-                q.pix[pos] = (uint32_t)((R * rg + r) * width + u0 + k);
-                q.diff[pos] = d[r][k];
-                q.pair[pos] = (uint16_t)pair;
-                ++pos;
+            const int v = R * rg[it] + r;
+            if (rg[it] < row_groups && v < height) {
+                a[it][r] = load_cols<T>(prev + (long long)v * width, u0[it], width, vec_ok);
+                b[it][r] = load_cols<T>(curr + (long long)v * width, u0[it], width, vec_ok);
             }
+        }
+    }
+
+    __shared__ unsigned warp_tot[THREADS / 32];
+    __shared__ unsigned long long cta_base;
+    __shared__ uint32_t s_pix[THREADS * C * R];
+    __shared__ float s_diff[THREADS * C * R];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned masks[ITER];  // bit r * C + k: the pixel casts a ray
+    unsigned any = 0;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        unsigned mask = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int v = R * rg[it] + r;
+            if (rg[it] < row_groups && v < height) {
+                T pa[C], pb[C];
+                memcpy(pa, &a[it][r], sizeof(pa));
+                memcpy(pb, &b[it][r], sizeof(pb));
+#pragma unroll
+                for (int k = 0; k < C; ++k)
+                    if (u0[it] + k < width && motion_casts_ray(motion_diff(pa[k], pb[k]), threshold)) mask |= 1u << (r * C + k);
+            }
+        }
+        masks[it] = mask;
+        any |= mask;
+    }
+    if (!__syncthreads_or(any != 0)) return;  // nothing moves in any of the CTA's blocks: one barrier and out
+    bool staged = false;                      // a previous block of this CTA has used the shared arrays (uniform)
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const unsigned mask = masks[it];
+        const int cnt = __popc(mask);
+        int incl = cnt;
+        if (__ballot_sync(0xffffffffu, cnt != 0) != 0) {
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+        }
+        if (staged) __syncthreads();  // the previous block's copy-out has read warp_tot / the staging arrays
+        staged = true;
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) {
+            const unsigned c = warp_tot[w];
+            if (w < warp) before += c;
+            tot += c;
+        }
+        if (tot == 0) continue;  // a still block: nothing to reserve, nothing to write (uniform over the CTA)
+        if (threadIdx.x == 0) cta_base = atomicAdd(&ctl->count, (unsigned long long)tot);
+        unsigned pos = before + (unsigned)(incl - cnt);
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (mask & (1u << (r * C + k))) {
+                    T pa[C], pb[C];
+                    memcpy(pa, &a[it][r], sizeof(pa));
+                    memcpy(pb, &b[it][r], sizeof(pb));
+                    s_pix[pos] = (uint32_t)((R * rg[it] + r) * width + u0[it] + k);
+                    s_diff[pos] = motion_diff(pa[k], pb[k]);
+                    ++pos;
+                }
+            }
+        }
+        __syncthreads();
+        // the host sizes the queue for the worst case (n_pairs * n_pix), so base + tot <= capacity always
+        const unsigned long long base = cta_base;
+        for (unsigned i = threadIdx.x; i < tot; i += THREADS) {
+            q.pix[base + i] = s_pix[i];
+            q.diff[base + i] = s_diff[i];
+            q.pair[base + i] = (uint16_t)pair;
         }
     }
 }
@@ -978,13 +1040,16 @@ static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_strid
 {
     constexpr int PX = FrameVec<T>::PX;
     if (row_group > 1) {
-        const bool vec = ((uintptr_t)frames_dev % sizeof(typename FrameVec<T>::V) == 0) && (frame_stride % PX == 0) && (width % PX == 0);
+        const size_t vec_bytes = sizeof(T) * K1T_COLS;  // one row segment of a thread
+        const bool vec = ((uintptr_t)frames_dev % vec_bytes == 0) && (frame_stride % K1T_COLS == 0) && (width % K1T_COLS == 0);
         const int R = row_group >= 8 ? 8 : row_group >= 4 ? 4 : 2;
-        const long long segs = (long long)((width + PX - 1) / PX) * ((height + R - 1) / R);
-        dim3 grid((unsigned)((segs + K1_THREADS - 1) / K1_THREADS), (unsigned)n_pairs);
+        const int threads = R == 8 ? K1Tile<8>::THREADS : R == 4 ? K1Tile<4>::THREADS : K1Tile<2>::THREADS;
+        const int per_cta = threads * (R == 8 ? K1Tile<8>::ITER : R == 4 ? K1Tile<4>::ITER : K1Tile<2>::ITER);
+        const long long segs = (long long)((width + K1T_COLS - 1) / K1T_COLS) * ((height + R - 1) / R);
+        dim3 grid((unsigned)((segs + per_cta - 1) / per_cta), (unsigned)n_pairs);
         LaunchScope scope(ctx, 1);
         auto k = R == 8 ? motion_compact_rowgroup_kernel<T, 8> : R == 4 ? motion_compact_rowgroup_kernel<T, 4> : motion_compact_rowgroup_kernel<T, 2>;
-        k<<<grid, K1_THREADS, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, width, height, threshold, vec, ctx->queue, ctx->ctl_dev);
+        k<<<grid, threads, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, width, height, threshold, vec, ctx->queue, ctx->ctl_dev);
         PVP_CUDA(cudaGetLastError());
         return PVP_OK;
     }
