@@ -26,6 +26,7 @@ struct GridP {
     float fixed_scale;  // 2^frac_bits
     int frac_shift;     // frac_bits (0 for float32 grids)
     float alpha;        // opt-in distance attenuation (0 = off, the reference's behaviour)
+    unsigned mul_n, mul_nn;  // floor(2^32 / n), floor(2^32 / n^2): division of a voxel offset by a multiply (udiv_by)
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }

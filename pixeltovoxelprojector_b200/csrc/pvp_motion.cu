@@ -592,6 +592,9 @@ __device__ __forceinline__ bool run_head(unsigned key)
 #ifndef PVP_LEAN_THREADS
 #define PVP_LEAN_THREADS 256  // measured at 1080p -> 512^3: 256-thread CTAs 503 G steps/s, 128 and 64 threads 489 G (same resident warps)
 #endif
+#ifndef PVP_LEAN2_MINB
+#define PVP_LEAN2_MINB 3  // resident CTAs of the default lean2 instantiation (80 registers at 256 threads)
+#endif
 constexpr int LEAN_THREADS = PVP_LEAN_THREADS;  // warps are independent; the CTA size only sets how registers divide an SM
 constexpr int LEAN_CTAS_A = 7 * 128 / LEAN_THREADS > 0 ? 7 * 128 / LEAN_THREADS : 1, LEAN_CTAS_B = 6 * 128 / LEAN_THREADS, LEAN_CTAS_C = 8 * 128 / LEAN_THREADS;
 
@@ -609,6 +612,16 @@ __device__ __forceinline__ float axis_limit(float tm0, float td, int rem)
     return bound == bound ? bound : -CUDART_INF_F;  // overflow (inf - inf): no proof, every step of this ray takes the exact test
 }
 
+// x / d for d >= 2 with m = floor(2^32 / d): umulhi(x, m) is the quotient or one below it (x * m / 2^32 > x / d - 1), one
+// correction step; d == 1 has m = 2^32, which does not fit, and is handled by the caller's geometry (N == 1: every offset is 0).
+__device__ __forceinline__ unsigned udiv_by(unsigned x, unsigned d, unsigned m)
+{
+    if (d == 1) return x;
+    unsigned q = __umulhi(x, m);
+    if (x - q * d >= d) ++q;
+    return q;
+}
+
 // Does the step along the chosen axis (cz / cy / else x) leave [0, N)?  Decodes the voxel the step starts from.  Slab kernels
 // hold x relative to the slab, possibly negative (N^3 <= 2^31 there, so the offset is a valid int).
 template <bool SLAB>
@@ -619,14 +632,14 @@ __device__ __forceinline__ bool step_leaves(unsigned cur, bool cz, bool cy, int 
     unsigned rest;
     if (SLAB) {
         const int rel = (int)cur;
-        const int q = rel >= 0 ? rel / NN : -((NN - 1 - rel) / NN);  // floor
+        const int q = rel >= 0 ? (int)udiv_by((unsigned)rel, (unsigned)NN, g.mul_nn) : -(int)udiv_by((unsigned)(NN - 1 - rel), (unsigned)NN, g.mul_nn);  // floor
         ix = q + g.slab_lo;
         rest = (unsigned)(rel - q * NN);
     } else {
-        ix = (int)(cur / (unsigned)NN);
+        ix = (int)udiv_by(cur, (unsigned)NN, g.mul_nn);
         rest = cur - (unsigned)ix * (unsigned)NN;
     }
-    const int iy = (int)(rest / (unsigned)N), iz = (int)(rest - (unsigned)iy * (unsigned)N);
+    const int iy = (int)udiv_by(rest, (unsigned)N, g.mul_n), iz = (int)(rest - (unsigned)iy * (unsigned)N);
     if (cz) return diz > 0 ? iz == N - 1 : iz == 0;
     if (cy) return diy > 0 ? iy == N - 1 : iy == 0;
     return dix > 0 ? ix == N - 1 : ix == 0;
@@ -792,6 +805,13 @@ __device__ __forceinline__ void rays_park(RayS &r)
     r.t_cur = 0.f;
     r.idx = KEY_NONE; r.dix = r.diy = r.diz = 0;
 }
+// parking a ray that has been walking: only what keeps it silent and "sure" for the rest of the chunk (the step's t stays
+// at 0 < lim = inf, the offset at KEY_NONE); t_end, tmy, tmz are never read again for a parked ray
+__device__ __forceinline__ void rays_retire(RayS &r)
+{
+    r.lim = CUDART_INF_F; r.tmx = 0.f; r.tdx = r.tdy = r.tdz = 0.f; r.t_cur = 0.f;
+    r.idx = KEY_NONE; r.dix = r.diy = r.diz = 0;
+}
 
 // queue entry -> walking state; returns the value to accumulate (0 when the ray casts no step)
 template <typename V>
@@ -913,11 +933,11 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
                 // (the original keys, not ka / kb: a slab kernel has replaced those outside its slab by KEY_NONE)
                 if (!(ma < a.lim) && rays_live(a) && rays_ended<SLAB>(a, ka0, ma, g)) {
                     my_steps += (unsigned long long)walked;
-                    rays_park(a); va = 0; da = 0.f;
+                    rays_retire(a); va = 0; da = 0.f;
                 }
                 if (!(mb < b.lim) && rays_live(b) && rays_ended<SLAB>(b, kb0, mb, g)) {
                     my_steps += (unsigned long long)walked;
-                    rays_park(b); vb = 0; db = 0.f;
+                    rays_retire(b); vb = 0; db = 0.f;
                 }
                 if (__all_sync(FULL, !rays_live(a) && !rays_live(b))) break;
                 heads = __ballot_sync(FULL, run_head(SLAB ? (a.idx < slab_cells ? a.idx : KEY_NONE) : a.idx));
@@ -1014,6 +1034,8 @@ static int make_gridp(const pvp_grid_desc *d, GridP *g)
     g->frac_shift = d->accum_mode == PVP_ACCUM_FIXED ? d->frac_bits : 0;
     PVP_REQUIRE(d->attenuation_alpha >= 0.f && d->attenuation_alpha < 1e30f, "attenuation_alpha must be finite and >= 0");
     g->alpha = d->attenuation_alpha;
+    g->mul_n = (unsigned)(0x100000000ull / (unsigned long long)d->n);  // n >= 2 here; n == 1 divides by shifting nothing: see udiv_by
+    g->mul_nn = (unsigned)(0x100000000ull / ((unsigned long long)d->n * d->n));
     return PVP_OK;
 }
 
@@ -1093,7 +1115,7 @@ static void launch_lean2(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width
     }
     // lean_regs: 0/80 -> 3 resident CTAs (24 warps; measured best: 670 G voxel-steps/s at 512^3), 128 -> 2 CTAs (622 G), 64 -> 4 CTAs
     auto k = ctx->opt_lean_regs == 128 ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 2>
-           : ctx->opt_lean_regs == 64  ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 4> : dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 3>;
+           : ctx->opt_lean_regs == 64  ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 4> : dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, PVP_LEAN2_MINB>;
     k<<<k2_grid_size(ctx, (const void *)k, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
                                                                                            width, height, ctx->ctl_dev, count_lo, count_hi);
 }
