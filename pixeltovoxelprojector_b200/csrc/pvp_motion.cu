@@ -752,9 +752,9 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
                 my_steps += park ? (unsigned long long)walked : 0ull;
                 idx = park ? KEY_NONE : idx; val = park ? (T)0 : val;
                 dix = park ? 0 : dix; diy = park ? 0 : diy; diz = park ? 0 : diz;
-                tmx = park ? 0.f : tmx; tmy = park ? 0.f : tmy; tmz = park ? 0.f : tmz;
+                tmx = park ? 0.f : tmx;  // the step's t of a parked lane stays at 0 < lim = inf; tmy, tmz, t_end are never read again
                 tdx = park ? 0.f : tdx; tdy = park ? 0.f : tdy; tdz = park ? 0.f : tdz;
-                t_end = park ? CUDART_INF_F : t_end; lim = park ? CUDART_INF_F : lim;
+                lim = park ? CUDART_INF_F : lim;
                 if (__all_sync(FULL, tdx == 0.f)) break;
                 if (!SLAB) {
                     heads = __ballot_sync(FULL, run_head(idx));
