@@ -32,8 +32,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=120)
     ap.add_argument("--format", default="png", choices=["pgm", "png"])
+    ap.add_argument("--n", type=int, default=512, help="grid size (BASELINE config 2: 256)")
     a = ap.parse_args()
-    H, W, N, vs, center = 1080, 1920, 512, 2.0, (0.0, 0.0, 500.0)
+    H, W, N, center = 1080, 1920, a.n, (0.0, 0.0, 500.0)
+    vs = 1024.0 / N
     exe = os.path.join(ROOT, "pixeltovoxelprojector_b200", "ray_voxel")
     with tempfile.TemporaryDirectory() as d:
         frames = synth.sparse_frames(a.frames, H, W, seed=1, blobs=6)
@@ -58,7 +60,7 @@ def main():
             assert r.returncode == 0, r.stderr
             outs[label] = open(out, "rb").read()
             if label != "warm-up":
-                print(f"{a.format} 1080p x {a.frames} frames, {label}: {dt:.2f} s wall = {a.frames / dt:.0f} frames/s (incl. process start, 512 MiB .bin write)  {r.stderr.strip()}")
+                print(f"{a.format} 1080p x {a.frames} frames, {label}: {dt:.2f} s wall = {a.frames / dt:.0f} frames/s (incl. process start, {4 * N ** 3 >> 20} MiB .bin write)  {r.stderr.strip()}")
         assert outs["1 decode thread"] == outs["default pool"], ".bin differs between decode-thread settings"
         print("identical .bin for both settings; host cores:", os.cpu_count())
 
