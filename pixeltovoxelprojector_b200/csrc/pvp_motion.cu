@@ -660,7 +660,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
     if (count < count_lo || count >= count_hi) return;  // auto mode launches both lock-step kernels; the ray count picks one
     const int N = g.n;
     const unsigned slab_cells = (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)N * (unsigned)N;
-    unsigned long long my_steps = 0, my_written = 0, my_atomics = 0;
+    unsigned steps32 = 0, written32 = 0, atomics32 = 0;  // per lane; see lean2
 
     for (;;) {
         unsigned long long base = 0;
@@ -749,7 +749,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
                 // exact end-of-ray test (:388-391, :365) for the lanes at their limit.  (live is "tdx != 0", not "idx != KEY_NONE": a
                 // ray that leaves the grid downwards from linear offset N^2-1 / N-1 / 0 wraps to exactly 0xffffffff)
                 const bool park = !sure && tdx != 0.f && (step_leaves<SLAB>(cur, cz, cy, dix, diy, diz, g) || !(m <= t_end));
-                my_steps += park ? (unsigned long long)walked : 0ull;
+                steps32 += park ? (unsigned)walked : 0u;
                 idx = park ? KEY_NONE : idx; val = park ? (T)0 : val;
                 dix = park ? 0 : dix; diy = park ? 0 : diy; diz = park ? 0 : diz;
                 tmx = park ? 0.f : tmx;  // the step's t of a parked lane stays at 0 < lim = inf; tmy, tmz, t_end are never read again
@@ -762,11 +762,11 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
                 }
             }
         }
-        my_atomics += (unsigned long long)n_issued;
-        if (SLAB) my_written += (unsigned long long)n_inslab;
+        atomics32 += (unsigned)n_issued;
+        if (SLAB) written32 += (unsigned)n_inslab;
 
     }
-    if (!SLAB) my_written = my_steps;
+    unsigned long long my_steps = steps32, my_written = SLAB ? written32 : steps32, my_atomics = atomics32;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         my_steps += __shfl_xor_sync(FULL, my_steps, o);
@@ -840,18 +840,46 @@ __device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, uns
     return V::make(diff, g);
 }
 
+// The axis choice of ray_voxel.cpp:375-387 for m = min(tmx, tmy, tmz) -- z iff tmz == m, else y iff tmy == m, else x -- as three
+// one-instruction predicates, and the step as predicated adds: t_max of the chosen axis += its t_delta, the voxel offset += its
+// stride.  (The compiler's own form of the same C++ was selects: 13 instructions per ray step, most on the ALU pipe; this is 10.)
+__device__ __forceinline__ void dda_advance(float m, float &tmx, float &tmy, float &tmz, unsigned &idx, float tdx, float tdy, float tdz,
+                                            int dix, int diy, int diz)
+{
+    asm("{\n\t.reg .pred pz, py, px;\n\t"
+        "setp.eq.f32 pz, %2, %4;\n\t"
+        "setp.eq.and.f32 py, %1, %4, !pz;\n\t"
+        "setp.neu.and.f32 px, %1, %4, !pz;\n\t"
+        "@px add.rn.f32 %0, %0, %5;\n\t"
+        "@py add.rn.f32 %1, %1, %6;\n\t"
+        "@pz add.rn.f32 %2, %2, %7;\n\t"
+        "@px add.s32 %3, %3, %8;\n\t"
+        "@py add.s32 %3, %3, %9;\n\t"
+        "@pz add.s32 %3, %3, %10;\n\t}"
+        : "+f"(tmx), "+f"(tmy), "+f"(tmz), "+r"(idx)
+        : "f"(m), "f"(tdx), "f"(tdy), "f"(tdz), "r"(dix), "r"(diy), "r"(diz));
+}
+
 // one DDA step (ray_voxel.cpp:375-391); returns the step's t (the minimum of the three t_max).  While it is below the ray's
 // limit the ray certainly goes on; otherwise rays_ended decides exactly.
+// PTX_ADVANCE picks the form of the axis choice + advance: the predicated PTX of dda_advance, or plain C++ (the compiler then
+// uses selects).  Same arithmetic; which one ptxas schedules better depends on the rest of the loop -- measured 1080p -> 512^3:
+// float32 786 G voxel-steps/s with the C++ form against 773, fixed point 758 with the PTX form against 742.
+template <bool PTX_ADVANCE>
 __device__ __forceinline__ float rays_step(RayS &s)
 {
     const float m = fmin3(s.tmx, s.tmy, s.tmz);
-    const bool cz = (s.tmz == m);
-    const bool cy = !cz && (s.tmy == m);
-    const bool cx = !cz && (s.tmy != m);
-    if (cx) s.tmx = fadd(s.tmx, s.tdx);
-    if (cy) s.tmy = fadd(s.tmy, s.tdy);
-    if (cz) s.tmz = fadd(s.tmz, s.tdz);
-    s.idx += (unsigned)(cz ? s.diz : (cy ? s.diy : s.dix));
+    if (PTX_ADVANCE) {
+        dda_advance(m, s.tmx, s.tmy, s.tmz, s.idx, s.tdx, s.tdy, s.tdz, s.dix, s.diy, s.diz);
+    } else {
+        const bool cz = (s.tmz == m);
+        const bool cy = !cz && (s.tmy == m);
+        const bool cx = !cz && (s.tmy != m);
+        if (cx) s.tmx = fadd(s.tmx, s.tdx);
+        if (cy) s.tmy = fadd(s.tmy, s.tdy);
+        if (cz) s.tmz = fadd(s.tmz, s.tdz);
+        s.idx += (unsigned)(cz ? s.diz : (cy ? s.diy : s.dix));
+    }
     s.t_cur = m;  // :376-386 (dead in the kernels that do not attenuate)
     return m;
 }
@@ -879,7 +907,9 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
     const unsigned long long count = ctl->count;
     if (count < count_lo || count >= count_hi) return;  // auto mode launches both lock-step kernels; the ray count picks one
     const unsigned slab_cells = (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)g.n * (unsigned)g.n;
-    unsigned long long my_steps = 0, my_written = 0, my_atomics = 0;
+    // per-lane counters in 32 bits (a lane walks count / 113 664 rays of at most 3 n steps each; the queue holds < 2^32 entries): three
+    // registers less in a loop that sits at its register cap; widened for the warp reduction below
+    unsigned steps32 = 0, written32 = 0, atomics32 = 0;
     for (;;) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&ctl->head, 64ull);
@@ -902,7 +932,7 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
                 va = V::make(attenuate(da, g.alpha, a.t_cur), g);
                 vb = V::make(attenuate(db, g.alpha, b.t_cur), g);
             }
-            const float ma = rays_step(a), mb = rays_step(b);
+            const float ma = rays_step<MODE == PVP_ACCUM_FIXED>(a), mb = rays_step<MODE == PVP_ACCUM_FIXED>(b);
             const bool any_unsure = __any_sync(FULL, !(ma < a.lim) || !(mb < b.lim));
             walked += 1.f;
             T sa = va, sb = vb;
@@ -932,21 +962,21 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
             if (any_unsure) {
                 // (the original keys, not ka / kb: a slab kernel has replaced those outside its slab by KEY_NONE)
                 if (!(ma < a.lim) && rays_live(a) && rays_ended<SLAB>(a, ka0, ma, g)) {
-                    my_steps += (unsigned long long)walked;
+                    steps32 += (unsigned)walked;
                     rays_retire(a); va = 0; da = 0.f;
                 }
                 if (!(mb < b.lim) && rays_live(b) && rays_ended<SLAB>(b, kb0, mb, g)) {
-                    my_steps += (unsigned long long)walked;
+                    steps32 += (unsigned)walked;
                     rays_retire(b); vb = 0; db = 0.f;
                 }
                 if (__all_sync(FULL, !rays_live(a) && !rays_live(b))) break;
                 heads = __ballot_sync(FULL, run_head(SLAB ? (a.idx < slab_cells ? a.idx : KEY_NONE) : a.idx));
             }
         }
-        my_atomics += (unsigned long long)n_issued;
-        if (SLAB) my_written += (unsigned long long)n_inslab;
+        atomics32 += (unsigned)n_issued;
+        if (SLAB) written32 += (unsigned)n_inslab;
     }
-    if (!SLAB) my_written = my_steps;
+    unsigned long long my_steps = steps32, my_written = SLAB ? written32 : steps32, my_atomics = atomics32;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         my_steps += __shfl_xor_sync(FULL, my_steps, o);
