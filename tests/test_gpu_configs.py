@@ -125,3 +125,32 @@ def test_headline_shape_all_variants_agree_1080p_dense_512(ctx):
         torch.testing.assert_close(gf.data[~small], exact[~small], rtol=1e-4, atol=0)
     finally:
         ctx.set_option("dda_variant", 0)
+
+
+def test_grid_near_the_32bit_offset_limit_variants_agree(ctx):
+    """N = 1500: 3.4e9 cells, voxel offsets just below the 2^32 key space of the lock-step kernels (N >= 1626 falls back to the
+    plain kernel), x-planes of 9 MB (auto mode: one-ray kernel on 8-row tiles).  The auto pick, lean2 and the plain one-RED-per-step
+    kernel must agree bit for bit in fixed point, counters included."""
+    H, W, N, vs, center = 480, 640, 1500, 0.7, (0.0, 0.0, 500.0)
+    frames = torch.as_tensor(synth.dense_frames(2, H, W, seed=91), device=DEV)
+    poses = synth.orbit_poses(2, N, vs, center, seed=92)
+    tab, _ = pvp.make_pairs(poses, W)
+    ref, ref_key = None, None
+    try:
+        for variant in (3, 0, 5):
+            ctx.set_option("dda_variant", variant)
+            g = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=4)          # 27 GB
+            st = pvp.accumulate_motion(frames, tab, g, 2.0)
+            key = (st["n_rays"], st["n_steps"], st["n_written"])
+            if ref is None:
+                ref, ref_key = g, key
+                assert st["n_rays"] > 290_000 and st["n_steps"] > 500 * st["n_rays"]
+                assert int(g.data.sum()) > 0
+            else:
+                assert key == ref_key, variant
+                assert torch.equal(g.data, ref.data), variant
+                del g
+    finally:
+        ctx.set_option("dda_variant", 0)
+        del ref
+        torch.cuda.empty_cache()
