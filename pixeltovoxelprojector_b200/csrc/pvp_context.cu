@@ -247,6 +247,7 @@ int pvp_ctx_set_option(pvp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "reduce_pull")) ctx->opt_reduce_pull = value;
     else if (!strcmp(key, "image_tile_h")) ctx->opt_image_tile_h = value;
     else if (!strcmp(key, "k1_row_group")) ctx->opt_k1_row_group = value;
+    else if (!strcmp(key, "k1_snake")) ctx->opt_k1_snake = value;
     else { set_error("pvp_ctx_set_option: unknown key '%s'", key); return PVP_ERR_INVALID; }
     return PVP_OK;
 }

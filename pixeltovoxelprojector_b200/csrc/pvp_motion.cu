@@ -142,7 +142,7 @@ __device__ __forceinline__ typename RowSeg<T>::V load_cols(const T *__restrict__
 template <typename T, int R>
 __global__ void __launch_bounds__(K1Tile<R>::THREADS)
 motion_compact_rowgroup_kernel(const T *__restrict__ frames, long long frame_stride, const pvp_pair *__restrict__ pairs,
-                               int width, int height, float threshold, bool vec_ok, Queue q, Ctl *__restrict__ ctl)
+                               int width, int height, float threshold, bool vec_ok, bool snake, Queue q, Ctl *__restrict__ ctl)
 {
     constexpr int THREADS = K1Tile<R>::THREADS, C = K1T_COLS, ITER = K1Tile<R>::ITER;
     const int pair = blockIdx.y;
@@ -223,7 +223,10 @@ motion_compact_rowgroup_kernel(const T *__restrict__ frames, long long frame_str
 #pragma unroll
         for (int k = 0; k < C; ++k) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
+            for (int rr = 0; rr < R; ++rr) {
+                // snake order (one ray per lane on tall tiles): odd columns bottom-up, so the lanes on either side of a column
+                // change are horizontal neighbours too and their runs can merge
+                const int r = (snake && (k & 1)) ? R - 1 - rr : rr;
                 if (mask & (1u << (r * C + k))) {
                     T pa[C], pb[C];
                     memcpy(pa, &a[it][r], sizeof(pa));
@@ -1088,7 +1091,7 @@ static int k2_grid_size(pvp_ctx *ctx, const void *kernel, int threads = K2_THREA
 
 template <typename T>
 static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_stride, long long n_pix, int n_pairs, float threshold,
-                     int width = 0, int height = 0, int row_group = 1)
+                     int width = 0, int height = 0, int row_group = 1, bool snake = false)
 {
     constexpr int PX = FrameVec<T>::PX;
     if (row_group > 1) {
@@ -1101,7 +1104,7 @@ static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_strid
         dim3 grid((unsigned)((segs + per_cta - 1) / per_cta), (unsigned)n_pairs);
         LaunchScope scope(ctx, 1);
         auto k = R == 8 ? motion_compact_rowgroup_kernel<T, 8> : R == 4 ? motion_compact_rowgroup_kernel<T, 4> : motion_compact_rowgroup_kernel<T, 2>;
-        k<<<grid, threads, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, width, height, threshold, vec, ctx->queue, ctx->ctl_dev);
+        k<<<grid, threads, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, width, height, threshold, vec, snake, ctx->queue, ctx->ctl_dev);
         PVP_CUDA(cudaGetLastError());
         return PVP_OK;
     }
@@ -1175,18 +1178,18 @@ constexpr unsigned long long LEAN2_MIN_RAYS_PER_WARP = 256;
 // Bytes of one x-plane of the grid (n * n cells).  Neighbouring image columns land in neighbouring x-planes, i.e. this
 // far apart in memory; once a plane outgrows a 2 MiB page the RED misses of a wide, flat ray tile dominate K2 (measured at
 // 768^3 / 1024^3 float32 and 512^3 int64: profiles/r1_summary.md, "large grids").  The auto settings follow it:
-//   <= 1 MiB: lean2, queue tiles of 2 image rows     (1080p -> 512^3 float32: 665 G voxel-steps/s)
-//   <= 2 MiB: lean2, tiles of 4 rows                 (512^3 int64: 570 -> 626 G)
-//   >  2 MiB: lean (32 rays per warp), tiles of 8 rows = 4 x 8 pixel chunks   (1024^3 float32: 294 -> 576 G)
+//   <= 2 MiB: lean2, queue tiles of 4 image rows (16 x 4 pixel chunks), snake order inside a tile
+//             (1080p -> 512^3 float32: 823 G voxel-steps/s against 786 with 2-row tiles: with the per-ray limits the rays of a
+//             compact tile also END in fewer distinct iterations, i.e. fewer trips through the slow path; 512^3 int64: 570 -> 626 G)
+//   >  2 MiB: lean (32 rays per warp), tiles of 8 rows = 4 x 8 pixel chunks, snake order   (1024^3 float32: 294 -> 576 -> 600 G)
 static size_t plane_bytes(const GridP &g, int accum_mode)
 {
     return (size_t)g.n * g.n * (accum_mode == PVP_ACCUM_F32 ? sizeof(float) : sizeof(unsigned long long));
 }
-constexpr size_t PLANE_SMALL = 1u << 20, PLANE_LARGE = 2u << 20;
+constexpr size_t PLANE_LARGE = 2u << 20;
 static int auto_row_group(const GridP &g, int accum_mode)
 {
-    const size_t pb = plane_bytes(g, accum_mode);
-    return pb <= PLANE_SMALL ? 2 : pb <= PLANE_LARGE ? 4 : 8;
+    return plane_bytes(g, accum_mode) <= PLANE_LARGE ? 4 : 8;
 }
 
 // dda_variant: 0 = auto (lean2 / lean by ray count where their 32-bit voxel keys allow, else 3), 1 = segmented-scan aggregation (round-1
@@ -1285,8 +1288,10 @@ static int run_batches(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, lo
         // queue order: tiles of R image rows (lean2 walks two vertically adjacent pixels per lane); 1 = plain row-major
         const int ev = effective_variant(ctx);
         const int row_group = ctx->opt_k1_row_group > 0 ? (int)ctx->opt_k1_row_group : ev == 0 ? auto_row_group(g, accum_mode) : ev >= 4 ? 2 : 1;
-        rc = frame_dtype == PVP_FRAME_U8 ? launch_k1<uint8_t>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group)
-                                         : launch_k1<float>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group);
+        // snake order of the tile columns: default for tiles of 4 rows and more (k1_snake: -1 auto, 0 off, 1 on)
+        const bool snake = ctx->opt_k1_snake >= 0 ? ctx->opt_k1_snake != 0 : row_group >= 4;
+        rc = frame_dtype == PVP_FRAME_U8 ? launch_k1<uint8_t>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group, snake)
+                                         : launch_k1<float>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group, snake);
         if (rc) return rc;
         // "integral" fixed-point sums: uint8 frames have integer diffs <= 255 (see LeanVal<FIXED, true>)
         const bool narrow_ok = frame_dtype == PVP_FRAME_U8;
