@@ -34,6 +34,10 @@ WORKLOADS = {
     # BASELINE config[2] shape: 3840x2160 frames into a 512^3 grid (frame-sharded over N GPUs with --gpus N)
     "4k_dense_512": dict(H=2160, W=3840, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=2, pool=20, motion="dense", accum="f32"),
     # BASELINE config[3] shape on ONE GPU: the whole 1024^3 grid (4 GiB; slab sharding itself is covered by tests/test_gpu_configs.py)
+    # BASELINE config[3]: the 1024^3 grid sharded into 8 x-slabs (x is the slowest index: contiguous byte ranges of the .bin); every rank walks
+    # every ray with full-grid arithmetic and writes only inside its slab.  On one GPU this runs rank 4 of 8; with --gpus N rank r takes slab r % 8.
+    # Same frames on every rank, no merge; `value` counts each voxel step once (the job's useful work), whatever the number of ranks.
+    "1080p_dense_1024_slab8": dict(H=1080, W=1920, N=1024, voxel_size=1.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=24, motion="dense", accum="f32", slabs=8),
     "1080p_dense_1024": dict(H=1080, W=1920, N=1024, voxel_size=1.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=24, motion="dense", accum="f32"),
     "1080p_dense_768": dict(H=1080, W=1920, N=768, voxel_size=4.0 / 3.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=24, motion="dense", accum="f32"),
     "1080p_dense_512_fixed": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=72, motion="dense", accum="fixed"),
@@ -428,7 +432,8 @@ def run_ours_image(args, wl):
 def workload_config(args, wl):
     return {"workload": args.workload, "k2_variant": getattr(args, "variant", 0), "frame": f"{wl['W']}x{wl['H']} uint8", "grid": f"{wl['N']}^3 {wl['accum']}", "voxel_size": wl["voxel_size"],
             "pairs_per_step": wl["pairs_per_step"], "motion": wl["motion"], "camera": "pose changes every frame (orbit inside the grid); N>1: same pose table, different frames on every rank",
-            "parallelism": f"frames sharded over {args.gpus} GPU(s), private grids, one grid merge per run inside the timed region: {getattr(args, 'reduce_how', 'NCCL reduce')}" if args.gpus > 1 else "1 GPU",
+            "parallelism": (f"grid sharded into {wl['slabs']} x-slabs; " + (f"{args.gpus} ranks, rank r owns slab r" if args.gpus > 1 else f"1 GPU running rank {wl['slabs'] // 2}'s slab") + f"; {getattr(args, 'reduce_how', '')}") if wl.get("slabs") else
+                           f"frames sharded over {args.gpus} GPU(s), private grids, one grid merge per run inside the timed region: {getattr(args, 'reduce_how', 'NCCL reduce')}" if args.gpus > 1 else "1 GPU",
             "l2": "256 MiB buffer written between timed steps (L2 flush); frame pool 149 MB and grid > L2" if wl["N"] >= 512 else
                   "256 MiB buffer written between timed steps (L2 flush)"}
 
@@ -453,11 +458,17 @@ def run_ours(args, wl):
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
 
-    frames_np, poses = make_inputs(wl, seed=1000 + rank)   # weak scaling: every rank has its own frames, same shape
+    slabs = wl.get("slabs")
+    frames_np, poses = make_inputs(wl, seed=1000 + (0 if slabs else rank))   # weak scaling: every rank has its own frames, same shape (slab mode: the same frames)
     frames_dev = torch.as_tensor(frames_np, device=dev)
     frames_pin = torch.as_tensor(frames_np).pin_memory()
     grid, reduce_how = None, "none (1 GPU)"
-    if world > 1:
+    if slabs:
+        from pixeltovoxelprojector_b200.distributed import slab_range
+        lo, hi = slab_range(wl["N"], (rank if world > 1 else slabs // 2) % slabs, slabs)
+        grid = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev, slab=(lo, hi))
+        reduce_how = f"none (slab sharding: rank writes x-planes [{lo}, {hi}) of the .bin)"
+    if world > 1 and not slabs:
         from pixeltovoxelprojector_b200 import distributed as pd
         if args.reduce == "peers":
             try:   # private grid in NVLink symmetric memory: the merge is our own kernel (multimem.ld_reduce over NVSwitch)
@@ -517,7 +528,7 @@ def run_ours(args, wl):
             step_device(args.warmup + s)
             ev[s][1].record()
         ev[-1][0].record()
-        if world > 1:                        # the run's single grid merge over NVLink (SURVEY 8e mode 1)
+        if world > 1 and not slabs:          # the run's single grid merge over NVLink (SURVEY 8e mode 1)
             if getattr(grid, "symm", None) is not None:
                 pd.reduce_grid_peers(grid, dst=0 if world == 2 else None, ctx=ctx)   # see distributed.ray_voxel_distributed
             else:
@@ -535,6 +546,8 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_max, all_steps, all_rays = float(t.item()), float(tot[0].item()), float(tot[1].item())
+    if slabs and world > 1:   # every rank walked the same rays: count each voxel step once
+        all_steps, all_rays = all_steps / world, all_rays / world
 
     # ---- timed region 2: end to end through the public API with HOST (pinned) frames ------------------------------
     grid.zero_()
@@ -552,6 +565,8 @@ def run_ours(args, wl):
     if world > 1:
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e_tot, op=dist.ReduceOp.SUM)
+        if slabs:
+            e_tot /= world
 
     if rank != 0:
         if world > 1:
@@ -603,10 +618,10 @@ def run_ours(args, wl):
 
     value = all_steps / (ms_max * 1e-3)
     e_value = float(e_tot.item()) / (float(e_ms.item()) * 1e-3)
-    frames_total = args.steps * B * world
+    frames_total = args.steps * B * (1 if slabs else world)
     line = {
         "metric": "voxel_steps_per_sec", "value": value, "unit": "voxel-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if slabs else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, wl),
         "frames_per_s": frames_total / (ms_max * 1e-3), "rays_per_s": all_rays / (ms_max * 1e-3), "voxel_steps_per_ray": all_steps / max(1.0, all_rays),
         "e2e": {"value": e_value, "unit": "voxel-steps/s", "h2d_bytes_per_step": (B + 1) * H * W, "d2h_bytes_per_step": 32,
