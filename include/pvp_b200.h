@@ -80,8 +80,11 @@ typedef struct pvp_pair {
 
 typedef struct pvp_stats {
     uint64_t n_rays;    /* pixels that passed the motion test and cast a ray (ray_voxel.cpp:496-503) */
-    uint64_t n_steps;   /* RayStep count = voxel-steps of the reference (ray_voxel.cpp:373,523) */
-    uint64_t n_written; /* grid updates issued (== n_steps unless a slab suppresses writes) */
+    uint64_t n_steps;   /* RayStep count = voxel-steps of the reference (ray_voxel.cpp:373,523).  Slab grids: the steps THIS call walked --
+                         * rays that cannot reach the slab are not walked and a walk stops once x has passed the slab -- so <= the whole-grid
+                         * count and >= n_written (the default kernels; dda_variant 1-3 walk every ray in full) */
+    uint64_t n_written; /* grid updates = voxel steps inside the grid's x-planes (== n_steps for a whole grid; over the slabs of a grid
+                         * they add up to the whole-grid n_steps) */
     uint64_t n_atomics; /* global atomic operations actually issued (<= n_written after aggregation) */
 } pvp_stats;
 

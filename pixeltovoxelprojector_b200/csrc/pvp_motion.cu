@@ -645,7 +645,27 @@ __device__ __forceinline__ bool step_leaves(unsigned cur, bool cz, bool cy, int 
     const int iy = (int)udiv_by(rest, (unsigned)N, g.mul_n), iz = (int)(rest - (unsigned)iy * (unsigned)N);
     if (cz) return diz > 0 ? iz == N - 1 : iz == 0;
     if (cy) return diy > 0 ? iy == N - 1 : iy == 0;
+    // an x step: out of the grid, or -- slab kernels -- past the far face of the slab: x only moves one way, the ray cannot
+    // write into this slab again, so this rank stops walking it (per-slab clipping that keeps the walk itself untouched)
+    if (SLAB) return dix > 0 ? ix + 1 >= g.slab_hi : ix - 1 < g.slab_lo;
     return dix > 0 ? ix == N - 1 : ix == 0;
+}
+
+// Slab kernels: can the ray write into x-planes [slab_lo, slab_hi) at all, and how many x steps until it has passed them?
+// x moves one way (sx); the last x index the walk can reach is within one voxel of the box exit point, estimated with two
+// voxels of margin.  Returns false when the ray need not be walked by this rank; else rem_x = x steps that stay on this side of
+// the slab's far face (the step after them ends the walk here: step_leaves).
+__device__ __forceinline__ bool slab_reach(const Ray &r, float cam_x, float dir_x, const GridP &g, int &rem_x)
+{
+    const float x_exit = (cam_x + r.t_end * dir_x - g.gmin[0]) / g.vs;  // in voxels; inf / NaN compare false below: not skipped
+    if (r.sx > 0) {
+        if (r.ix >= g.slab_hi || x_exit + 2.f < (float)g.slab_lo) return false;
+        rem_x = g.slab_hi - 1 - r.ix;
+    } else {
+        if (r.ix < g.slab_lo || x_exit - 2.f >= (float)g.slab_hi) return false;
+        rem_x = r.ix - g.slab_lo;
+    }
+    return true;
 }
 
 template <int MODE, bool SLAB, bool NARROW, int MINB>
@@ -688,12 +708,15 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
             float dx, dy, dz;
             pixel_ray(u, v, width, height, __ldg(&P->focal), P->R, dx, dy, dz);
             Ray r;
-            if (ray_setup(__ldg(&P->cam[0]), __ldg(&P->cam[1]), __ldg(&P->cam[2]), dx, dy, dz, g, r) && r.t_cur <= r.t_end) {
+            int rem_x = 0;
+            if (ray_setup(__ldg(&P->cam[0]), __ldg(&P->cam[1]), __ldg(&P->cam[2]), dx, dy, dz, g, r) && r.t_cur <= r.t_end &&
+                (!SLAB || slab_reach(r, __ldg(&P->cam[0]), dx, g, rem_x))) {
+                if (!SLAB) rem_x = r.sx > 0 ? N - 1 - r.ix : r.ix;
                 t_end = r.t_end;
                 tmx = r.tmx; tmy = r.tmy; tmz = r.tmz; tdx = r.tdx; tdy = r.tdy; tdz = r.tdz;
                 idx = (unsigned)((r.ix - g.slab_lo) * N + r.iy) * (unsigned)N + (unsigned)r.iz;  // negative x offsets wrap past slab_cells
                 dix = r.sx * N * N; diy = r.sy * N; diz = r.sz;
-                lim = fminf(fminf(axis_limit(r.tmx, r.tdx, r.sx > 0 ? N - 1 - r.ix : r.ix), axis_limit(r.tmy, r.tdy, r.sy > 0 ? N - 1 - r.iy : r.iy)),
+                lim = fminf(fminf(axis_limit(r.tmx, r.tdx, rem_x), axis_limit(r.tmy, r.tdy, r.sy > 0 ? N - 1 - r.iy : r.iy)),
                             fminf(axis_limit(r.tmz, r.tdz, r.sz > 0 ? N - 1 - r.iz : r.iz), r.t_end));
                 val = V::make(diff, g);
             }
@@ -817,7 +840,7 @@ __device__ __forceinline__ void rays_retire(RayS &r)
 }
 
 // queue entry -> walking state; returns the value to accumulate (0 when the ray casts no step)
-template <typename V>
+template <typename V, bool SLAB>
 __device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, unsigned long long i, unsigned long long count,
                                                     const pvp_pair *__restrict__ pairs, const GridP &g, int width, int height, float &raw_diff)
 {
@@ -833,12 +856,14 @@ __device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, uns
     Ray r;
     if (!(ray_setup(__ldg(&P->cam[0]), __ldg(&P->cam[1]), __ldg(&P->cam[2]), dx, dy, dz, g, r) && r.t_cur <= r.t_end)) return 0;
     const int N = g.n;
+    int rem_x = r.sx > 0 ? N - 1 - r.ix : r.ix;
+    if (SLAB && !slab_reach(r, __ldg(&P->cam[0]), dx, g, rem_x)) return 0;  // never writes into this slab: not walked here
     s.t_end = r.t_end; s.t_cur = r.t_cur;
     raw_diff = diff;
     s.tmx = r.tmx; s.tmy = r.tmy; s.tmz = r.tmz; s.tdx = r.tdx; s.tdy = r.tdy; s.tdz = r.tdz;
     s.idx = (unsigned)((r.ix - g.slab_lo) * N + r.iy) * (unsigned)N + (unsigned)r.iz;
     s.dix = r.sx * N * N; s.diy = r.sy * N; s.diz = r.sz;
-    s.lim = fminf(fminf(axis_limit(r.tmx, r.tdx, r.sx > 0 ? N - 1 - r.ix : r.ix), axis_limit(r.tmy, r.tdy, r.sy > 0 ? N - 1 - r.iy : r.iy)),
+    s.lim = fminf(fminf(axis_limit(r.tmx, r.tdx, rem_x), axis_limit(r.tmy, r.tdy, r.sy > 0 ? N - 1 - r.iy : r.iy)),
                   fminf(axis_limit(r.tmz, r.tdz, r.sz > 0 ? N - 1 - r.iz : r.iz), r.t_end));
     return V::make(diff, g);
 }
@@ -920,8 +945,8 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
         if (base >= count) break;
         RayS a, b;
         float da, db;  // the rays' pix_val (ray_voxel.cpp:500); the attenuating kernel derives every step's value from it
-        T va = rays_setup<V>(a, q, base + 2 * lane, count, pairs, g, width, height, da);
-        T vb = rays_setup<V>(b, q, base + 2 * lane + 1, count, pairs, g, width, height, db);
+        T va = rays_setup<V, SLAB>(a, q, base + 2 * lane, count, pairs, g, width, height, da);
+        T vb = rays_setup<V, SLAB>(b, q, base + 2 * lane + 1, count, pairs, g, width, height, db);
         float n_issued = 0.f, n_inslab = 0.f;
         float walked = 0.f;  // iterations of this chunk so far == voxels emitted by every ray that is still alive
         if (__all_sync(FULL, !rays_live(a) && !rays_live(b))) continue;

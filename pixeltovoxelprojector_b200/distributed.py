@@ -164,9 +164,10 @@ def ray_voxel_distributed(metadata_json: str, image_folder: str, output_bin: str
     if world > 1:
         dist.all_reduce(t, group=group)
     out = dict(zip(keys, (int(x) for x in t.tolist())))
-    if mode == "slabs":  # every rank walked every ray: ray/step counts are replicated, writes are not
-        for k in ("n_rays", "n_steps", "n_pairs", "n_frames_loaded"):
+    if mode == "slabs":  # every rank saw every ray (replicated counts); it walks only the rays that can reach its slab, and the
+        for k in ("n_rays", "n_pairs", "n_frames_loaded"):   # writes partition the run's voxel steps
             out[k] //= world
+        out["n_steps"] = out["n_written"]
     return out
 
 

@@ -4,8 +4,8 @@
 * config 3: 4 cameras x 3840x2160 frames into a 512^3 grid, frame pairs sharded over 2 / 4 / 8 ranks, private grids,
   one sum-reduce.  Property: the sum of the shard grids equals the whole run (fixed point: bit for bit; fp32 with
   uint8 frames: bit for bit too, every addend is an integer and the sums stay below 2^24).
-* config 4: a 1024^3 grid (4 GiB fp32) sharded into 8 x-slabs.  Property: every slab walks every ray with full-grid
-  arithmetic, writes partition the voxel steps, and the concatenated slabs equal the whole grid.
+* config 4: a 1024^3 grid (4 GiB fp32) sharded into 8 x-slabs.  Property: a slab walks the rays that can reach it with full-grid
+  arithmetic (from their start, until x has passed the slab), writes partition the voxel steps, and the concatenated slabs equal the whole grid.
 
 No CPU oracle at these sizes; the small-size bit-exact parity against the oracle is in test_gpu_motion.py."""
 import numpy as np
@@ -73,17 +73,19 @@ def test_config4_1024_grid_eight_x_slabs(ctx):
     whole = pvp.VoxelGrid(N, vs, center)                                   # 4 GiB
     st = pvp.accumulate_motion(frames, tab, whole, 2.0)
     assert st["n_steps"] > 200 * st["n_rays"] > 0 and st["n_written"] == st["n_steps"]
-    written, world = 0, 8
+    written, walked, world = 0, 0, 8
     for rank in range(world):
         lo, hi = slab_range(N, rank, world)
         assert hi - lo == 128
         slab = pvp.VoxelGrid(N, vs, center, slab=(lo, hi))                 # 512 MiB: x-planes [lo, hi) only
         s = pvp.accumulate_motion(frames, tab, slab, 2.0)
-        assert (s["n_rays"], s["n_steps"]) == (st["n_rays"], st["n_steps"])   # every rank walks every ray in full
+        assert s["n_rays"] == st["n_rays"] and s["n_written"] <= s["n_steps"] < st["n_steps"]   # clipped: rays that cannot reach the slab are not walked
+        walked += s["n_steps"]
         written += s["n_written"]
         assert torch.equal(slab.data, whole.data[lo:hi]), rank             # a contiguous byte range of the .bin
         del slab
     assert written == st["n_steps"]
+    assert walked < 4 * st["n_steps"]                 # 8 ranks walking every ray in full would be 8x
     # the fixed-point slab path (64-bit cells) on one slab
     lo, hi = slab_range(N, 3, world)
     fx = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=6, slab=(lo, hi))

@@ -123,7 +123,7 @@ def test_slabs_partition_the_grid(ctx):
     for lo, hi in ((0, 9), (9, 10), (10, 31), (31, N), (N, N)):
         grid = grid_like(g, slab=(lo, hi))
         st = pvp.accumulate_motion(frames, pairs, grid, float(g["threshold"]))
-        assert st["n_steps"] == int(g["n_steps"])   # every slab walks every ray in full
+        assert st["n_written"] <= st["n_steps"] <= int(g["n_steps"])   # a slab walks the rays that can reach it, until they have passed it
         written += st["n_written"]
         parts.append(grid.data)
     assert written == int(g["n_steps"])
@@ -357,7 +357,10 @@ def test_rays_leaving_through_low_corners_and_tiny_grids(ctx, oracle):
                     for hi in sorted({lo, min(N, lo + 1), N}):
                         s = pvp.VoxelGrid(N, vs, center, slab=(lo, hi))
                         ss = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, s, 2.0)
-                        assert (ss["n_rays"], ss["n_steps"]) == (tot[0], tot[1]), (N, variant, lo, hi)
+                        # variants 1-3 walk every ray in full on a slab; the default kernels clip (rays that cannot reach the slab are
+                        # not walked, a walk stops once x has passed it)
+                        assert ss["n_rays"] == tot[0] and ss["n_written"] <= ss["n_steps"] <= tot[1], (N, variant, lo, hi)
+                        assert variant in (0, 5) or ss["n_steps"] == tot[1], (N, variant, lo, hi)
                         assert np.array_equal(s.data.cpu().numpy(), want[lo:hi]), (N, variant, lo, hi)
                         if hi == lo + 1:
                             planes_written += ss["n_written"]
@@ -410,7 +413,8 @@ def _geometry_sweep(ctx, oracle, rng):
             hi = int(rng.integers(lo, N + 1))
             s = pvp.VoxelGrid(N, vs, center, accum=accum, frac_bits=9, slab=(lo, hi))
             ss = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, s, 2.0)
-            assert (ss["n_rays"], ss["n_steps"]) == (tot[0], tot[1]) and np.array_equal(s.data.cpu().numpy(), want[lo:hi]), (trial, accum, lo, hi)
+            assert np.array_equal(s.data.cpu().numpy(), want[lo:hi]), (trial, accum, lo, hi)
+            assert ss["n_rays"] == tot[0] and ss["n_written"] <= ss["n_steps"] <= tot[1], (trial, accum, lo, hi)   # slab walks are clipped
         total_steps += tot[1]
     return total_steps
 
