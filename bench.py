@@ -35,7 +35,7 @@ WORKLOADS = {
     "4k_dense_512": dict(H=2160, W=3840, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=2, pool=20, motion="dense", accum="f32"),
     # BASELINE config[3] shape on ONE GPU: the whole 1024^3 grid (4 GiB; slab sharding itself is covered by tests/test_gpu_configs.py)
     # BASELINE config[3]: the 1024^3 grid sharded into 8 x-slabs (x is the slowest index: contiguous byte ranges of the .bin); every rank walks
-    # every ray with full-grid arithmetic and writes only inside its slab.  On one GPU this runs rank 4 of 8; with --gpus N rank r takes slab r % 8.
+    # every ray with full-grid arithmetic and writes only inside its slab.  On one GPU this runs rank 4 of 8; with --gpus N the grid is cut into N slabs, one per rank (N = 8: config 4).
     # Same frames on every rank, no merge; `value` counts each voxel step once (the job's useful work), whatever the number of ranks.
     "1080p_dense_1024_slab8": dict(H=1080, W=1920, N=1024, voxel_size=1.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=24, motion="dense", accum="f32", slabs=8),
     "1080p_dense_1024": dict(H=1080, W=1920, N=1024, voxel_size=1.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=24, motion="dense", accum="f32"),
@@ -432,7 +432,7 @@ def run_ours_image(args, wl):
 def workload_config(args, wl):
     return {"workload": args.workload, "k2_variant": getattr(args, "variant", 0), "frame": f"{wl['W']}x{wl['H']} uint8", "grid": f"{wl['N']}^3 {wl['accum']}", "voxel_size": wl["voxel_size"],
             "pairs_per_step": wl["pairs_per_step"], "motion": wl["motion"], "camera": "pose changes every frame (orbit inside the grid); N>1: same pose table, different frames on every rank",
-            "parallelism": (f"grid sharded into {wl['slabs']} x-slabs; " + (f"{args.gpus} ranks, rank r owns slab r" if args.gpus > 1 else f"1 GPU running rank {wl['slabs'] // 2}'s slab") + f"; {getattr(args, 'reduce_how', '')}") if wl.get("slabs") else
+            "parallelism": (f"grid sharded into {args.gpus if args.gpus > 1 else wl['slabs']} x-slabs; " + (f"{args.gpus} ranks, rank r owns slab r" if args.gpus > 1 else f"1 GPU running rank {wl['slabs'] // 2}'s slab") + f"; {getattr(args, 'reduce_how', '')}") if wl.get("slabs") else
                            f"frames sharded over {args.gpus} GPU(s), private grids, one grid merge per run inside the timed region: {getattr(args, 'reduce_how', 'NCCL reduce')}" if args.gpus > 1 else "1 GPU",
             "l2": "256 MiB buffer written between timed steps (L2 flush); frame pool 149 MB and grid > L2" if wl["N"] >= 512 else
                   "256 MiB buffer written between timed steps (L2 flush)"}
@@ -465,7 +465,8 @@ def run_ours(args, wl):
     grid, reduce_how = None, "none (1 GPU)"
     if slabs:
         from pixeltovoxelprojector_b200.distributed import slab_range
-        lo, hi = slab_range(wl["N"], (rank if world > 1 else slabs // 2) % slabs, slabs)
+        n_slabs = world if world > 1 else slabs     # --gpus N: N slabs, one per rank (N = 8 is BASELINE config 4); 1 GPU: rank 4 of 8
+        lo, hi = slab_range(wl["N"], rank if world > 1 else slabs // 2, n_slabs)
         grid = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev, slab=(lo, hi))
         reduce_how = f"none (slab sharding: rank writes x-planes [{lo}, {hi}) of the .bin)"
     if world > 1 and not slabs:
