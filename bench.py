@@ -325,9 +325,10 @@ def run_ours_image(args, wl):
     ctx.get_profile(reset=True)
     ctx.profile(True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
+    sampler = ClockSampler(local)   # NVML start-up (100s of ms, different on every rank) before the barrier, not between it and the timed steps
     barrier()
     my_samples = 0
-    with ClockSampler(local) as clocks:
+    with sampler as clocks:
         for s in range(args.steps):
             flush.fill_(s & 0xFF)
             ev[s][0].record()
@@ -521,8 +522,9 @@ def run_ours(args, wl):
     # ---- timed region 1: inputs resident in HBM (`value`) ------------------------------------------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     ctx.profile(True)
-    barrier()
-    with ClockSampler(local) as clocks:
+    sampler = ClockSampler(local)   # NVML start-up (100s of ms, different on every rank) before the barrier: otherwise the skew between
+    barrier()                       # the ranks lands in the wait of the grid merge (measured once at 8 GPUs: 434 ms instead of 1.3 ms)
+    with sampler as clocks:
         for s in range(args.steps):
             flush.fill_(s & 0xFF)            # L2 flush, outside the timed events
             ev[s][0].record()
@@ -542,13 +544,14 @@ def run_ours(args, wl):
     ctx.profile(False)
     stats = pvp.accumulate_motion(frames_dev, pairs_for(0)[1], grid, 2.0, ctx=ctx, n_pairs=0, want_stats=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([stats["n_steps"], stats["n_rays"], stats["n_atomics"]], dtype=torch.float64, device=dev)
+    # slab mode over several ranks: the job's voxel steps are the ranks' WRITES (each step lands in exactly one slab); a rank's n_steps is what it walked
+    tot = torch.tensor([stats["n_written"] if (slabs and world > 1) else stats["n_steps"], stats["n_rays"], stats["n_atomics"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_max, all_steps, all_rays = float(t.item()), float(tot[0].item()), float(tot[1].item())
-    if slabs and world > 1:   # every rank walked the same rays: count each voxel step once
-        all_steps, all_rays = all_steps / world, all_rays / world
+    if slabs and world > 1:   # every rank saw the same rays
+        all_rays = all_rays / world
 
     # ---- timed region 2: end to end through the public API with HOST (pinned) frames ------------------------------
     grid.zero_()
@@ -558,7 +561,7 @@ def run_ours(args, wl):
     for s in range(args.steps):
         flush.fill_(s & 0xFF)
         e_ev[s][0].record()
-        e_steps += step_e2e(args.warmup + s)["n_steps"]      # H2D of B+1 frames inside; D2H of the step's counters
+        e_steps += step_e2e(args.warmup + s)["n_written" if (slabs and world > 1) else "n_steps"]      # H2D of B+1 frames inside; D2H of the step's counters
         e_ev[s][1].record()
     barrier()
     e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e_ev)], dtype=torch.float64, device=dev)
@@ -566,8 +569,6 @@ def run_ours(args, wl):
     if world > 1:
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e_tot, op=dist.ReduceOp.SUM)
-        if slabs:
-            e_tot /= world
 
     if rank != 0:
         if world > 1:
