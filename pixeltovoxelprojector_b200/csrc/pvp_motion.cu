@@ -517,8 +517,10 @@ dda_accumulate_agg_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, 
 //     of (boundary - camera) / dir with |dir| >= 1e-12: the host only selects this kernel when every camera and
 //     grid coordinate of the batch is below 1e25 in magnitude (lean_geometry_ok); anything else runs variant 3,
 //     which keeps the reference's compare structure.
-//   * per-axis "steps left inside [0,N)" counters are floats decremented by predicated FADDs (FMA pipe);
-//     the ray's step count is recovered from them when it ends -- no per-iteration counter.
+//   * no per-step bookkeeping of the grid bounds: one t limit per ray (axis_limit) below which a step provably neither
+//     leaves the grid nor passes t_end -- one compare per step; the reference's exact tests run in the slow path only
+//     (step_leaves).  The first version kept three float "steps left" counters per ray: 6 predicated FADDs, a 3-input
+//     min and two compares per step.  A ray's step count is the chunk's iteration counter when it parks.
 //   * no per-iteration select of key/value: a lane whose ray ended is parked in a state that keeps it
 //     harmless (key NONE, value 0, zero strides, t frozen) by a warp-uniform slow path that runs only in
 //     iterations where some ray ends (~5 %), which also decides the loop exit.
