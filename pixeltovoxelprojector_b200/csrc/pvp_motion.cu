@@ -810,11 +810,11 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
 }
 
 // ---- variant 5: "lean2", two rays per lane -------------------------------------------------------------------------
-// A warp takes 64 consecutive queue entries; lane l walks entries 2l (ray A) and 2l+1 (ray B), which the row-pair
+// A warp takes 64 consecutive queue entries; lane l walks entries 2l (ray A) and 2l+1 (ray B), which the tile
 // ordering of K1 makes vertical neighbours (u,v) / (u,v+1).  Both rays advance one DDA step per iteration.  B's voxel
 // is A's voxel ~89 % of the time: then B's value simply joins A's before the run scan, so ONE scan and ONE set of run
-// REDs serve 64 voxel steps instead of 32 -- the warp's rays form a 32 x 2 tile, and a tile touches fewer distinct
-// voxels than a 64 x 1 strip.  Where B sits in another voxel it issues its own RED.  Per ray the arithmetic, the step
+// REDs serve 64 voxel steps instead of 32 -- the warp's rays form a 16 x 4 (32 x 2, 8 x 8) tile, and a tile touches fewer
+// distinct voxels than a 64 x 1 strip.  Where B sits in another voxel it issues its own RED.  Per ray the arithmetic, the step
 // order and the counters are those of variant 4 (same bit-exact visited sets).
 struct RayS {
     float t_end, lim;  // box exit t_max (:293); lim: below it a step can neither leave the grid nor pass t_end (see axis_limit)
@@ -1173,7 +1173,7 @@ static void launch_lean2(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width
                                                                                                  width, height, ctx->ctl_dev, count_lo, count_hi);
         return;
     }
-    // lean_regs: 0/80 -> 3 resident CTAs (24 warps; measured best: 670 G voxel-steps/s at 512^3), 128 -> 2 CTAs (622 G), 64 -> 4 CTAs
+    // lean_regs: 0/80 -> 3 resident CTAs (24 warps; measured best: 780 G voxel-steps/s at 512^3 on 2-row tiles), 128 -> 2 CTAs (686 G), 64 -> 4 CTAs (722 G)
     auto k = ctx->opt_lean_regs == 128 ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 2>
            : ctx->opt_lean_regs == 64  ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 4> : dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, PVP_LEAN2_MINB>;
     k<<<k2_grid_size(ctx, (const void *)k, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
@@ -1221,7 +1221,7 @@ static int auto_row_group(const GridP &g, int accum_mode)
 
 // dda_variant: 0 = auto (lean2 / lean by ray count where their 32-bit voxel keys allow, else 3), 1 = segmented-scan aggregation (round-1
 // baseline), 2 = match.any aggregation, 3 = one RED per lane and step (no aggregation, any grid size),
-// 4 = lean lock-step kernel (one ray per lane), 5 = lean2 (two rays per lane, K1 in row-pair order).  narrow_ok: uint8 frames, i.e. integer addends (LeanVal<FIXED, true>).
+// 4 = lean lock-step kernel (one ray per lane), 5 = lean2 (two rays per lane, vertical neighbours of K1's tile order).  narrow_ok: uint8 frames, i.e. integer addends (LeanVal<FIXED, true>).
 static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_ok, bool lean_ok, void *grid_dev, int width, int height)  // NOLINT
 {
     LaunchScope scope(ctx, 2);
