@@ -225,3 +225,20 @@ def test_product_never_imports_oracle():
                 assert "oracle" not in text.lower(), f"{f} mentions the oracle"
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "libref" not in out
+
+
+def test_multiply_high_division_used_by_the_k2_slow_path():
+    """csrc/pvp_motion.cu::udiv_by decodes a voxel offset with q = umulhi(x, floor(2^32 / d)) and ONE correction step
+    (q += x - q d >= d) for d = n and n^2.  The claim "one step suffices for every 32-bit x" restated in numpy over all grid
+    sizes the library accepts: random x, the neighbourhood of every kind of multiple of d, and the top of the range."""
+    rng = np.random.default_rng(0)
+    for n in range(2, 2049):
+        for d in (n, n * n):
+            m = (1 << 32) // d
+            k = rng.integers(0, (1 << 32) // d, 300, dtype=np.uint64)
+            xs = np.concatenate([rng.integers(0, 1 << 32, 500, dtype=np.uint64), k * np.uint64(d), k * np.uint64(d) + np.uint64(d - 1),
+                                 np.uint64((1 << 32) - 1) - np.arange(0, 300, dtype=np.uint64), np.arange(0, 300, dtype=np.uint64)])
+            xs = xs[xs < (1 << 32)]
+            q = (xs * np.uint64(m)) >> np.uint64(32)
+            q = q + ((xs - q * np.uint64(d)) >= d)
+            assert np.array_equal(q, xs // np.uint64(d)), (n, d)
