@@ -1,0 +1,102 @@
+"""The arithmetic claims the lock-step kernels rest on, restated in numpy / exact rationals and checked on the CPU (the kernels
+themselves are compared with the oracle on the GPU; these tests pin the *reasons* they may skip work):
+
+* K2 `axis_limit` (csrc/pvp_motion.cu): tm0 + rem*td minus 2^-11 (|tm0| + rem*td) is a lower bound of the float32 value t_max has
+  after `rem` rounded additions of t_delta -- so a step whose t is below it cannot be the one that leaves the grid.
+* K3 `voxel_index_screened` (csrc/pvp_image.cu): when the 20 fraction bits read from the mantissa of a*K + (2^52 - 5) are below
+  0xFFFF6, the integer part read from it equals the reference's min(trunc(RN(RN(a/b) * n)), n - 1).
+* K3 `sample_keys2<2>`: the same read-out from ONE fused multiply-add y = RN(s*dx + x0) per axis equals the reference's index for
+  samples inside the grid whenever A*K <= 2^49 (the host's `affine_ok`) and the safe range's 32-unit margin holds."""
+from fractions import Fraction
+
+import numpy as np
+
+F32 = np.float32
+
+
+def test_k2_axis_limit_is_a_lower_bound_of_the_iterated_sum():
+    rng = np.random.default_rng(7)
+    n = 20000
+    tm0 = (rng.uniform(-1e3, 1e4, n) * rng.choice([1.0, 1e-3, 1e3], n)).astype(F32)
+    td = np.exp(rng.uniform(np.log(1e-4), np.log(1e5), n)).astype(F32)
+    rem = rng.integers(0, 2048, n)
+    s = tm0.copy()
+    worst = 0.0
+    for k in range(2047):                       # S_k = RN(S_{k-1} + td), frozen once a sample has done its `rem` additions
+        nxt = (s + td).astype(F32)
+        s = np.where(k < rem, nxt, s)
+    span = (rem.astype(F32) * td).astype(F32)
+    closed = (tm0 + span).astype(F32)
+    bound = (closed - ((np.abs(tm0) + span).astype(F32) * F32(2.0 ** -11)).astype(F32)).astype(F32)
+    assert np.all(bound <= s)
+    proven = (np.abs(tm0) + span) * 2.0 ** -13           # the error bound of the derivation; the kernel's slack is 4x that
+    worst = float(np.max(np.abs(s.astype(np.float64) - (tm0.astype(np.float64) + rem * td.astype(np.float64))) / np.maximum(proven, 1e-30)))
+    assert worst < 1.0, worst
+
+
+def _ref_index(a, b, n):
+    return np.minimum(np.trunc((a / b) * n).astype(np.int64), n - 1)      # process_image.cpp:94-104 (float64, RN each)
+
+
+def _read_out(y):
+    bits = y.view(np.uint64)
+    lo20 = bits & np.uint64(0xFFFFF)
+    idx = ((bits >> np.uint64(20)) & np.uint64(0xFFFFFFFF)).astype(np.int64)   # the funnel shift of the two mantissa words
+    return idx, lo20 < 0xFFFF6
+
+
+def test_k3_mantissa_read_out_equals_the_reference_index():
+    rng = np.random.default_rng(11)
+    checked = 0
+    for trial in range(60):
+        b = float(np.exp(rng.uniform(-8, 12)))
+        n = int(rng.choice([1, 2, 7, 64, 400, 512, 4096, 1 << 20, 1 << 24]))
+        K = (n / b) * 1048576.0
+        a = np.concatenate([rng.uniform(0, b, 200000), np.array([0.0, b])])
+        k = rng.integers(0, n + 1, 20000).astype(np.float64)                    # voxel boundaries and their neighbourhoods
+        edge = (k / n) * b
+        a = np.concatenate([a, edge, np.nextafter(edge, 0), np.nextafter(edge, 2 * b), edge * (1 + 3e-7), edge * (1 - 3e-7)])
+        a = a[(a >= 0) & (a <= b)]
+        y = a * K + (2.0 ** 52 - 5.0)
+        idx, safe = _read_out(y)
+        want = _ref_index(a, b, n)
+        assert np.array_equal(np.minimum(idx[safe], n - 1), want[safe]), (b, n)
+        assert safe.mean() > 0.5 or n >= 1 << 20 or b < 1e-3
+        checked += int(safe.sum())
+    assert checked > 5_000_000
+
+
+def test_k3_affine_coordinate_equals_the_reference_index_inside_the_safe_range():
+    rng = np.random.default_rng(13)
+    checked = flagged = 0
+    for trial in range(600):
+        n = int(rng.choice([16, 400, 512, 2048]))
+        b = float(rng.uniform(0.5, 4000.0))
+        lo = float(rng.uniform(-3000.0, 3000.0))
+        hi = lo + b
+        bb = hi - lo                                    # :94-96 divides by RN(max - min)
+        K = (n / bb) * 1048576.0
+        o = float(rng.uniform(lo - 3 * b, hi + 3 * b))
+        w = float(rng.uniform(-1, 1)) or 0.5
+        step = float(rng.uniform(0.01, 2.0) * b / n)
+        max_distance = 8 * b
+        A = abs(o) + max_distance + abs(lo) + abs(hi) + bb
+        if not A * K <= 2.0 ** 49:                      # make_fastp: affine_ok
+            continue
+        dx = (step * w) * K                             # affine_of()
+        x0 = (o - lo) * K + (2.0 ** 52 - 5.0)
+        margin = 2.0 ** -47 * (abs(o) + max_distance * abs(w) + abs(lo) + abs(hi)) + 32.0 / K    # safe_range: 2e + 32 units
+        for s in rng.integers(0, int(max_distance / step) + 1, 250):
+            s = int(s)
+            q = o + (s * step) * w                      # :344-347, RN each
+            if not (lo + margin <= q <= hi - margin):
+                continue
+            y = float(Fraction(s) * Fraction(dx) + Fraction(x0))   # one fused multiply-add: exact product and sum, rounded once
+            idx, safe = _read_out(np.array([y]))
+            if not safe[0]:
+                flagged += 1                            # the kernel takes the exact sequence there
+                continue
+            want = _ref_index(np.array([q - lo]), bb, n)[0]
+            assert idx[0] == want, (trial, s, n, b, o, w)
+            checked += 1
+    assert checked > 10000 and flagged < checked // 50
