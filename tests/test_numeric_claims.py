@@ -100,3 +100,43 @@ def test_k3_affine_coordinate_equals_the_reference_index_inside_the_safe_range()
             assert idx[0] == want, (trial, s, n, b, o, w)
             checked += 1
     assert checked > 10000 and flagged < checked // 50
+
+
+def test_k3_affine_coordinate_near_voxel_faces_at_the_largest_allowed_magnitudes():
+    """The hard corner of the claim above: sample positions steered to within a few 2^-20 voxel units of a voxel face, with
+    A*K between 2^46 and 2^49 (far observers, fine grids), where the affine value and the reference's own rounding differ most."""
+    rng = np.random.default_rng(17)
+    checked = flagged = 0
+    while checked + flagged < 6000:
+        n = int(rng.choice([512, 4096, 1 << 16, 1 << 20]))
+        b = float(rng.uniform(1.0, 1000.0))
+        lo = float(rng.uniform(-1000.0, 1000.0))
+        hi = lo + b
+        bb = hi - lo
+        K = (n / bb) * 1048576.0
+        target = 2.0 ** rng.uniform(46, 49)             # wanted A*K
+        far = target / K                                # ~ |o| + max_distance
+        w = float(rng.choice([-1, 1]) * rng.uniform(0.3, 1.0))
+        max_distance = 0.5 * far
+        step = max_distance / 4096
+        s = int(rng.integers(1, 4096))
+        k = int(rng.integers(1, n - 1))
+        delta = float(rng.integers(-12, 13)) + float(rng.uniform(-0.5, 0.5))
+        o = lo + (k + delta * 2.0 ** -20) * bb / n - (s * step) * w     # steer sample s to voxel face k (+ delta units)
+        A = abs(o) + max_distance + abs(lo) + abs(hi) + bb
+        if not (A * K <= 2.0 ** 49):
+            continue
+        q = o + (s * step) * w
+        margin = 2.0 ** -47 * (abs(o) + max_distance * abs(w) + abs(lo) + abs(hi)) + 32.0 / K
+        if not (lo + margin <= q <= hi - margin):
+            continue
+        dx = (step * w) * K
+        x0 = (o - lo) * K + (2.0 ** 52 - 5.0)
+        y = float(Fraction(s) * Fraction(dx) + Fraction(x0))
+        idx, safe = _read_out(np.array([y]))
+        if not safe[0]:
+            flagged += 1
+            continue
+        assert idx[0] == _ref_index(np.array([q - lo]), bb, n)[0], (n, b, lo, o, w, s, k, delta)
+        checked += 1
+    assert checked > 2000 and flagged > 500             # both outcomes exercised: the window really sits on the faces
