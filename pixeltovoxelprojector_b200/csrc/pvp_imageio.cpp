@@ -138,28 +138,34 @@ bool decode_png(const std::vector<uint8_t> &d, Decoded &out)
     const size_t bpp_bits = (size_t)chans * depth;
     const size_t stride = ((size_t)w * bpp_bits + 7) / 8;
     const size_t fbpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;  // filter byte distance
+    if (idat.empty() || (stride + 1) * (size_t)h / 1032 > idat.size() + 64) return false;  // deflate expands at most ~1032x
     std::vector<uint8_t> raw((stride + 1) * (size_t)h);
     uLongf raw_len = (uLongf)raw.size();
     if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) return false;
 
-    // un-filter in place (row r occupies raw[r*(stride+1)+1 ...])
+    // un-filter in place (row r occupies raw[r*(stride+1)+1 ...]); one tight loop per filter type
     std::vector<uint8_t> zero(stride, 0);
     for (size_t r = 0; r < h; ++r) {
         uint8_t *cur = &raw[r * (stride + 1) + 1];
         const uint8_t *up = r ? &raw[(r - 1) * (stride + 1) + 1] : zero.data();
-        const int ft = raw[r * (stride + 1)];
-        for (size_t i = 0; i < stride; ++i) {
-            const int a = i >= fbpp ? cur[i - fbpp] : 0, b = up[i], c = i >= fbpp ? up[i - fbpp] : 0;
-            int x = cur[i];
-            switch (ft) {
-                case 0: break;
-                case 1: x += a; break;
-                case 2: x += b; break;
-                case 3: x += (a + b) >> 1; break;
-                case 4: x += paeth(a, b, c); break;
-                default: return false;
-            }
-            cur[i] = (uint8_t)x;
+        const size_t head = fbpp < stride ? fbpp : stride;  // bytes without a left neighbour
+        switch (raw[r * (stride + 1)]) {
+            case 0: break;
+            case 1:
+                for (size_t i = head; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + cur[i - fbpp]);
+                break;
+            case 2:
+                for (size_t i = 0; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + up[i]);
+                break;
+            case 3:
+                for (size_t i = 0; i < head; ++i) cur[i] = (uint8_t)(cur[i] + (up[i] >> 1));
+                for (size_t i = head; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + ((cur[i - fbpp] + up[i]) >> 1));
+                break;
+            case 4:
+                for (size_t i = 0; i < head; ++i) cur[i] = (uint8_t)(cur[i] + up[i]);  // paeth(0, b, 0) = b
+                for (size_t i = head; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + paeth(cur[i - fbpp], up[i], up[i - fbpp]));
+                break;
+            default: return false;
         }
     }
 
@@ -169,6 +175,7 @@ bool decode_png(const std::vector<uint8_t> &d, Decoded &out)
     for (size_t r = 0; r < h; ++r) {
         const uint8_t *row = &raw[r * (stride + 1) + 1];
         uint8_t *o = &out.gray[r * (size_t)w];
+        if (depth == 8 && ctype == 0) { memcpy(o, row, w); continue; }
         for (size_t x = 0; x < w; ++x) {
             if (depth == 16) {
                 auto rd = [&](size_t k) { return (unsigned)((row[2 * k] << 8) | row[2 * k + 1]); };
@@ -203,13 +210,28 @@ bool decode_png(const std::vector<uint8_t> &d, Decoded &out)
 
 bool decode_any(const char *path, Decoded &out)
 {
-    std::vector<uint8_t> data;
-    if (!read_file(path, data)) return false;
-    if (data.size() >= 2 && data[0] == 'P') return decode_pnm(data, out);
-    return decode_png(data, out);
+    try {  // a damaged header must not take the process down with std::bad_alloc (also runs on the decode pool's threads)
+        std::vector<uint8_t> data;
+        if (!read_file(path, data)) return false;
+        if (data.size() >= 2 && data[0] == 'P') return decode_pnm(data, out);
+        return decode_png(data, out);
+    } catch (...) {
+        return false;
+    }
 }
 
 }  // namespace
+
+// One decode per file for the callers inside the library (the C entry below decodes once per call, so its
+// size query + read pattern would decode every file twice).
+bool pvp::decode_gray_file(const char *path, std::vector<uint8_t> &gray, int *width, int *height)
+{
+    Decoded d;
+    if (!path || !decode_any(path, d)) return false;
+    gray.swap(d.gray);
+    *width = d.w; *height = d.h;
+    return true;
+}
 
 extern "C" {
 

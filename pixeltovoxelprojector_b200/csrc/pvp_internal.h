@@ -107,6 +107,10 @@ struct LaunchScope {
     ~LaunchScope();
 };
 
+// pvp_imageio.cpp: `path` decoded to 8-bit gray (the bytes stbi_load(...,1) returns, ray_voxel.cpp:195) in ONE pass; false = the
+// reference's failed stbi_load.  Never throws.
+bool decode_gray_file(const char *path, std::vector<uint8_t> &gray, int *width, int *height);
+
 int ensure_queue(pvp_ctx *ctx, unsigned long long entries);
 int ensure_pairs(pvp_ctx *ctx, int n_pairs);
 int upload_pairs(pvp_ctx *ctx, const pvp_pair *pairs, int n_pairs);

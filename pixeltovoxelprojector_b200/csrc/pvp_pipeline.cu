@@ -274,7 +274,7 @@ public:
         for (auto &t : workers_) t.join();
     }
     // frame `idx` (consumed in increasing order); valid until release(idx)
-    const Item &get(int idx)
+    Item &get(int idx)
     {
         std::unique_lock<std::mutex> g(m_);
         cv_.wait(g, [&] { return state_[(size_t)idx % ring_.size()] == idx; });
@@ -304,11 +304,7 @@ private:
                 state_[slot] = -2;  // being filled
             }
             Item &it = ring_[slot];
-            it.ok = pvp_load_image_gray(paths_[(size_t)idx].c_str(), nullptr, 0, &it.w, &it.h) == PVP_OK;
-            if (it.ok) {
-                it.px.resize((size_t)it.w * it.h);
-                it.ok = pvp_load_image_gray(paths_[(size_t)idx].c_str(), it.px.data(), (int64_t)it.px.size(), &it.w, &it.h) == PVP_OK;
-            }
+            it.ok = pvp::decode_gray_file(paths_[(size_t)idx].c_str(), it.px, &it.w, &it.h);
             {
                 std::lock_guard<std::mutex> g(m_);
                 state_[slot] = idx;
@@ -438,9 +434,7 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
 
     auto load = [&](const pvp_frame_info &fi, int *w, int *h) -> bool {  // serial load (shard look-back only)
         std::string path = R.folder + "/" + fi.image_file;  // :467
-        if (pvp_load_image_gray(path.c_str(), nullptr, 0, w, h) != PVP_OK) return false;
-        tmp.resize((size_t)*w * *h);
-        return pvp_load_image_gray(path.c_str(), tmp.data(), (int64_t)tmp.size(), w, h) == PVP_OK;
+        return decode_gray_file(path.c_str(), tmp, w, h);
     };
     // every frame of this rank's block, in visiting order, goes through the decode pool
     std::vector<std::string> visit;
@@ -464,9 +458,9 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
     int visit_idx = 0;
     auto load_next = [&](int *w, int *h) -> bool {  // next frame of the visiting order -> tmp
         const int idx = visit_idx++;
-        const DecodePool::Item &it = pool.get(idx);
+        DecodePool::Item &it = pool.get(idx);
         const bool ok = it.ok;
-        if (ok) { *w = it.w; *h = it.h; tmp = it.px; }
+        if (ok) { *w = it.w; *h = it.h; tmp.swap(it.px); }  // the slot keeps the old buffer for its next decode
         pool.release(idx);
         return ok;
     };

@@ -192,6 +192,58 @@ def test_image_decode_pnm_png(tmp_path):
         pvp.load_image_gray(str(tmp_path / "junk.jpg"))
 
 
+def test_image_decode_survives_damaged_files(tmp_path):
+    """A damaged or hostile file is the reference's failed stbi_load (frame skipped, ray_voxel.cpp:470-473): the decoder must
+    answer "Failed to load image" -- never crash, never allocate what a forged header asks for.  It also runs on the decode
+    pool's threads, where an escaping exception would end the process."""
+    rng = np.random.default_rng(11)
+    gray = rng.integers(0, 256, (24, 31), dtype=np.uint8)
+    rgb = rng.integers(0, 256, (24, 31, 3), dtype=np.uint8)
+    seeds = {}
+    _png(tmp_path / "g.png", gray, 0); seeds["g.png"] = (tmp_path / "g.png").read_bytes()
+    _png(tmp_path / "c.png", rgb, 2); seeds["c.png"] = (tmp_path / "c.png").read_bytes()
+    _png(tmp_path / "g2.png", gray & 3, 0, depth=2); seeds["g2.png"] = (tmp_path / "g2.png").read_bytes()
+    pal = rng.integers(0, 256, (7, 3), dtype=np.uint8)
+    _png(tmp_path / "p.png", gray % 7, 3, palette=pal); seeds["p.png"] = (tmp_path / "p.png").read_bytes()
+    synth.write_pgm(str(tmp_path / "g.pgm"), gray); seeds["g.pgm"] = (tmp_path / "g.pgm").read_bytes()
+    synth.write_ppm(str(tmp_path / "c.ppm"), rgb); seeds["c.ppm"] = (tmp_path / "c.ppm").read_bytes()
+
+    def probe(data):
+        f = tmp_path / "x.bin"
+        f.write_bytes(data)
+        try:
+            img = pvp.load_image_gray(str(f))
+        except pvp.PvpError as e:
+            assert "Failed to load image" in str(e)
+            return None
+        assert img.ndim == 2 and img.size > 0
+        return img
+
+    n_ok = 0
+    for name, data in seeds.items():
+        assert probe(data) is not None, name
+        for cut in sorted(set(int(c) for c in rng.integers(0, len(data), 25)) | {0, 1, 8, len(data) - 1}):
+            img = probe(data[:cut])       # truncated
+            # a cut inside the trailing IEND chunk leaves a complete image; anything shorter must fail
+            assert img is None or (name.endswith(".png") and cut >= len(data) - 12), (name, cut)
+        for _ in range(60):               # random byte damage (headers included)
+            b = bytearray(data)
+            for pos in rng.integers(0, len(b), int(rng.integers(1, 4))):
+                b[int(pos)] = int(rng.integers(0, 256))
+            n_ok += probe(bytes(b)) is not None
+    assert n_ok > 0   # PNG CRCs are not checked (stb_image does not check them either), so pixel damage still decodes
+
+    # forged sizes: headers that announce far more pixels than the file can hold
+    g = seeds["g.png"]
+    ihdr = g.index(b"IHDR") + 4
+    for w, h in ((1 << 24, 1 << 24), (1 << 23, 3), (31, 1 << 24), (0, 24), (31, 0), (0xFFFFFFFF, 0xFFFFFFFF)):
+        assert probe(g[:ihdr] + struct.pack(">II", w, h) + g[ihdr + 8:]) is None
+    for hdr in (b"P5\n1000000 1000000\n255\n", b"P6\n99999999 99999999\n255\n", b"P5\n31 24\n0\n", b"P5\n31 24\n70000\n",
+                b"P5\n-3 24\n255\n", b"P5\n99999999999999999999 24\n255\n", b"P5\n31\n"):
+        assert probe(hdr + gray.tobytes()) is None
+    assert probe(b"") is None and probe(b"P") is None and probe(b"\x89PNG\r\n\x1a\n") is None
+
+
 def test_bin_roundtrip_matches_reference_layout(tmp_path):
     rng = np.random.default_rng(0)
     grid = rng.random((7, 7, 7)).astype(np.float32)
