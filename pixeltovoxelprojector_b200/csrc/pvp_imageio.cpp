@@ -7,9 +7,10 @@
 //   - colour -> gray:   y = (77 r + 150 g + 29 b) >> 8  (integer, alpha ignored)
 //   - 16-bit -> 8-bit:  v >> 8, applied after the colour conversion
 //   - gray bit depths 1/2/4: scaled by 255/85/17
-// Formats: binary PNM (P5, P6; maxval <= 65535) and non-interlaced PNG (all colour types, 8/16
-// bit and sub-byte gray/palette).  Anything else (JPEG, BMP, interlaced PNG ...) fails to load,
-// which the pipeline treats like the reference treats a failed stbi_load: the frame is skipped
+// Formats: binary PNM (P5, P6; maxval <= 65535), PNG (all colour types, 8/16 bit and sub-byte
+// gray/palette, plain or Adam7-interlaced) and uncompressed BMP (1/4/8-bit palettised, 24 and
+// 32 bit).  Anything else (JPEG, TGA, GIF, RLE or 16-bit BMP ...) fails to load, which the
+// pipeline treats like the reference treats a failed stbi_load: the frame is skipped
 // (ray_voxel.cpp:470-473).  JPEG parity is unpinned by design (stb's IDCT != libjpeg).
 #include <stdint.h>
 #include <stdio.h>
@@ -123,7 +124,7 @@ bool decode_png(const std::vector<uint8_t> &d, Decoded &out)
         }
         pos += 12 + (size_t)len;
     }
-    if (!have_ihdr || w == 0 || h == 0 || w > (1u << 24) || h > (1u << 24) || interlace != 0) return false;
+    if (!have_ihdr || w == 0 || h == 0 || w > (1u << 24) || h > (1u << 24) || interlace > 1) return false;
     int chans;
     switch (ctype) {
         case 0: chans = 1; break;
@@ -136,73 +137,168 @@ bool decode_png(const std::vector<uint8_t> &d, Decoded &out)
     if (!(depth == 8 || depth == 16 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4)))) return false;
     if (ctype == 3 && (depth == 16 || pal.size() < 3)) return false;
     const size_t bpp_bits = (size_t)chans * depth;
-    const size_t stride = ((size_t)w * bpp_bits + 7) / 8;
     const size_t fbpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;  // filter byte distance
-    if (idat.empty() || (stride + 1) * (size_t)h / 1032 > idat.size() + 64) return false;  // deflate expands at most ~1032x
-    std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+
+    // The image is one pass, or the seven Adam7 passes of an interlaced file: each pass is a sub-image of the pixels
+    // (x0 + i*dx, y0 + j*dy) with its own scanlines and filters; empty passes take no bytes.
+    struct Pass { size_t x0, y0, dx, dy, pw, ph, stride, offset; };
+    static const unsigned adam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    Pass passes[7];
+    int n_pass = 0;
+    size_t raw_bytes = 0, max_stride = 0;
+    for (int k = 0; k < (interlace ? 7 : 1); ++k) {
+        Pass ps;
+        ps.x0 = interlace ? adam7[k][0] : 0; ps.y0 = interlace ? adam7[k][1] : 0;
+        ps.dx = interlace ? adam7[k][2] : 1; ps.dy = interlace ? adam7[k][3] : 1;
+        if (ps.x0 >= w || ps.y0 >= h) continue;
+        ps.pw = (w - ps.x0 + ps.dx - 1) / ps.dx; ps.ph = (h - ps.y0 + ps.dy - 1) / ps.dy;
+        ps.stride = (ps.pw * bpp_bits + 7) / 8;
+        ps.offset = raw_bytes;
+        raw_bytes += (ps.stride + 1) * ps.ph;
+        if (ps.stride > max_stride) max_stride = ps.stride;
+        passes[n_pass++] = ps;
+    }
+    if (idat.empty() || raw_bytes / 1032 > idat.size() + 64) return false;  // deflate expands at most ~1032x: a forged size
+    std::vector<uint8_t> raw(raw_bytes);
     uLongf raw_len = (uLongf)raw.size();
     if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) return false;
-
-    // un-filter in place (row r occupies raw[r*(stride+1)+1 ...]); one tight loop per filter type
-    std::vector<uint8_t> zero(stride, 0);
-    for (size_t r = 0; r < h; ++r) {
-        uint8_t *cur = &raw[r * (stride + 1) + 1];
-        const uint8_t *up = r ? &raw[(r - 1) * (stride + 1) + 1] : zero.data();
-        const size_t head = fbpp < stride ? fbpp : stride;  // bytes without a left neighbour
-        switch (raw[r * (stride + 1)]) {
-            case 0: break;
-            case 1:
-                for (size_t i = head; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + cur[i - fbpp]);
-                break;
-            case 2:
-                for (size_t i = 0; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + up[i]);
-                break;
-            case 3:
-                for (size_t i = 0; i < head; ++i) cur[i] = (uint8_t)(cur[i] + (up[i] >> 1));
-                for (size_t i = head; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + ((cur[i - fbpp] + up[i]) >> 1));
-                break;
-            case 4:
-                for (size_t i = 0; i < head; ++i) cur[i] = (uint8_t)(cur[i] + up[i]);  // paeth(0, b, 0) = b
-                for (size_t i = head; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + paeth(cur[i - fbpp], up[i], up[i - fbpp]));
-                break;
-            default: return false;
-        }
-    }
 
     out.w = (int)w; out.h = (int)h; out.gray.resize((size_t)w * h);
     const int npal = (int)(pal.size() / 3);
     static const int scale_tab[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
-    for (size_t r = 0; r < h; ++r) {
-        const uint8_t *row = &raw[r * (stride + 1) + 1];
-        uint8_t *o = &out.gray[r * (size_t)w];
-        if (depth == 8 && ctype == 0) { memcpy(o, row, w); continue; }
-        for (size_t x = 0; x < w; ++x) {
-            if (depth == 16) {
-                auto rd = [&](size_t k) { return (unsigned)((row[2 * k] << 8) | row[2 * k + 1]); };
-                unsigned y;
-                if (chans <= 2) y = rd(x * chans);
-                else y = luma16(rd(x * chans), rd(x * chans + 1), rd(x * chans + 2));
-                o[x] = (uint8_t)(y >> 8);
-            } else if (depth == 8) {
-                if (ctype == 3) {
-                    int idx = row[x];
-                    if (idx >= npal) idx = 0;
-                    o[x] = luma8(pal[3 * idx], pal[3 * idx + 1], pal[3 * idx + 2]);
-                } else if (chans <= 2) {
-                    o[x] = row[x * chans];
-                } else {
-                    o[x] = luma8(row[x * chans], row[x * chans + 1], row[x * chans + 2]);
-                }
-            } else {  // 1/2/4 bit gray or palette
-                const size_t bit = x * depth;
-                int v = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
-                if (ctype == 3) {
-                    if (v >= npal) v = 0;
-                    o[x] = luma8(pal[3 * v], pal[3 * v + 1], pal[3 * v + 2]);
-                } else {
-                    o[x] = (uint8_t)(v * scale_tab[depth]);
-                }
+    std::vector<uint8_t> zero(max_stride, 0);
+    for (int k = 0; k < n_pass; ++k) {
+        const Pass &ps = passes[k];
+        const size_t stride = ps.stride;
+        // un-filter in place (row r occupies raw[offset + r*(stride+1) + 1 ...]); one tight loop per filter type
+        for (size_t r = 0; r < ps.ph; ++r) {
+            uint8_t *cur = &raw[ps.offset + r * (stride + 1) + 1];
+            const uint8_t *up = r ? cur - (stride + 1) : zero.data();
+            const size_t head = fbpp < stride ? fbpp : stride;  // bytes without a left neighbour
+            switch (cur[-1]) {
+                case 0: break;
+                case 1:
+                    for (size_t i = head; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + cur[i - fbpp]);
+                    break;
+                case 2:
+                    for (size_t i = 0; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + up[i]);
+                    break;
+                case 3:
+                    for (size_t i = 0; i < head; ++i) cur[i] = (uint8_t)(cur[i] + (up[i] >> 1));
+                    for (size_t i = head; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + ((cur[i - fbpp] + up[i]) >> 1));
+                    break;
+                case 4:
+                    for (size_t i = 0; i < head; ++i) cur[i] = (uint8_t)(cur[i] + up[i]);  // paeth(0, b, 0) = b
+                    for (size_t i = head; i < stride; ++i) cur[i] = (uint8_t)(cur[i] + paeth(cur[i - fbpp], up[i], up[i - fbpp]));
+                    break;
+                default: return false;
             }
+        }
+        // pixels of the pass -> gray, scattered to (x0 + x*dx, y0 + r*dy)
+        for (size_t r = 0; r < ps.ph; ++r) {
+            const uint8_t *row = &raw[ps.offset + r * (stride + 1) + 1];
+            uint8_t *o = &out.gray[(ps.y0 + r * ps.dy) * (size_t)w + ps.x0];
+            const size_t dx = ps.dx;
+            if (depth == 8 && ctype == 0 && dx == 1) { memcpy(o, row, ps.pw); continue; }
+            for (size_t x = 0; x < ps.pw; ++x) {
+                uint8_t g;
+                if (depth == 16) {
+                    auto rd = [&](size_t i) { return (unsigned)((row[2 * i] << 8) | row[2 * i + 1]); };
+                    unsigned y;
+                    if (chans <= 2) y = rd(x * chans);
+                    else y = luma16(rd(x * chans), rd(x * chans + 1), rd(x * chans + 2));
+                    g = (uint8_t)(y >> 8);
+                } else if (depth == 8) {
+                    if (ctype == 3) {
+                        int idx = row[x];
+                        if (idx >= npal) idx = 0;
+                        g = luma8(pal[3 * idx], pal[3 * idx + 1], pal[3 * idx + 2]);
+                    } else if (chans <= 2) {
+                        g = row[x * chans];
+                    } else {
+                        g = luma8(row[x * chans], row[x * chans + 1], row[x * chans + 2]);
+                    }
+                } else {  // 1/2/4 bit gray or palette
+                    const size_t bit = x * depth;
+                    int v = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+                    if (ctype == 3) {
+                        if (v >= npal) v = 0;
+                        g = luma8(pal[3 * v], pal[3 * v + 1], pal[3 * v + 2]);
+                    } else {
+                        g = (uint8_t)(v * scale_tab[depth]);
+                    }
+                }
+                o[x * dx] = g;
+            }
+        }
+    }
+    return true;
+}
+
+// ---- BMP (uncompressed) -----------------------------------------------------------
+// stb_image's BMP reader for req_comp = 1 decodes to RGB(A) and applies the integer luma; palette entries likewise.
+// Handled: 1/4/8-bit palettised, 24-bit, 32-bit (BI_RGB, or BI_BITFIELDS with the plain 8-bit masks); bottom-up and top-down.
+// Not handled (load fails, frame skipped): RLE, 16-bit and exotic bit-field layouts -- their expansion to 8 bits changed between
+// stb_image versions and the reference pins none.
+inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint32_t le16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+bool decode_bmp(const std::vector<uint8_t> &d, Decoded &out)
+{
+    if (d.size() < 14 + 12 || d[0] != 'B' || d[1] != 'M') return false;
+    const size_t data_off = le32(&d[10]);
+    const uint32_t hsz = le32(&d[14]);
+    if (hsz != 12 && hsz != 40 && hsz != 56 && hsz != 108 && hsz != 124) return false;
+    if (d.size() < 14 + (size_t)hsz) return false;
+    long w, hh;
+    int bpp;
+    uint32_t compress = 0;
+    if (hsz == 12) {
+        w = (long)le16(&d[18]); hh = (long)le16(&d[20]);
+        if (le16(&d[22]) != 1) return false;
+        bpp = (int)le16(&d[24]);
+    } else {
+        w = (long)(int32_t)le32(&d[18]); hh = (long)(int32_t)le32(&d[22]);
+        if (le16(&d[26]) != 1) return false;
+        bpp = (int)le16(&d[28]);
+        compress = le32(&d[30]);
+    }
+    const bool flip = hh > 0;  // positive height: rows stored bottom-up
+    if (hh < 0) hh = -hh;
+    if (w <= 0 || hh <= 0 || w > (1 << 24) || hh > (1 << 24)) return false;
+    if (!(bpp == 1 || bpp == 4 || bpp == 8 || bpp == 24 || bpp == 32)) return false;
+    if (compress == 3) {  // BI_BITFIELDS: only the layout BI_RGB means anyway
+        if (bpp != 32) return false;
+        const size_t m = 14 + 40;  // the masks follow the 40-byte core header (inside the larger headers)
+        if (d.size() < m + 12) return false;
+        if (le32(&d[m]) != 0x00ff0000u || le32(&d[m + 4]) != 0x0000ff00u || le32(&d[m + 8]) != 0x000000ffu) return false;
+    } else if (compress != 0) {
+        return false;
+    }
+    // palette: RGBQUAD (b, g, r, x), or RGBTRIPLE for the 12-byte header; like stb_image, every entry between the header and
+    // the pixel data counts (biClrUsed is not consulted)
+    uint8_t pal_gray[256];
+    if (bpp <= 8) {
+        const size_t esz = hsz == 12 ? 3 : 4;
+        const size_t pal_off = 14 + (size_t)hsz;
+        if (data_off < pal_off) return false;
+        const size_t ncol = (data_off - pal_off) / esz;
+        if (ncol == 0 || ncol > 256 || pal_off + ncol * esz > d.size()) return false;
+        memset(pal_gray, 0, sizeof(pal_gray));
+        for (size_t i = 0; i < ncol; ++i) { const uint8_t *e = &d[pal_off + i * esz]; pal_gray[i] = luma8(e[2], e[1], e[0]); }
+    }
+    const size_t stride = (((size_t)w * bpp + 31) / 32) * 4;
+    if (data_off < 14 + (size_t)hsz || data_off > d.size() || stride * (size_t)hh > d.size() - data_off) return false;
+    out.w = (int)w; out.h = (int)hh; out.gray.resize((size_t)w * hh);
+    for (size_t r = 0; r < (size_t)hh; ++r) {
+        const uint8_t *row = &d[data_off + r * stride];
+        uint8_t *o = &out.gray[(flip ? (size_t)hh - 1 - r : r) * (size_t)w];
+        switch (bpp) {
+            case 1: for (size_t x = 0; x < (size_t)w; ++x) o[x] = pal_gray[(row[x >> 3] >> (7 - (x & 7))) & 1]; break;
+            case 4: for (size_t x = 0; x < (size_t)w; ++x) o[x] = pal_gray[(x & 1) ? (row[x >> 1] & 15) : (row[x >> 1] >> 4)]; break;
+            case 8: for (size_t x = 0; x < (size_t)w; ++x) o[x] = pal_gray[row[x]]; break;
+            case 24: for (size_t x = 0; x < (size_t)w; ++x) o[x] = luma8(row[3 * x + 2], row[3 * x + 1], row[3 * x]); break;
+            default: for (size_t x = 0; x < (size_t)w; ++x) o[x] = luma8(row[4 * x + 2], row[4 * x + 1], row[4 * x]); break;
         }
     }
     return true;
@@ -214,6 +310,7 @@ bool decode_any(const char *path, Decoded &out)
         std::vector<uint8_t> data;
         if (!read_file(path, data)) return false;
         if (data.size() >= 2 && data[0] == 'P') return decode_pnm(data, out);
+        if (data.size() >= 2 && data[0] == 'B' && data[1] == 'M') return decode_bmp(data, out);
         return decode_png(data, out);
     } catch (...) {
         return false;

@@ -90,7 +90,8 @@ def test_metadata_defaults_and_order(tmp_path):
         pvp.load_metadata(str(tmp_path / "missing.json"))
 
 
-def _png(path, arr, ctype, depth=8, palette=None):
+def _png_scanlines(arr, ctype, depth, rng):
+    """Filtered scanlines (filter byte + data per row) of one image or one Adam7 pass; random filter types."""
     h, w = arr.shape[:2]
     raw = b""
     rows = arr.reshape(h, -1)
@@ -101,14 +102,13 @@ def _png(path, arr, ctype, depth=8, palette=None):
         pad = (-rows.shape[1]) % per
         r = np.pad(rows, ((0, 0), (0, pad))).reshape(h, -1, per).astype(np.uint32)
         rows = sum(r[:, :, k] << (8 - depth * (k + 1)) for k in range(per)).astype(np.uint8)
-    rng = np.random.default_rng(0)
     prev = np.zeros(rows.shape[1], np.int32)
     bpp = max(1, {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype] * depth // 8)
     for y in range(h):  # exercise all five filter types
         cur = rows[y].astype(np.int32)
         ft = int(rng.integers(0, 5))
-        left = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
-        ul = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        left = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])[:len(cur)]
+        ul = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])[:len(cur)]
         if ft == 0: f = cur
         elif ft == 1: f = cur - left
         elif ft == 2: f = cur - prev
@@ -120,11 +120,24 @@ def _png(path, arr, ctype, depth=8, palette=None):
             f = cur - pred
         raw += bytes([ft]) + (f & 255).astype(np.uint8).tobytes()
         prev = cur
+    return raw
+
+
+ADAM7 = ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2))
+
+
+def _png(path, arr, ctype, depth=8, palette=None, interlace=False):
+    h, w = arr.shape[:2]
+    rng = np.random.default_rng(0)
+    if interlace:   # seven reduced images, each with its own scanlines; empty passes contribute nothing
+        raw = b"".join(_png_scanlines(arr[y0::dy, x0::dx], ctype, depth, rng) for x0, y0, dx, dy in ADAM7 if x0 < w and y0 < h)
+    else:
+        raw = _png_scanlines(arr, ctype, depth, rng)
 
     def chunk(t, d):
         return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
     comp = zlib.compress(raw)
-    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, int(interlace)))
     if palette is not None:
         out += chunk(b"PLTE", palette.astype(np.uint8).tobytes())
     out += chunk(b"IDAT", comp[: len(comp) // 2]) + chunk(b"IDAT", comp[len(comp) // 2:]) + chunk(b"IEND", b"")
@@ -192,6 +205,71 @@ def test_image_decode_pnm_png(tmp_path):
         pvp.load_image_gray(str(tmp_path / "junk.jpg"))
 
 
+def test_image_decode_interlaced_png_and_bmp(tmp_path):
+    """stb_image also reads Adam7-interlaced PNG and uncompressed BMP; same gray bytes as the non-interlaced / PNM file."""
+    rng = np.random.default_rng(4)
+    for h, w in ((13, 17), (1, 1), (2, 3), (5, 1), (1, 9), (8, 8), (9, 16), (33, 20)):   # incl. sizes with empty Adam7 passes
+        gray = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = luma(rgb[..., 0], rgb[..., 1], rgb[..., 2]).astype(np.uint8)
+        _png(tmp_path / "ig.png", gray, 0, interlace=True)
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "ig.png")), gray), (h, w)
+        _png(tmp_path / "ic.png", rgb, 2, interlace=True)
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "ic.png")), want), (h, w)
+        rgba = np.concatenate([rgb, rng.integers(0, 256, (h, w, 1), dtype=np.uint8)], -1)
+        _png(tmp_path / "ica.png", rgba, 6, interlace=True)
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "ica.png")), want), (h, w)
+        g16 = rng.integers(0, 65536, (h, w)).astype(np.uint16)
+        _png(tmp_path / "ig16.png", g16, 0, depth=16, interlace=True)
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "ig16.png")), (g16 >> 8).astype(np.uint8)), (h, w)
+        for depth in (1, 2, 4):
+            gd = rng.integers(0, 1 << depth, (h, w), dtype=np.uint8)
+            _png(tmp_path / "igd.png", gd, 0, depth=depth, interlace=True)
+            assert np.array_equal(pvp.load_image_gray(str(tmp_path / "igd.png")), gd * (255 // ((1 << depth) - 1))), (h, w, depth)
+        pal = rng.integers(0, 256, (16, 3), dtype=np.uint8)
+        idx = rng.integers(0, 16, (h, w), dtype=np.uint8)
+        _png(tmp_path / "ip4.png", idx, 3, depth=4, palette=pal, interlace=True)
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "ip4.png")), luma(pal[idx, 0], pal[idx, 1], pal[idx, 2]).astype(np.uint8)), (h, w)
+    Image = pytest.importorskip("PIL.Image")
+    # the test's own Adam7 writer agrees with an independent reader
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "ig.png")), gray)
+    # BMP as PIL writes it: 8-bit palettised gray, 24-bit, 32-bit, 1-bit, 8-bit colour palette
+    for h, w in ((13, 17), (1, 1), (4, 6), (7, 33)):
+        gray = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = luma(rgb[..., 0], rgb[..., 1], rgb[..., 2]).astype(np.uint8)
+        Image.fromarray(gray).save(tmp_path / "g.bmp")
+        gg = gray.astype(np.uint32)                      # a gray palette entry (v, v, v) -> (77 v + 150 v + 29 v) >> 8 = v
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "g.bmp")), luma(gg, gg, gg).astype(np.uint8)) and np.array_equal(luma(gg, gg, gg), gg)
+        Image.fromarray(rgb).save(tmp_path / "c.bmp")
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "c.bmp")), want), (h, w)
+        rgba = np.concatenate([rgb, rng.integers(0, 256, (h, w, 1), dtype=np.uint8)], -1)
+        Image.fromarray(rgba).save(tmp_path / "ca.bmp")
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "ca.bmp")), want), (h, w)
+        bits1 = rng.integers(0, 2, (h, w), dtype=np.uint8)
+        Image.fromarray(bits1 * 255).convert("1").save(tmp_path / "b1.bmp")
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "b1.bmp")), bits1 * 255), (h, w)
+        pimg = Image.fromarray(rgb).quantize(16)
+        pimg.save(tmp_path / "p.bmp")
+        prgb = np.asarray(pimg.convert("RGB")).astype(np.uint32)
+        assert np.array_equal(pvp.load_image_gray(str(tmp_path / "p.bmp")), luma(prgb[..., 0], prgb[..., 1], prgb[..., 2]).astype(np.uint8)), (h, w)
+    # top-down BMP (negative height) built by hand from the bottom-up 24-bit file
+    data = bytearray((tmp_path / "c.bmp").read_bytes())
+    off = struct.unpack_from("<I", data, 10)[0]
+    hh = struct.unpack_from("<i", data, 22)[0]
+    stride = (w * 3 + 3) // 4 * 4
+    rows = [bytes(data[off + r * stride: off + (r + 1) * stride]) for r in range(hh)]
+    struct.pack_into("<i", data, 22, -hh)
+    data[off:off + hh * stride] = b"".join(reversed(rows))
+    (tmp_path / "td.bmp").write_bytes(bytes(data))
+    assert np.array_equal(pvp.load_image_gray(str(tmp_path / "td.bmp")), want)
+    # RLE-compressed BMP is refused (frame skipped), as documented
+    struct.pack_into("<I", data, 30, 1)
+    (tmp_path / "rle.bmp").write_bytes(bytes(data))
+    with pytest.raises(pvp.PvpError, match="Failed to load image"):
+        pvp.load_image_gray(str(tmp_path / "rle.bmp"))
+
+
 def test_image_decode_survives_damaged_files(tmp_path):
     """A damaged or hostile file is the reference's failed stbi_load (frame skipped, ray_voxel.cpp:470-473): the decoder must
     answer "Failed to load image" -- never crash, never allocate what a forged header asks for.  It also runs on the decode
@@ -205,8 +283,15 @@ def test_image_decode_survives_damaged_files(tmp_path):
     _png(tmp_path / "g2.png", gray & 3, 0, depth=2); seeds["g2.png"] = (tmp_path / "g2.png").read_bytes()
     pal = rng.integers(0, 256, (7, 3), dtype=np.uint8)
     _png(tmp_path / "p.png", gray % 7, 3, palette=pal); seeds["p.png"] = (tmp_path / "p.png").read_bytes()
+    _png(tmp_path / "ic.png", rgb, 2, interlace=True); seeds["ic.png"] = (tmp_path / "ic.png").read_bytes()
     synth.write_pgm(str(tmp_path / "g.pgm"), gray); seeds["g.pgm"] = (tmp_path / "g.pgm").read_bytes()
     synth.write_ppm(str(tmp_path / "c.ppm"), rgb); seeds["c.ppm"] = (tmp_path / "c.ppm").read_bytes()
+    try:
+        from PIL import Image
+        Image.fromarray(rgb).save(tmp_path / "c.bmp"); seeds["c.bmp"] = (tmp_path / "c.bmp").read_bytes()
+        Image.fromarray(rgb).quantize(16).save(tmp_path / "p.bmp"); seeds["p.bmp"] = (tmp_path / "p.bmp").read_bytes()
+    except ImportError:
+        pass
 
     def probe(data):
         f = tmp_path / "x.bin"
