@@ -220,6 +220,8 @@ int pvp_fixed_to_f32(pvp_ctx *ctx, const int64_t *src_dev, float *dst_dev, int64
 int pvp_fixed_to_f64(pvp_ctx *ctx, const int64_t *src_dev, double *dst_dev, int64_t n, int frac_bits);
 /* replaces the writer of ray_voxel.cpp:542-555: int32 N, float32 voxel_size, N^3 float32 */
 int pvp_write_bin(const char *path, int32_t n, float voxel_size, const float *grid_host);
+/* the same writer fed from device memory (float32 cells; D2H chunks overlap the file writes); synchronises */
+int pvp_write_bin_dev(pvp_ctx *ctx, const char *path, int32_t n, float voxel_size, const float *grid_f32_dev);
 /* reader for the same layout (the format's only consumer is voxelmotionviewer.py:28-53) */
 int pvp_read_bin_header(const char *path, int32_t *n, float *voxel_size);
 int pvp_read_bin(const char *path, int32_t n, float *grid_host);

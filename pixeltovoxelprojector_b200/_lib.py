@@ -122,6 +122,7 @@ SIGNATURES = {
     "pvp_fixed_to_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
     "pvp_fixed_to_f64": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
     "pvp_write_bin": (C.c_int, [C.c_char_p, C.c_int32, C.c_float, _P]),
+    "pvp_write_bin_dev": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_float, _P]),
     "pvp_read_bin_header": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "pvp_read_bin": (C.c_int, [C.c_char_p, C.c_int32, _P]),
     "pvp_grid_reduce_peers": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, C.c_int, _P, C.c_int64, C.c_int]),

@@ -588,7 +588,6 @@ int pvp_ray_voxel_main(int argc, char **argv)
     const size_t cells = (size_t)opt.grid.n * opt.grid.n * opt.grid.n;
     void *grid_dev = nullptr;
     float *grid_f32_dev = nullptr;
-    std::vector<float> host;
     int rc = pvp_dev_malloc(ctx, pvp_grid_bytes(&opt.grid), &grid_dev);
     if (!rc) rc = pvp_dev_memset(ctx, grid_dev, 0, pvp_grid_bytes(&opt.grid));
     pvp_stats st = {0, 0, 0, 0};
@@ -601,23 +600,18 @@ int pvp_ray_voxel_main(int argc, char **argv)
         pvp_ctx_destroy(ctx);
         return 1;
     }
-    // .bin payload is always float32 (ray_voxel.cpp:552)
-    try { host.resize(cells); } catch (...) { fprintf(stderr, "out of host memory\n"); return 1; }
+    // .bin payload is always float32 (ray_voxel.cpp:552); it streams from the device to the file (:542-555)
+    const float *cells_dev = (const float *)grid_dev;
     if (opt.grid.accum_mode == PVP_ACCUM_FIXED) {
         rc = pvp_dev_malloc(ctx, cells * sizeof(float), (void **)&grid_f32_dev);
         if (!rc) rc = pvp_fixed_to_f32(ctx, (const int64_t *)grid_dev, grid_f32_dev, (int64_t)cells, opt.grid.frac_bits);
-        if (!rc) rc = pvp_memcpy_d2h(ctx, host.data(), grid_f32_dev, cells * sizeof(float));
-        if (grid_f32_dev) pvp_dev_free(ctx, grid_f32_dev);
-    } else {
-        rc = pvp_memcpy_d2h(ctx, host.data(), grid_dev, cells * sizeof(float));
+        cells_dev = grid_f32_dev;
     }
+    if (!rc) rc = pvp_write_bin_dev(ctx, argv[3], opt.grid.n, opt.grid.voxel_size, cells_dev);  // "Cannot open output file: ..." (:545)
+    if (grid_f32_dev) pvp_dev_free(ctx, grid_f32_dev);
     pvp_dev_free(ctx, grid_dev);
     pvp_ctx_destroy(ctx);
     if (rc) { fprintf(stderr, "%s\n", pvp_last_error()); return 1; }
-    if (pvp_write_bin(argv[3], opt.grid.n, opt.grid.voxel_size, host.data()) != PVP_OK) {
-        fprintf(stderr, "%s\n", pvp_last_error());  // "Cannot open output file: ..." (:545)
-        return 1;
-    }
     printf("Saved voxel grid to %s\n", argv[3]);  // :554
     if (want_stats)
         fprintf(stderr, "frames=%llu pairs=%llu rays=%llu voxel_steps=%llu\n", (unsigned long long)rep.n_frames_loaded,

@@ -137,3 +137,20 @@ def test_cli_loader_noise_matches_seeded_reference(tmp_path):
     np.testing.assert_allclose(fa[gn["nz_index"]], gn["nz_value"], rtol=1e-5, atol=2.0 ** -16 * 64)
     with pytest.raises(pvp.PvpError, match="cannot be frame-sharded"):
         pvp.ray_voxel_accumulate(meta, str(tmp_path), c, loader_noise_seed=1, shard=(0, 2))
+
+
+def test_write_bin_from_device_matches_host_writer(tmp_path):
+    """pvp_write_bin_dev (the CLI's writer: chunked D2H overlapping the file writes) produces the bytes of pvp_write_bin
+    (ray_voxel.cpp:542-555), for a grid smaller than one chunk and for one that ends in a ragged chunk."""
+    import ctypes as C
+    ctx = pvp.default_context()
+    for n in (1, 37, 170):     # 170^3 * 4 B = 19.7 MB: one full 16 MiB chunk + a tail
+        g = torch.randn((n, n, n), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        a, b = str(tmp_path / f"dev_{n}.bin"), str(tmp_path / f"host_{n}.bin")
+        ctx.use_current_stream()
+        pvp._lib.check(ctx._lib.pvp_write_bin_dev(ctx.handle, os.fsencode(a), n, C.c_float(0.75), g.data_ptr()))
+        pvp.write_bin(b, g.cpu().numpy(), 0.75)
+        assert open(a, "rb").read() == open(b, "rb").read()
+    with pytest.raises(pvp.PvpError, match="Cannot open output file"):
+        pvp._lib.check(ctx._lib.pvp_write_bin_dev(ctx.handle, os.fsencode(str(tmp_path / "no_such_dir" / "x.bin")), 1, C.c_float(1.0), g.data_ptr()))
