@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <map>
 #include <mutex>
@@ -583,8 +584,12 @@ int pvp_ray_voxel_main(int argc, char **argv)
         else if (!strcmp(argv[i], "--stats")) want_stats = 1;
         else { fprintf(stderr, "ray_voxel: unknown or incomplete option '%s'\n", argv[i]); return 1; }
     }
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t_start = now();
     pvp_ctx *ctx = nullptr;
     if (pvp_ctx_create(device, nullptr, &ctx) != PVP_OK) { fprintf(stderr, "%s\n", pvp_last_error()); return 1; }
+    const auto t_ctx = now();
     const size_t cells = (size_t)opt.grid.n * opt.grid.n * opt.grid.n;
     void *grid_dev = nullptr;
     float *grid_f32_dev = nullptr;
@@ -600,6 +605,7 @@ int pvp_ray_voxel_main(int argc, char **argv)
         pvp_ctx_destroy(ctx);
         return 1;
     }
+    const auto t_run = now();
     // .bin payload is always float32 (ray_voxel.cpp:552); it streams from the device to the file (:542-555)
     const float *cells_dev = (const float *)grid_dev;
     if (opt.grid.accum_mode == PVP_ACCUM_FIXED) {
@@ -609,13 +615,15 @@ int pvp_ray_voxel_main(int argc, char **argv)
     }
     if (!rc) rc = pvp_write_bin_dev(ctx, argv[3], opt.grid.n, opt.grid.voxel_size, cells_dev);  // "Cannot open output file: ..." (:545)
     if (grid_f32_dev) pvp_dev_free(ctx, grid_f32_dev);
+    const auto t_write = now();
     pvp_dev_free(ctx, grid_dev);
     pvp_ctx_destroy(ctx);
     if (rc) { fprintf(stderr, "%s\n", pvp_last_error()); return 1; }
     printf("Saved voxel grid to %s\n", argv[3]);  // :554
     if (want_stats)
-        fprintf(stderr, "frames=%llu pairs=%llu rays=%llu voxel_steps=%llu\n", (unsigned long long)rep.n_frames_loaded,
-                (unsigned long long)rep.n_pairs, (unsigned long long)st.n_rays, (unsigned long long)st.n_steps);
+        fprintf(stderr, "frames=%llu pairs=%llu rays=%llu voxel_steps=%llu  seconds: context %.2f, frames %.2f, .bin %.2f\n",
+                (unsigned long long)rep.n_frames_loaded, (unsigned long long)rep.n_pairs, (unsigned long long)st.n_rays,
+                (unsigned long long)st.n_steps, secs(t_start, t_ctx), secs(t_ctx, t_run), secs(t_run, t_write));
     return 0;
 }
 

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--frames", type=int, default=120)
     ap.add_argument("--format", default="png", choices=["pgm", "png"])
     ap.add_argument("--n", type=int, default=512, help="grid size (BASELINE config 2: 256)")
+    ap.add_argument("--ab-lib", default=None, help="directory with another build of libpvp_b200.so: extra runs with it, interleaved (A/B)")
     a = ap.parse_args()
     H, W, N, center = 1080, 1920, a.n, (0.0, 0.0, 500.0)
     vs = 1024.0 / N
@@ -51,16 +52,20 @@ def main():
                 os.remove(src)
             json.dump(entries, open(meta, "w"))
         outs = {}
-        for label, threads in (("warm-up", 0), ("1 decode thread", 1), ("default pool", 0)):
+        plan = [("warm-up", 0, None), ("1 decode thread", 1, None), ("default pool", 0, None)]
+        if a.ab_lib:
+            plan += [("B: 1 decode thread", 1, a.ab_lib), ("B: default pool", 0, a.ab_lib), ("default pool, again", 0, None)]
+        for label, threads, libdir in plan:
             out = os.path.join(d, f"out_{threads}.bin")
+            env = dict(os.environ, LD_LIBRARY_PATH=os.path.abspath(libdir)) if libdir else None
             t0 = time.perf_counter()
             r = subprocess.run([exe, meta, d, out, "--n", str(N), "--voxel-size", str(vs), "--quiet", "--stats"] +
-                               (["--decode-threads", str(threads)] if threads else []), capture_output=True, text=True)
+                               (["--decode-threads", str(threads)] if threads else []), capture_output=True, text=True, env=env)
             dt = time.perf_counter() - t0
             assert r.returncode == 0, r.stderr
             outs[label] = open(out, "rb").read()
             if label != "warm-up":
-                print(f"{a.format} 1080p x {a.frames} frames, {label}: {dt:.2f} s wall = {a.frames / dt:.0f} frames/s (incl. process start, {4 * N ** 3 >> 20} MiB .bin write)  {r.stderr.strip()}")
+                print(f"{a.format} 1080p x {a.frames} frames, {label}: {dt:.2f} s wall = {a.frames / dt:.0f} frames/s (incl. process start, {4 * N ** 3 >> 20} MiB .bin write)  {r.stderr.strip()}", flush=True)
         assert outs["1 decode thread"] == outs["default pool"], ".bin differs between decode-thread settings"
         print("identical .bin for both settings; host cores:", os.cpu_count())
 
