@@ -126,6 +126,27 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def issue_roofline(workload, units_per_s, clocks, dev):
+    """The bound the lock-step kernels actually sit on: warp-instruction issue.  Instructions per voxel step come from the
+    committed ncu capture (profiles/traffic.json), the rate from this run's CUDA-event timing, the peak from the SM count x 4
+    schedulers x the SM clock sampled during this run.  Extra information next to `roofline`; never breaks the bench line."""
+    try:
+        import torch
+        e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+        if not e or "warp_inst_per_launch" not in e:
+            return None   # no ncu capture committed for this workload
+        per_unit = e["warp_inst_per_launch"] / e["voxel_steps_per_launch"]
+        c = clocks.summary()
+        mhz = c["sm_mhz"] or c["sm_max_mhz"]
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        peak = sms * 4 * float(mhz) * 1e6
+        achieved = per_unit * units_per_s
+        return {"bound": "issue", "unit": "warp instructions/s", "achieved": achieved, "peak": peak, "frac": achieved / peak,
+                "warp_inst_per_voxel_step": per_unit, "source": "profiles/traffic.json (ncu smsp__inst_executed.sum) x live rate; peak = SMs x 4 x sampled SM clock"}
+    except Exception as ex:
+        return {"error": repr(ex)}
+
+
 def cpu_reference(wl, frames, poses, pairs, rows=None):
     """Time the reference CPU implementation (oracle/_ref = the unmodified ray_voxel.cpp compiled; else the C port) on
     the given pairs, optionally restricted to a band of rows (pixels outside the band are made motion-free).
@@ -424,7 +445,9 @@ def run_ours_image(args, wl):
         "e2e": {"value": e_value, "unit": "voxel-steps/s", "h2d_bytes_per_step": H * W * 8, "d2h_bytes_per_step": 16,
                 "frames_per_s": args.steps * world / (float(t[1].item()) * 1e-3),
                 "api": "pixeltovoxelprojector_b200.process_image_cpp(CUDA tensors; image staged from pinned host memory, double buffered) -> pvp_process_image"},
-        "gpu_launches": int(prof["launches_k3"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+        "gpu_launches": int(prof["launches_k3"]), "roofline": roofline,
+        "issue_roofline": issue_roofline(args.workload, my_samples / k3_s if k3_s > 0 else 0.0, clocks, dev),
+        "cpu_baseline": cpu, "clocks": clocks.summary(),
     }))
     if world > 1:
         dist.destroy_process_group()
@@ -629,7 +652,9 @@ def run_ours(args, wl):
         "e2e": {"value": e_value, "unit": "voxel-steps/s", "h2d_bytes_per_step": (B + 1) * H * W, "d2h_bytes_per_step": 32,
                 "frames_per_s": frames_total / (float(e_ms.item()) * 1e-3), "api": "pixeltovoxelprojector_b200.accumulate_motion(pinned host frames) -> pvp_motion_accumulate_host"},
         "gpu_launches": int(prof["launches_k1"] + prof["launches_k2"]),
-        "roofline": roofline, "l2_atomic_roofline": l2, "cpu_baseline": cpu, "clocks": clocks.summary(),
+        "roofline": roofline, "l2_atomic_roofline": l2,
+        "issue_roofline": issue_roofline(args.workload, per_rank_steps / k2_s if k2_s > 0 else 0.0, clocks, dev),
+        "cpu_baseline": cpu, "clocks": clocks.summary(),
         "atomics_per_voxel_step": float(tot[2].item()) / max(1.0, all_steps),
         "grid_merge_ms": reduce_ms if world > 1 else None,
     }
