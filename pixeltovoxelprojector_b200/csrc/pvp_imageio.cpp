@@ -8,10 +8,11 @@
 //   - 16-bit -> 8-bit:  v >> 8, applied after the colour conversion
 //   - gray bit depths 1/2/4: scaled by 255/85/17
 // Formats: binary PNM (P5, P6; maxval <= 65535), PNG (all colour types, 8/16 bit and sub-byte
-// gray/palette, plain or Adam7-interlaced) and uncompressed BMP (1/4/8-bit palettised, 24 and
-// 32 bit).  Anything else (JPEG, TGA, GIF, RLE or 16-bit BMP ...) fails to load, which the
+// gray/palette, plain or Adam7-interlaced), uncompressed BMP (1/4/8-bit palettised, 24 and 32 bit)
+// and baseline JPEG (luma plane; see the JPEG section: this one format is parity-UNPINNED).
+// Anything else (progressive JPEG, TGA, GIF, RLE or 16-bit BMP ...) fails to load, which the
 // pipeline treats like the reference treats a failed stbi_load: the frame is skipped
-// (ray_voxel.cpp:470-473).  JPEG parity is unpinned by design (stb's IDCT != libjpeg).
+// (ray_voxel.cpp:470-473).
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -304,6 +305,350 @@ bool decode_bmp(const std::vector<uint8_t> &d, Decoded &out)
     return true;
 }
 
+// ---- JPEG (baseline / extended sequential Huffman, 8 bit) ------------------------------------
+// What stbi_load(..., 1) returns for a YCbCr or gray JPEG is the LUMA PLANE as its integer IDCT produces it (chroma is not
+// touched when one channel is requested), so this reader entropy-decodes every component but reconstructs only component 0,
+// with stb_image's published IDCT arithmetic: the LL&M butterfly in 12-bit fixed point, columns kept with 2 extra bits
+// ((x + 512) >> 10), rows rounded and biased in one step ((x + 65536 + (128 << 17)) >> 17), clamped to 0..255.  The reference
+// pins no stb_image version and none exists in the build image, so this format's parity is UNPINNED; the
+// test holds it to +-1 grey level of libjpeg and to exact values on flat blocks.  Not handled (load fails, frame skipped):
+// progressive and arithmetic-coded files, 12-bit samples, CMYK / RGB-coded components, a subsampled luma plane.
+static const uint8_t jpeg_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                        35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct JHuff {
+    bool present = false;
+    uint8_t fast_len[512], fast_sym[512];  // codes of up to 9 bits, indexed by the next 9 bits of the stream
+    int16_t fast_ac[512];                  // AC tables: code + magnitude bits within 9 bits -> (value << 8) | (run << 4) | bits used; else 0
+    int mincode[17], maxcode[17], valptr[17];
+    uint8_t vals[256];
+    bool build(const uint8_t counts[16], const uint8_t *syms, int n_syms)
+    {
+        memset(fast_len, 0, sizeof(fast_len));
+        int code = 0, k = 0;
+        for (int len = 1; len <= 16; ++len) {
+            mincode[len] = code; valptr[len] = k; maxcode[len] = -1;
+            for (int i = 0; i < counts[len - 1]; ++i, ++code, ++k) {
+                if (k >= n_syms || k >= 256 || code >= (1 << len)) return false;  // more codes than the length has room for
+                vals[k] = syms[k];
+                if (len <= 9)
+                    for (int f = 0; f < (1 << (9 - len)); ++f) { fast_len[(code << (9 - len)) | f] = (uint8_t)len; fast_sym[(code << (9 - len)) | f] = syms[k]; }
+            }
+            if (counts[len - 1]) maxcode[len] = code - 1;
+            code <<= 1;
+        }
+        for (int i = 0; i < 512; ++i) {  // a short code followed by a short magnitude decodes in one lookup (same value as the two-step path)
+            fast_ac[i] = 0;
+            const int len = fast_len[i], run = fast_sym[i] >> 4, mag = fast_sym[i] & 15;
+            if (len && mag && len + mag <= 9) {
+                int v = ((i << len) & 511) >> (9 - mag);
+                if (v < (1 << (mag - 1))) v += -(1 << mag) + 1;
+                if (v >= -128 && v <= 127) fast_ac[i] = (int16_t)(v * 256 + run * 16 + len + mag);
+            }
+        }
+        present = true;
+        return true;
+    }
+};
+
+struct JBits {
+    const uint8_t *p, *end;
+    uint64_t buf = 0;  // the next bits of the entropy-coded segment, left aligned at bit n-1
+    int n = 0;
+    int marker = 0;    // the marker that ended the segment (then zero bits are fed, as stb_image does)
+    void fill()
+    {
+        if (n > 32) return;  // every caller needs at most 16 bits
+        while (n <= 56) {
+            unsigned b = 0;
+            if (!marker) {
+                if (p >= end) { marker = 0xD9; }
+                else {
+                    b = *p++;
+                    if (b == 0xFF) {
+                        while (p < end && *p == 0xFF) ++p;  // fill bytes
+                        const unsigned c = p < end ? *p++ : 0xD9;
+                        if (c != 0) { marker = (int)c; b = 0; }
+                    }
+                }
+            }
+            buf = (buf << 8) | b;
+            n += 8;
+        }
+    }
+    unsigned peek(int k) { return (unsigned)((buf >> (n - k)) & ((1u << k) - 1)); }
+    void skip(int k) { n -= k; }
+    int decode(const JHuff &h)
+    {
+        fill();
+        const unsigned f = peek(9);
+        if (h.fast_len[f]) { skip(h.fast_len[f]); return h.fast_sym[f]; }
+        for (int len = 10; len <= 16; ++len) {
+            const int c = (int)peek(len);
+            if (h.maxcode[len] >= 0 && c <= h.maxcode[len] && c >= h.mincode[len]) { skip(len); return h.vals[h.valptr[len] + c - h.mincode[len]]; }
+        }
+        return -1;
+    }
+    int receive_extend(int s)  // s magnitude bits -> signed value (ITU T.81 F.2.2.1)
+    {
+        if (s == 0) return 0;
+        fill();
+        const int v = (int)peek(s);
+        skip(s);
+        return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+    }
+    void reset() { buf = 0; n = 0; marker = 0; }
+};
+
+// The butterfly runs in unsigned 32-bit arithmetic (wraps; the same low 32 bits as the signed form) and is read back as
+// two's-complement int at the shifts, so damaged files with absurd coefficients cannot overflow a signed int.
+#define PVP_F2F(x) ((unsigned)(int)(((x) * 4096 + 0.5)))
+// one 8-point pass; leaves the even part in x0..x3 and the odd part in t0..t3
+#define PVP_IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)                                  \
+    unsigned t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                       \
+    p2 = (unsigned)(s2); p3 = (unsigned)(s6);                                          \
+    p1 = (p2 + p3) * PVP_F2F(0.5411961f);                                              \
+    t2 = p1 + p3 * PVP_F2F(-1.847759065f);                                             \
+    t3 = p1 + p2 * PVP_F2F(0.765366865f);                                              \
+    p2 = (unsigned)(s0); p3 = (unsigned)(s4);                                          \
+    t0 = (p2 + p3) * 4096u; t1 = (p2 - p3) * 4096u;                                    \
+    x0 = t0 + t3; x3 = t0 - t3; x1 = t1 + t2; x2 = t1 - t2;                            \
+    t0 = (unsigned)(s7); t1 = (unsigned)(s5); t2 = (unsigned)(s3); t3 = (unsigned)(s1); \
+    p3 = t0 + t2; p4 = t1 + t3; p1 = t0 + t3; p2 = t1 + t2;                            \
+    p5 = (p3 + p4) * PVP_F2F(1.175875602f);                                            \
+    t0 = t0 * PVP_F2F(0.298631336f); t1 = t1 * PVP_F2F(2.053119869f);                  \
+    t2 = t2 * PVP_F2F(3.072711026f); t3 = t3 * PVP_F2F(1.501321110f);                  \
+    p1 = p5 + p1 * PVP_F2F(-0.899976223f); p2 = p5 + p2 * PVP_F2F(-2.562915447f);      \
+    p3 = p3 * PVP_F2F(-1.961570560f); p4 = p4 * PVP_F2F(-0.390180644f);                \
+    t3 += p1 + p4; t2 += p2 + p3; t1 += p2 + p4; t0 += p1 + p3;
+
+inline uint8_t jclamp(int x) { return (uint8_t)(x < 0 ? 0 : x > 255 ? 255 : x); }
+inline int jsar(unsigned x, int k) { return (int)x >> k; }  // arithmetic shift of the two's-complement value
+
+void jpeg_idct_block(uint8_t *out, size_t out_stride, const short d[64])
+{
+    int val[64];
+    for (int i = 0; i < 8; ++i) {  // columns
+        int *v = val + i;
+        if (!(d[8 + i] | d[16 + i] | d[24 + i] | d[32 + i] | d[40 + i] | d[48 + i] | d[56 + i])) {
+            // the butterfly with only s0 set: every output is (s0 * 4096 + 512) >> 10 = s0 * 4, exactly
+            v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = d[i] * 4;
+            continue;
+        }
+        PVP_IDCT_1D(d[i], d[8 + i], d[16 + i], d[24 + i], d[32 + i], d[40 + i], d[48 + i], d[56 + i])
+        x0 += 512; x1 += 512; x2 += 512; x3 += 512;
+        v[0] = jsar(x0 + t3, 10); v[56] = jsar(x0 - t3, 10);
+        v[8] = jsar(x1 + t2, 10); v[48] = jsar(x1 - t2, 10);
+        v[16] = jsar(x2 + t1, 10); v[40] = jsar(x2 - t1, 10);
+        v[24] = jsar(x3 + t0, 10); v[32] = jsar(x3 - t0, 10);
+    }
+    for (int i = 0; i < 8; ++i) {  // rows: 1 << 17 to remove, rounded, and the level shift of 128 added before the shift
+        const int *v = val + 8 * i;
+        uint8_t *o = out + (size_t)i * out_stride;
+        const unsigned bias = 65536u + (128u << 17);
+        if (!(v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7])) {  // the same formulas with s1..s7 = 0: one value for the row
+            memset(o, jclamp(jsar((unsigned)v[0] * 4096u + bias, 17)), 8);
+            continue;
+        }
+        PVP_IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
+        x0 += bias; x1 += bias; x2 += bias; x3 += bias;
+        o[0] = jclamp(jsar(x0 + t3, 17)); o[7] = jclamp(jsar(x0 - t3, 17));
+        o[1] = jclamp(jsar(x1 + t2, 17)); o[6] = jclamp(jsar(x1 - t2, 17));
+        o[2] = jclamp(jsar(x2 + t1, 17)); o[5] = jclamp(jsar(x2 - t1, 17));
+        o[3] = jclamp(jsar(x3 + t0, 17)); o[4] = jclamp(jsar(x3 - t0, 17));
+    }
+}
+
+struct JComp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dc_pred = 0; };
+
+bool decode_jpeg(const std::vector<uint8_t> &d, Decoded &out)
+{
+    if (d.size() < 4 || d[0] != 0xFF || d[1] != 0xD8) return false;
+    uint16_t quant[4][64];
+    bool have_quant[4] = {false, false, false, false};
+    JHuff hdc[4], hac[4];
+    JComp comp[3];
+    int n_comp = 0, width = 0, height = 0, hmax = 1, vmax = 1, restart_interval = 0;
+    int mcu_x = 0, mcu_y = 0;
+    bool have_sof = false, rgb_coded = false, decoded_luma = false;
+    size_t y_w2 = 0;
+    std::vector<uint8_t> luma;  // component 0, padded to whole MCUs
+    size_t pos = 2;
+    auto be16 = [&](size_t at) { return (unsigned)((d[at] << 8) | d[at + 1]); };
+    int pending = 0;  // a marker the entropy decoder ran into
+    for (;;) {
+        int m;
+        if (pending) { m = pending; pending = 0; }
+        else {
+            while (pos < d.size() && d[pos] != 0xFF) ++pos;  // stb_image also hunts for the next 0xFF
+            while (pos < d.size() && d[pos] == 0xFF) ++pos;
+            if (pos >= d.size()) break;
+            m = d[pos++];
+            if (m == 0) continue;
+        }
+        if (m == 0xD9) break;                                     // EOI
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;  // no payload
+        if (pos + 2 > d.size()) return false;
+        const size_t len = be16(pos);
+        if (len < 2 || pos + len > d.size()) return false;
+        const size_t seg = pos + 2, seg_end = pos + len;
+        pos = seg_end;
+        if (m == 0xDB) {                                          // DQT
+            size_t q = seg;
+            while (q < seg_end) {
+                const int pq = d[q] >> 4, tq = d[q] & 15;
+                ++q;
+                if (pq > 1 || tq > 3 || q + (pq ? 128 : 64) > seg_end) return false;
+                for (int i = 0; i < 64; ++i) { quant[tq][i] = (uint16_t)(pq ? be16(q + 2 * i) : d[q + i]); }  // kept in zigzag order
+                q += pq ? 128 : 64;
+                have_quant[tq] = true;
+            }
+        } else if (m == 0xC4) {                                   // DHT
+            size_t q = seg;
+            while (q < seg_end) {
+                if (q + 17 > seg_end) return false;
+                const int tc = d[q] >> 4, th = d[q] & 15;
+                if (tc > 1 || th > 3) return false;
+                int total = 0;
+                for (int i = 0; i < 16; ++i) total += d[q + 1 + i];
+                if (total > 256 || q + 17 + total > seg_end) return false;
+                if (!(tc ? hac[th] : hdc[th]).build(&d[q + 1], &d[q + 17], total)) return false;
+                q += 17 + total;
+            }
+        } else if (m == 0xDD) {                                   // DRI
+            if (len != 4) return false;
+            restart_interval = (int)be16(seg);
+        } else if (m == 0xEE) {                                   // APP14 "Adobe": colour transform 0 with three components = RGB
+            if (len >= 14 && !memcmp(&d[seg], "Adobe", 5) && d[seg + 11] == 0) rgb_coded = true;
+        } else if (m == 0xC0 || m == 0xC1) {                      // SOF0 / SOF1
+            if (have_sof || len < 8 || d[seg] != 8) return false;
+            height = (int)be16(seg + 1); width = (int)be16(seg + 3); n_comp = d[seg + 5];
+            if (height == 0 || width == 0 || (n_comp != 1 && n_comp != 3) || len != (size_t)(8 + 3 * n_comp)) return false;
+            for (int i = 0; i < n_comp; ++i) {
+                comp[i].id = d[seg + 6 + 3 * i];
+                comp[i].h = d[seg + 7 + 3 * i] >> 4; comp[i].v = d[seg + 7 + 3 * i] & 15; comp[i].tq = d[seg + 8 + 3 * i];
+                if (comp[i].h < 1 || comp[i].h > 4 || comp[i].v < 1 || comp[i].v > 4 || comp[i].tq > 3) return false;
+                if (comp[i].h > hmax) hmax = comp[i].h;
+                if (comp[i].v > vmax) vmax = comp[i].v;
+            }
+            if (n_comp == 3 && comp[0].id == 'R' && comp[1].id == 'G' && comp[2].id == 'B') rgb_coded = true;
+            if (comp[0].h != hmax || comp[0].v != vmax) return false;  // a subsampled luma plane would need stb's resampler
+            mcu_x = (width + 8 * hmax - 1) / (8 * hmax); mcu_y = (height + 8 * vmax - 1) / (8 * vmax);
+            y_w2 = (size_t)mcu_x * hmax * 8;
+            luma.assign(y_w2 * ((size_t)mcu_y * vmax * 8), 0);
+            have_sof = true;
+        } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
+            return false;                                         // progressive, lossless, arithmetic: not handled
+        } else if (m == 0xDA) {                                   // SOS + the entropy-coded segment
+            if (!have_sof || (n_comp == 3 && rgb_coded)) return false;
+            const int ns = d[seg];
+            if (ns < 1 || ns > n_comp || len != (size_t)(6 + 2 * ns)) return false;
+            int order[3];
+            for (int i = 0; i < ns; ++i) {
+                int which = -1;
+                for (int c = 0; c < n_comp; ++c) if (comp[c].id == d[seg + 1 + 2 * i]) which = c;
+                if (which < 0) return false;
+                comp[which].td = d[seg + 2 + 2 * i] >> 4; comp[which].ta = d[seg + 2 + 2 * i] & 15;
+                if (comp[which].td > 3 || comp[which].ta > 3 || !hdc[comp[which].td].present || !hac[comp[which].ta].present || !have_quant[comp[which].tq]) return false;
+                order[i] = which;
+            }
+            if (d[seg + 1 + 2 * ns] != 0 || d[seg + 2 + 2 * ns] != 63 || d[seg + 3 + 2 * ns] != 0) return false;  // spectral selection of a sequential scan
+            JBits br{&d[0] + seg_end, &d[0] + d.size()};
+            for (int c = 0; c < n_comp; ++c) comp[c].dc_pred = 0;
+            short blk[64];
+            auto decode_block = [&](JComp &c, bool keep) -> bool {
+                const JHuff &dc = hdc[c.td], &ac = hac[c.ta];
+                const uint16_t *q = quant[c.tq];
+                if (keep) memset(blk, 0, sizeof(blk));
+                const int t = br.decode(dc);
+                if (t < 0 || t > 16) return false;
+                const long long dcv = (long long)c.dc_pred + br.receive_extend(t);
+                if (dcv < -32768 || dcv > 32767 || dcv * q[0] < -32768 || dcv * q[0] > 32767) return false;  // no valid file gets here
+                c.dc_pred = (int)dcv;
+                if (keep) blk[0] = (short)(c.dc_pred * q[0]);
+                int k = 1;
+                do {
+                    br.fill();
+                    const int fa = ac.fast_ac[br.peek(9)];
+                    if (fa) {  // run, size and value from one lookup
+                        k += (fa >> 4) & 15;
+                        if (k > 63) return false;
+                        br.skip(fa & 15);
+                        const long long v = (long long)(fa >> 8) * q[k];
+                        if (v < -32768 || v > 32767) return false;
+                        if (keep) blk[jpeg_zigzag[k]] = (short)v;
+                        ++k;
+                        continue;
+                    }
+                    const int rs = br.decode(ac);
+                    if (rs < 0) return false;
+                    const int r = rs >> 4, sz = rs & 15;
+                    if (sz == 0) {
+                        if (rs != 0xF0) break;  // end of block
+                        k += 16;
+                    } else {
+                        k += r;
+                        if (k > 63) return false;
+                        const long long v = (long long)br.receive_extend(sz) * q[k];
+                        if (v < -32768 || v > 32767) return false;
+                        if (keep) blk[jpeg_zigzag[k]] = (short)v;
+                        ++k;
+                    }
+                } while (k < 64);
+                return true;
+            };
+            int todo = restart_interval ? restart_interval : 0x7fffffff;
+            bool stop = false;
+            auto after_mcu = [&]() {  // restart intervals: the segment must continue with RSTn, predictors start over
+                if (--todo > 0) return;
+                br.fill();
+                if (!(br.marker >= 0xD0 && br.marker <= 0xD7)) { stop = true; return; }
+                br.reset();
+                for (int c = 0; c < n_comp; ++c) comp[c].dc_pred = 0;
+                todo = restart_interval;
+            };
+            if (ns == 1) {  // non-interleaved: the component's own blocks in raster order
+                JComp &c = comp[order[0]];
+                const int cw = (width * c.h + hmax - 1) / hmax, chh = (height * c.v + vmax - 1) / vmax;
+                const int bw = (cw + 7) >> 3, bh = (chh + 7) >> 3;
+                const bool keep = order[0] == 0;
+                for (int by = 0; by < bh && !stop; ++by)
+                    for (int bx = 0; bx < bw && !stop; ++bx) {
+                        if (!decode_block(c, keep)) return false;
+                        if (keep) jpeg_idct_block(&luma[(size_t)by * 8 * y_w2 + (size_t)bx * 8], y_w2, blk);
+                        after_mcu();
+                    }
+                if (keep) decoded_luma = true;
+            } else {
+                for (int my = 0; my < mcu_y && !stop; ++my)
+                    for (int mx = 0; mx < mcu_x && !stop; ++mx) {
+                        for (int i = 0; i < ns; ++i) {
+                            JComp &c = comp[order[i]];
+                            const bool keep = order[i] == 0;
+                            for (int y = 0; y < c.v; ++y)
+                                for (int x = 0; x < c.h; ++x) {
+                                    if (!decode_block(c, keep)) return false;
+                                    if (keep) jpeg_idct_block(&luma[((size_t)(my * c.v + y) * 8) * y_w2 + (size_t)(mx * c.h + x) * 8], y_w2, blk);
+                                }
+                            if (keep) decoded_luma = true;
+                        }
+                        after_mcu();
+                    }
+            }
+            // continue with the marker the bit reader met (or hunt for the next one behind the consumed bytes)
+            br.fill();
+            pending = br.marker == 0xD9 && br.p >= br.end ? 0 : br.marker;
+            pos = (size_t)(br.p - &d[0]);
+            if (br.marker == 0xD9) break;
+        }
+        // APPn, COM and everything else: skipped
+    }
+    if (!have_sof || !decoded_luma) return false;
+    out.w = width; out.h = height; out.gray.resize((size_t)width * height);
+    for (int y = 0; y < height; ++y) memcpy(&out.gray[(size_t)y * width], &luma[(size_t)y * y_w2], (size_t)width);
+    return true;
+}
+
 bool decode_any(const char *path, Decoded &out)
 {
     try {  // a damaged header must not take the process down with std::bad_alloc (also runs on the decode pool's threads)
@@ -311,6 +656,7 @@ bool decode_any(const char *path, Decoded &out)
         if (!read_file(path, data)) return false;
         if (data.size() >= 2 && data[0] == 'P') return decode_pnm(data, out);
         if (data.size() >= 2 && data[0] == 'B' && data[1] == 'M') return decode_bmp(data, out);
+        if (data.size() >= 2 && data[0] == 0xFF && data[1] == 0xD8) return decode_jpeg(data, out);
         return decode_png(data, out);
     } catch (...) {
         return false;

@@ -200,7 +200,7 @@ def test_image_decode_pnm_png(tmp_path):
     for bad in ("nope.pgm",):
         with pytest.raises(pvp.PvpError, match="Failed to load image"):
             pvp.load_image_gray(str(tmp_path / bad))
-    (tmp_path / "junk.jpg").write_bytes(b"\xff\xd8\xff\xe0 not really a jpeg")
+    (tmp_path / "junk.jpg").write_bytes(b"\xff\xd8\xff\xe0 not really a jpeg")   # SOI + a segment that runs past the end
     with pytest.raises(pvp.PvpError, match="Failed to load image"):
         pvp.load_image_gray(str(tmp_path / "junk.jpg"))
 
@@ -270,6 +270,54 @@ def test_image_decode_interlaced_png_and_bmp(tmp_path):
         pvp.load_image_gray(str(tmp_path / "rle.bmp"))
 
 
+def test_image_decode_jpeg_luma_plane(tmp_path):
+    """Baseline JPEG: stbi_load(..., 1) returns the luma plane of its integer IDCT.  No stb_image exists in the image and the
+    reference pins no version, so this format is UNPINNED; the decoder is held to +-1 grey level of libjpeg's luma plane (two
+    integer IDCTs of different fixed-point precision), to exact values where both are exact (flat blocks), and to refusing
+    what it does not implement (progressive)."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(6)
+
+    def picture(h, w, c):
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.stack([128 + 100 * np.sin(x / 17.0 + k) * np.cos(y / 23.0 - k) + 20 * rng.standard_normal((h, w)) for k in range(c)], -1)
+        img[h // 3:h // 2, w // 4:w // 2] = 240
+        return np.clip(img, 0, 255).astype(np.uint8)
+
+    def libjpeg_luma(path):
+        im = Image.open(path)
+        if im.mode != "L":
+            im.draft("L", im.size)          # libjpeg hands out the Y plane, no colour conversion
+        assert im.mode == "L"
+        return np.asarray(im)
+
+    variants = (("L", {}), ("RGB", dict(subsampling=0)), ("RGB", dict(subsampling=1)), ("RGB", dict(subsampling=2)),
+                ("RGB", dict(subsampling=2, optimize=True)), ("L", dict(optimize=True, quality=95)), ("RGB", dict(quality=30)),
+                ("RGB", dict(quality=100, subsampling=0)), ("RGB", dict(subsampling=2, restart_marker_blocks=3)), ("L", dict(restart_marker_rows=1)))
+    f = str(tmp_path / "t.jpg")
+    for h, w in ((64, 64), (37, 53), (8, 8), (1, 1), (17, 16), (120, 161)):
+        for mode, kw in variants:
+            img = picture(h, w, 1 if mode == "L" else 3)
+            Image.fromarray(img[..., 0] if mode == "L" else img, mode).save(f, **kw)
+            got, want = pvp.load_image_gray(f), libjpeg_luma(f)
+            assert got.shape == want.shape == (h, w)
+            diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            assert diff.max() <= 1 and (diff == 0).mean() >= 0.95, (h, w, mode, kw, int(diff.max()), float((diff == 0).mean()))
+    # flat 8x8 blocks at quality 100: only DC terms, where every integer IDCT gives 128 + ((dc + 4) >> 3) -- exact equality
+    flat = np.kron(rng.integers(0, 256, (5, 7)), np.ones((8, 8))).astype(np.uint8)
+    Image.fromarray(flat).save(f, quality=100)
+    assert np.array_equal(pvp.load_image_gray(f), libjpeg_luma(f))
+    Image.fromarray(np.stack([flat, flat, flat], -1)).save(f, quality=100, subsampling=2)
+    assert np.array_equal(pvp.load_image_gray(f), libjpeg_luma(f))
+    # not implemented -> the reference's failed-load path (frame skipped), never a wrong image
+    Image.fromarray(picture(32, 32, 3)).save(f, progressive=True)
+    with pytest.raises(pvp.PvpError, match="Failed to load image"):
+        pvp.load_image_gray(f)
+    Image.fromarray(picture(32, 32, 4), "CMYK").save(f)
+    with pytest.raises(pvp.PvpError, match="Failed to load image"):
+        pvp.load_image_gray(f)
+
+
 def test_image_decode_survives_damaged_files(tmp_path):
     """A damaged or hostile file is the reference's failed stbi_load (frame skipped, ray_voxel.cpp:470-473): the decoder must
     answer "Failed to load image" -- never crash, never allocate what a forged header asks for.  It also runs on the decode
@@ -290,6 +338,8 @@ def test_image_decode_survives_damaged_files(tmp_path):
         from PIL import Image
         Image.fromarray(rgb).save(tmp_path / "c.bmp"); seeds["c.bmp"] = (tmp_path / "c.bmp").read_bytes()
         Image.fromarray(rgb).quantize(16).save(tmp_path / "p.bmp"); seeds["p.bmp"] = (tmp_path / "p.bmp").read_bytes()
+        Image.fromarray(rgb).save(tmp_path / "c.jpg", subsampling=2, restart_marker_blocks=2); seeds["c.jpg"] = (tmp_path / "c.jpg").read_bytes()
+        Image.fromarray(gray).save(tmp_path / "g.jpg", optimize=True); seeds["g.jpg"] = (tmp_path / "g.jpg").read_bytes()
     except ImportError:
         pass
 
@@ -310,7 +360,8 @@ def test_image_decode_survives_damaged_files(tmp_path):
         for cut in sorted(set(int(c) for c in rng.integers(0, len(data), 25)) | {0, 1, 8, len(data) - 1}):
             img = probe(data[:cut])       # truncated
             # a cut inside the trailing IEND chunk leaves a complete image; anything shorter must fail
-            assert img is None or (name.endswith(".png") and cut >= len(data) - 12), (name, cut)
+            # (a JPEG cut inside its entropy-coded data still decodes -- zero bits are fed, as stb_image does -- with a wrong tail)
+            assert img is None or (name.endswith(".png") and cut >= len(data) - 12) or name.endswith(".jpg"), (name, cut)
         for _ in range(60):               # random byte damage (headers included)
             b = bytearray(data)
             for pos in rng.integers(0, len(b), int(rng.integers(1, 4))):
