@@ -175,3 +175,26 @@ def test_frame_loop_edge_cases(replay, tmp_path):
         got, rep = replay(meta, str(tmp_path), threads=2, shard=(rank, 4))
         lo, hi = len(slots) * rank // 4, len(slots) * (rank + 1) // 4
         assert got == [rec for key, rec in want if key in set(slots[lo:hi])]
+
+
+def test_frame_loop_is_blind_to_the_container_format(replay, tmp_path):
+    """The same frames stored as PGM, PNG and BMP (what stbi_load would read) give the same pairs."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(3)
+    frames = [rng.integers(0, 256, (10, 14), dtype=np.uint8) for _ in range(7)]
+    lists = {}
+    for ext in ("pgm", "png", "bmp"):
+        d = tmp_path / ext
+        d.mkdir()
+        entries = []
+        for k, img in enumerate(frames):
+            name = f"f{k}.{ext}"
+            if ext == "pgm":
+                synth.write_pgm(str(d / name), img)
+            else:
+                Image.fromarray(img).save(d / name)
+            entries.append({"camera_index": 0, "frame_index": k, "camera_position": [0.0, 1.0, 2.0], "yaw": 3.0 * k, "image_file": name})
+        json.dump(entries, open(d / "metadata.json", "w"))
+        lists[ext], rep = replay(str(d / "metadata.json"), str(d), threads=3, chunk=3)
+        assert rep["pairs"] == 6 and rep["loaded"] == 7
+    assert lists["pgm"] == lists["png"] == lists["bmp"] and len(lists["pgm"]) == 6
