@@ -203,7 +203,7 @@ typedef struct pvp_run_report {
 int pvp_load_metadata(const char *json_path, pvp_frame_info **frames_out, int *n_out);
 void pvp_free_metadata(pvp_frame_info *frames);
 /* replaces stbi_load(path,&w,&h,&c,1) of load_image_gray, ray_voxel.cpp:195, without the unseeded
- * noise of :206-215 (PNM P5/P6, PNG incl. Adam7, uncompressed BMP, baseline JPEG; stb_image's integer luma / IDCT).  out may be NULL. */
+ * noise of :206-215 (PNM P5/P6, PNG incl. Adam7, uncompressed BMP, JPEG; stb_image's integer luma / IDCT).  out may be NULL. */
 int pvp_load_image_gray(const char *path, uint8_t *out, int64_t cap, int *width, int *height);
 void pvp_run_options_default(pvp_run_options *opt);
 /* replaces the frame loop of main, ray_voxel.cpp:450-537, accumulating into grid_dev */

@@ -9,8 +9,8 @@
 //   - gray bit depths 1/2/4: scaled by 255/85/17
 // Formats: binary PNM (P5, P6; maxval <= 65535), PNG (all colour types, 8/16 bit and sub-byte
 // gray/palette, plain or Adam7-interlaced), uncompressed BMP (1/4/8-bit palettised, 24 and 32 bit)
-// and baseline JPEG (luma plane; see the JPEG section: this one format is parity-UNPINNED).
-// Anything else (progressive JPEG, TGA, GIF, RLE or 16-bit BMP ...) fails to load, which the
+// and JPEG (luma plane; see the JPEG section: this one format is parity-UNPINNED).
+// Anything else (TGA, GIF, RLE or 16-bit BMP ...) fails to load, which the
 // pipeline treats like the reference treats a failed stbi_load: the frame is skipped
 // (ray_voxel.cpp:470-473).
 #include <stdint.h>
@@ -305,14 +305,15 @@ bool decode_bmp(const std::vector<uint8_t> &d, Decoded &out)
     return true;
 }
 
-// ---- JPEG (baseline / extended sequential Huffman, 8 bit) ------------------------------------
+// ---- JPEG (sequential and progressive Huffman, 8 bit) ----------------------------------------
 // What stbi_load(..., 1) returns for a YCbCr or gray JPEG is the LUMA PLANE as its integer IDCT produces it (chroma is not
 // touched when one channel is requested), so this reader entropy-decodes every component but reconstructs only component 0,
 // with stb_image's published IDCT arithmetic: the LL&M butterfly in 12-bit fixed point, columns kept with 2 extra bits
 // ((x + 512) >> 10), rows rounded and biased in one step ((x + 65536 + (128 << 17)) >> 17), clamped to 0..255.  The reference
 // pins no stb_image version and none exists in the build image, so this format's parity is UNPINNED; the
-// test holds it to +-1 grey level of libjpeg and to exact values on flat blocks.  Not handled (load fails, frame skipped):
-// progressive and arithmetic-coded files, 12-bit samples, CMYK / RGB-coded components, a subsampled luma plane.
+// test holds it to +-1 grey level of libjpeg and to exact values on flat blocks.  Sequential and progressive Huffman files are
+// read.  Not handled (load fails, frame skipped): arithmetic-coded and lossless files, 12-bit samples, CMYK / RGB-coded
+// components, a subsampled luma plane.
 static const uint8_t jpeg_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
                                         35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
@@ -470,7 +471,9 @@ bool decode_jpeg(const std::vector<uint8_t> &d, Decoded &out)
     JComp comp[3];
     int n_comp = 0, width = 0, height = 0, hmax = 1, vmax = 1, restart_interval = 0;
     int mcu_x = 0, mcu_y = 0;
-    bool have_sof = false, rgb_coded = false, decoded_luma = false;
+    bool have_sof = false, rgb_coded = false, decoded_luma = false, progressive = false;
+    std::vector<short> coef;  // progressive files: the luma coefficients (64 per block, natural order, not yet dequantised)
+    size_t blocks_w = 0, blocks_h = 0;
     size_t y_w2 = 0;
     std::vector<uint8_t> luma;  // component 0, padded to whole MCUs
     size_t pos = 2;
@@ -520,7 +523,8 @@ bool decode_jpeg(const std::vector<uint8_t> &d, Decoded &out)
             restart_interval = (int)be16(seg);
         } else if (m == 0xEE) {                                   // APP14 "Adobe": colour transform 0 with three components = RGB
             if (len >= 14 && !memcmp(&d[seg], "Adobe", 5) && d[seg + 11] == 0) rgb_coded = true;
-        } else if (m == 0xC0 || m == 0xC1) {                      // SOF0 / SOF1
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {          // SOF0 / SOF1 / SOF2 (progressive)
+            progressive = m == 0xC2;
             if (have_sof || len < 8 || d[seg] != 8) return false;
             height = (int)be16(seg + 1); width = (int)be16(seg + 3); n_comp = d[seg + 5];
             if (height == 0 || width == 0 || (n_comp != 1 && n_comp != 3) || len != (size_t)(8 + 3 * n_comp)) return false;
@@ -536,9 +540,11 @@ bool decode_jpeg(const std::vector<uint8_t> &d, Decoded &out)
             mcu_x = (width + 8 * hmax - 1) / (8 * hmax); mcu_y = (height + 8 * vmax - 1) / (8 * vmax);
             y_w2 = (size_t)mcu_x * hmax * 8;
             luma.assign(y_w2 * ((size_t)mcu_y * vmax * 8), 0);
+            blocks_w = y_w2 / 8; blocks_h = (size_t)mcu_y * vmax;
+            if (progressive) coef.assign(blocks_w * blocks_h * 64, 0);
             have_sof = true;
-        } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
-            return false;                                         // progressive, lossless, arithmetic: not handled
+        } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return false;                                         // lossless, hierarchical, arithmetic: not handled
         } else if (m == 0xDA) {                                   // SOS + the entropy-coded segment
             if (!have_sof || (n_comp == 3 && rgb_coded)) return false;
             const int ns = d[seg];
@@ -549,12 +555,137 @@ bool decode_jpeg(const std::vector<uint8_t> &d, Decoded &out)
                 for (int c = 0; c < n_comp; ++c) if (comp[c].id == d[seg + 1 + 2 * i]) which = c;
                 if (which < 0) return false;
                 comp[which].td = d[seg + 2 + 2 * i] >> 4; comp[which].ta = d[seg + 2 + 2 * i] & 15;
-                if (comp[which].td > 3 || comp[which].ta > 3 || !hdc[comp[which].td].present || !hac[comp[which].ta].present || !have_quant[comp[which].tq]) return false;
+                if (comp[which].td > 3 || comp[which].ta > 3) return false;
+                if (!progressive && (!hdc[comp[which].td].present || !hac[comp[which].ta].present || !have_quant[comp[which].tq])) return false;
                 order[i] = which;
             }
-            if (d[seg + 1 + 2 * ns] != 0 || d[seg + 2 + 2 * ns] != 63 || d[seg + 3 + 2 * ns] != 0) return false;  // spectral selection of a sequential scan
+            const int ss = d[seg + 1 + 2 * ns], se = d[seg + 2 + 2 * ns], ah = d[seg + 3 + 2 * ns] >> 4, al = d[seg + 3 + 2 * ns] & 15;
+            if (!progressive && (ss != 0 || se != 63 || ah != 0 || al != 0)) return false;  // spectral selection of a sequential scan
             JBits br{&d[0] + seg_end, &d[0] + d.size()};
             for (int c = 0; c < n_comp; ++c) comp[c].dc_pred = 0;
+            if (progressive) {
+                // ITU T.81 G.1.2: a scan carries either the DC terms (first pass: value >> al; later passes: one more bit) of its
+                // components, or a band ss..se of the AC terms of ONE component (first pass with end-of-band runs, refinement
+                // passes that add one bit to the non-zero history and place new +-1 << al values).  Only luma is kept; a chroma
+                // AC scan is stepped over without decoding.  Dequantisation and the IDCT follow when all scans are in.
+                if (ss > 63 || se > 63 || ss > se || ah > 13 || al > 13 || (ss == 0 && se != 0) || (ss != 0 && ns != 1)) return false;
+                if (ss != 0 && order[0] != 0) {  // chroma AC band: find the marker that ends its entropy-coded segment
+                    size_t q = seg_end;
+                    while (q + 1 < d.size() && !(d[q] == 0xFF && d[q + 1] != 0 && d[q + 1] != 0xFF && !(d[q + 1] >= 0xD0 && d[q + 1] <= 0xD7))) ++q;
+                    pos = q;
+                    continue;
+                }
+                auto bit1 = [&]() -> int { br.fill(); const int b = (int)br.peek(1); br.skip(1); return b; };
+                auto bits = [&](int k) -> int { if (k == 0) return 0; br.fill(); const int b = (int)br.peek(k); br.skip(k); return b; };
+                int eob_run = 0;
+                int todo = restart_interval ? restart_interval : 0x7fffffff;
+                bool stop = false;
+                auto after_mcu = [&]() {
+                    if (--todo > 0) return;
+                    br.fill();
+                    if (!(br.marker >= 0xD0 && br.marker <= 0xD7)) { stop = true; return; }
+                    br.reset();
+                    for (int c = 0; c < n_comp; ++c) comp[c].dc_pred = 0;
+                    eob_run = 0;
+                    todo = restart_interval;
+                };
+                auto dc_block = [&](JComp &c, short *blk) -> bool {  // blk == nullptr: a chroma block, decoded only to stay in step
+                    if (ah == 0) {
+                        if (!hdc[c.td].present) return false;
+                        const int t = br.decode(hdc[c.td]);
+                        if (t < 0 || t > 16) return false;
+                        const long long dcv = (long long)c.dc_pred + br.receive_extend(t);
+                        if (dcv < -32768 || dcv > 32767 || dcv * (1 << al) < -32768 || dcv * (1 << al) > 32767) return false;
+                        c.dc_pred = (int)dcv;
+                        if (blk) blk[0] = (short)(c.dc_pred * (1 << al));
+                    } else if (bit1() && blk) {
+                        blk[0] = (short)(blk[0] + (1 << al));
+                    }
+                    return true;
+                };
+                auto ac_block = [&](JComp &c, short *blk) -> bool {
+                    const JHuff &ac = hac[c.ta];
+                    if (!ac.present) return false;
+                    if (ah == 0) {  // first pass over the band
+                        if (eob_run) { --eob_run; return true; }
+                        int k = ss;
+                        do {
+                            const int rs = br.decode(ac);
+                            if (rs < 0) return false;
+                            const int r = rs >> 4, sz = rs & 15;
+                            if (sz == 0) {
+                                if (r < 15) { eob_run = (1 << r) + bits(r) - 1; break; }
+                                k += 16;
+                            } else {
+                                k += r;
+                                if (k > 63) return false;
+                                const long long v = (long long)br.receive_extend(sz) * (1 << al);
+                                if (v < -32768 || v > 32767) return false;
+                                blk[jpeg_zigzag[k++]] = (short)v;
+                            }
+                        } while (k <= se);
+                        return true;
+                    }
+                    const short bit = (short)(1 << al);  // refinement pass
+                    auto refine = [&](short *p) { if (bit1() && (*p & bit) == 0) *p = (short)(*p > 0 ? *p + bit : *p - bit); };
+                    if (eob_run) {
+                        --eob_run;
+                        for (int k = ss; k <= se; ++k) { short *p = &blk[jpeg_zigzag[k]]; if (*p != 0) refine(p); }
+                        return true;
+                    }
+                    int k = ss;
+                    do {
+                        const int rs = br.decode(ac);
+                        if (rs < 0) return false;
+                        int r = rs >> 4, sz = rs & 15, val = 0;
+                        if (sz == 0) {
+                            if (r < 15) { eob_run = (1 << r) - 1 + bits(r); r = 64; }  // the rest of the band only gets refined
+                        } else {
+                            if (sz != 1) return false;
+                            val = bit1() ? bit : -bit;
+                        }
+                        while (k <= se) {  // walk over r still-zero coefficients, refining the non-zero ones passed on the way
+                            short *p = &blk[jpeg_zigzag[k++]];
+                            if (*p != 0) refine(p);
+                            else if (r == 0) { *p = (short)val; break; }
+                            else --r;
+                        }
+                    } while (k <= se);
+                    return true;
+                };
+                if (ns == 1) {
+                    JComp &c = comp[order[0]];
+                    const int cw = (width * c.h + hmax - 1) / hmax, chh = (height * c.v + vmax - 1) / vmax;
+                    const int bw = (cw + 7) >> 3, bh = (chh + 7) >> 3;
+                    const bool keep = order[0] == 0;
+                    for (int by = 0; by < bh && !stop; ++by)
+                        for (int bx = 0; bx < bw && !stop; ++bx) {
+                            short *blk = keep ? &coef[((size_t)by * blocks_w + bx) * 64] : nullptr;
+                            if (!(ss == 0 ? dc_block(c, blk) : ac_block(c, blk))) return false;
+                            after_mcu();
+                        }
+                    if (keep) decoded_luma = true;
+                } else {
+                    for (int my = 0; my < mcu_y && !stop; ++my)
+                        for (int mx = 0; mx < mcu_x && !stop; ++mx) {
+                            for (int i = 0; i < ns; ++i) {
+                                JComp &c = comp[order[i]];
+                                for (int y = 0; y < c.v; ++y)
+                                    for (int x = 0; x < c.h; ++x) {
+                                        short *blk = order[i] == 0 ? &coef[((size_t)(my * c.v + y) * blocks_w + (size_t)(mx * c.h + x)) * 64] : nullptr;
+                                        if (!dc_block(c, blk)) return false;
+                                    }
+                                if (order[i] == 0) decoded_luma = true;
+                            }
+                            after_mcu();
+                        }
+                }
+                br.fill();
+                pending = br.marker == 0xD9 && br.p >= br.end ? 0 : br.marker;
+                pos = (size_t)(br.p - &d[0]);
+                if (br.marker == 0xD9) break;
+                continue;
+            }
             short blk[64];
             auto decode_block = [&](JComp &c, bool keep) -> bool {
                 const JHuff &dc = hdc[c.td], &ac = hac[c.ta];
@@ -644,6 +775,17 @@ bool decode_jpeg(const std::vector<uint8_t> &d, Decoded &out)
         // APPn, COM and everything else: skipped
     }
     if (!have_sof || !decoded_luma) return false;
+    if (progressive) {  // all scans are in: dequantise (16-bit wrap like the sequential path) and transform the luma blocks
+        if (!have_quant[comp[0].tq]) return false;
+        const uint16_t *q = quant[comp[0].tq];
+        short blk[64];
+        for (size_t by = 0; by < blocks_h; ++by)
+            for (size_t bx = 0; bx < blocks_w; ++bx) {
+                const short *c = &coef[(by * blocks_w + bx) * 64];
+                for (int k = 0; k < 64; ++k) blk[jpeg_zigzag[k]] = (short)(c[jpeg_zigzag[k]] * q[k]);
+                jpeg_idct_block(&luma[by * 8 * y_w2 + bx * 8], y_w2, blk);
+            }
+    }
     out.w = width; out.h = height; out.gray.resize((size_t)width * height);
     for (int y = 0; y < height; ++y) memcpy(&out.gray[(size_t)y * width], &luma[(size_t)y * y_w2], (size_t)width);
     return true;

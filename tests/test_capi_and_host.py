@@ -271,10 +271,10 @@ def test_image_decode_interlaced_png_and_bmp(tmp_path):
 
 
 def test_image_decode_jpeg_luma_plane(tmp_path):
-    """Baseline JPEG: stbi_load(..., 1) returns the luma plane of its integer IDCT.  No stb_image exists in the image and the
+    """JPEG (sequential and progressive Huffman): stbi_load(..., 1) returns the luma plane of its integer IDCT.  No stb_image exists in the image and the
     reference pins no version, so this format is UNPINNED; the decoder is held to +-1 grey level of libjpeg's luma plane (two
     integer IDCTs of different fixed-point precision), to exact values where both are exact (flat blocks), and to refusing
-    what it does not implement (progressive)."""
+    what it does not implement (CMYK)."""
     Image = pytest.importorskip("PIL.Image")
     rng = np.random.default_rng(6)
 
@@ -309,10 +309,21 @@ def test_image_decode_jpeg_luma_plane(tmp_path):
     assert np.array_equal(pvp.load_image_gray(f), libjpeg_luma(f))
     Image.fromarray(np.stack([flat, flat, flat], -1)).save(f, quality=100, subsampling=2)
     assert np.array_equal(pvp.load_image_gray(f), libjpeg_luma(f))
+    # progressive files (spectral selection + successive approximation): the same picture stored progressively and sequentially
+    # holds the same quantised coefficients, so the two decodes must agree bit for bit; and +-1 of libjpeg as above
+    f2 = str(tmp_path / "s.jpg")
+    for h, w in ((64, 64), (37, 53), (8, 8), (1, 1), (120, 161)):
+        for mode, kw in (("L", {}), ("RGB", dict(subsampling=0)), ("RGB", dict(subsampling=2)), ("RGB", dict(subsampling=1, optimize=True, quality=30)),
+                         ("L", dict(quality=95)), ("RGB", dict(subsampling=2, restart_marker_blocks=3))):
+            img = picture(h, w, 1 if mode == "L" else 3)
+            im = Image.fromarray(img[..., 0] if mode == "L" else img, mode)
+            im.save(f, progressive=True, **kw)
+            im.save(f2, **{k: v for k, v in kw.items() if not k.startswith("restart")})
+            got, want = pvp.load_image_gray(f), libjpeg_luma(f)
+            diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            assert diff.max() <= 1 and (diff == 0).mean() >= 0.95, (h, w, mode, kw)
+            assert np.array_equal(got, pvp.load_image_gray(f2)), (h, w, mode, kw)
     # not implemented -> the reference's failed-load path (frame skipped), never a wrong image
-    Image.fromarray(picture(32, 32, 3)).save(f, progressive=True)
-    with pytest.raises(pvp.PvpError, match="Failed to load image"):
-        pvp.load_image_gray(f)
     Image.fromarray(picture(32, 32, 4), "CMYK").save(f)
     with pytest.raises(pvp.PvpError, match="Failed to load image"):
         pvp.load_image_gray(f)
@@ -340,6 +351,7 @@ def test_image_decode_survives_damaged_files(tmp_path):
         Image.fromarray(rgb).quantize(16).save(tmp_path / "p.bmp"); seeds["p.bmp"] = (tmp_path / "p.bmp").read_bytes()
         Image.fromarray(rgb).save(tmp_path / "c.jpg", subsampling=2, restart_marker_blocks=2); seeds["c.jpg"] = (tmp_path / "c.jpg").read_bytes()
         Image.fromarray(gray).save(tmp_path / "g.jpg", optimize=True); seeds["g.jpg"] = (tmp_path / "g.jpg").read_bytes()
+        Image.fromarray(rgb).save(tmp_path / "p.jpg", progressive=True); seeds["p.jpg"] = (tmp_path / "p.jpg").read_bytes()
     except ImportError:
         pass
 
