@@ -10,6 +10,6 @@ from .motion import (Context, FramePose, VoxelGrid, accumulate_motion, cast_rays
                      read_bin, rotation_matrix, write_bin)
 from .process_image import process_image_cpp  # noqa: F401
 from .analysis import extract_top_percentile_z_up, grid_percentile, load_voxel_grid  # noqa: F401
-from .sky import analyze_voxel_grid, normalize_image  # noqa: F401
+from .sky import analyze_voxel_grid, field_of_view_rad, normalize_image  # noqa: F401
 
 __version__ = "0.1.0"

@@ -2,6 +2,7 @@
 drain the extension inside spacevoxelviewer.py, on the device, so that a FITS loop keeps image, grid and texture in HBM.
 
 * :func:`normalize_image`      spacevoxelviewer.py:179-184  (nan_to_num, min-max normalise, zero-range error)
+* :func:`field_of_view_rad`    spacevoxelviewer.py:197-215  (FITS header 'FOV' | CD matrix | default 2.7 arcmin -> radians; host scalars)
 * :func:`analyze_voxel_grid`   spacevoxelviewer.py:317-347  (average, percentile threshold over the positive cells,
                                object voxels -> world coordinates, intensities, brightest voxel)
 
@@ -38,6 +39,25 @@ def _percentile_of(values: torch.Tensor, percentile) -> np.generic:
     lo = torch.kthvalue(values, prev_i + 1).values
     hi = lo if next_i == prev_i else torch.kthvalue(values, next_i + 1).values
     return lerp_like_numpy(dt(lo.item()), dt(hi.item()), gamma)
+
+
+def field_of_view_rad(header, width: int, height: int, default_fov_arcminutes: float = 2.7) -> np.float64:
+    """spacevoxelviewer.py:197-215: the ``fov`` argument of ``process_image_cpp`` (radians) from a FITS header mapping: the
+    'FOV' card in degrees if present, else the larger side of the image from the CD matrix' pixel scales, else the reference's
+    default of 2.7 arcminutes (``:44``).  Per-file host scalars (numpy float64, the reference's own expressions)."""
+    fov = header.get('FOV')
+    if fov is None:
+        cd = [header.get(k) for k in ('CD1_1', 'CD1_2', 'CD2_1', 'CD2_2')]
+        if all(c is not None for c in cd):
+            cd1_1, cd1_2, cd2_1, cd2_2 = cd
+            pixel_scale_x = np.sqrt(cd1_1**2 + cd2_1**2)
+            pixel_scale_y = np.sqrt(cd1_2**2 + cd2_2**2)
+            fov = max(pixel_scale_x * width, pixel_scale_y * height)
+        else:
+            fov = default_fov_arcminutes / 60  # degrees
+    else:
+        fov = float(fov)
+    return np.deg2rad(fov)
 
 
 def analyze_voxel_grid(voxel_grid: torch.Tensor, n_images: int, voxel_grid_extent, brightness_threshold_percentile=.1) -> dict:

@@ -98,3 +98,17 @@ def test_fits_loop_stays_on_device(ctx):
     thr, xc, yc, zc, inten, brightest = numpy_analyze(grid.cpu().numpy(), files, ext, 0.1)
     assert float(out["threshold"]) == float(thr) and len(inten) > 100
     assert np.array_equal(bits(out["intensities"].cpu().numpy()), bits(inten)) and out["brightest"] == tuple(float(v) for v in brightest)
+
+
+def test_field_of_view_matches_the_reference_lines():
+    """tests/golden/fov_golden.npz: the reference's own statements (spacevoxelviewer.py:197-215) executed on synthetic headers."""
+    import json
+    import os
+    from conftest import ROOT
+    import pixeltovoxelprojector_b200 as pvp
+    g = np.load(os.path.join(ROOT, "tests", "golden", "fov_golden.npz"))
+    cases = json.loads(str(g["cases"]))
+    assert len(cases) >= 20
+    for c, want in zip(cases, g["fov_rad"]):
+        got = pvp.field_of_view_rad(c["header"], c["width"], c["height"])
+        assert np.float64(got).tobytes() == np.float64(want).tobytes(), c
