@@ -4,10 +4,11 @@ the GPU box, gloo in CPU tests).  Two sharding modes, neither needs a collective
 * frame sharding  -- every rank accumulates a contiguous block of the frame pairs into a PRIVATE full grid; the run
   ends with ONE sum-reduce of the N^3 cells to rank 0 (fp32: tolerance mode, int64 fixed point: bit-exact and
   order independent).
-* slab sharding   -- every rank owns the x-planes [lo, hi) of a grid too large for one GPU; all ranks walk all rays with
-  full-grid arithmetic and suppress writes outside their slab (a clipped restart would change the reference's
-  accumulated t_max roundings).  No reduce: x is the slowest index (ray_voxel.cpp:527), so slabs are contiguous byte
-  ranges of the .bin and each rank writes its own range.
+* slab sharding   -- every rank owns the x-planes [lo, hi) of a grid too large for one GPU; all ranks see all rays and walk
+  them from their start with full-grid arithmetic (a walk restarted at the slab face would change the reference's
+  accumulated t_max roundings), writing only inside their slab.  The clipping is exact: a ray whose x range misses the
+  slab is not walked, and a walk stops once x has passed the slab.  No reduce: x is the slowest index
+  (ray_voxel.cpp:527), so slabs are contiguous byte ranges of the .bin and each rank writes its own range.
 """
 from __future__ import annotations
 
