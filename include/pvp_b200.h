@@ -50,7 +50,8 @@ typedef struct pvp_ctx pvp_ctx; /* device + stream + workspace (ray queue, count
  * The voxel grid of ray_voxel.cpp:434-440, with the compile-time constants of :434-437
  * turned into fields.  Storage is [x][y][z], z fastest (ray_voxel.cpp:527).  A grid
  * pointer may address only the x-planes [slab_lo, slab_hi) ("slab shard", SURVEY 8e mode 2):
- * rays are walked with full-grid arithmetic and writes outside the slab are suppressed.
+ * rays are walked from their start with full-grid arithmetic and nothing is written outside the slab; the default kernels
+ * clip exactly (a ray that cannot reach the slab is not walked, a walk stops once x has passed it).
  */
 typedef struct pvp_grid_desc {
     int32_t n;            /* N (ray_voxel.cpp:434) */
