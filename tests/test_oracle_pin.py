@@ -176,3 +176,30 @@ def test_process_image_vs_reference(oracle):
             m.process_image_cpp(img, list(pos), list(pointing), 0.9, W, H, g1, ext, 60.0, 300, t1, *sky, upd, bg)
             oracle.process_image(img, pos, pointing, 0.9, W, H, g2, ext, 60.0, 300, t2, *sky, upd, bg)
             assert np.array_equal(bits(g1), bits(g2)) and np.array_equal(bits(t1), bits(t2)), (trial, upd, bg)
+
+
+def test_cast_ray_vs_reference_exotic_floats(oracle, reflib):
+    """hypothesis over raw float32 bit patterns (zeros of both signs, subnormals, huge values, infinities, NaN) for camera,
+    direction, voxel size and centre: the restatement and the compiled reference must visit the same voxels with the same t
+    bits, or both nothing -- the regimes where fminf/fmaxf, the 1e-12 tests and int() of NaN / out-of-range values decide."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    f32 = st.one_of(st.floats(width=32, allow_nan=True, allow_infinity=True, allow_subnormal=True),
+                    st.sampled_from([0.0, -0.0, 1e-12, -1e-12, 9.9e-13, 1e-13, 1.0, -1.0, 0.5, 3.4e38, -3.4e38, 1e25, 1e-38, 2.0 ** -126, 2.0 ** -149]),
+                    st.floats(min_value=-600.0, max_value=600.0, width=32))
+    vec = st.tuples(f32, f32, f32)
+    n_checked = [0, 0]
+
+    @hyp.settings(max_examples=1500, deadline=None, derandomize=True, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(cam=vec, d=vec, n=st.integers(1, 48), vs=f32, center=vec)
+    def run(cam, d, n, vs, center):
+        cam, d, center = (np.array(v, np.float32) for v in (cam, d, center))
+        vs = np.float32(vs)
+        a, ta = oracle.cast_ray(cam, d, n, vs, center, cap=4 * n + 8, want_t=True)
+        b, tb = reflib.cast_ray(cam, d, n, vs, center, cap=4 * n + 8, want_t=True)
+        assert a.shape == b.shape and np.array_equal(a, b) and np.array_equal(bits(ta), bits(tb)), (cam, d, n, vs, center)
+        n_checked[0] += 1
+        n_checked[1] += len(a) > 0
+
+    run()
+    assert n_checked[0] >= 1000 and n_checked[1] > 50      # a good share of the exotic inputs still produce steps
