@@ -203,3 +203,49 @@ def test_cast_ray_vs_reference_exotic_floats(oracle, reflib):
 
     run()
     assert n_checked[0] >= 1000 and n_checked[1] > 50      # a good share of the exotic inputs still produce steps
+
+
+def test_process_image_vs_reference_property(oracle):
+    """hypothesis over path B's geometry: observer inside / outside / on a face of the grid, pointing along the axes (the `up`
+    switch of process_image.cpp:203-211), tiny and huge fields of view, one march step, textures of one cell, images with zero,
+    negative and huge brightness, thin grids.  The restatement and the compiled reference module must agree bit for bit."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    from oracle import REF_DIR, ref_process_image_module
+    if not os.path.isdir(REF_DIR):
+        pytest.skip("oracle/_ref not built")
+    m = ref_process_image_module()
+    coord = st.one_of(st.sampled_from([0.0, -0.0, 1.0, -1.0, 5.0, -5.0, 10.0, 1e-9, -1e-9, 1e6, -1e6]), st.floats(-30.0, 30.0, allow_nan=False, width=64))
+    direction = st.one_of(st.sampled_from([(0.0, 0.0, 1.0), (0.0, 0.0, -2.0), (1e-9, 0.0, 1.0), (1.0, 0.0, 0.0), (0.0, -3.0, 0.0), (1.0, 1.0, 1.0), (1e-8, 1e-8, -1.0)]),
+                          st.tuples(coord, coord, coord).filter(lambda v: any(abs(c) > 1e-6 for c in v)))
+    lohi = st.tuples(st.floats(-20.0, 19.0, width=64), st.floats(0.015625, 25.0, width=64)).map(lambda p: (p[0], p[0] + p[1]))
+    pixel = st.one_of(st.sampled_from([0.0, -0.0, -1.0, 1.0, 1e-300, 1e300, 0.5]), st.floats(0.0, 1.0, width=64))
+    n_calls = [0, 0]
+
+    @hyp.settings(max_examples=800, deadline=None, derandomize=True, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(data=st.data(), h=st.integers(1, 5), w=st.integers(1, 5), pos=st.tuples(coord, coord, coord), pointing=direction,
+               fov=st.sampled_from([1e-6, 0.01, 0.5, 0.9, 1.5, 3.0, 3.1415]), shape=st.tuples(st.integers(1, 5), st.integers(1, 5), st.integers(1, 5)),
+               ext=st.tuples(lohi, lohi, lohi), max_distance=st.sampled_from([0.5, 7.0, 60.0, 1e3]), num_steps=st.sampled_from([1, 2, 17, 64]),
+               tex=st.tuples(st.integers(1, 4), st.integers(1, 4)), sky=st.tuples(st.floats(0.0, 6.28), st.floats(-1.5, 1.5), st.floats(0.01, 6.0), st.floats(0.01, 3.0)),
+               flags=st.sampled_from([(True, False), (False, True), (False, False), (True, True)]), with_grid=st.booleans(), aim=st.integers(0, 3))
+    def run(data, h, w, pos, pointing, fov, shape, ext, max_distance, num_steps, tex, sky, flags, with_grid, aim):
+        if aim:      # three times out of four look at the grid (from wherever the observer is), so that rays do cross it
+            to_centre = [0.5 * (lo + hi) - p for (lo, hi), p in zip(ext, pos)]
+            if any(abs(c) > 1e-6 for c in to_centre):
+                pointing = tuple(to_centre)
+        img = np.array(data.draw(st.lists(pixel, min_size=h * w, max_size=h * w)), np.float64).reshape(h, w)
+        g1 = np.zeros(shape if with_grid else (0,))
+        g2 = g1.copy()
+        t1 = np.full(tex, 0.25)
+        t2 = t1.copy()
+        upd, bg = flags
+        # bg-subtraction while updating reads the texture another pixel of the same call may have written: serial in both (1 thread)
+        m.process_image_cpp(img, list(pos), list(pointing), fov, w, h, g1, [tuple(e) for e in ext], max_distance, num_steps, t1, *sky, upd, bg)
+        oracle.process_image(img, pos, pointing, fov, w, h, g2, [tuple(e) for e in ext], max_distance, num_steps, t2, *sky, upd, bg)
+        assert np.array_equal(bits(g1), bits(g2)) and np.array_equal(bits(t1), bits(t2)), (pos, pointing, fov, shape, ext, max_distance, num_steps, tex, sky, flags)
+        n_calls[0] += 1
+        n_calls[1] += bool(g1.any())
+
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    run()
+    assert n_calls[0] >= 500 and n_calls[1] >= 40      # calls in which rays did cross the grid
