@@ -22,13 +22,15 @@ from .motion import Context, default_context
 last_stats: dict | None = None  # counters of the most recent call (n_rays, n_samples), for benchmarks
 
 
-def _as_f64_array(x, name: str, ndim: int | None):
+def _as_f64_array(x, name: str, ndim: int | None, mutated: bool = True):
     """pybind11's ``py::array_t<double>`` (forcecast) conversion: a non-float64 input is silently
-    converted into a temporary, so in-place updates are lost to the caller -- as in the reference."""
+    converted into a temporary, so in-place updates are lost to the caller -- as in the reference
+    (hence the warning for the two arrays the call mutates; the image is only read)."""
     a = x if isinstance(x, np.ndarray) else np.asarray(x)
     if a.dtype != np.float64:
-        warnings.warn(f"process_image_cpp: {name} is {a.dtype}, not float64; it is converted to a temporary copy and "
-                      "updates will not be visible to the caller (same as the reference's pybind11 forcecast)", stacklevel=3)
+        if mutated:
+            warnings.warn(f"process_image_cpp: {name} is {a.dtype}, not float64; it is converted to a temporary copy and "
+                          "updates will not be visible to the caller (same as the reference's pybind11 forcecast)", stacklevel=3)
         a = a.astype(np.float64)
     if ndim is not None and a.ndim != ndim:
         raise ValueError(f"array has incorrect number of dimensions: {a.ndim}; expected {ndim}")
@@ -124,7 +126,7 @@ def process_image_cpp(image, earth_position, pointing_direction, fov, image_widt
     else:
         if accum_mode != "f64":
             raise ValueError("fixed-point accumulation needs CUDA int64 tensors (device path)")
-        img = _as_f64_array(image, "image", 2)
+        img = _as_f64_array(image, "image", 2, mutated=False)
         tex = _as_f64_array(celestial_sphere_texture, "celestial_sphere_texture", 2)
         grid = voxel_grid if isinstance(voxel_grid, np.ndarray) else np.asarray(voxel_grid)
         have_grid = grid.size > 0  # process_image.cpp:152 -- an empty array of any ndim skips the voxel stage
