@@ -154,3 +154,4 @@ def test_write_bin_from_device_matches_host_writer(tmp_path):
         assert open(a, "rb").read() == open(b, "rb").read()
     with pytest.raises(pvp.PvpError, match="Cannot open output file"):
         pvp._lib.check(ctx._lib.pvp_write_bin_dev(ctx.handle, os.fsencode(str(tmp_path / "no_such_dir" / "x.bin")), 1, C.c_float(1.0), g.data_ptr()))
+

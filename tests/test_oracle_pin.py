@@ -249,3 +249,29 @@ def test_process_image_vs_reference_property(oracle):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     run()
     assert n_calls[0] >= 500 and n_calls[1] >= 40      # calls in which rays did cross the grid
+
+
+def test_config1_oracle_reproduces_the_reference_cli_output(oracle, tmp_path):
+    """BASELINE configs[0] (640x480 short sequence, default grid): the restated frame loop, fed the fixture's frames and poses,
+    rebuilds the reference CLI's 500 000 008-byte .bin byte for byte (tests/golden/config1_golden.npz holds its SHA-256)."""
+    import hashlib
+    import json
+    import struct
+    from golden.make_golden_config1 import H, W, SQUARE, VALUE
+    g = golden("config1_golden.npz")
+    entries = json.loads(str(g["metadata"]))
+    N, vs, center = 500, np.float32(6.0), np.array([0.0, 0.0, 500.0], np.float32)      # ray_voxel.cpp:434-437
+    grid = np.zeros((N, N, N), np.float32)
+    prev = None
+    for e, (x, y) in zip(entries, g["track"]):
+        img = g["bg"].copy()
+        img[y:y + SQUARE, x:x + SQUARE] = VALUE
+        if prev is not None:
+            R = oracle.rotation_matrix(e["yaw"], e["pitch"], e["roll"])
+            oracle.accumulate_pair(prev, img, np.array(e["camera_position"], np.float32), R, oracle.focal_length(e["fov_degrees"], W), grid, N, vs, center, 2.0)
+        prev = img
+    assert img.shape == (H, W)
+    sha = hashlib.sha256(struct.pack("<if", N, 6.0))
+    sha.update(grid.tobytes())
+    assert int(np.count_nonzero(grid)) == int(g["nnz"]) and float(grid.astype(np.float64).sum()) == float(g["total"])
+    assert sha.hexdigest() == str(g["sha256"])
