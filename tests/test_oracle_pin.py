@@ -275,3 +275,43 @@ def test_config1_oracle_reproduces_the_reference_cli_output(oracle, tmp_path):
     sha.update(grid.tobytes())
     assert int(np.count_nonzero(grid)) == int(g["nnz"]) and float(grid.astype(np.float64).sum()) == float(g["total"])
     assert sha.hexdigest() == str(g["sha256"])
+
+
+def test_accumulate_pair_vs_reference_exotic_poses(oracle, reflib):
+    """The whole per-pair loop (ray_voxel.cpp:484-531: detect_motion, ray set-up, cast_ray_into_grid, accumulate) on small
+    frames with camera positions, grid centres, voxel sizes, focal lengths and rotation entries drawn from raw float32
+    patterns (NaN, infinities, subnormals, the neighbourhood of 1e-12): the restatement and the compiled reference loop
+    must produce the same ray / step counts and the same grid bits.  tools/exotic_pose_check.py asks the CUDA kernels the
+    same question against the oracle."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    f32 = st.one_of(st.floats(width=32, allow_nan=True, allow_infinity=True, allow_subnormal=True),
+                    st.sampled_from([0.0, -0.0, 1e-12, -1e-12, 9.9e-13, 1.0, -1.0, 3.4e38, 1e25, 2.0 ** -126, 16777216.0, 2147483648.0]),
+                    st.floats(min_value=-80.0, max_value=80.0, width=32))
+    tame = st.floats(min_value=-60.0, max_value=60.0, width=32)
+    coord = st.one_of(f32, tame, tame)
+    seen = [0, 0]
+
+    @hyp.settings(max_examples=600, deadline=None, derandomize=True, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(n=st.integers(1, 24), h=st.integers(1, 6), w=st.integers(1, 8), seed=st.integers(0, 10 ** 6), cam=st.tuples(coord, coord, coord),
+               center=st.tuples(coord, coord, coord), vs=st.one_of(f32, st.floats(min_value=0.25, max_value=8.0, width=32)),
+               ypr=st.tuples(st.sampled_from([0.0, 90.0, 180.0, -90.0, 33.0]), st.sampled_from([0.0, 90.0, -45.0, 10.0]), st.sampled_from([0.0, 180.0, 170.0, -20.0])),
+               fov=st.sampled_from([1.0, 60.0, 120.0, 179.0, 180.0, 0.0]), poke=st.one_of(st.none(), st.tuples(st.integers(0, 8), f32)))
+    def run(n, h, w, seed, cam, center, vs, ypr, fov, poke):
+        rng = np.random.default_rng(seed)
+        prev = rng.integers(0, 256, (h, w)).astype(np.float32)
+        curr = rng.integers(0, 256, (h, w)).astype(np.float32)
+        R = reflib.rotation_matrix(*ypr).copy()
+        if poke is not None:
+            R[poke[0]] = np.float32(poke[1])          # an arbitrary float in the rotation (the loop takes R as data)
+        f = reflib.focal_length(fov, w)                # fov 0 / 180 give an infinite / ~zero focal length
+        cam, center, vs = np.array(cam, np.float32), np.array(center, np.float32), np.float32(vs)
+        g1, g2 = np.zeros((n, n, n), np.float32), np.zeros((n, n, n), np.float32)
+        s1 = oracle.accumulate_pair(prev, curr, cam, R, f, g1, n, vs, center, 2.0)
+        s2 = reflib.accumulate_pair(prev, curr, cam, R, f, g2, n, vs, center, 2.0)
+        assert s1[:2] == s2 and np.array_equal(bits(g1), bits(g2)), (n, h, w, seed, cam, center, vs, ypr, fov, poke)
+        seen[0] += 1
+        seen[1] += s2[1] > 0
+
+    run()
+    assert seen[0] >= 400 and seen[1] >= 40
