@@ -140,3 +140,59 @@ def test_k3_affine_coordinate_near_voxel_faces_at_the_largest_allowed_magnitudes
         assert idx[0] == _ref_index(np.array([q - lo]), bb, n)[0], (n, b, lo, o, w, s, k, delta)
         checked += 1
     assert checked > 2000 and flagged > 500             # both outcomes exercised: the window really sits on the faces
+
+
+def test_k2_slab_reach_never_skips_a_ray_that_enters_the_slab():
+    """K2 `slab_reach` (csrc/pvp_motion.cu): a rank skips a ray when the x index of its box-exit point, two voxels of margin
+    added, stays short of the rank's slab -- x_exit = (cam_x + t_end * dir_x - gmin_x) / vs in float32, skip iff
+    x_exit + 2 < slab_lo (walking +x) or x_exit - 2 >= slab_hi (walking -x).  Restated here with the reference's own slab test
+    for t_end (ray_voxel.cpp:296-317, float32) and checked against the voxel lists of the oracle: the furthest x index a ray
+    really visits is never beyond that estimate, for cameras inside and outside, grazing and axis-parallel rays."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import Oracle
+    o = Oracle()
+    rng = np.random.default_rng(23)
+    slack = []
+    n_rays = 0
+    for k in range(14000):
+        N = int(rng.integers(2, 96))
+        vs = F32(rng.choice([0.37, 1.0, 2.0, 6.0]) if k % 2 else rng.uniform(0.05, 9.0))
+        center = rng.uniform(-300, 300, 3).astype(F32)
+        half = F32(0.5) * (F32(N) * vs)
+        gmin, gmax = (center - half).astype(F32), (center + half).astype(F32)           # make_gridp
+        cam = (center + rng.uniform(-2.0, 2.0, 3) * half).astype(F32)
+        d = ((center + rng.uniform(-1.1, 1.1, 3) * half) - cam).astype(F32) if k % 3 else rng.normal(size=3).astype(F32)
+        if k % 5 == 0:
+            d[rng.integers(1, 3)] = F32(rng.choice([0.0, -0.0, 1e-13]))                  # parallel to y or z
+        if k % 11 == 0:
+            d[0] *= F32(1e-4)                                                            # nearly parallel to the x-planes: grazing in x
+        nrm = np.sqrt(np.sum(d.astype(np.float64) ** 2))
+        if nrm == 0:
+            continue
+        d = (d / F32(nrm)).astype(F32)
+        vox = o.cast_ray(cam, d, N, vs, center)
+        if len(vox) == 0:
+            continue
+        # t_end: the reference's slab test, float32, fminf / fmaxf
+        t_min, t_max, hit = F32(-np.inf), F32(np.inf), True
+        for a in range(3):
+            if abs(d[a]) < 1e-12:
+                if cam[a] < gmin[a] or cam[a] > gmax[a]:
+                    hit = False
+                continue
+            t1, t2 = F32((gmin[a] - cam[a]) / d[a]), F32((gmax[a] - cam[a]) / d[a])
+            t_min, t_max = max(t_min, min(t1, t2)), min(t_max, max(t1, t2))
+        assert hit and t_min <= t_max
+        x_exit = F32(F32(F32(cam[0] + F32(t_max * d[0])) - gmin[0]) / vs)
+        ix = vox[:, 0]
+        if d[0] >= 0:           # sx = +1 (ray_voxel.cpp:337: dir >= 0, incl. -0.0)
+            assert not (F32(x_exit + F32(2.0)) < F32(ix.max())), (k, x_exit, ix.max())      # a slab starting at the last visited plane is reached
+            slack.append(float(ix.max()) - float(x_exit))
+        else:
+            assert not (F32(x_exit - F32(2.0)) >= F32(ix.min() + 1)), (k, x_exit, ix.min())
+            slack.append(float(x_exit) - float(ix.min() + 1))
+        n_rays += 1
+    assert n_rays > 5000
+    assert max(slack) < 1.0, max(slack)     # the estimate is within one voxel; the kernel allows two
