@@ -196,3 +196,24 @@ def test_k2_slab_reach_never_skips_a_ray_that_enters_the_slab():
         n_rays += 1
     assert n_rays > 5000
     assert max(slack) < 1.0, max(slack)     # the estimate is within one voxel; the kernel allows two
+
+
+def test_k2_axis_choice_by_min3_equals_the_reference_chain():
+    """K2's DDA step picks the axis from one three-input minimum: z iff tmz == m, else y iff tmy == m, else x (m = min of the
+    three).  The reference's chain is `x if tx < ty && tx < tz; else y if ty < tz; else z` (ray_voxel.cpp:375-387: strict
+    comparisons, ties go to the later axis).  Equal for every NaN-free triple, including ties, both zeros and infinities (the
+    host keeps NaN out: lean_geometry_ok)."""
+    vals = np.array([0.0, -0.0, 1.0, 1.0 + 2.0 ** -23, 2.0, -1.0, np.inf, 2.0 ** -149, 3.5, 1e30, -np.inf], F32)
+    tx, ty, tz = (a.ravel() for a in np.meshgrid(vals, vals, vals, indexing="ij"))
+    ref = np.where((tx < ty) & (tx < tz), 0, np.where(ty < tz, 1, 2))
+    m = np.minimum(np.minimum(tx, ty), tz)
+    cz = tz == m
+    cy = ~cz & (ty == m)
+    ours = np.where(cz, 2, np.where(cy, 1, 0))
+    assert np.array_equal(ref, ours) and len(ref) == len(vals) ** 3
+    rng = np.random.default_rng(3)
+    t = rng.integers(0, 6, (200000, 3)).astype(F32) * F32(0.25)          # many ties
+    ref = np.where((t[:, 0] < t[:, 1]) & (t[:, 0] < t[:, 2]), 0, np.where(t[:, 1] < t[:, 2], 1, 2))
+    m = t.min(1)
+    ours = np.where(t[:, 2] == m, 2, np.where(t[:, 1] == m, 1, 0))
+    assert np.array_equal(ref, ours)
