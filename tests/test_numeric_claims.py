@@ -6,7 +6,10 @@ themselves are compared with the oracle on the GPU; these tests pin the *reasons
 * K3 `voxel_index_screened` (csrc/pvp_image.cu): when the 20 fraction bits read from the mantissa of a*K + (2^52 - 5) are below
   0xFFFF6, the integer part read from it equals the reference's min(trunc(RN(RN(a/b) * n)), n - 1).
 * K3 `sample_keys2<2>`: the same read-out from ONE fused multiply-add y = RN(s*dx + x0) per axis equals the reference's index for
-  samples inside the grid whenever A*K <= 2^49 (the host's `affine_ok`) and the safe range's 32-unit margin holds."""
+  samples inside the grid whenever A*K <= 2^49 (the host's `affine_ok`) and the safe range's 32-unit margin holds.
+* K3 `div_by_extent`: the five-operation FMA sequence is the correctly rounded quotient (exact rationals).
+* K2 axis choice from one three-input minimum == the reference's strict-comparison chain; K2 `slab_reach`: the box-exit x index
+  bounds the planes a ray visits."""
 from fractions import Fraction
 
 import numpy as np
@@ -217,3 +220,40 @@ def test_k2_axis_choice_by_min3_equals_the_reference_chain():
     m = t.min(1)
     ours = np.where(t[:, 2] == m, 2, np.where(t[:, 1] == m, 1, 0))
     assert np.array_equal(ref, ours)
+
+
+def test_k3_division_by_extent_is_the_correctly_rounded_quotient():
+    """K3 `div_by_extent` (csrc/pvp_image.cu): q = a*y; r = fma(-q, b, a); q = fma(r, y, q); r = fma(-q, b, a); q = fma(r, y, q)
+    with y = RN(1/b) equals RN(a / b) -- the reference's `/` (process_image.cpp:94-96) -- for every divisor the host admits
+    (`make_fastp`: significand not all ones).  Restated with exact rationals (a fused multiply-add is one rounding of the
+    exact value); the GPU self-test runs the real instruction sequence on 4e7 numerators per extent."""
+    def rn(x):
+        return float(x)                      # Fraction -> float: one correctly rounded conversion
+
+    def fma(a, b, c):
+        return rn(Fraction(a) * Fraction(b) + Fraction(c))
+
+    rng = np.random.default_rng(41)
+    extents = [20.0, 17.0, 3.0, 1.0 / 3.0, 1e-3, 6e12, 2.0 ** 40 + 1.0, 1.9999999999999996, 1.0000000000000002, 0.7, 123456.789, 5e-324 * 2 ** 600,
+               float(np.nextafter(4.0, 0.0) / 1.0), 400.0 * 0.1, np.pi, 2.0 / 3.0]
+    checked = 0
+    for b in extents:
+        m, _ = np.frexp(b)
+        if m == 1.0 - 2.0 ** -53:            # make_fastp refuses this divisor (the case Markstein's theorem excludes)
+            continue
+        y = 1.0 / b
+        n = 512
+        a_list = list(rng.uniform(0.0, b, 300)) + [b * k / n for k in range(0, n + 1, 37)]
+        for k in (1, 2, 255, 256, 511):      # the neighbourhood of voxel boundaries, where a wrong last bit would change an index
+            base = b * k / n
+            a_list += [float(np.nextafter(base, 0.0)), base, float(np.nextafter(base, np.inf))]
+        a_list += [0.0, b, float(np.nextafter(b, 0.0)), 5e-324, b * 2.0 ** -60]
+        for a in a_list:
+            q = a * y
+            r = fma(-q, b, a)
+            q = fma(r, y, q)
+            r = fma(-q, b, a)
+            q = fma(r, y, q)
+            assert q == a / b, (a, b, q, a / b)
+            checked += 1
+    assert checked > 4000
