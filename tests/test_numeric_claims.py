@@ -257,3 +257,65 @@ def test_k3_division_by_extent_is_the_correctly_rounded_quotient():
             assert q == a / b, (a, b, q, a / b)
             checked += 1
     assert checked > 4000
+
+
+def test_k3_safe_range_samples_pass_the_reference_bounds_test():
+    """K3 `safe_range` (csrc/pvp_image.cu): (1) the computed sample position q(s) = RN(o + RN(RN(s*step) * w)) of
+    process_image.cpp:344-347 lies within 2^-48 (|o| + d_max |w|) of the exact, linear x(s) = o + s*step*w (exact rationals);
+    (2) therefore, when the first and last sample of a span keep the margin 2^-47 (|o| + d_max |w| + |ext_lo| + |ext_hi|) to all
+    six faces, EVERY computed position between them passes the inclusive bounds test of :85 -- which is what lets the march skip
+    the test there.  (2) is checked by brute force on spans the restated routine accepts, incl. rays that graze a face."""
+    rng = np.random.default_rng(97)
+    # (1) the error bound
+    for _ in range(3000):
+        scale = float(rng.choice([1.0, 1e3, 6e12]))
+        o = float(rng.uniform(-scale, scale))
+        w = float(rng.uniform(-1, 1))
+        step = float(rng.uniform(1e-3, 10.0) * scale / 1e3)
+        s = int(rng.integers(0, 20001))
+        d = float(s) * step
+        q = o + d * w
+        exact = Fraction(o) + Fraction(s) * Fraction(step) * Fraction(w)
+        bound = Fraction(2) ** -48 * (abs(Fraction(o)) + abs(Fraction(d) * Fraction(w)))
+        assert abs(Fraction(q) - exact) <= bound, (o, w, step, s)
+    # (2) spans accepted by the routine contain only samples that pass the reference's test
+    accepted = grazing = 0
+    for case in range(400):
+        scale = float(rng.choice([1.0, 50.0, 6e12]))
+        ext = np.sort(rng.uniform(-scale, scale, (3, 2)), axis=1)
+        o = rng.uniform(-2 * scale, 2 * scale, 3)
+        target = ext[:, 0] + rng.uniform(0.02, 0.98, 3) * (ext[:, 1] - ext[:, 0])
+        w = target - o
+        if case % 4 == 0:                       # run along a face: one coordinate sits (almost) on ext_lo all the way
+            k = int(rng.integers(0, 3))
+            o[k] = ext[k, 0] + (ext[k, 1] - ext[k, 0]) * float(rng.choice([0.0, 1e-18, 1e-13]))
+            w[k] = 0.0
+            grazing += 1
+        w = w / np.sqrt(np.sum(w * w))
+        n_steps = int(rng.choice([200, 2000, 20000]))
+        step = 4.0 * scale * 2 / n_steps
+        s_all = np.arange(0, n_steps + 1, dtype=np.float64)
+        d = s_all * step
+        q = o[None, :] + d[:, None] * w[None, :]                                             # :344-347, float64, RN each
+        ok = np.all((q >= ext[None, :, 0]) & (q <= ext[None, :, 1]), axis=1)                 # :85 inclusive
+        inside_idx = np.flatnonzero(ok)
+        if len(inside_idx) < 8:
+            continue
+        lo, hi = int(inside_idx[0]), int(inside_idx[-1])
+        dmax = abs(hi * step) + abs(lo * step)
+        e = 2.0 ** -47 * (np.abs(o) + dmax * np.abs(w) + np.abs(ext[:, 0]) + np.abs(ext[:, 1]))
+
+        def inside(s):
+            qq = o + (float(s) * step) * w
+            return bool(np.all((ext[:, 0] + e <= qq) & (qq <= ext[:, 1] - e)))
+        a, b = lo, hi
+        for _ in range(3):
+            if a <= hi and not inside(a):
+                a += 1
+        for _ in range(3):
+            if b >= lo and not inside(b):
+                b -= 1
+        if a <= b and inside(a) and inside(b):
+            accepted += 1
+            assert ok[a:b + 1].all(), (case, a, b)
+    assert accepted > 150 and grazing > 50
