@@ -1,5 +1,5 @@
 """Frames/s through the ray_voxel CLI boundary (files on disk -> .bin) as a function of the decode threads.
-    python tools/cli_throughput.py [--frames 120] [--format pgm|png]
+    python tools/cli_throughput.py [--frames 120] [--format pgm|png|jpg]
 Writes a synthetic single-camera 1080p sequence (sparse motion), runs the CLI with 1 decode thread and with the default pool,
 checks that both .bin files are identical, prints frames/s."""
 import argparse
@@ -31,7 +31,7 @@ def write_png_gray(path, img):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=120)
-    ap.add_argument("--format", default="png", choices=["pgm", "png"])
+    ap.add_argument("--format", default="png", choices=["pgm", "png", "jpg"], help="jpg needs PIL (quality 90, 4:2:0)")
     ap.add_argument("--n", type=int, default=512, help="grid size (BASELINE config 2: 256)")
     ap.add_argument("--ab-lib", default=None, help="directory with another build of libpvp_b200.so: extra runs with it, interleaved (A/B)")
     a = ap.parse_args()
@@ -42,13 +42,17 @@ def main():
         frames = synth.sparse_frames(a.frames, H, W, seed=1, blobs=6)
         poses = synth.orbit_poses(a.frames, N, vs, center, seed=2)
         meta = synth.write_sequence(d, {0: frames}, {0: poses})
-        if a.format == "png":
+        if a.format != "pgm":
             import json
             entries = json.load(open(meta))
             for e in entries:
                 src = os.path.join(d, e["image_file"])
-                e["image_file"] = e["image_file"].replace(".pgm", ".png")
-                write_png_gray(os.path.join(d, e["image_file"]), frames[e["frame_index"]])
+                e["image_file"] = e["image_file"].replace(".pgm", "." + a.format)
+                if a.format == "png":
+                    write_png_gray(os.path.join(d, e["image_file"]), frames[e["frame_index"]])
+                else:
+                    from PIL import Image
+                    Image.fromarray(frames[e["frame_index"]]).save(os.path.join(d, e["image_file"]), quality=90)
                 os.remove(src)
             json.dump(entries, open(meta, "w"))
         outs = {}
