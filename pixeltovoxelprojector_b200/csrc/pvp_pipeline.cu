@@ -16,6 +16,8 @@
 #include <condition_variable>
 #include <map>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <random>
 #include <string>
 #include <thread>
@@ -162,7 +164,7 @@ extern "C" {
 // pvp_free_metadata.  Defaults follow :157-163 (camera_index 0, frame_index 0, yaw/pitch/roll 0,
 // fov_degrees 60, image_file "").  A missing / short camera_position leaves the reference's
 // Vec3 uninitialised (:166-173); here it is (0,0,0) with has_position = 0.
-int pvp_load_metadata(const char *json_path, pvp_frame_info **frames_out, int *n_out)
+static int load_metadata_impl(const char *json_path, pvp_frame_info **frames_out, int *n_out)
 {
     PVP_REQUIRE(json_path && frames_out && n_out, "pvp_load_metadata: NULL argument");
     *frames_out = nullptr; *n_out = 0;
@@ -213,6 +215,26 @@ int pvp_load_metadata(const char *json_path, pvp_frame_info **frames_out, int *n
     }
     *frames_out = out; *n_out = (int)cnt;
     return PVP_OK;
+}
+
+// No C++ exception crosses the C ABI: the parser and the frame loop allocate (strings, vectors, threads).
+#define PVP_GUARDED(call)                                                                      \
+    try {                                                                                      \
+        return call;                                                                           \
+    } catch (const std::bad_alloc &) {                                                         \
+        set_error("%s: out of host memory", __func__);                                         \
+        return PVP_ERR_NOMEM;                                                                  \
+    } catch (const std::exception &e) {                                                        \
+        set_error("%s: %s", __func__, e.what());                                               \
+        return PVP_ERR_INVALID;                                                                \
+    } catch (...) {                                                                            \
+        set_error("%s: unexpected exception", __func__);                                       \
+        return PVP_ERR_INVALID;                                                                \
+    }
+
+int pvp_load_metadata(const char *json_path, pvp_frame_info **frames_out, int *n_out)
+{
+    PVP_GUARDED(load_metadata_impl(json_path, frames_out, n_out))
 }
 
 void pvp_free_metadata(pvp_frame_info *frames) { free(frames); }
@@ -397,8 +419,8 @@ extern "C" {
 // not written to disk).  With shard_count > 1 this rank handles a contiguous block of the
 // (camera, frame) slots; pairing across skipped frames is resolved exactly as the reference
 // would (the previous frame of a block is the last loadable frame before it).
-int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char *image_folder, void *grid_dev,
-                             const pvp_run_options *opt, pvp_stats *stats, pvp_run_report *report)
+static int ray_voxel_accumulate_impl(pvp_ctx *ctx, const char *metadata_json, const char *image_folder, void *grid_dev,
+                                     const pvp_run_options *opt, pvp_stats *stats, pvp_run_report *report)
 {
     PVP_REQUIRE(ctx && metadata_json && image_folder && grid_dev && opt, "pvp_ray_voxel_accumulate: NULL argument");
     PVP_REQUIRE(opt->shard_count >= 1 && opt->shard_rank >= 0 && opt->shard_rank < opt->shard_count, "bad shard %d/%d",
@@ -554,6 +576,12 @@ int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char
         report->n_pairs = R.pairs_done; report->n_size_mismatch = mismatched;
     }
     return PVP_OK;
+}
+
+int pvp_ray_voxel_accumulate(pvp_ctx *ctx, const char *metadata_json, const char *image_folder, void *grid_dev,
+                             const pvp_run_options *opt, pvp_stats *stats, pvp_run_report *report)
+{
+    PVP_GUARDED(ray_voxel_accumulate_impl(ctx, metadata_json, image_folder, grid_dev, opt, stats, report))
 }
 
 // The CLI of ray_voxel.cpp:400-558: `ray_voxel <metadata.json> <image_folder> <output_voxel_bin>`
