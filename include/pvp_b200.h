@@ -12,7 +12,11 @@
  *   - all device work is enqueued on the context's stream; entry points that return
  *     host-visible results (stats, host copies) synchronise that stream before returning,
  *     the others are asynchronous;
- *   - there is NO CPU fallback: without a usable CUDA device pvp_ctx_create fails.
+ *   - there is NO CPU fallback: without a usable CUDA device pvp_ctx_create fails;
+ *   - threading: a pvp_ctx is not thread-safe (one context per host thread, or external locking; the reference
+ *     extension likewise holds the GIL for a whole call, process_image.cpp:369-390); distinct contexts may run
+ *     concurrently; the host-only helpers (pose, metadata, image decode, .bin) are re-entrant;
+ *   - no C++ exception leaves the library: allocation failures come back as PVP_ERR_NOMEM.
  */
 #ifndef PVP_B200_H
 #define PVP_B200_H
