@@ -16,7 +16,8 @@
  *   - threading: a pvp_ctx is not thread-safe (one context per host thread, or external locking; the reference
  *     extension likewise holds the GIL for a whole call, process_image.cpp:369-390); distinct contexts may run
  *     concurrently; the host-only helpers (pose, metadata, image decode, .bin) are re-entrant;
- *   - no C++ exception leaves the library: allocation failures come back as PVP_ERR_NOMEM.
+ *   - the entry points that parse files or run the frame loop (metadata, image decode, pvp_ray_voxel_accumulate) catch every
+ *     C++ exception and report it as a status (allocation failures: PVP_ERR_NOMEM); the others allocate only small bookkeeping.
  */
 #ifndef PVP_B200_H
 #define PVP_B200_H
