@@ -1,5 +1,5 @@
-"""K2 against the oracle on exotic geometry (a GPU tool for the start of a round, not part of tests/):
-    python tools/exotic_pose_check.py [--cases 400] [--seed 0]
+"""K2 against the oracle on exotic geometry (a GPU script for the start of a round; lives under tests/ because it uses the oracle, but is not collected by pytest):
+    python tests/exotic_pose_check.py [--cases 400] [--seed 0]
 Random small scenes whose camera positions, grid centres and voxel sizes are drawn from raw float32 patterns -- zeros of both
 signs, subnormals, values next to the 1e-12 / 1e25 thresholds of the code, huge magnitudes, infinities, NaN -- and whose poses
 include axis-aligned views (rays with zero direction components).  Every K2 variant (auto, 1-5) in float32 and fixed point must

@@ -281,7 +281,7 @@ def test_accumulate_pair_vs_reference_exotic_poses(oracle, reflib):
     """The whole per-pair loop (ray_voxel.cpp:484-531: detect_motion, ray set-up, cast_ray_into_grid, accumulate) on small
     frames with camera positions, grid centres, voxel sizes, focal lengths and rotation entries drawn from raw float32
     patterns (NaN, infinities, subnormals, the neighbourhood of 1e-12): the restatement and the compiled reference loop
-    must produce the same ray / step counts and the same grid bits.  tools/exotic_pose_check.py asks the CUDA kernels the
+    must produce the same ray / step counts and the same grid bits.  tests/exotic_pose_check.py asks the CUDA kernels the
     same question against the oracle."""
     hyp = pytest.importorskip("hypothesis")
     st = pytest.importorskip("hypothesis.strategies")
