@@ -26,11 +26,15 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
 WORKLOADS = {
     # the configuration BASELINE.json's metric is quoted on: 1080p frames into a 512^3 fp32 grid, one camera whose
     # pose changes every frame, dense motion (iid uint8 frames: ~98 % of the pixels cast a ray)
-    "1080p_dense_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=72, motion="dense", accum="f32"),
+    "1080p_dense_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=136, motion="dense", accum="f32"),
     # BASELINE config[1]: 256^3 grid (L2 resident)
-    "1080p_dense_256": dict(H=1080, W=1920, N=256, voxel_size=4.0, center=(0.0, 0.0, 500.0), pairs_per_step=4, pool=72, motion="dense", accum="f32"),
+    "1080p_dense_256": dict(H=1080, W=1920, N=256, voxel_size=4.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=136, motion="dense", accum="f32"),
     # sparse motion (moving blobs, ~1 % of the pixels): frames/s matters, many pairs per step
     "1080p_sparse_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=72, motion="sparse", accum="f32"),
+    # scattered motion: 10 % of the pixels, iid positions, change between consecutive frames -- consecutive queue entries are NOT image
+    # neighbours, so run merging gets little; and a moving textured object at a realistic density (~3.6 % of the pixels, one compact region)
+    "1080p_scatter10_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=72, motion="scatter10", accum="f32"),
+    "1080p_object_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=72, motion="object", accum="f32"),
     # BASELINE config[2] shape: 3840x2160 frames into a 512^3 grid (frame-sharded over N GPUs with --gpus N)
     "4k_dense_512": dict(H=2160, W=3840, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=2, pool=20, motion="dense", accum="f32"),
     # BASELINE config[3] shape on ONE GPU: the whole 1024^3 grid (4 GiB; slab sharding itself is covered by tests/test_gpu_configs.py)
@@ -50,14 +54,6 @@ WORKLOADS = {
     # small smoke-sized case for CPU-side checks of this script
     "tiny": dict(H=120, W=160, N=64, voxel_size=16.0, center=(0.0, 0.0, 500.0), pairs_per_step=2, pool=8, motion="dense", accum="f32"),
 }
-def measured_traffic(workload):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]["bytes_per_launch"]
-    except Exception:
-        return None
-
-
 ALGO_BYTES_PER_STEP = {"f32": 8, "fixed": 16}   # one atomic RMW: 4 B read + 4 B write (fp32), 8 + 8 (int64) -- SURVEY 8d
 
 
@@ -68,6 +64,10 @@ def make_inputs(wl, seed, pose_seed=1001):
     F = wl["pool"]
     if wl["motion"] == "dense":
         frames = synth.dense_frames(F, wl["H"], wl["W"], seed=seed)
+    elif wl["motion"] == "scatter10":
+        frames = synth.scatter_frames(F, wl["H"], wl["W"], seed=seed, fraction=0.10)
+    elif wl["motion"] == "object":
+        frames = synth.object_frames(F, wl["H"], wl["W"], seed=seed)
     else:
         frames = synth.sparse_frames(F, wl["H"], wl["W"], seed=seed, blobs=6)
     poses = synth.orbit_poses(F, wl["N"], wl["voxel_size"], wl["center"], seed=pose_seed)
@@ -122,41 +122,22 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+            return {"sm_mhz": None, "sm_mhz_min": None, "sm_max_mhz": self.max_mhz, "samples": 0, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_mhz_min": float(np.min(self.samples)), "sm_max_mhz": self.max_mhz, "samples": len(self.samples),
+                "reasons": sorted(self.reasons)}
 
 
-def issue_roofline(workload, units_per_s, clocks, dev):
-    """The bound the lock-step kernels actually sit on: warp-instruction issue.  Instructions per voxel step come from the
-    committed ncu capture (profiles/traffic.json), the rate from this run's CUDA-event timing, the peak from the SM count x 4
-    schedulers x the SM clock sampled during this run.  Extra information next to `roofline`; never breaks the bench line."""
-    try:
-        import torch
-        e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
-        if not e or "warp_inst_per_launch" not in e:
-            return None   # no ncu capture committed for this workload
-        per_unit = e["warp_inst_per_launch"] / e["voxel_steps_per_launch"]
-        c = clocks.summary()
-        mhz = c["sm_mhz"] or c["sm_max_mhz"]
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        peak = sms * 4 * float(mhz) * 1e6
-        achieved = per_unit * units_per_s
-        return {"bound": "issue", "unit": "warp instructions/s", "achieved": achieved, "peak": peak, "frac": achieved / peak,
-                "warp_inst_per_voxel_step": per_unit, "source": "profiles/traffic.json (ncu smsp__inst_executed.sum) x live rate; peak = SMs x 4 x sampled SM clock"}
-    except Exception as ex:
-        return {"error": repr(ex)}
-
-
-def cpu_reference(wl, frames, poses, pairs, rows=None):
+def cpu_reference(wl, frames, poses, pairs, rows=None, want_grid=False):
     """Time the reference CPU implementation (oracle/_ref = the unmodified ray_voxel.cpp compiled; else the C port) on
     the given pairs, optionally restricted to a band of rows (pixels outside the band are made motion-free).
-    Returns (voxel_steps, seconds, kind).  The reference is serial: 1 thread."""
+    Returns (voxel_steps, seconds, kind) -- with want_grid also the grid it accumulated and its ray count (for `parity`).
+    The reference is serial: 1 thread."""
     import oracle
     use_ref = oracle.have_ref()
     lib = oracle.RefLib() if use_ref else oracle.Oracle()
     N = wl["N"]
     grid = np.zeros((N, N, N), np.float32)
-    steps, secs = 0, 0.0
+    steps, secs, rays = 0, 0.0, 0
     for (p, c) in pairs:
         prev, curr = frames[p].astype(np.float32), frames[c].astype(np.float32)
         if rows is not None:
@@ -167,12 +148,14 @@ def cpu_reference(wl, frames, poses, pairs, rows=None):
         f = lib.focal_length(poses[c].fov_degrees, wl["W"])
         t0 = time.perf_counter()
         if use_ref:
-            _, ns = lib.accumulate_pair(prev, curr, np.array(poses[c].camera_position, np.float32), R, f, grid, N, wl["voxel_size"], wl["center"], 2.0)
+            nr, ns = lib.accumulate_pair(prev, curr, np.array(poses[c].camera_position, np.float32), R, f, grid, N, wl["voxel_size"], wl["center"], 2.0)
         else:
-            _, ns, _ = lib.accumulate_pair(prev, curr, np.array(poses[c].camera_position, np.float32), R, f, grid, N, wl["voxel_size"], np.array(wl["center"], np.float32), 2.0)
+            nr, ns, _ = lib.accumulate_pair(prev, curr, np.array(poses[c].camera_position, np.float32), R, f, grid, N, wl["voxel_size"], np.array(wl["center"], np.float32), 2.0)
         secs += time.perf_counter() - t0
         steps += ns
-    return steps, secs, ("reference" if use_ref else "port")
+        rays += nr
+    kind = "reference" if use_ref else "port"
+    return (steps, secs, kind, grid, rays) if want_grid else (steps, secs, kind)
 
 
 def run_reference(args, wl):
@@ -288,24 +271,119 @@ def run_reference_image(args, wl):
     }))
 
 
-def run_ours_image(args, wl):
-    import torch
-    import torch.distributed as dist
+def workload_config(args, wl):
+    return {"workload": args.workload, "k2_variant": getattr(args, "variant", 0), "frame": f"{wl['W']}x{wl['H']} uint8", "grid": f"{wl['N']}^3 {wl['accum']}", "voxel_size": wl["voxel_size"],
+            "pairs_per_step": wl["pairs_per_step"], "motion": wl["motion"], "camera": "pose changes every frame (orbit inside the grid); N>1: same pose table, different frames on every rank",
+            "parallelism": (f"grid sharded into {args.gpus if args.gpus > 1 else wl['slabs']} x-slabs; " + (f"{args.gpus} ranks, rank r owns slab r" if args.gpus > 1 else f"1 GPU running rank {wl['slabs'] // 2}'s slab") + f"; {getattr(args, 'reduce_how', '')}") if wl.get("slabs") else
+                           f"frames sharded over {args.gpus} GPU(s), private grids, one grid merge per run inside the timed region: {getattr(args, 'reduce_how', 'NCCL reduce')}" if args.gpus > 1 else "1 GPU",
+            "l2": "256 MiB buffer written between timed steps (L2 flush); frame pool 149 MB and grid > L2" if wl["N"] >= 512 else
+                  "256 MiB buffer written between timed steps (L2 flush)"}
 
-    import pixeltovoxelprojector_b200 as pvp
+
+
+# ---- our arm ---------------------------------------------------------------------------------------------------------
+class Env:
+    """One process per GPU (torchrun exports RANK / LOCAL_RANK / WORLD_SIZE); the process group, the library context and the
+    L2-flush buffer are made once and shared by the primary measurement and the `also` runs."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        import pixeltovoxelprojector_b200 as pvp
+        self.torch, self.dist, self.pvp = torch, dist, pvp
+        self.rank, self.world, self.local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.ctx = pvp.default_context(self.dev)
+        if args.variant:
+            self.ctx.set_option("dda_variant", args.variant)
+        for kv in args.opt or []:
+            k, v = kv.split("=")
+            self.ctx.set_option(k, int(v))
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.peak_gbs, self.peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def reduce(self, values, op="max"):
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def sass_fresh(workload):
+    """Does the kernel the committed ncu figures (profiles/traffic.json) were captured from still have the same SASS in the library
+    that is loaded?  None when it cannot be told (no cuobjdump, no entry)."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sass_md5
+        return sass_md5.check().get(workload)
+    except Exception:
+        return None
+
+
+def rooflines(env, workload, kernel, units_per_launch, launch_ms, algo_bytes, clocks, share):
+    """`roofline` of the dominant kernel.  PRIMARY bound = the one the lock-step kernels sit on: warp-instruction issue (ncu: ~80 % of the
+    issue slots busy, DRAM at 1-2 % of its peak).  achieved = warp instructions per voxel step (committed ncu capture of this very SASS,
+    see sass_md5_ok) x the live rate; peak = SMs x 4 schedulers x the SM clock sampled in this run.  `algorithmic_model` keeps SURVEY 8(d)'s
+    figure -- the read-modify-write bytes the reference's loop implies (8 B per voxel step, 16 B for 64-bit cells) against the measured HBM
+    copy peak -- and says how much of that traffic exists at all (`traffic_ratio` = measured DRAM bytes / algorithmic bytes): warp
+    aggregation issues ~0.18 REDs per voxel step and the L2 absorbs nearly all of those, so frac > 1 there is un-issued, not hidden, traffic."""
+    rate = units_per_launch / (launch_ms * 1e-3) if launch_ms > 0 else 0.0
+    e = {}
+    try:
+        e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload) or {}
+    except Exception:
+        pass
+    algo_bytes_launch = algo_bytes * units_per_launch
+    traffic = None
+    if "bytes_per_launch" in e and e.get("voxel_steps_per_launch"):
+        traffic = e["bytes_per_launch"] / e["voxel_steps_per_launch"] * units_per_launch    # the capture's DRAM bytes per unit x this run's units per launch
+    model = {"bound": "hbm", "achieved": algo_bytes * rate / 1e9, "peak": env.peak_gbs, "unit": "GB/s", "frac": algo_bytes * rate / 1e9 / env.peak_gbs,
+             "peak_source": env.peak_src, "algorithmic_bytes_per_voxel_step": algo_bytes, "algorithmic_bytes_per_launch": algo_bytes_launch,
+             "traffic": traffic, "traffic_ratio": (traffic / algo_bytes_launch) if (traffic and algo_bytes_launch) else None,
+             "note": "nominal: the RMW bytes of the reference's loop against the HBM copy peak; traffic_ratio says how little of it reaches DRAM"}
+    c = clocks.summary()
+    mhz = c["sm_mhz"] or c["sm_max_mhz"] or 0
+    peak_issue = env.sms * 4 * float(mhz) * 1e6
+    out = {"kernel": kernel, "voxel_steps_per_launch": units_per_launch, "avg_launch_ms": launch_ms, "share_of_step": share, "traffic": traffic,
+           "algorithmic_model": model}
+    if e.get("warp_inst_per_launch") and e.get("voxel_steps_per_launch") and peak_issue > 0:
+        per_unit = e["warp_inst_per_launch"] / e["voxel_steps_per_launch"]
+        out = {"bound": "issue", "achieved": per_unit * rate, "peak": peak_issue, "unit": "warp-instructions/s", "frac": per_unit * rate / peak_issue,
+               "warp_inst_per_voxel_step": per_unit, "sass_md5_ok": sass_fresh(workload),
+               "peak_source": f"{env.sms} SMs x 4 schedulers x {mhz:.0f} MHz (SM clock sampled during the timed region)",
+               "source": f"{e.get('source', 'profiles/traffic.json')}: smsp__inst_executed.sum per voxel step x live rate", **out}
+    else:   # no ncu capture committed for this workload: only the nominal model can be stated
+        out = {"bound": "hbm", "achieved": model["achieved"], "peak": model["peak"], "unit": "GB/s", "frac": model["frac"], **out}
+    return out
+
+
+def measure_image(env, args, name, steps, warmup, full):
+    """Path B (process_image_cpp): one image per step."""
+    torch, dist, pvp, ctx, dev, world, rank = env.torch, env.dist, env.pvp, env.ctx, env.dev, env.world, env.rank
     from pixeltovoxelprojector_b200 import process_image as pi
-
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    ctx = pvp.default_context(dev)
-    for kv in args.opt or []:
-        k, v = kv.split("=")
-        ctx.set_option(k, int(v))
+    wl = WORKLOADS[name]
     images_np, geom = image_scene(wl, seed=2000 + rank)
     n, H, W = wl["N"], wl["H"], wl["W"]
     cell = torch.int64 if wl["accum"] == "fixed" else torch.float64
@@ -325,7 +403,7 @@ def run_ours_image(args, wl):
     if symm is None:
         grid = torch.zeros((n, n, n), dtype=cell, device=dev)
     tex = torch.zeros((8, 8), dtype=cell, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = env.flush
     kw = dict(accum_mode=wl["accum"], frac_bits=wl["frac_bits"], ctx=ctx)
 
     def call(img, want_stats):
@@ -333,24 +411,18 @@ def run_ours_image(args, wl):
                               geom["num_steps"], tex, *geom["sky"], False, False, want_stats=want_stats, **kw)
         return pi.last_stats if want_stats else None
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for s in range(args.warmup):
+    for s in range(warmup):
         call(images_dev[s % wl["pool"]], False)
     samples_per_image = [call(images_dev[i], True)["n_samples"] for i in range(wl["pool"])]
     grid.zero_()
     ctx.get_profile(reset=True)
     ctx.profile(True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
-    sampler = ClockSampler(local)   # NVML start-up (100s of ms, different on every rank) before the barrier, not between it and the timed steps
-    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps + 1)]
+    sampler = ClockSampler(env.local)   # NVML start-up (100s of ms, different on every rank) before the barrier, not between it and the timed steps
+    env.barrier()
     my_samples = 0
     with sampler as clocks:
-        for s in range(args.steps):
+        for s in range(steps):
             flush.fill_(s & 0xFF)
             ev[s][0].record()
             call(images_dev[s % wl["pool"]], False)
@@ -369,15 +441,15 @@ def run_ours_image(args, wl):
             else:
                 dist.reduce(grid, dst=0)
         ev[-1][1].record()
-        barrier()
+        env.barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     prof = ctx.get_profile(reset=True)
     ctx.profile(False)
     # e2e: the image of every step comes from pinned HOST memory (H2D inside), the step's counters go back (D2H)
     grid.zero_()
-    e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     e_samples = 0
-    barrier()
+    env.barrier()
     # double-buffered staging, as a host loop over image files would do it: the H2D copy of image s+1 is enqueued on a copy
     # stream at the start of step s and overlaps step s's kernel; every copy starts inside a timed interval
     stages = [stage, torch.empty_like(stage)]
@@ -394,94 +466,71 @@ def run_ours_image(args, wl):
             ready[b].record(copy_stream)
     for b in range(2):
         freed[b].record(main)
-    for s in range(args.steps):
+    for s in range(steps):
         flush.fill_(s & 0xFF)
         e_ev[s][0].record()
         if s == 0:
             prefetch(0)
-        if s + 1 < args.steps:
+        if s + 1 < steps:
             prefetch(s + 1)
         main.wait_event(ready[s % 2])
         e_samples += call(stages[s % 2], True)["n_samples"]
         freed[s % 2].record(main)
         e_ev[s][1].record()
-    barrier()
-    t = torch.tensor([ms, sum(a.elapsed_time(b) for a, b in e_ev)], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(my_samples), float(e_samples)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    env.barrier()
+    t = env.reduce([ms, sum(a.elapsed_time(b) for a, b in e_ev)], "max")
+    tot = env.reduce([my_samples, e_samples], "sum")
+    del grid, images_dev, stages, stage
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-    k3_s = prof["ms_k3"] * 1e-3
-    achieved = 16 * my_samples / k3_s / 1e9 if k3_s > 0 else 0.0     # one 8-byte atomic RMW per sample
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": measured_traffic(args.workload), "kernel": "process_image_lockstep2_kernel (K3)", "peak_source": peak_src, "algorithmic_bytes_per_voxel_step": 16,
-                "voxel_steps_per_launch": my_samples / max(1, prof["launches_k3"]), "avg_launch_ms": prof["ms_k3"] / max(1, prof["launches_k3"]),
-                "k3_share_of_step": prof["ms_k3"] / ms if ms > 0 else None}
-    if args.no_cpu:
+        return None
+    launches = max(1, int(prof["launches_k3"]))
+    roofline = rooflines(env, name, "process_image_lockstep2_kernel (K3)", my_samples / launches, prof["ms_k3"] / launches, 16, clocks,
+                         prof["ms_k3"] / ms if ms > 0 else None)
+    if not full or args.no_cpu:
         cpu = {"value": 0.0, "unit": "voxel-steps/s", "cores": 0, "kind": "skipped", "sample": ""}
     else:
-        import io, contextlib
+        import contextlib
+        import io
         buf = io.StringIO()
-        a2 = argparse.Namespace(**{**vars(args), "steps": 3, "warmup": 1})
+        a2 = argparse.Namespace(**{**vars(args), "steps": 3, "warmup": 1, "workload": name})
         with contextlib.redirect_stdout(buf):
             run_reference_image(a2, wl)
         cpu = json.loads(buf.getvalue().strip().splitlines()[-1])["cpu_baseline"]
-    value = float(tot[0].item()) / (float(t[0].item()) * 1e-3)
-    e_value = float(tot[1].item()) / (float(t[1].item()) * 1e-3)
-    print(json.dumps({
-        "metric": "voxel_steps_per_sec", "value": value, "unit": "voxel-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": float(t[0].item()) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": image_config(args, wl), "frames_per_s": args.steps * world / (float(t[0].item()) * 1e-3),
-        "e2e": {"value": e_value, "unit": "voxel-steps/s", "h2d_bytes_per_step": H * W * 8, "d2h_bytes_per_step": 16,
-                "frames_per_s": args.steps * world / (float(t[1].item()) * 1e-3),
+    a2 = argparse.Namespace(**{**vars(args), "workload": name})
+    return {
+        "metric": "voxel_steps_per_sec", "value": tot[0] / (t[0] * 1e-3), "unit": "voxel-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": t[0] / steps, "timed_region_s": t[0] * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": image_config(a2, wl), "frames_per_s": steps * world / (t[0] * 1e-3),
+        "e2e": {"value": tot[1] / (t[1] * 1e-3), "unit": "voxel-steps/s", "h2d_bytes_per_step": H * W * 8, "d2h_bytes_per_step": 16,
+                "frames_per_s": steps * world / (t[1] * 1e-3),
                 "api": "pixeltovoxelprojector_b200.process_image_cpp(CUDA tensors; image staged from pinned host memory, double buffered) -> pvp_process_image"},
-        "gpu_launches": int(prof["launches_k3"]), "roofline": roofline,
-        "issue_roofline": issue_roofline(args.workload, my_samples / k3_s if k3_s > 0 else 0.0, clocks, dev),
-        "cpu_baseline": cpu, "clocks": clocks.summary(),
-    }))
-    if world > 1:
-        dist.destroy_process_group()
+        "gpu_launches": int(prof["launches_k3"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+    }
 
 
-def workload_config(args, wl):
-    return {"workload": args.workload, "k2_variant": getattr(args, "variant", 0), "frame": f"{wl['W']}x{wl['H']} uint8", "grid": f"{wl['N']}^3 {wl['accum']}", "voxel_size": wl["voxel_size"],
-            "pairs_per_step": wl["pairs_per_step"], "motion": wl["motion"], "camera": "pose changes every frame (orbit inside the grid); N>1: same pose table, different frames on every rank",
-            "parallelism": (f"grid sharded into {args.gpus if args.gpus > 1 else wl['slabs']} x-slabs; " + (f"{args.gpus} ranks, rank r owns slab r" if args.gpus > 1 else f"1 GPU running rank {wl['slabs'] // 2}'s slab") + f"; {getattr(args, 'reduce_how', '')}") if wl.get("slabs") else
-                           f"frames sharded over {args.gpus} GPU(s), private grids, one grid merge per run inside the timed region: {getattr(args, 'reduce_how', 'NCCL reduce')}" if args.gpus > 1 else "1 GPU",
-            "l2": "256 MiB buffer written between timed steps (L2 flush); frame pool 149 MB and grid > L2" if wl["N"] >= 512 else
-                  "256 MiB buffer written between timed steps (L2 flush)"}
+def parity_of_pair(env, wl, frames_dev, poses, pair, ref_grid, ref_rays, ref_steps):
+    """The pair the cpu_baseline leg has just run through the reference: the same pair on the GPU (float32 atomics and fixed point),
+    compared cell by cell (oracle.parity_report; this is the checker at work inside the cpu_baseline leg, not a product path)."""
+    import oracle
+    pvp, ctx = env.pvp, env.ctx
+    tab, _ = pvp.make_pairs(poses, wl["W"], pairs=[pair])
+    g32 = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], device=env.dev)
+    st = pvp.accumulate_motion(frames_dev, tab, g32, 2.0, ctx=ctx)
+    gfx = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], accum="fixed", frac_bits=8, device=env.dev)
+    stx = pvp.accumulate_motion(frames_dev, tab, gfx, 2.0, ctx=ctx)
+    rep = oracle.parity_report(g32.data.cpu().numpy(), ref_grid, gfx.data.cpu().numpy() >> 8)
+    rep["counters_equal"] = bool((st["n_rays"], st["n_steps"]) == (ref_rays, ref_steps) == (stx["n_rays"], stx["n_steps"]))
+    rep["against"] = "unmodified ray_voxel.cpp (oracle/_ref), one frame pair of the workload, serial fp32 sum; exact = the GPU's int64 fixed-point grid"
+    rep["fixed_point_equals_reference_below_2p24"] = rep.pop("reference_equals_exact_below_2p24")
+    return rep
 
 
-def run_ours(args, wl):
-    import torch
-    import torch.distributed as dist
-
-    import pixeltovoxelprojector_b200 as pvp
-
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    ctx = pvp.default_context(dev)
-    if args.variant:
-        ctx.set_option("dda_variant", args.variant)
-    for kv in args.opt or []:
-        k, v = kv.split("=")
-        ctx.set_option(k, int(v))
-
+def measure_motion(env, args, name, steps, warmup, full):
+    """Path A (K1 diff/threshold/compact + K2 DDA/accumulate): `pairs_per_step` frame pairs per step."""
+    torch, dist, pvp, ctx, dev, world, rank = env.torch, env.dist, env.pvp, env.ctx, env.dev, env.world, env.rank
+    wl = WORKLOADS[name]
+    a2 = argparse.Namespace(**{**vars(args), "workload": name})
     slabs = wl.get("slabs")
     frames_np, poses = make_inputs(wl, seed=1000 + (0 if slabs else rank))   # weak scaling: every rank has its own frames, same shape (slab mode: the same frames)
     frames_dev = torch.as_tensor(frames_np, device=dev)
@@ -505,8 +554,8 @@ def run_ours(args, wl):
             reduce_how = "NCCL reduce"
     if grid is None:
         grid = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev)
-    args.reduce_how = reduce_how
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    a2.reduce_how = reduce_how
+    flush = env.flush
     B, H, W = wl["pairs_per_step"], wl["H"], wl["W"]
     pair_tabs = {}
 
@@ -528,14 +577,8 @@ def run_ours(args, wl):
         start, tab = pairs_for(step, rebase=True)
         return pvp.accumulate_motion(frames_pin[start:start + B + 1], tab, grid, 2.0, ctx=ctx, n_pairs=B, want_stats=True)
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     # ---- warm-up -------------------------------------------------------------------------------------------------
-    for s in range(args.warmup):
+    for s in range(warmup):
         step_device(s)
         step_e2e(s)
     pvp.accumulate_motion(frames_dev, pairs_for(0)[1], grid, 2.0, ctx=ctx, n_pairs=0, want_stats=True)  # drain counters
@@ -543,15 +586,15 @@ def run_ours(args, wl):
     ctx.get_profile(reset=True)
 
     # ---- timed region 1: inputs resident in HBM (`value`) ------------------------------------------------------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps + 1)]
     ctx.profile(True)
-    sampler = ClockSampler(local)   # NVML start-up (100s of ms, different on every rank) before the barrier: otherwise the skew between
-    barrier()                       # the ranks lands in the wait of the grid merge (measured once at 8 GPUs: 434 ms instead of 1.3 ms)
+    sampler = ClockSampler(env.local)   # NVML start-up (100s of ms, different on every rank) before the barrier: otherwise the skew between
+    env.barrier()                       # the ranks lands in the wait of the grid merge (measured once at 8 GPUs: 434 ms instead of 1.3 ms)
     with sampler as clocks:
-        for s in range(args.steps):
+        for s in range(steps):
             flush.fill_(s & 0xFF)            # L2 flush, outside the timed events
             ev[s][0].record()
-            step_device(args.warmup + s)
+            step_device(warmup + s)
             ev[s][1].record()
         ev[-1][0].record()
         if world > 1 and not slabs:          # the run's single grid merge over NVLink (SURVEY 8e mode 1)
@@ -560,128 +603,155 @@ def run_ours(args, wl):
             else:
                 dist.reduce(grid.data, dst=0)
         ev[-1][1].record()
-        barrier()
+        env.barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     reduce_ms = ev[-1][0].elapsed_time(ev[-1][1])
     prof = ctx.get_profile(reset=True)
     ctx.profile(False)
     stats = pvp.accumulate_motion(frames_dev, pairs_for(0)[1], grid, 2.0, ctx=ctx, n_pairs=0, want_stats=True)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
     # slab mode over several ranks: the job's voxel steps are the ranks' WRITES (each step lands in exactly one slab); a rank's n_steps is what it walked
-    tot = torch.tensor([stats["n_written"] if (slabs and world > 1) else stats["n_steps"], stats["n_rays"], stats["n_atomics"]], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_max, all_steps, all_rays = float(t.item()), float(tot[0].item()), float(tot[1].item())
+    ms_max, = env.reduce([ms], "max")
+    all_steps, all_rays, all_atomics = env.reduce([stats["n_written"] if (slabs and world > 1) else stats["n_steps"], stats["n_rays"], stats["n_atomics"]], "sum")
     if slabs and world > 1:   # every rank saw the same rays
         all_rays = all_rays / world
 
     # ---- timed region 2: end to end through the public API with HOST (pinned) frames ------------------------------
     grid.zero_()
-    e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     e_steps = 0
-    barrier()
-    for s in range(args.steps):
+    env.barrier()
+    for s in range(steps):
         flush.fill_(s & 0xFF)
         e_ev[s][0].record()
-        e_steps += step_e2e(args.warmup + s)["n_written" if (slabs and world > 1) else "n_steps"]      # H2D of B+1 frames inside; D2H of the step's counters
+        e_steps += step_e2e(warmup + s)["n_written" if (slabs and world > 1) else "n_steps"]      # H2D of B+1 frames inside; D2H of the step's counters
         e_ev[s][1].record()
-    barrier()
-    e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e_ev)], dtype=torch.float64, device=dev)
-    e_tot = torch.tensor([float(e_steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e_tot, op=dist.ReduceOp.SUM)
-
+    env.barrier()
+    e_ms, = env.reduce([sum(a.elapsed_time(b) for a, b in e_ev)], "max")
+    e_tot, = env.reduce([e_steps], "sum")
+    del grid
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---- roofline of the dominant kernel (K2), live CUDA-event timing ---------------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     k2_s = prof["ms_k2"] * 1e-3
     per_rank_steps = stats["n_steps"]
-    achieved = ALGO_BYTES_PER_STEP[wl["accum"]] * per_rank_steps / k2_s / 1e9 if k2_s > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": measured_traffic(args.workload), "kernel": "dda_accumulate_lean2_kernel (K2)", "peak_source": peak_src,
-                "algorithmic_bytes_per_voxel_step": ALGO_BYTES_PER_STEP[wl["accum"]],
-                # one batch per step; in the default auto mode a batch launches both lock-step kernels and the one the ray count
-                # does not pick exits in ~2.5 us, so "launch" here means the batch's working K2 launch
-                "voxel_steps_per_launch": per_rank_steps / max(1, args.steps), "avg_launch_ms": prof["ms_k2"] / max(1, args.steps),
-                "k2_kernels_launched": int(prof["launches_k2"]),
-                "k2_share_of_step": prof["ms_k2"] / ms if ms > 0 else None, "k1_ms_total": prof["ms_k1"]}
+    # a batch (at most max_queue / pixels = 32 1080p pairs) is one K1 + one K2 launch; in the default auto mode a batch launches both
+    # lock-step kernels and the one the ray count does not pick exits in ~2.5 us, so "launch" here means the batch's working K2 launch
+    n_batches = max(1, int(prof["launches_k1"]))
+    roofline = rooflines(env, name, "dda_accumulate_lean2_kernel (K2)", per_rank_steps / n_batches, prof["ms_k2"] / n_batches, ALGO_BYTES_PER_STEP[wl["accum"]],
+                         clocks, prof["ms_k2"] / ms if ms > 0 else None)
+    roofline["k2_kernels_launched"] = int(prof["launches_k2"])
+    roofline["k1_ms_total"] = prof["ms_k1"]
+    line = {
+        "metric": "voxel_steps_per_sec", "value": all_steps / (ms_max * 1e-3), "unit": "voxel-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_max / steps, "timed_region_s": ms_max * 1e-3, "higher_is_better": True, "scaling": "strong" if slabs else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a2, wl),
+    }
+    frames_total = steps * B * (1 if slabs else world)
+    line.update({
+        "frames_per_s": frames_total / (ms_max * 1e-3), "rays_per_s": all_rays / (ms_max * 1e-3), "voxel_steps_per_ray": all_steps / max(1.0, all_rays),
+        "e2e": {"value": e_tot / (e_ms * 1e-3), "unit": "voxel-steps/s", "h2d_bytes_per_step": (B + 1) * H * W, "d2h_bytes_per_step": 32,
+                "frames_per_s": frames_total / (e_ms * 1e-3), "api": "pixeltovoxelprojector_b200.accumulate_motion(pinned host frames) -> pvp_motion_accumulate_host"},
+        "gpu_launches": int(prof["launches_k1"] + prof["launches_k2"]), "roofline": roofline,
+        "atomics_per_voxel_step": all_atomics / max(1.0, all_steps), "grid_merge_ms": reduce_ms if (world > 1 and not slabs) else None,
+        "clocks": clocks.summary(),
+    })
+    if not full:
+        return line
     # L2-atomic roofline: measured peak of independent red.global.add on this GPU, same run
     l2 = None
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import atomic_roofline
         elem = 4 if wl["accum"] == "f32" else 8
-        buf = torch.zeros(grid.data.numel() * grid.data.element_size() // 8, dtype=torch.int64, device=dev)  # same footprint as the grid
-        nbytes = buf.numel() * 8
-        peak_ops = {name: atomic_roofline.measure(ctx, buf, nbytes, elem, pat, 1 << 30) for pat, name in ((0, "random_per_lane"), (3, "random_line_per_warp"))}
+        nbytes = wl["N"] ** 3 * elem                                                    # same footprint as the grid
+        buf = torch.zeros(nbytes // 8, dtype=torch.int64, device=dev)
+        peak_ops = {nm: atomic_roofline.measure(ctx, buf, nbytes, elem, pat, 1 << 30) for pat, nm in ((0, "random_per_lane"), (3, "random_line_per_warp"))}
         k2_rate = per_rank_steps / k2_s if k2_s > 0 else 0.0
         l2 = {"unit": "atomic adds/s", "buffer_bytes": nbytes, "peak_random_per_lane": peak_ops["random_per_lane"],
               "peak_coalesced_line_per_warp": peak_ops["random_line_per_warp"], "achieved_voxel_steps_per_s_in_k2": k2_rate,
               "frac_of_random_peak": k2_rate / peak_ops["random_per_lane"]}
+        del buf
     except Exception as e:  # the micro-benchmark must never break the bench line
         l2 = {"error": repr(e)}
+    line["l2_atomic_roofline"] = l2
 
-    # ---- CPU baseline on this box's host cores (bounded sample: one frame pair of the same workload) -------------
-    _, p0 = step_pairs(args.warmup, wl)
+    # ---- CPU baseline on this box's host cores (bounded sample: one frame pair of the same workload) + parity of that pair ------
+    _, p0 = step_pairs(warmup, wl)
     if args.no_cpu:
-        c_steps, c_s, kind = 0, 1.0, "skipped"
+        line["cpu_baseline"] = {"value": 0.0, "unit": "voxel-steps/s", "cores": 0, "kind": "skipped", "sample": ""}
     else:
-        c_steps, c_s, kind = cpu_reference(wl, frames_np, poses, p0[:1])
-    cpu = {"value": c_steps / c_s, "unit": "voxel-steps/s", "cores": 1, "kind": kind,
-           "sample": f"one {W}x{H} frame pair of the workload ({c_steps} voxel-steps, {c_s:.1f} s); reference is single-threaded: 1 of {os.cpu_count()} host cores"}
+        c_steps, c_s, kind, c_grid, c_rays = cpu_reference(wl, frames_np, poses, p0[:1], want_grid=True)
+        line["cpu_baseline"] = {"value": c_steps / c_s, "unit": "voxel-steps/s", "cores": 1, "kind": kind,
+                                "sample": f"one {W}x{H} frame pair of the workload ({c_steps} voxel-steps, {c_s:.1f} s); reference is single-threaded: 1 of {os.cpu_count()} host cores"}
+        try:
+            line["parity"] = parity_of_pair(env, wl, frames_dev, poses, p0[0], c_grid, c_rays, c_steps)
+        except Exception as e:
+            line["parity"] = {"error": repr(e)}
+    return line
 
-    value = all_steps / (ms_max * 1e-3)
-    e_value = float(e_tot.item()) / (float(e_ms.item()) * 1e-3)
-    frames_total = args.steps * B * (1 if slabs else world)
-    line = {
-        "metric": "voxel_steps_per_sec", "value": value, "unit": "voxel-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if slabs else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, wl),
-        "frames_per_s": frames_total / (ms_max * 1e-3), "rays_per_s": all_rays / (ms_max * 1e-3), "voxel_steps_per_ray": all_steps / max(1.0, all_rays),
-        "e2e": {"value": e_value, "unit": "voxel-steps/s", "h2d_bytes_per_step": (B + 1) * H * W, "d2h_bytes_per_step": 32,
-                "frames_per_s": frames_total / (float(e_ms.item()) * 1e-3), "api": "pixeltovoxelprojector_b200.accumulate_motion(pinned host frames) -> pvp_motion_accumulate_host"},
-        "gpu_launches": int(prof["launches_k1"] + prof["launches_k2"]),
-        "roofline": roofline, "l2_atomic_roofline": l2,
-        "issue_roofline": issue_roofline(args.workload, per_rank_steps / k2_s if k2_s > 0 else 0.0, clocks, dev),
-        "cpu_baseline": cpu, "clocks": clocks.summary(),
-        "atomics_per_voxel_step": float(tot[2].item()) / max(1.0, all_steps),
-        "grid_merge_ms": reduce_ms if world > 1 else None,
-    }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+def compact(line):
+    """An `also` entry: the figures of a secondary workload without the long descriptions."""
+    if line is None:
+        return None
+    r = line.get("roofline", {})
+    out = {k: line[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "timed_region_s", "frames_per_s", "scaling", "gpu_launches", "atomics_per_voxel_step", "grid_merge_ms") if k in line}
+    out["e2e"] = {k: line["e2e"][k] for k in ("value", "frames_per_s", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+    out["config"] = {k: line["config"][k] for k in ("workload", "grid", "parallelism") if k in line["config"]}
+    out["roofline"] = {k: r.get(k) for k in ("bound", "frac", "kernel", "share_of_step", "avg_launch_ms", "warp_inst_per_voxel_step", "sass_md5_ok")}
+    am = r.get("algorithmic_model") or {}
+    out["roofline"]["algorithmic_model"] = {k: am.get(k) for k in ("frac", "traffic_ratio", "algorithmic_bytes_per_voxel_step")}
+    out["clocks"] = line.get("clocks")
+    return out
+
+
+# secondary workloads measured by the default run (the contract is ONE line: they ride in its `also` dict), short runs
+ALSO_DEFAULT = [("image_4096_512_fixed", 5, 3), ("1080p_dense_256", 3, 3), ("1080p_scatter10_512", 3, 3), ("1080p_object_512", 3, 3)]
+ALSO_8GPU = [("1080p_dense_1024_slab8", 10, 3), ("1080p_dense_1024", 10, 3)]
+
+
+def run_ours(args):
+    env = Env(args)
+    wl = WORKLOADS[args.workload]
+    measure = measure_image if wl.get("path") == "B" else measure_motion
+    line = measure(env, args, args.workload, args.steps, args.warmup, full=True)
+    if args.workload == "1080p_dense_512" and not args.no_also:
+        also = {}
+        for name, st, wu in ALSO_DEFAULT + (ALSO_8GPU if env.world == 8 else []):
+            if name not in WORKLOADS:
+                continue
+            m = measure_image if WORKLOADS[name].get("path") == "B" else measure_motion
+            try:
+                also[name] = compact(m(env, args, name, st, wu, full=False))
+            except Exception as e:   # a secondary workload must never cost the primary line (collective calls inside are symmetric over ranks)
+                also[name] = {"error": repr(e)}
+        if line is not None:
+            line["also"] = also
+    if line is not None:
+        print(json.dumps(line))
+    env.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p_dense_512", choices=sorted(WORKLOADS))
     ap.add_argument("--opt", action="append", help="context option key=value (pvp_ctx_set_option), repeatable; kernel experiments")
     ap.add_argument("--variant", type=int, default=0, help="K2 variant (0 = library default; see pvp_motion.cu launch_k2)")
     ap.add_argument("--reduce", default="peers", choices=["peers", "nccl"], help="N>1: grid merge by our peer-memory kernel (default) or by NCCL")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments only)")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads of the default run")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if wl.get("path") == "B":
-        (run_reference_image if args.impl == "reference" else run_ours_image)(args, wl)
-    elif args.impl == "reference":
-        run_reference(args, wl)
+    if args.impl == "reference":
+        (run_reference_image if wl.get("path") == "B" else run_reference)(args, wl)
     else:
-        run_ours(args, wl)
+        run_ours(args)
 
 
 if __name__ == "__main__":

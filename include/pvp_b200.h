@@ -158,12 +158,13 @@ int pvp_cast_rays(pvp_ctx *ctx, const float *origins_dev, const float *dirs_dev,
 /* ---- path A, fused: diff/threshold -> ray queue -> DDA -> accumulate ------- */
 /*
  * replaces the body of main's frame loop, ray_voxel.cpp:484-531, for a batch of frame pairs.
- * frames_dev: [n_frames][height][width] (frame_stride elements between frames), device memory.
+ * frames_dev: [n_frames][height][width] (frame_stride elements between frames), device memory; every pair's prev / curr must
+ *             lie in [0, n_frames) (PVP_ERR_INVALID otherwise: K1 would read past the frames).
  * grid_dev:   float32 or int64 [slab_hi-slab_lo][n][n], accumulated in place (never zeroed here).
  * stats:      NULL => fully asynchronous; else counters are ADDED into *stats after a stream sync.
  */
 int pvp_motion_accumulate(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, int64_t frame_stride, int width,
-                          int height, const pvp_pair *pairs, int n_pairs, float threshold, void *grid_dev,
+                          int height, int n_frames, const pvp_pair *pairs, int n_pairs, float threshold, void *grid_dev,
                           const pvp_grid_desc *grid, pvp_stats *stats);
 /*
  * Same, frames in HOST memory (pinned for full copy bandwidth): frames are staged to the

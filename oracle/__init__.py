@@ -259,3 +259,36 @@ def ref_process_image_module():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def parity_report(got: np.ndarray, ref: np.ndarray, exact: np.ndarray | None = None) -> dict:
+    """Distance between an accumulated float32 grid (``got``: the CUDA path) and the reference's own grid (``ref``: the serial fp32
+    sum of ray_voxel.cpp:523-529 from RefLib / the C port) for integer-valued addends (uint8 frames).  Below 2^24 every partial sum of
+    the reference is an exact integer, so the two must agree bit for bit; from 2^24 on both sides round at every addition (the
+    reference at each of its serial adds, the GPU at each RED of a warp-aggregated run sum) and only a relative distance is defined.
+    ``exact``: the same grid as exact integers (fixed-point accumulation) -- then both float grids are also measured against it."""
+    got, ref = np.ascontiguousarray(got, np.float32).reshape(-1), np.ascontiguousarray(ref, np.float32).reshape(-1)
+    assert got.shape == ref.shape
+    big = ref >= np.float32(2 ** 24)
+    if exact is not None:
+        ex = np.asarray(exact).reshape(-1).astype(np.float64)
+        big = ex >= 2.0 ** 24
+    small = ~big
+    rep = {
+        "cells": int(got.size), "cells_nonzero": int(np.count_nonzero(ref)),
+        "support_equal": bool(np.array_equal(got != 0, ref != 0)),
+        "cells_below_2p24": int(small.sum()), "bit_mismatches_below_2p24": int(np.count_nonzero(got[small].view(np.uint32) != ref[small].view(np.uint32))),
+        "cells_at_or_above_2p24": int(big.sum()),
+    }
+
+    def rel(a, b):
+        b = b.astype(np.float64)
+        return float(np.max(np.abs(a.astype(np.float64) - b) / b)) if b.size else 0.0
+
+    rep["max_rel_err_vs_reference_at_or_above_2p24"] = rel(got[big], ref[big])
+    rep["max_value"] = float(ref.max()) if ref.size else 0.0
+    if exact is not None:
+        rep["gpu_max_rel_err_vs_exact"] = rel(got[big], ex[big])
+        rep["reference_max_rel_err_vs_exact"] = rel(ref[big], ex[big])
+        rep["reference_equals_exact_below_2p24"] = bool(np.array_equal(ref[small].astype(np.float64), ex[small]))
+    return rep

@@ -107,7 +107,7 @@ SIGNATURES = {
     "pvp_detect_motion": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_float, _P, _P]),
     "pvp_pixel_rays": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(Pair), _P]),
     "pvp_cast_rays": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(GridDesc), _P, _P, _P, _P]),
-    "pvp_motion_accumulate": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(Pair), C.c_int, C.c_float,
+    "pvp_motion_accumulate": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(Pair), C.c_int, C.c_float,
                                         _P, C.POINTER(GridDesc), C.POINTER(Stats)]),
     "pvp_motion_accumulate_host": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(Pair), C.c_int,
                                              C.c_float, _P, C.POINTER(GridDesc), C.POINTER(Stats)]),

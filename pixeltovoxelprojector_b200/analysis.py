@@ -76,6 +76,14 @@ def grid_percentile(voxel_grid: torch.Tensor, percentile, ctx: Context | None = 
     return lerp_like_numpy(a, b, gamma)
 
 
+def _threshold_as_numpy_compares(thresh) -> float:
+    """The value `float32_array > thresh` (:77) really compares with: a Python scalar is weak and is rounded to float32 first; a numpy
+    scalar promotes by its dtype (float32 / small ints stay float32, float64 makes the comparison double)."""
+    if isinstance(thresh, np.generic) or isinstance(thresh, np.ndarray):
+        return float(thresh) if np.result_type(np.float32, np.asarray(thresh).dtype) == np.float64 else float(np.float32(thresh))
+    return float(np.float32(thresh))
+
+
 def extract_top_percentile_z_up(voxel_grid, voxel_size, grid_center, percentile=99.5, use_hard_thresh=False, hard_thresh=700,
                                 ctx: Context | None = None):
     """voxelmotionviewer.py:56-96 on the device.  Returns (points [M,3] float64, intensities [M] float32) as CUDA
@@ -89,23 +97,26 @@ def extract_top_percentile_z_up(voxel_grid, voxel_size, grid_center, percentile=
         raise ValueError("voxel_grid must be N x N x N")
     ctx = ctx or default_context(g.device)
     ctx.use_current_stream()
-    half_side = (np.int32(N) * voxel_size) * 0.5            # :68-69 with the dtypes load_voxel_grid returns
+    # :67-69 -- N is a Python int there (shape[0]), so with the np.float32 voxel_size load_voxel_grid returns the product and the
+    # half stay float32 (a weak scalar does not promote); np.int32(N) would promote to float64 and move grid_min by an ulp of float32
+    half_side = (int(N) * voxel_size) * 0.5
     grid_min = np.asarray(grid_center) - half_side
     if use_hard_thresh:
         thresh = hard_thresh
     else:
         thresh = grid_percentile(g, percentile, ctx)
+    thresh_cmp = _threshold_as_numpy_compares(thresh)
     gm = (C.c_double * 3)(*[float(x) for x in np.asarray(grid_min, np.float64)])
     count = C.c_int64()
     lib = ctx._lib
-    check(lib.pvp_grid_extract_above(ctx.handle, g.data_ptr(), N, float(thresh), float(voxel_size), gm, 0, None, None, None, C.byref(count)))
+    check(lib.pvp_grid_extract_above(ctx.handle, g.data_ptr(), N, thresh_cmp, float(voxel_size), gm, 0, None, None, None, C.byref(count)))
     m = count.value
     if m == 0:
         print(f"No voxels above threshold {thresh}. Nothing to display.")
         return None, None
     points = torch.empty((m, 3), dtype=torch.float64, device=g.device)
     intens = torch.empty((m,), dtype=torch.float32, device=g.device)
-    check(lib.pvp_grid_extract_above(ctx.handle, g.data_ptr(), N, float(thresh), float(voxel_size), gm, m, points.data_ptr(), intens.data_ptr(), None,
+    check(lib.pvp_grid_extract_above(ctx.handle, g.data_ptr(), N, thresh_cmp, float(voxel_size), gm, m, points.data_ptr(), intens.data_ptr(), None,
                                      C.byref(count)))
     return points, intens
 
@@ -117,6 +128,7 @@ def argwhere_above(voxel_grid: torch.Tensor, thresh, ctx: Context | None = None)
     ctx = ctx or default_context(g.device)
     ctx.use_current_stream()
     count = C.c_int64()
+    thresh = _threshold_as_numpy_compares(thresh)
     check(ctx._lib.pvp_grid_extract_above(ctx.handle, g.data_ptr(), N, float(thresh), 1.0, None, 0, None, None, None, C.byref(count)))
     coords = torch.empty((count.value, 3), dtype=torch.int32, device=g.device)
     if count.value:

@@ -1395,7 +1395,7 @@ int pvp_cast_rays(pvp_ctx *ctx, const float *origins_dev, const float *dirs_dev,
 }
 
 int pvp_motion_accumulate(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, int64_t frame_stride, int width, int height,
-                          const pvp_pair *pairs, int n_pairs, float threshold, void *grid_dev, const pvp_grid_desc *grid,
+                          int n_frames, const pvp_pair *pairs, int n_pairs, float threshold, void *grid_dev, const pvp_grid_desc *grid,
                           pvp_stats *stats)
 {
     int rc = check_common(ctx, frames_dev, frame_dtype, frame_stride, width, height, pairs, n_pairs, grid_dev);
@@ -1403,7 +1403,7 @@ int pvp_motion_accumulate(pvp_ctx *ctx, const void *frames_dev, int frame_dtype,
     GridP g;
     if ((rc = make_gridp(grid, &g))) return rc;
     PVP_REQUIRE(grid_dev != nullptr || g.slab_lo == g.slab_hi, "grid_dev is NULL");  // an empty slab stores nothing
-    if ((rc = validate_pairs(pairs, n_pairs, -1))) return rc;
+    if ((rc = validate_pairs(pairs, n_pairs, n_frames))) return rc;
     DeviceGuard guard(ctx->device);
     if (n_pairs > 0) {
         rc = run_batches(ctx, frames_dev, frame_dtype, frame_stride, width, height, pairs, n_pairs, threshold, grid_dev, g, grid->accum_mode);
@@ -1435,11 +1435,16 @@ int pvp_motion_accumulate_host(pvp_ctx *ctx, const void *frames_host, int frame_
     struct Chunk { int p0, np, fmin, fmax; };
     std::vector<Chunk> chunks;
     size_t max_frames = 0;
-    for (int p0 = 0; p0 < n_pairs; p0 += chunk_pairs) {
-        Chunk c{p0, std::min(chunk_pairs, n_pairs - p0), INT32_MAX, -1};
+    // chunk sizes ramp up (8, 16, 32, ... pairs): only the first, small copy is exposed; every later copy runs under the kernels of
+    // the chunk before it
+    int ramp = std::min(chunk_pairs, 8);
+    for (int p0 = 0; p0 < n_pairs;) {
+        Chunk c{p0, std::min(ramp, n_pairs - p0), INT32_MAX, -1};
+        p0 += c.np;
+        ramp = std::min(chunk_pairs, ramp * 2);
         for (int i = 0; i < c.np; ++i) {
-            c.fmin = std::min(c.fmin, std::min(pairs[p0 + i].prev, pairs[p0 + i].curr));
-            c.fmax = std::max(c.fmax, std::max(pairs[p0 + i].prev, pairs[p0 + i].curr));
+            c.fmin = std::min(c.fmin, std::min(pairs[c.p0 + i].prev, pairs[c.p0 + i].curr));
+            c.fmax = std::max(c.fmax, std::max(pairs[c.p0 + i].prev, pairs[c.p0 + i].curr));
         }
         max_frames = std::max(max_frames, (size_t)(c.fmax - c.fmin + 1));
         chunks.push_back(c);

@@ -135,11 +135,12 @@ struct JParser {
         if (end - p >= 4 && !strncmp(p, "null", 4)) { v.kind = JValue::Null; p += 4; return true; }
         {
             std::string tok;
-            while (p < end && (strchr("+-.eE", *p) || (*p >= '0' && *p <= '9'))) tok += *p++;
+            // (strchr would also match the terminating NUL of its own pattern: an embedded 0x00 byte must end the token, not join it)
+            while (p < end && *p != '\0' && (strchr("+-.eE", *p) || (*p >= '0' && *p <= '9'))) tok += *p++;
             if (tok.empty()) return fail("unexpected character");
             char *e = nullptr;
             v.num = strtod(tok.c_str(), &e);
-            if (!e || *e) return fail("bad number");
+            if (!e || e == tok.c_str() || *e) return fail("bad number");
             v.kind = JValue::Num;
             return true;
         }
@@ -196,7 +197,12 @@ static int load_metadata_impl(const char *json_path, pvp_frame_info **frames_out
             if (!v) continue;
             double x;
             if (!jnum(v, &x)) { free(out); set_error("ERROR: metadata entry %zu: '%s' is not a number", i, fd.key); return PVP_ERR_FORMAT; }
-            if (fd.ip) *fd.ip = (int)x; else *fd.fp = (float)x;
+            if (fd.ip) {  // a double outside int's range (or NaN) has no defined conversion: reject it like nlohmann's get<int> range error
+                if (!(x >= -2147483648.0 && x <= 2147483647.0)) { free(out); set_error("ERROR: metadata entry %zu: '%s' is out of the int range", i, fd.key); return PVP_ERR_FORMAT; }
+                *fd.ip = (int)x;
+            } else {
+                *fd.fp = (float)x;
+            }
         }
         if (const JValue *v = e.find("image_file")) {
             if (v->kind != JValue::Str) { free(out); set_error("ERROR: metadata entry %zu: 'image_file' is not a string", i); return PVP_ERR_FORMAT; }
@@ -376,11 +382,13 @@ struct Runner {
         for (auto &c : chunk) PVP_CUDA(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
         return PVP_OK;
     }
-    void destroy()
+    // the pinned chunk buffers and their events go with the Runner on every path out of the frame loop, error returns and
+    // exceptions (caught at the C ABI) included
+    ~Runner()
     {
         for (auto &c : chunk) {
-            if (c.done) { cudaEventSynchronize(c.done); cudaEventDestroy(c.done); }
-            if (c.buf) cudaFreeHost(c.buf);
+            if (c.done) { cudaEventSynchronize(c.done); cudaEventDestroy(c.done); c.done = nullptr; }
+            if (c.buf) { cudaFreeHost(c.buf); c.buf = nullptr; c.cap = 0; }
         }
     }
     // Submit the open chunk; keep its last frame as frame 0 of the next chunk when `carry`.
@@ -525,7 +533,7 @@ static int ray_voxel_accumulate_impl(pvp_ctx *ctx, const char *metadata_json, co
         for (long long k = a - 1; k >= 0 && !prev_valid; --k) {
             int w, h;
             if (load(cf[(size_t)k], &w, &h)) {
-                if ((rc = push_frame(w, h))) { R.destroy(); return rc; }
+                if ((rc = push_frame(w, h))) return rc;
                 prev_valid = true;
             }
         }
@@ -538,15 +546,15 @@ static int ray_voxel_accumulate_impl(pvp_ctx *ctx, const char *metadata_json, co
                 continue;
             }
             if (!prev_valid) {  // :475-481
-                if ((rc = push_frame(w, h))) { R.destroy(); return rc; }
+                if ((rc = push_frame(w, h))) return rc;
                 prev_valid = true;
                 continue;
             }
             if (w != R.W || h != R.H) {  // detect_motion's size check, :238-243: no rays, prev still advances (:534)
                 if (opt->verbose) fprintf(stderr, "Images differ in size. Can't do motion detection!\n");
                 ++mismatched;
-                if ((rc = R.flush(false))) { R.destroy(); return rc; }
-                if ((rc = push_frame(w, h))) { R.destroy(); return rc; }
+                if ((rc = R.flush(false))) return rc;
+                if ((rc = push_frame(w, h))) return rc;
                 continue;
             }
             if (R.n_frames >= R.max_frames) {
@@ -554,9 +562,9 @@ static int ray_voxel_accumulate_impl(pvp_ctx *ctx, const char *metadata_json, co
                 keep.swap(tmp);  // flush() carries the previous frame over; tmp holds the current one
                 rc = R.flush(true);
                 tmp.swap(keep);
-                if (rc) { R.destroy(); return rc; }
+                if (rc) return rc;
             }
-            if ((rc = push_frame(w, h))) { R.destroy(); return rc; }
+            if ((rc = push_frame(w, h))) return rc;
             pvp_pair p;  // pose of the CURRENT frame, :486-491
             memcpy(p.cam, ci.camera_position, sizeof(p.cam));
             pvp_rotation_matrix(ci.yaw, ci.pitch, ci.roll, p.R);
@@ -564,11 +572,10 @@ static int ray_voxel_accumulate_impl(pvp_ctx *ctx, const char *metadata_json, co
             p.prev = R.n_frames - 2; p.curr = R.n_frames - 1;
             R.pairs.push_back(p);
         }
-        if ((rc = R.flush(false))) { R.destroy(); return rc; }  // camera boundary: no pair across cameras
+        if ((rc = R.flush(false))) return rc;  // camera boundary: no pair across cameras
     }
     pvp_stats st = {0, 0, 0, 0};
-    rc = pvp_motion_accumulate(ctx, nullptr, PVP_FRAME_U8, 1, 1, 1, nullptr, 0, 0.f, grid_dev, &opt->grid, &st);  // sync + counters
-    R.destroy();
+    rc = pvp_motion_accumulate(ctx, nullptr, PVP_FRAME_U8, 1, 1, 1, 0, nullptr, 0, 0.f, grid_dev, &opt->grid, &st);  // sync + counters
     if (rc) return rc;
     if (stats) { stats->n_rays += st.n_rays; stats->n_steps += st.n_steps; stats->n_written += st.n_written; stats->n_atomics += st.n_atomics; }
     if (report) {

@@ -251,7 +251,7 @@ def accumulate_motion(frames, pairs, grid: VoxelGrid, threshold: float = 2.0, ct
     if isinstance(frames, torch.Tensor) and frames.is_cuda:
         if frames.stride(2) != 1 or frames.stride(1) != W:
             raise ValueError("each frame must be contiguous")
-        check(lib.pvp_motion_accumulate(ctx.handle, frames.data_ptr(), _frame_dtype(frames), frames.stride(0), W, H, pairs, n_pairs,
+        check(lib.pvp_motion_accumulate(ctx.handle, frames.data_ptr(), _frame_dtype(frames), frames.stride(0), W, H, F, pairs, n_pairs,
                                         C.c_float(threshold), grid.data.data_ptr(), C.byref(desc), st_ref))
     else:
         if isinstance(frames, torch.Tensor):

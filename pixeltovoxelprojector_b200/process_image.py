@@ -100,6 +100,8 @@ def process_image_cpp(image, earth_position, pointing_direction, fov, image_widt
         if image.dtype != torch.float64 or image.ndim != 2:
             raise ValueError(f"array has incorrect number of dimensions: {image.ndim}; expected 2" if image.ndim != 2
                              else "image must be a float64 CUDA tensor")
+        if image.shape[0] < int(image_height) or image.shape[1] < int(image_width):
+            raise ValueError(f"image of shape {tuple(image.shape)} is smaller than image_height x image_width = {int(image_height)} x {int(image_width)}")
         if not (isinstance(tex, torch.Tensor) and tex.is_cuda and tex.dtype == cell):
             raise TypeError(f"celestial_sphere_texture must be a CUDA {cell} tensor on the device path")
         if tex.ndim != 2:
@@ -127,6 +129,8 @@ def process_image_cpp(image, earth_position, pointing_direction, fov, image_widt
         if accum_mode != "f64":
             raise ValueError("fixed-point accumulation needs CUDA int64 tensors (device path)")
         img = _as_f64_array(image, "image", 2, mutated=False)
+        if img.shape[0] < int(image_height) or img.shape[1] < int(image_width):   # the reference reads out of bounds here (unchecked<2>)
+            raise ValueError(f"image of shape {img.shape} is smaller than image_height x image_width = {int(image_height)} x {int(image_width)}")
         tex = _as_f64_array(celestial_sphere_texture, "celestial_sphere_texture", 2)
         grid = voxel_grid if isinstance(voxel_grid, np.ndarray) else np.asarray(voxel_grid)
         have_grid = grid.size > 0  # process_image.cpp:152 -- an empty array of any ndim skips the voxel stage

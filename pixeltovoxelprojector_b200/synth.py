@@ -46,6 +46,39 @@ def sparse_frames(n_frames: int, height: int, width: int, seed: int = 0, blob: i
     return frames
 
 
+def scatter_frames(n_frames: int, height: int, width: int, seed: int = 0, fraction: float = 0.10) -> np.ndarray:
+    """Scattered motion: a static background in which, between consecutive frames, a fresh iid-random `fraction` of the pixels jumps by
+    64 grey levels (well above the threshold) -- the motion pixels of a pair are isolated, not neighbours of each other."""
+    rng = np.random.default_rng(seed)
+    frames = np.empty((n_frames, height, width), np.uint8)
+    frames[0] = rng.integers(40, 200, (height, width), dtype=np.uint8)
+    for f in range(1, n_frames):
+        hit = rng.random((height, width)) < fraction
+        frames[f] = np.where(hit, frames[f - 1] + np.uint8(64), frames[f - 1])   # uint8 wrap-around: |diff| is 64 or 192
+    return frames
+
+
+def object_frames(n_frames: int, height: int, width: int, seed: int = 0) -> np.ndarray:
+    """A moving textured object at a realistic density: a static noise background and one textured disc (radius height/7, ~3.6 % of a
+    16:9 frame) drifting a few pixels per frame; its whole area changes between frames (the texture moves with it), the rest is still."""
+    rng = np.random.default_rng(seed)
+    bg = rng.integers(20, 61, (height, width), dtype=np.uint8)
+    r = max(2, height // 7)
+    tex = rng.integers(90, 256, (2 * r + 1, 2 * r + 1), dtype=np.uint8)
+    yy, xx = np.mgrid[-r:r + 1, -r:r + 1]
+    disc = (yy * yy + xx * xx) <= r * r
+    frames = np.repeat(bg[None], n_frames, 0)
+    x0, y0 = rng.integers(r, max(r + 1, width - r)), rng.integers(r, max(r + 1, height - r))
+    vx, vy = int(rng.integers(3, 8)), int(rng.integers(2, 6))
+    for f in range(n_frames):
+        cx = r + (x0 - r + f * vx) % max(1, width - 2 * r)
+        cy = r + (y0 - r + f * vy) % max(1, height - 2 * r)
+        ys, xs = slice(cy - r, cy + r + 1), slice(cx - r, cx + r + 1)
+        h, w = frames[f, ys, xs].shape
+        frames[f, ys, xs] = np.where(disc[:h, :w], tex[:h, :w], frames[f, ys, xs])
+    return frames
+
+
 def orbit_poses(n_frames: int, n: int, voxel_size: float, center, fov_degrees: float = 60.0, seed: int = 0,
                 camera_index: int = 0, radius_frac: float = 0.35) -> list[FramePose]:
     """A camera moving INSIDE the grid (rays entering through a max face are dropped by the reference,

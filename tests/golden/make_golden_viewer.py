@@ -35,11 +35,15 @@ def main():
         "dense": (33, 1.5, rng.gamma(2.0, 50.0, (33, 33, 33)).astype(np.float32)),
         # all zeros: nothing above the threshold
         "empty": (16, 2.0, np.zeros((16, 16, 16), np.float32)),
+        # voxel size that is not a float32 number (N * voxel_size must round in float32, :68) and cells EQUAL to float32(hard_thresh) for a
+        # hard threshold that is not one either (`grid > 0.3` compares in float32: float32(0.3) > 0.3 is False there, True in double)
+        "inexact": (25, 0.1, rng.choice(np.array([0.0, 0.1, 0.2, 0.3, 0.4, 0.7], np.float32), (25, 25, 25))),
     }
     params = {"sparse": [dict(percentile=99.5), dict(percentile=97.0), dict(use_hard_thresh=True, hard_thresh=700)],
               "dense": [dict(percentile=99.5), dict(percentile=12.5), dict(percentile=100.0), dict(percentile=0.0)],
-              "empty": [dict(percentile=99.5)]}
-    centers = {"sparse": np.array([0, 0, 500]), "dense": np.array([10.5, -3.25, 7.0]), "empty": np.array([0, 0, 0])}
+              "empty": [dict(percentile=99.5)],
+              "inexact": [dict(use_hard_thresh=True, hard_thresh=0.3), dict(percentile=60.0), dict(use_hard_thresh=True, hard_thresh=np.float64(0.3))]}
+    centers = {"sparse": np.array([0, 0, 500]), "dense": np.array([10.5, -3.25, 7.0]), "empty": np.array([0, 0, 0]), "inexact": np.array([0.3, -1.7, 12.9])}
     for name, (n, vs, grid) in cases.items():
         with tempfile.TemporaryDirectory() as d:
             path = os.path.join(d, "g.bin")
@@ -54,7 +58,8 @@ def main():
             for i, kw in enumerate(params[name]):
                 pts, inten = extract(g, voxel_size, centers[name], **kw)
                 out[f"{name}_{i}_percentile"] = np.float64(kw.get("percentile", 99.5))
-                out[f"{name}_{i}_hard"] = np.int64(kw.get("hard_thresh", 700) if kw.get("use_hard_thresh") else -1)
+                out[f"{name}_{i}_hard"] = np.float64(kw.get("hard_thresh", 700) if kw.get("use_hard_thresh") else -1)
+                out[f"{name}_{i}_hard_is_np64"] = np.bool_(isinstance(kw.get("hard_thresh"), np.float64))
                 out[f"{name}_{i}_points"] = np.zeros((0, 3)) if pts is None else pts
                 out[f"{name}_{i}_intensities"] = np.zeros((0,), np.float32) if inten is None else inten
                 out[f"{name}_{i}_none"] = np.bool_(pts is None)

@@ -41,7 +41,7 @@ int pvp_motion_accumulate_host(pvp_ctx *, const void *frames, int dtype, int64_t
     }
     return PVP_OK;
 }
-int pvp_motion_accumulate(pvp_ctx *, const void *, int, int64_t, int, int, const pvp_pair *, int, float, void *, const pvp_grid_desc *, pvp_stats *) { return PVP_OK; }
+int pvp_motion_accumulate(pvp_ctx *, const void *, int, int64_t, int, int, int, const pvp_pair *, int, float, void *, const pvp_grid_desc *, pvp_stats *) { return PVP_OK; }
 // pose helpers: transparent stand-ins, so the record shows WHICH frame's pose went into a pair (ray_voxel.cpp:486-491: the current one)
 void pvp_rotation_matrix(float yaw, float pitch, float roll, float R[9]) { for (int i = 0; i < 9; ++i) R[i] = 0.f; R[0] = yaw; R[1] = pitch; R[2] = roll; }
 float pvp_focal_length(float fov_degrees, int width) { return fov_degrees * 65536.f + (float)width; }

@@ -10,7 +10,17 @@ from conftest import bits, golden
 
 from pixeltovoxelprojector_b200 import analysis
 
-CASES = [("sparse", i) for i in range(3)] + [("dense", i) for i in range(4)] + [("empty", 0)]
+CASES = [("sparse", i) for i in range(3)] + [("dense", i) for i in range(4)] + [("empty", 0)] + [("inexact", i) for i in range(3)]
+
+
+def _hard(g, name, i):
+    """hard_thresh as the golden run passed it: a Python number (weak: compared in float32) or np.float64 (compared in double); None = percentile."""
+    h = float(g[f"{name}_{i}_hard"])
+    if h < 0:
+        return None
+    if bool(g[f"{name}_{i}_hard_is_np64"]):
+        return np.float64(h)
+    return int(h) if h == int(h) else h
 
 
 def test_percentile_index_arithmetic_equals_numpy():
@@ -38,8 +48,8 @@ def test_golden_is_the_numpy_recipe(name, i):
     """The committed golden vectors (made by the reference's functions) equal the recipe of :56-96 re-evaluated here."""
     g = golden("viewer_golden.npz")
     grid, vs, center = g[f"{name}_grid"], g[f"{name}_voxel_size"], g[f"{name}_center"]
-    hard = int(g[f"{name}_{i}_hard"])
-    thresh = hard if hard >= 0 else np.percentile(grid.ravel(), float(g[f"{name}_{i}_percentile"]))
+    hard = _hard(g, name, i)
+    thresh = hard if hard is not None else np.percentile(grid.ravel(), float(g[f"{name}_{i}_percentile"]))
     coords = np.argwhere(grid > thresh)
     assert len(coords) == len(g[f"{name}_{i}_points"]) and bool(g[f"{name}_{i}_none"]) == (len(coords) == 0)
     assert np.array_equal(grid[coords[:, 0], coords[:, 1], coords[:, 2]], g[f"{name}_{i}_intensities"])
@@ -54,8 +64,8 @@ def test_extract_top_percentile_matches_reference_golden(ctx, name, i, capsys, t
     pvp.write_bin(path, g[f"{name}_grid"], float(g[f"{name}_voxel_size"]))
     grid, vs = pvp.load_voxel_grid(path)                       # CUDA tensor + np.float32, like the reference's pair
     assert grid.is_cuda and isinstance(vs, np.float32) and vs == g[f"{name}_voxel_size"]
-    hard = int(g[f"{name}_{i}_hard"])
-    kw = dict(use_hard_thresh=True, hard_thresh=hard) if hard >= 0 else dict(percentile=float(g[f"{name}_{i}_percentile"]))
+    hard = _hard(g, name, i)
+    kw = dict(use_hard_thresh=True, hard_thresh=hard) if hard is not None else dict(percentile=float(g[f"{name}_{i}_percentile"]))
     pts, inten = pvp.extract_top_percentile_z_up(grid, vs, g[f"{name}_center"], **kw)
     if bool(g[f"{name}_{i}_none"]):
         assert pts is None and inten is None

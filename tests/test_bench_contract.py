@@ -37,7 +37,10 @@ def test_our_arm_line(workload):
     assert COMMON | {"roofline", "clocks", "gpu_launches"} <= set(d) and "impl" not in d
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak" and d["data"] == "synthetic"
     r = d["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 1000 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["bound"] in ("issue", "hbm") and r["peak"] > 1000 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    m = r["algorithmic_model"]     # SURVEY 8(d)'s figure stays beside the bound the kernel is on
+    assert m["bound"] == "hbm" and m["unit"] == "GB/s" and abs(m["frac"] - m["achieved"] / m["peak"]) < 1e-9
+    assert d["timed_region_s"] > 0
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["gpu_launches"] >= 3 and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
-    assert set(d["clocks"]) == {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert {"sm_mhz", "sm_mhz_min", "sm_max_mhz", "reasons"} <= set(d["clocks"])
