@@ -34,6 +34,9 @@ WORKLOADS = {
     # scattered motion: 10 % of the pixels, iid positions, change between consecutive frames -- consecutive queue entries are NOT image
     # neighbours, so run merging gets little; and a moving textured object at a realistic density (~3.6 % of the pixels, one compact region)
     "1080p_scatter10_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=72, motion="scatter10", accum="f32"),
+    "1080p_scatter30_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=72, motion="scatter30", accum="f32"),
+    "1080p_scatter60_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=72, motion="scatter60", accum="f32"),
+    "1080p_scatter2_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=72, motion="scatter2", accum="f32"),
     "1080p_object_512": dict(H=1080, W=1920, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=64, pool=72, motion="object", accum="f32"),
     # BASELINE config[2] shape: 3840x2160 frames into a 512^3 grid (frame-sharded over N GPUs with --gpus N)
     "4k_dense_512": dict(H=2160, W=3840, N=512, voxel_size=2.0, center=(0.0, 0.0, 500.0), pairs_per_step=2, pool=20, motion="dense", accum="f32"),
@@ -51,6 +54,11 @@ WORKLOADS = {
     "image_4096_512_f64": dict(path="B", H=4096, W=4096, N=512, accum="f64", frac_bits=0, pool=3),
     "image_1024_256_f64": dict(path="B", H=1024, W=1024, N=256, accum="f64", frac_bits=0, pool=3),
     "image_tiny": dict(path="B", H=96, W=96, N=32, accum="f64", frac_bits=0, pool=2),
+    # files -> .bin (BASELINE config[1] end to end through the reference's own formats): 1000 1080p PGM frames + metadata.json on disk
+    # (page cache) -> decode pool -> pinned ring -> device ring -> K1/K2 -> 256^3 grid -> .bin file; sparse (moving blobs) and dense motion
+    "files_1080p_1000": dict(path="files", H=1080, W=1920, N=256, voxel_size=4.0, center=(0.0, 0.0, 500.0), frames=1000, motion="sparse", accum="f32"),
+    "files_1080p_1000_dense": dict(path="files", H=1080, W=1920, N=256, voxel_size=4.0, center=(0.0, 0.0, 500.0), frames=1000, motion="dense", accum="f32"),
+    "files_tiny": dict(path="files", H=120, W=160, N=64, voxel_size=16.0, center=(0.0, 0.0, 500.0), frames=12, motion="dense", accum="f32"),
     # small smoke-sized case for CPU-side checks of this script
     "tiny": dict(H=120, W=160, N=64, voxel_size=16.0, center=(0.0, 0.0, 500.0), pairs_per_step=2, pool=8, motion="dense", accum="f32"),
 }
@@ -64,8 +72,8 @@ def make_inputs(wl, seed, pose_seed=1001):
     F = wl["pool"]
     if wl["motion"] == "dense":
         frames = synth.dense_frames(F, wl["H"], wl["W"], seed=seed)
-    elif wl["motion"] == "scatter10":
-        frames = synth.scatter_frames(F, wl["H"], wl["W"], seed=seed, fraction=0.10)
+    elif wl["motion"].startswith("scatter"):
+        frames = synth.scatter_frames(F, wl["H"], wl["W"], seed=seed, fraction=int(wl["motion"][7:]) / 100.0)
     elif wl["motion"] == "object":
         frames = synth.object_frames(F, wl["H"], wl["W"], seed=seed)
     else:
@@ -692,12 +700,84 @@ def measure_motion(env, args, name, steps, warmup, full):
     return line
 
 
+def measure_files(env, args, name, steps, warmup, full):
+    """The whole CLI path in-process (pvp_ray_voxel_accumulate + pvp_write_bin_dev = what `ray_voxel` runs after context creation): a step
+    reads the sequence's image files, decodes them on the pool's host threads, stages them over PCIe once each, runs K1 / K2 per batch
+    and writes the .bin.  Timed with CUDA events around the whole step (the .bin write ends with a stream sync) and with the host clock."""
+    import ctypes as C
+    import shutil
+    import tempfile
+    torch, pvp, ctx, dev, world, rank = env.torch, env.pvp, env.ctx, env.dev, env.world, env.rank
+    from pixeltovoxelprojector_b200 import synth
+    wl = WORKLOADS[name]
+    F, H, W, N = wl["frames"], wl["H"], wl["W"], wl["N"]
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2 * F * H * W + (1 << 30) else None
+    folder = tempfile.mkdtemp(prefix=f"pvp_bench_r{rank}_", dir=base)
+    try:
+        frames = synth.dense_frames(F, H, W, seed=3000 + rank) if wl["motion"] == "dense" else synth.sparse_frames(F, H, W, seed=3000 + rank, blobs=6)
+        poses = synth.orbit_poses(F, N, wl["voxel_size"], wl["center"], seed=3001)
+        meta = synth.write_sequence(folder, {0: frames}, {0: poses})
+        del frames
+        out = os.path.join(folder, "voxel_grid.bin")
+        grid = pvp.VoxelGrid(N, wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev)
+        reps, ms, wall, bin_s = [], [], [], []
+
+        def one():
+            grid.zero_()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
+            rep = pvp.ray_voxel_accumulate(meta, folder, grid, 2.0, ctx=ctx)
+            t1 = time.perf_counter()
+            pvp._lib.check(ctx._lib.pvp_write_bin_dev(ctx.handle, os.fsencode(out), N, C.c_float(wl["voxel_size"]), grid.data.data_ptr()))
+            bin_s.append(time.perf_counter() - t1)
+            b.record()
+            torch.cuda.synchronize(dev)
+            return rep, a.elapsed_time(b), time.perf_counter() - t0
+
+        for _ in range(warmup):
+            one()
+        env.barrier()
+        sampler = ClockSampler(env.local)
+        with sampler as clocks:
+            for _ in range(steps):
+                r, m, w = one()
+                reps.append(r), ms.append(m), wall.append(w)
+        env.barrier()
+    finally:
+        shutil.rmtree(folder, ignore_errors=True)
+    t_ms, = env.reduce([sum(ms)], "max")
+    w_s, = env.reduce([sum(wall)], "max")
+    tot_steps, tot_frames = env.reduce([sum(r["n_steps"] for r in reps), sum(r["n_frames_loaded"] for r in reps)], "sum")
+    del grid
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    v = tot_steps / (t_ms * 1e-3)
+    r0 = reps[-1]
+    e2e = {"value": tot_steps / w_s, "unit": "voxel-steps/s", "h2d_bytes_per_step": int(r0["n_frames_loaded"]) * H * W, "d2h_bytes_per_step": 8 + 4 * N ** 3,
+           "frames_per_s": tot_frames / w_s, "api": "pixeltovoxelprojector_b200.ray_voxel_accumulate(metadata.json, folder) + pvp_write_bin_dev; host clock, files in the page cache"}
+    return {
+        "metric": "voxel_steps_per_sec", "value": v, "unit": "voxel-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": t_ms / steps,
+        "timed_region_s": t_ms * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "path": "files -> .bin: metadata.json + %d %dx%d PGM files per rank -> %d^3 %s grid -> .bin" % (F, W, H, N, wl["accum"]), "grid": f"{N}^3 {wl['accum']}",
+                   "motion": wl["motion"], "parallelism": f"{world} GPU(s), own sequence each" if world > 1 else "1 GPU", "l2": "inputs come from files every step (2 GB per step >> L2)"},
+        "frames_per_s": tot_frames / (t_ms * 1e-3), "e2e": e2e, "gpu_launches": None,
+        "stages_s_per_step": {k: r0[k] for k in ("seconds_total", "seconds_setup", "seconds_decode_wait", "seconds_upload", "seconds_launch", "seconds_drain")} | {"seconds_bin_write": bin_s[-1]}, "decode_threads": r0["decode_threads"],
+        "host_cores": os.cpu_count(), "clocks": clocks.summary(),
+        "roofline": {"bound": "host", "kernel": "none dominant: decode pool + PCIe + K1/K2 overlap", "frac": None},
+        "cpu_baseline": {"value": 0.0, "unit": "voxel-steps/s", "cores": 0, "kind": "skipped", "sample": ""},
+    }
+
+
 def compact(line):
     """An `also` entry: the figures of a secondary workload without the long descriptions."""
     if line is None:
         return None
     r = line.get("roofline", {})
-    out = {k: line[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "timed_region_s", "frames_per_s", "scaling", "gpu_launches", "atomics_per_voxel_step", "grid_merge_ms") if k in line}
+    out = {k: line[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "timed_region_s", "frames_per_s", "scaling", "gpu_launches", "atomics_per_voxel_step", "grid_merge_ms",
+                                "stages_s_per_step", "decode_threads", "host_cores") if k in line}
     out["e2e"] = {k: line["e2e"][k] for k in ("value", "frames_per_s", "h2d_bytes_per_step", "d2h_bytes_per_step")}
     out["config"] = {k: line["config"][k] for k in ("workload", "grid", "parallelism") if k in line["config"]}
     out["roofline"] = {k: r.get(k) for k in ("bound", "frac", "kernel", "share_of_step", "avg_launch_ms", "warp_inst_per_voxel_step", "sass_md5_ok")}
@@ -708,23 +788,22 @@ def compact(line):
 
 
 # secondary workloads measured by the default run (the contract is ONE line: they ride in its `also` dict), short runs
-ALSO_DEFAULT = [("image_4096_512_fixed", 5, 3), ("1080p_dense_256", 3, 3), ("1080p_scatter10_512", 3, 3), ("1080p_object_512", 3, 3)]
+ALSO_DEFAULT = [("image_4096_512_fixed", 5, 3), ("1080p_dense_256", 3, 3), ("1080p_scatter10_512", 3, 3), ("1080p_object_512", 3, 3), ("files_1080p_1000", 3, 1)]
 ALSO_8GPU = [("1080p_dense_1024_slab8", 10, 3), ("1080p_dense_1024", 10, 3)]
 
 
 def run_ours(args):
     env = Env(args)
     wl = WORKLOADS[args.workload]
-    measure = measure_image if wl.get("path") == "B" else measure_motion
-    line = measure(env, args, args.workload, args.steps, args.warmup, full=True)
+    pick = lambda w: measure_image if w.get("path") == "B" else measure_files if w.get("path") == "files" else measure_motion   # noqa: E731
+    line = pick(wl)(env, args, args.workload, args.steps, args.warmup, full=True)
     if args.workload == "1080p_dense_512" and not args.no_also:
         also = {}
         for name, st, wu in ALSO_DEFAULT + (ALSO_8GPU if env.world == 8 else []):
             if name not in WORKLOADS:
                 continue
-            m = measure_image if WORKLOADS[name].get("path") == "B" else measure_motion
             try:
-                also[name] = compact(m(env, args, name, st, wu, full=False))
+                also[name] = compact(pick(WORKLOADS[name])(env, args, name, st, wu, full=False))
             except Exception as e:   # a secondary workload must never cost the primary line (collective calls inside are symmetric over ranks)
                 also[name] = {"error": repr(e)}
         if line is not None:
@@ -749,6 +828,8 @@ def main():
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
+        if wl.get("path") == "files":
+            raise SystemExit("bench.py: the files workloads have no reference arm of their own (the reference arm of the kernels' workloads times the same loop body)")
         (run_reference_image if wl.get("path") == "B" else run_reference)(args, wl)
     else:
         run_ours(args)

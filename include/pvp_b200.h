@@ -37,7 +37,8 @@ typedef enum pvp_status {
     PVP_ERR_CUDA = -2,      /* CUDA runtime / launch failure */
     PVP_ERR_NOMEM = -3,     /* host or device allocation failed */
     PVP_ERR_IO = -4,        /* file could not be opened / read / written */
-    PVP_ERR_FORMAT = -5     /* malformed .bin / image / metadata */
+    PVP_ERR_FORMAT = -5,    /* malformed .bin / image / metadata */
+    PVP_ERR_CHECK = -6      /* checked build only (libpvp_b200_checked.so): a kernel computed an out-of-bounds index (skipped and counted) */
 } pvp_status;
 
 /* frame element types accepted by the motion pipeline */
@@ -96,6 +97,8 @@ typedef struct pvp_stats {
 
 /* ---- library / context ---------------------------------------------------- */
 int pvp_version(void);
+/* bit 0 set: this is the checked build (libpvp_b200_checked.so: the kernels test every index they compute, PVP_ERR_CHECK) */
+int pvp_build_flags(void);
 const char *pvp_last_error(void);
 /* stream: a cudaStream_t to enqueue on (e.g. torch's current stream) or NULL for a private non-blocking one;
  * pass cudaStreamLegacy ((cudaStream_t)0x1) to name the legacy default stream, whose own handle is NULL */
@@ -192,9 +195,9 @@ typedef struct pvp_run_options {
     float threshold;      /* default 2.0 (:447) */
     int32_t shard_rank;   /* frame sharding: this process handles block shard_rank of shard_count */
     int32_t shard_count;
-    int32_t chunk_frames; /* frames staged per H2D chunk (0 = 32) */
+    int32_t chunk_frames; /* frames per K1/K2 batch (0 = 33: 32 pairs); results do not depend on it */
     int32_t verbose;      /* print the reference's per-frame diagnostics to stderr */
-    int32_t decode_threads; /* host threads decoding image files ahead of the GPU (0 = $PVP_DECODE_THREADS or min(16, cores)) */
+    int32_t decode_threads; /* host threads decoding image files ahead of the GPU (0 = $PVP_DECODE_THREADS or min(32, cores / $LOCAL_WORLD_SIZE)) */
     int32_t loader_noise; /* 1: add the reference loader's per-pixel uniform noise in [-1,1) (ray_voxel.cpp:203-218): the same
                              std::mt19937 / uniform_real_distribution<float> stream over all frames in load order, clamped to
                              [0,255]; frames are then float32.  The reference seeds it from std::random_device (not
@@ -204,6 +207,13 @@ typedef struct pvp_run_options {
 
 typedef struct pvp_run_report {
     uint64_t n_frames_listed, n_frames_loaded, n_frames_skipped, n_pairs, n_size_mismatch;
+    /* where the host side of the frame loop spent its wall time (the same ranges carry NVTX names "pvp:decode wait", "pvp:H2D frame",
+     * "pvp:K1+K2 batch"): waiting for the decode pool, enqueueing H2D copies (incl. the noise of loader_noise), launching batches */
+    double seconds_total, seconds_decode_wait, seconds_upload, seconds_launch;
+    double seconds_setup;    /* metadata.json, the first frame's size probe, ring allocation (first call of a context) */
+    double seconds_drain;    /* the final wait for the GPU after the last batch was submitted */
+    int32_t decode_threads;  /* threads the decode pool ran with */
+    int32_t reserved;
 } pvp_run_report;
 
 /* replaces load_metadata, ray_voxel.cpp:140-178; free the array with pvp_free_metadata */

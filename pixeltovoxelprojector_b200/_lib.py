@@ -53,10 +53,12 @@ class RunOptions(C.Structure):
 
 class RunReport(C.Structure):
     _fields_ = [("n_frames_listed", C.c_uint64), ("n_frames_loaded", C.c_uint64), ("n_frames_skipped", C.c_uint64),
-                ("n_pairs", C.c_uint64), ("n_size_mismatch", C.c_uint64)]
+                ("n_pairs", C.c_uint64), ("n_size_mismatch", C.c_uint64),
+                ("seconds_total", C.c_double), ("seconds_decode_wait", C.c_double), ("seconds_upload", C.c_double), ("seconds_launch", C.c_double),
+                ("seconds_setup", C.c_double), ("seconds_drain", C.c_double), ("decode_threads", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+        return {k: (float if k.startswith("seconds") else int)(getattr(self, k)) for k, _ in self._fields_ if k != "reserved"}
 
 
 class ImageArgs(C.Structure):
@@ -87,6 +89,7 @@ class ImageStats(C.Structure):
 _P = C.c_void_p
 SIGNATURES = {
     "pvp_version": (C.c_int, []),
+    "pvp_build_flags": (C.c_int, []),
     "pvp_last_error": (C.c_char_p, []),
     "pvp_ctx_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "pvp_ctx_destroy": (C.c_int, [_P]),
@@ -143,11 +146,14 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = LIB_PATH
+    if os.environ.get("PVP_LIB_VARIANT") == "checked":   # the same sources with -DPVP_CHECKED: every index a kernel computes is tested (make checked)
+        path = LIB_PATH.replace("libpvp_b200.so", "libpvp_b200_checked.so")
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing. Build it with `make -C pixeltovoxelprojector_b200/csrc` "
+            f"{path} is missing. Build it with `make -C pixeltovoxelprojector_b200/csrc` "
             "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError => header/library mismatch
         fn.restype = res

@@ -7,6 +7,8 @@
 
 #include <cmath>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "pvp_internal.h"
 
 namespace pvp {
@@ -39,6 +41,8 @@ LaunchScope::LaunchScope(pvp_ctx *c, int k) : ctx(c), kind(k)
 {
     uint64_t *cnt[4] = {&c->prof.launches_other, &c->prof.launches_k1, &c->prof.launches_k2, &c->prof.launches_k3};
     ++*cnt[k];
+    static const char *const names[4] = {"pvp:stage kernel", "pvp:K1 diff/threshold/compact", "pvp:K2 DDA/accumulate", "pvp:K3 process_image"};
+    nvtxRangePushA(names[k]);   // NVTX range per stage; a no-op unless a tool is attached
     if (c->profiling && k != 0) {
         a = pool_get(c); b = pool_get(c);
         cudaEventRecord(a, c->stream);
@@ -47,10 +51,32 @@ LaunchScope::LaunchScope(pvp_ctx *c, int k) : ctx(c), kind(k)
 
 LaunchScope::~LaunchScope()
 {
+    nvtxRangePop();
     if (a) {
         cudaEventRecord(b, ctx->stream);
         ctx->timed.push_back({a, b, kind});
     }
+}
+
+int checked_verify(pvp_ctx *ctx, const char *where)
+{
+#ifdef PVP_CHECKED
+    Ctl h;
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    PVP_CUDA(cudaMemcpy(&h, ctx->ctl_dev, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    unsigned long long bad = 0;
+    for (int i = 0; i < 8; ++i) bad += h.check[i];
+    if (bad) {
+        set_error("%s: checked build caught out-of-bounds indices: queue write %llu, staging %llu, queue read %llu, queue entry %llu, grid cell %llu, "
+                  "image grid cell %llu, texture cell %llu, other %llu", where, h.check[0], h.check[1], h.check[2], h.check[3], h.check[4], h.check[5],
+                  h.check[6], h.check[7]);
+        PVP_CUDA(cudaMemset(&ctx->ctl_dev->check[0], 0, sizeof(h.check)));
+        return PVP_ERR_CHECK;
+    }
+#else
+    (void)ctx; (void)where;
+#endif
+    return PVP_OK;
 }
 
 int ensure_queue(pvp_ctx *ctx, unsigned long long entries)
@@ -74,25 +100,30 @@ int ensure_pairs(pvp_ctx *ctx, int n_pairs)
     PVP_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->pairs_dev) cudaFree(ctx->pairs_dev);
     if (ctx->pairs_pinned) cudaFreeHost(ctx->pairs_pinned);
+    if (ctx->fs_hring) cudaFreeHost(ctx->fs_hring);
+    if (ctx->fs_dring) cudaFree(ctx->fs_dring);
+    for (auto p : ctx->bin_pin) if (p) cudaFreeHost(p);
     ctx->pairs_dev = nullptr; ctx->pairs_pinned = nullptr; ctx->pairs_cap = 0;
     int cap = n_pairs < 64 ? 64 : n_pairs;
     PVP_CUDA(cudaMalloc(&ctx->pairs_dev, sizeof(pvp_pair) * (size_t)cap));
-    PVP_CUDA(cudaMallocHost(&ctx->pairs_pinned, sizeof(pvp_pair) * (size_t)cap));
+    PVP_CUDA(cudaMallocHost(&ctx->pairs_pinned, sizeof(pvp_pair) * (size_t)cap * PVP_PAIR_SLOTS));
     ctx->pairs_cap = cap;
     return PVP_OK;
 }
 
-// Pair table -> device through the pinned staging buffer; the event keeps a later call from
-// overwriting the staging area while this copy is still in flight.
+// Pair table -> device through a ring of pinned staging slots.  The copy is stream-ordered behind the kernels of the batch before
+// it, so its event only fires when THAT batch has finished: with one slot the host would stall a whole batch of K2 time in every
+// call (measured through the file pipeline on dense motion: 0.70 of 0.81 s); with the ring it runs PVP_PAIR_SLOTS - 1 batches ahead.
 int upload_pairs(pvp_ctx *ctx, const pvp_pair *pairs, int n_pairs)
 {
     int rc = ensure_pairs(ctx, n_pairs);
     if (rc) return rc;
-    PVP_CUDA(cudaEventSynchronize(ctx->ev_pairs));
-    memcpy(ctx->pairs_pinned, pairs, sizeof(pvp_pair) * (size_t)n_pairs);
-    PVP_CUDA(cudaMemcpyAsync(ctx->pairs_dev, ctx->pairs_pinned, sizeof(pvp_pair) * (size_t)n_pairs,
-                             cudaMemcpyHostToDevice, ctx->stream));
-    PVP_CUDA(cudaEventRecord(ctx->ev_pairs, ctx->stream));
+    const int slot = (int)(ctx->pairs_seq++ % PVP_PAIR_SLOTS);
+    pvp_pair *stage = ctx->pairs_pinned + (size_t)slot * (size_t)ctx->pairs_cap;
+    PVP_CUDA(cudaEventSynchronize(ctx->ev_pairs[slot]));
+    memcpy(stage, pairs, sizeof(pvp_pair) * (size_t)n_pairs);
+    PVP_CUDA(cudaMemcpyAsync(ctx->pairs_dev, stage, sizeof(pvp_pair) * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    PVP_CUDA(cudaEventRecord(ctx->ev_pairs[slot], ctx->stream));
     return PVP_OK;
 }
 
@@ -103,6 +134,16 @@ using namespace pvp;
 extern "C" {
 
 int pvp_version(void) { return PVP_VERSION; }
+
+// bit 0: checked build (own bounds checks compiled into the kernels, see pvp_internal.h)
+int pvp_build_flags(void)
+{
+#ifdef PVP_CHECKED
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 const char *pvp_last_error(void) { return g_err; }
 
@@ -146,7 +187,7 @@ int pvp_ctx_create(int device, void *stream, pvp_ctx **out)
             PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
             PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
         }
-        PVP_CUDA(cudaEventCreateWithFlags(&ctx->ev_pairs, cudaEventDisableTiming));
+        for (auto &e : ctx->ev_pairs) PVP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         PVP_CUDA(cudaMalloc(&ctx->ctl_dev, sizeof(Ctl)));
         PVP_CUDA(cudaMemset(ctx->ctl_dev, 0, sizeof(Ctl)));
         return PVP_OK;
@@ -181,7 +222,7 @@ int pvp_ctx_destroy(pvp_ctx *ctx)
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
-    if (ctx->ev_pairs) cudaEventDestroy(ctx->ev_pairs);
+    for (auto e : ctx->ev_pairs) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -248,6 +289,8 @@ int pvp_ctx_set_option(pvp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "image_tile_h")) ctx->opt_image_tile_h = value;
     else if (!strcmp(key, "k1_row_group")) ctx->opt_k1_row_group = value;
     else if (!strcmp(key, "k1_snake")) ctx->opt_k1_snake = value;
+    else if (!strcmp(key, "lean2_paired")) ctx->opt_lean2_density = value;
+    else if (!strcmp(key, "inject_fault")) ctx->opt_inject_fault = value;
     else { set_error("pvp_ctx_set_option: unknown key '%s'", key); return PVP_ERR_INVALID; }
     return PVP_OK;
 }
@@ -374,14 +417,21 @@ int pvp_write_bin_dev(pvp_ctx *ctx, const char *path, int32_t n, float voxel_siz
     DeviceGuard guard(ctx->device);
     FILE *f = fopen(path, "wb");
     if (!f) { set_error("Cannot open output file: %s", path); return PVP_ERR_IO; }
+    nvtxRangePushA("pvp:.bin D2H + write");
     const size_t total = (size_t)n * n * n * sizeof(float);
     const size_t chunk = total < ((size_t)16 << 20) ? total : ((size_t)16 << 20);
     const size_t n_chunks = (total + chunk - 1) / chunk;
     uint8_t *pin[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     auto body = [&]() -> int {
+        if (ctx->bin_pin_bytes < chunk) {   // the two pinned chunk buffers stay with the context
+            for (auto &p : ctx->bin_pin) { if (p) cudaFreeHost(p); p = nullptr; }
+            ctx->bin_pin_bytes = 0;
+            for (auto &p : ctx->bin_pin) PVP_CUDA(cudaMallocHost((void **)&p, chunk));
+            ctx->bin_pin_bytes = chunk;
+        }
         for (int i = 0; i < 2; ++i) {
-            PVP_CUDA(cudaMallocHost((void **)&pin[i], chunk));
+            pin[i] = ctx->bin_pin[i];
             PVP_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
         }
         auto issue = [&](size_t k) -> int {
@@ -404,11 +454,10 @@ int pvp_write_bin_dev(pvp_ctx *ctx, const char *path, int32_t n, float voxel_siz
         return PVP_OK;
     };
     int rc = body();
+    nvtxRangePop();
     cudaStreamSynchronize(ctx->stream);  // no copy may still target the pinned buffers when they are released
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2; ++i)
         if (ev[i]) cudaEventDestroy(ev[i]);
-        if (pin[i]) cudaFreeHost(pin[i]);
-    }
     if (fclose(f) != 0 && rc == PVP_OK) { set_error("pvp_write_bin_dev: short write to %s", path); rc = PVP_ERR_IO; }
     return rc;
 }

@@ -37,6 +37,17 @@ struct ImageP {
     double scale;          // 2^frac_bits
 };
 
+// checked build (see pvp_internal.h): every grid / texture offset handed to a RED must lie inside the span the caller's shape and
+// strides describe; the spans and the violation counters live in this translation unit
+#ifdef PVP_CHECKED
+__device__ unsigned long long g_img_span_grid, g_img_span_tex, g_img_bad[2];
+#define PVP_IMG_CHECK_GRID(off) ((unsigned long long)(off) < g_img_span_grid ? true : (atomicAdd(&g_img_bad[0], 1ull), false))
+#define PVP_IMG_CHECK_TEX(off) ((unsigned long long)(off) < g_img_span_tex ? true : (atomicAdd(&g_img_bad[1], 1ull), false))
+#else
+#define PVP_IMG_CHECK_GRID(off) true
+#define PVP_IMG_CHECK_TEX(off) true
+#endif
+
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
@@ -117,7 +128,7 @@ __device__ __forceinline__ bool pixel_setup(const double *__restrict__ image, ty
             if (brightness <= 0) return false;
         }
         val = C::make(brightness, p.scale);
-        if (p.update_tex && within) C::add(texel, val);  // :310-314
+        if (p.update_tex && within && PVP_IMG_CHECK_TEX(v_idx * p.ts0 + u_idx * p.ts1)) C::add(texel, val);  // :310-314
     } else {
         val = C::make(brightness, p.scale);
     }
@@ -180,7 +191,7 @@ process_image_kernel(const double *__restrict__ image, typename Cell<MODE>::T *_
             xi = min(max(xi, 0ll), p.gn[0] - 1);
             yi = min(max(yi, 0ll), p.gn[1] - 1);
             zi = min(max(zi, 0ll), p.gn[2] - 1);
-            C::add(grid + (xi * p.gs[0] + yi * p.gs[1] + zi * p.gs[2]), val);  // :356-357
+            if (PVP_IMG_CHECK_GRID(xi * p.gs[0] + yi * p.gs[1] + zi * p.gs[2])) C::add(grid + (xi * p.gs[0] + yi * p.gs[1] + zi * p.gs[2]), val);  // :356-357
             ++my_samples;
         }
     }
@@ -395,7 +406,7 @@ __device__ __forceinline__ unsigned march_lockstep(CellT *__restrict__ grid, con
         t = __shfl_up_sync(FULL, sum, 4);  if (!(heads & lm.w4))  sum += t;
         t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum += t;
         t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum += t;
-        if ((heads & lm.next) && live) img_red(grid + key, sum);  // :356-357, once per run
+        if ((heads & lm.next) && live && PVP_IMG_CHECK_GRID(key)) img_red(grid + key, sum);  // :356-357, once per run
         if (s == whi) break;
         heads = __ballot_sync(FULL, head_n);
         key = key_n;
@@ -532,8 +543,8 @@ __device__ __forceinline__ void march2_accumulate(CellT *__restrict__ grid, cons
     t = __shfl_up_sync(FULL, sum, 4);  scan_add(!(m.heads & lm.w4), sum, t);
     t = __shfl_up_sync(FULL, sum, 8);  scan_add(!(m.heads & lm.w8), sum, t);
     t = __shfl_up_sync(FULL, sum, 16); scan_add(!(m.heads & lm.w16), sum, t);
-    if ((m.heads & lm.next) && live_a) img_red(grid + m.ka, sum);
-    if (b_alone) img_red(grid + m.kb, val_b);
+    if ((m.heads & lm.next) && live_a && PVP_IMG_CHECK_GRID(m.ka)) img_red(grid + m.ka, sum);
+    if (b_alone && PVP_IMG_CHECK_GRID(m.kb)) img_red(grid + m.kb, val_b);
 }
 
 // iterations s .. s_stop-1; each first computes the keys of sample s+1 (their arithmetic and shuffle overlap the scan of
@@ -883,7 +894,30 @@ int pvp_process_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, voi
     DeviceGuard guard(ctx->device);
     // the counters describe THIS call: clear whatever earlier calls without `stats` left behind
     if (stats) PVP_CUDA(cudaMemsetAsync(&ctx->ctl_dev->img_rays, 0, 2 * sizeof(unsigned long long), ctx->stream));
+#ifdef PVP_CHECKED
+    {
+        unsigned long long spans[2] = {(unsigned long long)std::max(0ll, span_elems(args->grid_shape, args->grid_stride, 3)),
+                                       (unsigned long long)std::max(0ll, span_elems(args->tex_shape, args->tex_stride, 2))};
+        if (ctx->opt_inject_fault == 2) spans[0] /= 2;   // a test of the check itself
+        const unsigned long long zero[2] = {0, 0};
+        PVP_CUDA(cudaMemcpyToSymbolAsync(g_img_span_grid, &spans[0], sizeof(unsigned long long), 0, cudaMemcpyHostToDevice, ctx->stream));
+        PVP_CUDA(cudaMemcpyToSymbolAsync(g_img_span_tex, &spans[1], sizeof(unsigned long long), 0, cudaMemcpyHostToDevice, ctx->stream));
+        PVP_CUDA(cudaMemcpyToSymbolAsync(g_img_bad, zero, sizeof(zero), 0, cudaMemcpyHostToDevice, ctx->stream));
+        PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+#endif
     if ((rc = launch_image(ctx, image_dev, grid_dev, tex_dev, p, args->accum_mode))) return rc;
+#ifdef PVP_CHECKED
+    {
+        unsigned long long bad[2] = {0, 0};
+        PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+        PVP_CUDA(cudaMemcpyFromSymbol(bad, g_img_bad, sizeof(bad)));
+        if (bad[0] | bad[1]) {
+            set_error("pvp_process_image: checked build caught out-of-bounds offsets: voxel grid %llu, texture %llu", bad[0], bad[1]);
+            return PVP_ERR_CHECK;
+        }
+    }
+#endif
     return fetch_image_stats(ctx, stats);
 }
 

@@ -17,6 +17,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <vector>
@@ -816,6 +818,64 @@ bool pvp::decode_gray_file(const char *path, std::vector<uint8_t> &gray, int *wi
     gray.swap(d.gray);
     *width = d.w; *height = d.h;
     return true;
+}
+
+// Streaming variant for the decode pool: the pixels go straight into the caller's buffer -- a slot of the pinned
+// staging ring -- so a raw 8-bit PGM frame is ONE copy, page cache -> pinned memory (pread), with no heap traffic: a pool that
+// allocates two 2 MB vectors per frame spends its time in mmap/munmap under the process-wide mm lock.  Other formats decode into
+// the thread's scratch vectors (kept across calls) and are copied in.  Returns 1 = decoded into dst, 0 = the reference's failed
+// stbi_load, -1 = decoded but larger than cap: the pixels are in `spill`.  Same acceptance as decode_gray_file (a truncated
+// PNM payload fails, ray_voxel.cpp:196-199).
+int pvp::decode_gray_file_into(const char *path, uint8_t *dst, size_t cap, int *width, int *height, std::vector<uint8_t> &spill)
+{
+    if (!path) return 0;
+    int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return 0;
+    uint8_t head[64];
+    const ssize_t got = pread(fd, head, sizeof(head), 0);
+    if (got >= 7 && head[0] == 'P' && head[1] == '5') {   // binary PGM: parse the header from the first bytes
+        size_t pos = 2;
+        int v[3];
+        bool ok = true;
+        for (int k = 0; k < 3 && ok; ++k) {
+            for (;;) {
+                while (pos < (size_t)got && (head[pos] == ' ' || head[pos] == '\t' || head[pos] == '\n' || head[pos] == '\r')) ++pos;
+                if (pos < (size_t)got && head[pos] == '#') { ok = false; break; }   // comments: the general decoder handles them
+                break;
+            }
+            if (!ok || pos >= (size_t)got || head[pos] < '0' || head[pos] > '9') { ok = false; break; }
+            long x = 0;
+            while (pos < (size_t)got && head[pos] >= '0' && head[pos] <= '9') { x = x * 10 + (head[pos] - '0'); if (x > (1 << 30)) { ok = false; break; } ++pos; }
+            v[k] = (int)x;
+        }
+        // the token must have ended inside the 64 bytes read (otherwise the number may continue) and maxval must be one byte per sample
+        if (ok && pos < (size_t)got && v[0] > 0 && v[1] > 0 && v[2] > 0 && v[2] <= 255) {
+            ++pos;  // the single whitespace byte after maxval
+            const size_t npx = (size_t)v[0] * (size_t)v[1];
+            *width = v[0]; *height = v[1];
+            uint8_t *out = dst;
+            int rc = 1;
+            if (npx > cap) {
+                try { spill.resize(npx); } catch (...) { close(fd); return 0; }
+                out = spill.data(); rc = -1;
+            }
+            size_t done = 0;
+            while (done < npx) {
+                const ssize_t r = pread(fd, out + done, npx - done, (off_t)(pos + done));
+                if (r <= 0) break;
+                done += (size_t)r;
+            }
+            close(fd);
+            return done == npx ? rc : 0;   // short payload: decode_pnm refuses it too
+        }
+    }
+    close(fd);
+    thread_local Decoded d;   // scratch kept per pool thread
+    if (!decode_any(path, d)) return 0;
+    *width = d.w; *height = d.h;
+    if (d.gray.size() > cap) { spill.swap(d.gray); return -1; }
+    memcpy(dst, d.gray.data(), d.gray.size());
+    return 1;
 }
 
 extern "C" {

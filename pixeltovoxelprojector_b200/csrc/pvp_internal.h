@@ -16,13 +16,29 @@ namespace pvp {
 struct Ctl {
     unsigned long long count;      // entries appended by the compaction kernel
     unsigned long long head;       // next entry to be claimed by the traversal kernel
+    unsigned long long n_paired;   // motion pixels of the batch whose vertical partner moves too (Z-order K1; picks lean2 / lean)
     unsigned long long n_rays;
     unsigned long long n_steps;
     unsigned long long n_written;
     unsigned long long n_atomics;
     unsigned long long img_rays;   // path B
     unsigned long long img_samples;
+    unsigned long long n_pairs;    // checked build: pairs of the batch (written by K1)
+    unsigned long long check[8];   // checked build: violations per PVP_CHK_* site class
 };
+
+// ---- checked build (make checked -> libpvp_b200_checked.so, -DPVP_CHECKED) ---------------------------------------------------------
+// compute-sanitizer is not available on the GPU pool this project runs on, so the library carries its own memcheck for the indices it
+// computes: every queue slot K1 writes, every shared-memory staging slot, every queue entry K2 reads (and what it decodes from it), and
+// every grid / texture cell address K2 and K3 hand to a RED is tested against the buffer it must lie in.  A violating access is
+// SKIPPED and counted in Ctl::check; the host turns a non-zero count into PVP_ERR_CHECK after the call.  In the normal build the macro
+// is the constant `true` and the kernels' SASS is unchanged (tests/test_profiles_fresh.py pins the md5).
+enum { PVP_CHK_QUEUE_WRITE = 0, PVP_CHK_STAGE = 1, PVP_CHK_QUEUE_READ = 2, PVP_CHK_ENTRY = 3, PVP_CHK_GRID = 4, PVP_CHK_IMG_GRID = 5, PVP_CHK_IMG_TEX = 6, PVP_CHK_OTHER = 7 };
+#ifdef PVP_CHECKED
+#define PVP_DEV_CHECK(ctl, id, cond) ((cond) ? true : (atomicAdd(&(ctl)->check[id], 1ull), false))
+#else
+#define PVP_DEV_CHECK(ctl, id, cond) true
+#endif
 
 // SoA ray queue: one entry per motion pixel of the batch.
 struct Queue {
@@ -33,6 +49,8 @@ struct Queue {
 };
 
 }  // namespace pvp
+
+constexpr int PVP_PAIR_SLOTS = 4;
 
 struct pvp_ctx {
     int device = 0;
@@ -49,7 +67,13 @@ struct pvp_ctx {
     pvp_pair *pairs_dev = nullptr;
     pvp_pair *pairs_pinned = nullptr;
     int pairs_cap = 0;
-    cudaEvent_t ev_pairs = nullptr;  // guards reuse of pairs_pinned
+    cudaEvent_t ev_pairs[4] = {nullptr, nullptr, nullptr, nullptr};  // guard reuse of the pinned pair slots (PVP_PAIR_SLOTS)
+    unsigned long long pairs_seq = 0;
+
+    // buffers of the file pipeline (pvp_ray_voxel_accumulate) and of the .bin writer, kept across calls: pinning 75 MB costs ~25 ms
+    uint8_t *fs_hring = nullptr; size_t fs_hring_bytes = 0;   // pinned frame ring
+    uint8_t *fs_dring = nullptr; size_t fs_dring_bytes = 0;   // device frame ring
+    uint8_t *bin_pin[2] = {nullptr, nullptr}; size_t bin_pin_bytes = 0;
 
     void *stage_dev[2] = {nullptr, nullptr};  // frame staging buffers for *_host
     size_t stage_bytes = 0;
@@ -72,6 +96,8 @@ struct pvp_ctx {
     int64_t opt_reduce_pull = 0;       // grid merge to one rank with multicast: 0 = every rank reduces a slice (default), 1 = the destination pulls the whole grid
     int64_t opt_image_tile_h = 0;      // lock-step path-B kernel: rows of a warp's pixel tile (0/2 default, 1, 4, 8)
     int64_t opt_image_variant = 0;     // path B kernel: 0 = auto, 1 = generic per-pixel, 2 = lock-step
+    int64_t opt_lean2_density = 0;     // auto K2 ("lean2_paired"): lean2 from this percentage of the rays in vertical pairs up (0 = default 50), lean below
+    int64_t opt_inject_fault = 0;      // checked build only: 1 = K1 is told a quarter of the queue's capacity, 2 = K3 half of the grid's span (tests of the checks themselves)
     int64_t opt_lean_regs = 0;         // register budget of the lean K2 kernel: 0/72, 80 or 64
 };
 
@@ -111,7 +137,12 @@ struct LaunchScope {
 // reference's failed stbi_load.  Never throws.
 bool decode_gray_file(const char *path, std::vector<uint8_t> &gray, int *width, int *height);
 
+// Same decode straight into `dst` (capacity cap bytes; a pinned staging slot): 1 = ok, 0 = failed, -1 = ok but larger than cap (pixels in spill).
+int decode_gray_file_into(const char *path, uint8_t *dst, size_t cap, int *width, int *height, std::vector<uint8_t> &spill);
+
 int ensure_queue(pvp_ctx *ctx, unsigned long long entries);
+// checked build: synchronise, read Ctl::check and fail with PVP_ERR_CHECK when a kernel skipped an out-of-bounds access (no-op otherwise)
+int checked_verify(pvp_ctx *ctx, const char *where);
 int ensure_pairs(pvp_ctx *ctx, int n_pairs);
 int upload_pairs(pvp_ctx *ctx, const pvp_pair *pairs, int n_pairs);
 

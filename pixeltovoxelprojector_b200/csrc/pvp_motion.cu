@@ -19,6 +19,19 @@
 
 namespace pvp {
 
+#ifdef PVP_CHECKED
+#define PVP_CHECKED_NOTE_PAIRS(ctl) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) (ctl)->n_pairs = gridDim.y; } while (0)
+#else
+#define PVP_CHECKED_NOTE_PAIRS(ctl) do { } while (0)
+#endif
+
+// checked build: is queue slot i inside the queue, and is what it holds a pixel of the frame, a pair of the batch and a number?
+__device__ __forceinline__ bool queue_slot_ok(Ctl *ctl, const Queue &q, unsigned long long i) { return PVP_DEV_CHECK(ctl, PVP_CHK_QUEUE_READ, i < q.capacity); }
+__device__ __forceinline__ bool queue_entry_ok(Ctl *ctl, uint32_t pix, unsigned pair, float diff, int width, int height)
+{
+    return PVP_DEV_CHECK(ctl, PVP_CHK_ENTRY, pix < (uint32_t)width * (uint32_t)height && pair < ctl->n_pairs && diff == diff);
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: diff / threshold / compact
 // ------------------------------------------------------------------------------------------
@@ -53,6 +66,7 @@ motion_compact_kernel(const T *__restrict__ frames, long long frame_stride, cons
 {
     constexpr int PX = FrameVec<T>::PX;
     const int pair = blockIdx.y;
+    PVP_CHECKED_NOTE_PAIRS(ctl);
     const T *prev = frames + (long long)pairs[pair].prev * frame_stride;
     const T *curr = frames + (long long)pairs[pair].curr * frame_stride;
     const long long first = ((long long)blockIdx.x * K1_THREADS + threadIdx.x) * PX;
@@ -97,7 +111,7 @@ motion_compact_kernel(const T *__restrict__ frames, long long frame_stride, cons
     // the host sizes the queue for the worst case (n_pairs * n_pix), so pos < capacity always
 #pragma unroll
     for (int k = 0; k < PX; ++k) {
-        if (mask & (1u << k)) {
+        if ((mask & (1u << k)) && PVP_DEV_CHECK(ctl, PVP_CHK_QUEUE_WRITE, pos < q.capacity)) {
             q.pix[pos] = (uint32_t)(first + k);
             q.diff[pos] = d[k];
             q.pair[pos] = (uint16_t)pair;
@@ -146,6 +160,7 @@ motion_compact_rowgroup_kernel(const T *__restrict__ frames, long long frame_str
 {
     constexpr int THREADS = K1Tile<R>::THREADS, C = K1T_COLS, ITER = K1Tile<R>::ITER;
     const int pair = blockIdx.y;
+    PVP_CHECKED_NOTE_PAIRS(ctl);
     const T *prev = frames + (long long)pairs[pair].prev * frame_stride;
     const T *curr = frames + (long long)pairs[pair].curr * frame_stride;
     const int segs = (width + C - 1) / C, row_groups = (height + R - 1) / R;
@@ -227,7 +242,7 @@ motion_compact_rowgroup_kernel(const T *__restrict__ frames, long long frame_str
                 // snake order (one ray per lane on tall tiles): odd columns bottom-up, so the lanes on either side of a column
                 // change are horizontal neighbours too and their runs can merge
                 const int r = (snake && (k & 1)) ? R - 1 - rr : rr;
-                if (mask & (1u << (r * C + k))) {
+                if ((mask & (1u << (r * C + k))) && PVP_DEV_CHECK(ctl, PVP_CHK_STAGE, pos < (unsigned)(THREADS * C * R))) {
                     T pa[C], pb[C];
                     memcpy(pa, &a[it][r], sizeof(pa));
                     memcpy(pb, &b[it][r], sizeof(pb));
@@ -241,10 +256,158 @@ motion_compact_rowgroup_kernel(const T *__restrict__ frames, long long frame_str
         // the host sizes the queue for the worst case (n_pairs * n_pix), so base + tot <= capacity always
         const unsigned long long base = cta_base;
         for (unsigned i = threadIdx.x; i < tot; i += THREADS) {
+            if (!PVP_DEV_CHECK(ctl, PVP_CHK_QUEUE_WRITE, base + i < q.capacity && i < (unsigned)(THREADS * C * R))) continue;
             q.pix[base + i] = s_pix[i];
             q.diff[base + i] = s_diff[i];
             q.pair[base + i] = (uint16_t)pair;
         }
+    }
+}
+
+// Z-order queue: the order that keeps a warp's rays together at EVERY motion density.  A thread owns a 4 x 8 pixel block and emits
+// its motion pixels column by column in snake order (the order that merges best when everything moves: entries 2i / 2i+1 are
+// vertical neighbours, which is what lean2 pairs up, and the lanes on either side of a column change are horizontal neighbours);
+// the threads of a CTA follow the Z-order (Morton order) of their blocks inside a 64 x 64 pixel footprint (thread bit 0 -> x,
+// bit 1 -> y, ...).  So ANY run of consecutive queue entries is a compact 2-D cluster of the image: 64 entries are an 8 x 8 square
+// when everything moves, a ~25 x 25 pixel neighbourhood when 10 % of the pixels move -- not a 160 x 4 strip of a row tile.  Rays of
+// one neighbourhood visit the same voxels: fewer distinct voxels per lock-step iteration (fewer REDs) and more even ray lengths
+// (measured, G voxel-steps/s, row tiles of 4 rows -> Z-order: 10 % iid motion 274 -> 493, 2 % 136 -> 288; dense 842 -> 846).
+// A full Morton order INSIDE the blocks as well loses the snake's run merging on dense motion (0.219 REDs per voxel step against
+// 0.186: 824 G).  Same filters, same entries as motion_compact_kernel; only the order differs.
+// The kernel also counts the motion pixels whose vertical partner (rows 2j / 2j+1 of the block) moves too: the share of rays that
+// lean2 can pair decides between lean2 and lean on the device (launch_k2).
+// R = rows of a thread's block: 8 (16 x 8 blocks per footprint, 128 threads) or 4 (16 x 16 blocks, 256 threads).  A dense 64-entry
+// chunk of lean2 is then an 8 x 8 or a 16 x 4 pixel tile; like the round-1 row tiles the host takes 4 rows while an x-plane of the
+// grid stays within 2 MiB (wide, flat tiles merge slightly better: 730 against 711 G voxel-steps/s on a moving object) and 8 rows
+// above (neighbouring image columns land in neighbouring x-planes: the RED misses of a wide tile dominate, 1024^3: 457 -> 600 G).
+constexpr int K1M_FOOT = 64;
+template <int R> struct K1Morton { static constexpr int THREADS = 16 * (K1M_FOOT / R); };
+
+// bits 0, 2, 4, 6 of t -> x (block column, 0..15); bits 1, 3, 5 (, 7) -> y (block row)
+__device__ __forceinline__ void morton_block(unsigned t, int &bx, int &by)
+{
+    bx = (int)((t & 1u) | ((t >> 1) & 2u) | ((t >> 2) & 4u) | ((t >> 3) & 8u));
+    by = (int)(((t >> 1) & 1u) | ((t >> 2) & 2u) | ((t >> 3) & 4u) | ((t >> 4) & 8u));
+}
+
+template <typename T, int R>
+__global__ void __launch_bounds__(K1Morton<R>::THREADS)
+motion_compact_morton_kernel(const T *__restrict__ frames, long long frame_stride, const pvp_pair *__restrict__ pairs,
+                             int width, int height, float threshold, bool vec_ok, Queue q, Ctl *__restrict__ ctl)
+{
+    constexpr int THREADS = K1Morton<R>::THREADS, C = K1T_COLS;
+    const int pair = blockIdx.y;
+    PVP_CHECKED_NOTE_PAIRS(ctl);
+    const T *prev = frames + (long long)pairs[pair].prev * frame_stride;
+    const T *curr = frames + (long long)pairs[pair].curr * frame_stride;
+    const int foot_per_row = (width + K1M_FOOT - 1) / K1M_FOOT;
+    const int fy = (int)(blockIdx.x / (unsigned)foot_per_row), fx = (int)(blockIdx.x - (unsigned)fy * (unsigned)foot_per_row);
+    int bx, by;
+    morton_block(threadIdx.x, bx, by);
+    const int u0 = fx * K1M_FOOT + bx * C, v0 = fy * K1M_FOOT + by * R;
+
+    typename RowSeg<T>::V a[R] = {}, b[R] = {};
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int v = v0 + r;
+        if (u0 < width && v < height) {
+            a[r] = load_cols<T>(prev + (long long)v * width, u0, width, vec_ok);
+            b[r] = load_cols<T>(curr + (long long)v * width, u0, width, vec_ok);
+        }
+    }
+    __shared__ unsigned warp_tot[THREADS / 32];
+    __shared__ unsigned long long cta_base;
+    __shared__ uint32_t s_pix[THREADS * C * R];
+    __shared__ float s_diff[THREADS * C * R];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned mask = 0;  // bit r * C + k: the pixel casts a ray
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int v = v0 + r;
+        if (u0 < width && v < height) {
+            T pa[C], pb[C];
+            memcpy(pa, &a[r], sizeof(pa));
+            memcpy(pb, &b[r], sizeof(pb));
+#pragma unroll
+            for (int k = 0; k < C; ++k)
+                if (u0 + k < width && motion_casts_ray(motion_diff(pa[k], pb[k]), threshold)) mask |= 1u << (r * C + k);
+        }
+    }
+    if (!__syncthreads_or(mask != 0)) return;  // nothing moves in the CTA's footprint: one barrier and out
+    const int cnt = __popc(mask);
+    // motion pixels in even rows whose lower neighbour moves too (rows are C bits apart in the mask): each is one pair of lean2
+    int paired = __popc(mask & (mask >> C) & 0x0f0f0f0fu);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) paired += __shfl_xor_sync(0xffffffffu, paired, o);
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) {
+        const unsigned c = warp_tot[w];
+        if (w < warp) before += c;
+        tot += c;
+    }
+    if (threadIdx.x == 0) cta_base = atomicAdd(&ctl->count, (unsigned long long)tot);
+    if (lane == 0 && paired) atomicAdd(&ctl->n_paired, (unsigned long long)paired);
+    unsigned pos = before + (unsigned)(incl - cnt);
+    // A footprint in which most pixels move is emitted strip by strip instead (block rows of 16 blocks, left to right): there every
+    // block is full, consecutive blocks of a strip are seamless for the snake (a block ends at the top of its last column, the next
+    // one starts at the top of its first), and the Z-order's jumps between blocks would only break runs (dense motion: 0.200 -> 0.186
+    // REDs per voxel step).  Same entries, other positions: the exclusive prefix is taken over the threads in strip order.
+    if (tot * 2 >= (unsigned)(THREADS * C * R)) {   // uniform over the CTA
+        __shared__ unsigned s_cnt[THREADS];
+        const unsigned rank = (unsigned)(by * 16 + bx);
+        __syncthreads();                 // warp_tot has been read by everyone
+        s_cnt[rank] = (unsigned)cnt;
+        __syncthreads();
+        int inc2 = (int)s_cnt[threadIdx.x];
+        const int own = inc2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc2, o);
+            if (lane >= o) inc2 += t;
+        }
+        if (lane == 31) warp_tot[warp] = (unsigned)inc2;
+        __syncthreads();
+        unsigned before2 = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w)
+            if (w < warp) before2 += warp_tot[w];
+        s_cnt[threadIdx.x] = before2 + (unsigned)(inc2 - own);   // exclusive prefix of strip position threadIdx.x
+        __syncthreads();
+        pos = s_cnt[rank];
+    }
+    // inside the block: column by column, odd columns bottom-up (snake)
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = (k & 1) ? R - 1 - rr : rr;
+            if ((mask & (1u << (r * C + k))) && PVP_DEV_CHECK(ctl, PVP_CHK_STAGE, pos < (unsigned)(THREADS * C * R))) {
+                T pa[C], pb[C];
+                memcpy(pa, &a[r], sizeof(pa));
+                memcpy(pb, &b[r], sizeof(pb));
+                s_pix[pos] = (uint32_t)((v0 + r) * width + u0 + k);
+                s_diff[pos] = motion_diff(pa[k], pb[k]);
+                ++pos;
+            }
+        }
+    }
+    __syncthreads();
+    // the host sizes the queue for the worst case (n_pairs * n_pix), so base + tot <= capacity always
+    const unsigned long long base = cta_base;
+    for (unsigned i = threadIdx.x; i < tot; i += THREADS) {
+        if (!PVP_DEV_CHECK(ctl, PVP_CHK_QUEUE_WRITE, base + i < q.capacity && i < (unsigned)(THREADS * C * R))) continue;
+        q.pix[base + i] = s_pix[i];
+        q.diff[base + i] = s_diff[i];
+        q.pair[base + i] = (uint16_t)pair;
     }
 }
 
@@ -299,10 +462,12 @@ dda_accumulate_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, type
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= count) break;
         const unsigned long long i = base + lane;
-        if (i < count) {
+        if (i < count && queue_slot_ok(ctl, q, i)) {
             const uint32_t pix = __ldg(q.pix + i);
             const float diff = __ldg(q.diff + i);
-            const pvp_pair *P = pairs + __ldg(q.pair + i);
+            const unsigned pair_id = __ldg(q.pair + i);
+            if (!queue_entry_ok(ctl, pix, pair_id, diff, width, height)) continue;
+            const pvp_pair *P = pairs + pair_id;
             const int v = (int)(pix / (uint32_t)width), u = (int)(pix - (uint32_t)v * (uint32_t)width);
             float dx, dy, dz;
             pixel_ray(u, v, width, height, __ldg(&P->focal), P->R, dx, dy, dz);
@@ -312,8 +477,9 @@ dda_accumulate_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, type
                 while (r.t_cur <= r.t_end) {
                     ++my_steps;
                     if (r.ix >= g.slab_lo && r.ix < g.slab_hi) {
-                        A::add(grid + ((long long)(r.ix - g.slab_lo) * sx_stride + (long long)r.iy * N + r.iz),
-                               g.alpha > 0.f ? A::make(attenuate(diff, g.alpha, r.t_cur), g) : val);
+                        const long long cell = (long long)(r.ix - g.slab_lo) * sx_stride + (long long)r.iy * N + r.iz;
+                        if (PVP_DEV_CHECK(ctl, PVP_CHK_GRID, cell >= 0 && cell < (long long)(g.slab_hi - g.slab_lo) * sx_stride && r.iy >= 0 && r.iy < N && r.iz >= 0 && r.iz < N))
+                            A::add(grid + cell, g.alpha > 0.f ? A::make(attenuate(diff, g.alpha, r.t_cur), g) : val);
                         ++my_written;
                     }
                     if (!ray_advance(r, N)) break;
@@ -421,7 +587,7 @@ dda_accumulate_agg_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, 
         bool active = false;
         Walk w;
         typename V::T val = 0;
-        if (i < count) {
+        if (i < count && queue_slot_ok(ctl, q, i) && queue_entry_ok(ctl, __ldg(q.pix + i), __ldg(q.pair + i), __ldg(q.diff + i), width, height)) {
             const uint32_t pix = __ldg(q.pix + i);
             const float diff = __ldg(q.diff + i);
             const pvp_pair *P = pairs + __ldg(q.pair + i);
@@ -486,7 +652,7 @@ dda_accumulate_agg_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, 
                 }
                 issue = writes && (lane == 31 || ((heads >> (lane + 1)) & 1u));
             }
-            if (issue) { A::add(grid + key, sum); ++my_atomics; }
+            if (issue && PVP_DEV_CHECK(ctl, PVP_CHK_GRID, key < (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)g.n * (unsigned)g.n)) { A::add(grid + key, sum); ++my_atomics; }
             my_steps += active;
             my_written += writes;
             if (active) active = walk_advance(w);
@@ -670,10 +836,22 @@ __device__ __forceinline__ bool slab_reach(const Ray &r, float cam_x, float dir_
     return true;
 }
 
+// The device-side choice between the two lock-step kernels of a batch (both are launched; the other one exits at once).
+// min_rays: lean2 needs that many rays (its 64-ray chunks leave SMs idle on small batches); paired_pct: ... and at least that share
+// of the rays in vertical pairs (counted by K1), i.e. locally dense motion -- with scattered motion the second ray of a lane rarely
+// shares the first one's voxel, every lane issues two REDs and lean does the same work better (10 % iid motion: 493 against 444 G
+// voxel-steps/s; a moving object covering 3.6 % of the frame is locally dense: 730 against 566 G the other way round).
+// Forced variants: min_rays = 0, paired_pct = 0 (always lean2) or min_rays = ~0 (never).
+__device__ __forceinline__ bool pick_lean2(const Ctl *ctl, unsigned long long count, unsigned long long min_rays, unsigned long long paired_pct)
+{
+    if (count < min_rays) return false;
+    return paired_pct == 0 || 200ull * ctl->n_paired >= paired_pct * count;
+}
+
 template <int MODE, bool SLAB, bool NARROW, int MINB>
 __global__ void __launch_bounds__(LEAN_THREADS, MINB)
 dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
-                           int width, int height, Ctl *__restrict__ ctl, unsigned long long count_lo, unsigned long long count_hi)
+                           int width, int height, Ctl *__restrict__ ctl, unsigned long long min_rays, unsigned long long paired_pct)
 {
     using A = Accum<MODE>;
     using V = LeanVal<MODE, NARROW>;
@@ -682,7 +860,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
     const unsigned lane = threadIdx.x & 31;
     const LaneMasks lm = lane_masks(lane);
     const unsigned long long count = ctl->count;
-    if (count < count_lo || count >= count_hi) return;  // auto mode launches both lock-step kernels; the ray count picks one
+    if (pick_lean2(ctl, count, min_rays, paired_pct)) return;  // auto mode launches both lock-step kernels; the batch's rays pick one on the device
     const int N = g.n;
     const unsigned slab_cells = (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)N * (unsigned)N;
     unsigned steps32 = 0, written32 = 0, atomics32 = 0;  // per lane; see lean2
@@ -702,7 +880,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
         T val = 0;
         float n_issued = 0.f, n_inslab = 0.f;
 
-        if (i < count) {
+        if (i < count && queue_slot_ok(ctl, q, i) && queue_entry_ok(ctl, __ldg(q.pix + i), __ldg(q.pair + i), __ldg(q.diff + i), width, height)) {
             const uint32_t pix = __ldg(q.pix + i);
             const float diff = __ldg(q.diff + i);
             const pvp_pair *P = pairs + __ldg(q.pair + i);
@@ -769,7 +947,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
             t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t);
             t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t);
             const bool issue = (heads & lm.next) && key != KEY_NONE;
-            red_if(issue, grid + key, V::cell_value(sum, g));
+            red_if(issue && PVP_DEV_CHECK(ctl, PVP_CHK_GRID, key < slab_cells), grid + key, V::cell_value(sum, g));
             if (issue) n_issued += 1.f;
             if (!SLAB) heads = __ballot_sync(FULL, next_head);
             // ---- rays that ended: park the lane; leave when the whole warp is parked ---------------------
@@ -844,13 +1022,14 @@ __device__ __forceinline__ void rays_retire(RayS &r)
 // queue entry -> walking state; returns the value to accumulate (0 when the ray casts no step)
 template <typename V, bool SLAB>
 __device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, unsigned long long i, unsigned long long count,
-                                                    const pvp_pair *__restrict__ pairs, const GridP &g, int width, int height, float &raw_diff)
+                                                    const pvp_pair *__restrict__ pairs, const GridP &g, int width, int height, float &raw_diff, Ctl *ctl)
 {
     rays_park(s);
     raw_diff = 0.f;
-    if (i >= count) return 0;
+    if (i >= count || !queue_slot_ok(ctl, q, i)) return 0;
     const uint32_t pix = __ldg(q.pix + i);
     const float diff = __ldg(q.diff + i);
+    if (!queue_entry_ok(ctl, pix, __ldg(q.pair + i), diff, width, height)) return 0;
     const pvp_pair *P = pairs + __ldg(q.pair + i);
     const int v = (int)(pix / (uint32_t)width), u = (int)(pix - (uint32_t)v * (uint32_t)width);
     float dx, dy, dz;
@@ -927,7 +1106,7 @@ __device__ __forceinline__ bool rays_ended(const RayS &s, unsigned cur, float m,
 template <int MODE, bool SLAB, bool NARROW, int MINB, bool ATT = false>
 __global__ void __launch_bounds__(LEAN_THREADS, MINB)
 dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
-                            int width, int height, Ctl *__restrict__ ctl, unsigned long long count_lo, unsigned long long count_hi)
+                            int width, int height, Ctl *__restrict__ ctl, unsigned long long min_rays, unsigned long long paired_pct)
 {
     using V = LeanVal<MODE, NARROW>;
     using T = typename V::T;
@@ -935,7 +1114,7 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
     const unsigned lane = threadIdx.x & 31;
     const LaneMasks lm = lane_masks(lane);
     const unsigned long long count = ctl->count;
-    if (count < count_lo || count >= count_hi) return;  // auto mode launches both lock-step kernels; the ray count picks one
+    if (!pick_lean2(ctl, count, min_rays, paired_pct)) return;  // auto mode launches both lock-step kernels; the batch's rays pick one on the device
     const unsigned slab_cells = (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)g.n * (unsigned)g.n;
     // per-lane counters in 32 bits (a lane walks count / 113 664 rays of at most 3 n steps each; the queue holds < 2^32 entries): three
     // registers less in a loop that sits at its register cap; widened for the warp reduction below
@@ -947,8 +1126,8 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
         if (base >= count) break;
         RayS a, b;
         float da, db;  // the rays' pix_val (ray_voxel.cpp:500); the attenuating kernel derives every step's value from it
-        T va = rays_setup<V, SLAB>(a, q, base + 2 * lane, count, pairs, g, width, height, da);
-        T vb = rays_setup<V, SLAB>(b, q, base + 2 * lane + 1, count, pairs, g, width, height, db);
+        T va = rays_setup<V, SLAB>(a, q, base + 2 * lane, count, pairs, g, width, height, da, ctl);
+        T vb = rays_setup<V, SLAB>(b, q, base + 2 * lane + 1, count, pairs, g, width, height, db, ctl);
         float n_issued = 0.f, n_inslab = 0.f;
         float walked = 0.f;  // iterations of this chunk so far == voxels emitted by every ray that is still alive
         if (__all_sync(FULL, !rays_live(a) && !rays_live(b))) continue;
@@ -983,8 +1162,8 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
             t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t);
             t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t);
             const bool issue = (heads & lm.next) && ka != KEY_NONE;
-            red_if(issue, grid + ka, V::cell_value(sum, g));
-            red_if(b_alone, grid + kb, V::cell_value(sb, g));
+            red_if(issue && PVP_DEV_CHECK(ctl, PVP_CHK_GRID, ka < slab_cells), grid + ka, V::cell_value(sum, g));
+            red_if(b_alone && PVP_DEV_CHECK(ctl, PVP_CHK_GRID, kb < slab_cells), grid + kb, V::cell_value(sb, g));
             if (issue) n_issued += 1.f;
             if (b_alone) n_issued += 1.f;
             heads = __ballot_sync(FULL, next_head);
@@ -1116,11 +1295,37 @@ static int k2_grid_size(pvp_ctx *ctx, const void *kernel, int threads = K2_THREA
     return ctx->sm_count * per_sm;  // persistent: every CTA resident, a multiple of the SM count
 }
 
+// the queue as K1 sees it; the checked build can be told to under-state its capacity (option inject_fault = 1) so that a test can see the
+// bounds checks fire: the writes past the stated capacity are skipped and counted, PVP_ERR_CHECK comes back
+static Queue k1_queue(const pvp_ctx *ctx)
+{
+    Queue q = ctx->queue;
+#ifdef PVP_CHECKED
+    if (ctx->opt_inject_fault == 1) q.capacity /= 4;
+#endif
+    return q;
+}
+
 template <typename T>
 static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_stride, long long n_pix, int n_pairs, float threshold,
                      int width = 0, int height = 0, int row_group = 1, bool snake = false)
 {
     constexpr int PX = FrameVec<T>::PX;
+    if (row_group < 0) {  // Z-order queue
+        const size_t vec_bytes = sizeof(T) * K1T_COLS;
+        const bool vec = ((uintptr_t)frames_dev % vec_bytes == 0) && (frame_stride % K1T_COLS == 0) && (width % K1T_COLS == 0);
+        const long long foots = (long long)((width + K1M_FOOT - 1) / K1M_FOOT) * ((height + K1M_FOOT - 1) / K1M_FOOT);
+        dim3 grid((unsigned)foots, (unsigned)n_pairs);
+        LaunchScope scope(ctx, 1);
+        if (row_group == -4)
+            motion_compact_morton_kernel<T, 4><<<grid, K1Morton<4>::THREADS, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, width, height, threshold, vec,
+                                                                                                k1_queue(ctx), ctx->ctl_dev);
+        else
+            motion_compact_morton_kernel<T, 8><<<grid, K1Morton<8>::THREADS, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, width, height, threshold, vec,
+                                                                                                k1_queue(ctx), ctx->ctl_dev);
+        PVP_CUDA(cudaGetLastError());
+        return PVP_OK;
+    }
     if (row_group > 1) {
         const size_t vec_bytes = sizeof(T) * K1T_COLS;  // one row segment of a thread
         const bool vec = ((uintptr_t)frames_dev % vec_bytes == 0) && (frame_stride % K1T_COLS == 0) && (width % K1T_COLS == 0);
@@ -1131,7 +1336,7 @@ static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_strid
         dim3 grid((unsigned)((segs + per_cta - 1) / per_cta), (unsigned)n_pairs);
         LaunchScope scope(ctx, 1);
         auto k = R == 8 ? motion_compact_rowgroup_kernel<T, 8> : R == 4 ? motion_compact_rowgroup_kernel<T, 4> : motion_compact_rowgroup_kernel<T, 2>;
-        k<<<grid, threads, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, width, height, threshold, vec, snake, ctx->queue, ctx->ctl_dev);
+        k<<<grid, threads, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, width, height, threshold, vec, snake, k1_queue(ctx), ctx->ctl_dev);
         PVP_CUDA(cudaGetLastError());
         return PVP_OK;
     }
@@ -1139,7 +1344,7 @@ static int launch_k1(pvp_ctx *ctx, const void *frames_dev, long long frame_strid
     dim3 grid((unsigned)((n_pix + (long long)K1_THREADS * PX - 1) / ((long long)K1_THREADS * PX)), (unsigned)n_pairs);
     LaunchScope scope(ctx, 1);
     motion_compact_kernel<T><<<grid, K1_THREADS, 0, ctx->stream>>>((const T *)frames_dev, frame_stride, ctx->pairs_dev, n_pix,
-                                                                   threshold, vec_ok, ctx->queue, ctx->ctl_dev);
+                                                                   threshold, vec_ok, k1_queue(ctx), ctx->ctl_dev);
     PVP_CUDA(cudaGetLastError());
     return PVP_OK;
 }
@@ -1154,30 +1359,30 @@ static void launch_agg(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, 
 
 // lean_regs: register budget = resident warps per SM: 0/72 -> 28 warps at 128-thread CTAs (24 at 256), 80 -> 24 warps, 64 -> 32 warps
 template <int MODE, bool SLAB, bool NARROW>
-static void launch_lean(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height, unsigned long long count_lo = 0,
-                        unsigned long long count_hi = ~0ull)
+static void launch_lean(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height, unsigned long long min_rays = ~0ull,
+                        unsigned long long paired_pct = 0)  // defaults: lean2 is never picked, this kernel always runs
 {
     auto k = ctx->opt_lean_regs == 64 ? dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_C>
            : ctx->opt_lean_regs == 80 ? dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_B> : dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_A>;
     k<<<k2_grid_size(ctx, (const void *)k, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
-                                                                                           width, height, ctx->ctl_dev, count_lo, count_hi);
+                                                                                           width, height, ctx->ctl_dev, min_rays, paired_pct);
 }
 
 template <int MODE, bool SLAB, bool NARROW>
-static void launch_lean2(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height, unsigned long long count_lo = 0,
-                         unsigned long long count_hi = ~0ull)
+static void launch_lean2(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height, unsigned long long min_rays = 0,
+                         unsigned long long paired_pct = 0)  // defaults: always picked
 {
     if (g.alpha > 0.f) {  // opt-in distance attenuation: values change every step, so no integral shortcut (NARROW is false here)
         auto ka = dda_accumulate_lean2_kernel<MODE, SLAB, false, 3, true>;
         ka<<<k2_grid_size(ctx, (const void *)ka, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
-                                                                                                 width, height, ctx->ctl_dev, count_lo, count_hi);
+                                                                                                 width, height, ctx->ctl_dev, min_rays, paired_pct);
         return;
     }
     // lean_regs: 0/80 -> 3 resident CTAs (24 warps; measured best: 780 G voxel-steps/s at 512^3 on 2-row tiles), 128 -> 2 CTAs (686 G), 64 -> 4 CTAs (722 G)
     auto k = ctx->opt_lean_regs == 128 ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 2>
            : ctx->opt_lean_regs == 64  ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 4> : dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, PVP_LEAN2_MINB>;
     k<<<k2_grid_size(ctx, (const void *)k, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
-                                                                                           width, height, ctx->ctl_dev, count_lo, count_hi);
+                                                                                           width, height, ctx->ctl_dev, min_rays, paired_pct);
 }
 
 // See the lean kernel's header: no t value of the batch can overflow to -inf.
@@ -1214,15 +1419,11 @@ static size_t plane_bytes(const GridP &g, int accum_mode)
     return (size_t)g.n * g.n * (accum_mode == PVP_ACCUM_F32 ? sizeof(float) : sizeof(unsigned long long));
 }
 constexpr size_t PLANE_LARGE = 2u << 20;
-static int auto_row_group(const GridP &g, int accum_mode)
-{
-    return plane_bytes(g, accum_mode) <= PLANE_LARGE ? 4 : 8;
-}
-
 // dda_variant: 0 = auto (lean2 / lean by ray count where their 32-bit voxel keys allow, else 3), 1 = segmented-scan aggregation (round-1
 // baseline), 2 = match.any aggregation, 3 = one RED per lane and step (no aggregation, any grid size),
 // 4 = lean lock-step kernel (one ray per lane), 5 = lean2 (two rays per lane, vertical neighbours of K1's tile order).  narrow_ok: uint8 frames, i.e. integer addends (LeanVal<FIXED, true>).
-static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_ok, bool lean_ok, void *grid_dev, int width, int height)  // NOLINT
+static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_ok, bool lean_ok, void *grid_dev, int width, int height,
+                     unsigned long long batch_pixels)  // NOLINT
 {
     LaunchScope scope(ctx, 2);
     int variant = effective_variant(ctx);
@@ -1238,16 +1439,20 @@ static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_o
     if (variant == 0 && plane_bytes(g, accum_mode) > PLANE_LARGE) variant = 4;
     if (variant == 0) {
         ++ctx->prof.launches_k2;  // two kernels are launched (the scope above counted one); the one not chosen exits at once
+        // both lock-step kernels are launched; K1's counters pick one on the device (pick_lean2): lean2 from LEAN2_MIN_RAYS_PER_WARP rays per
+        // resident warp up AND lean2_paired percent of the rays in vertical pairs (default 50), lean otherwise
         const unsigned long long T = (unsigned long long)ctx->sm_count * 3 * (LEAN_THREADS / 32) * LEAN2_MIN_RAYS_PER_WARP;
+        const unsigned long long pct = (unsigned long long)(ctx->opt_lean2_density > 0 ? ctx->opt_lean2_density : 50);
+        (void)batch_pixels;
         if (f32) {
-            if (slab) { launch_lean<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height, T); }
-            else { launch_lean<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height, T); }
+            if (slab) { launch_lean<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height, T, pct); }
+            else { launch_lean<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height, T, pct); }
         } else if (narrow_ok) {
-            if (slab) { launch_lean<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height, T); }
-            else { launch_lean<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height, T); }
+            if (slab) { launch_lean<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height, T, pct); }
+            else { launch_lean<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height, T, pct); }
         } else {
-            if (slab) { launch_lean<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height, T); }
-            else { launch_lean<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height, 0, T); launch_lean2<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height, T); }
+            if (slab) { launch_lean<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height, T, pct); }
+            else { launch_lean<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height, T, pct); }
         }
     } else if (variant == 5) {
         if (f32) { if (slab) launch_lean2<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height); else launch_lean2<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height); }
@@ -1311,10 +1516,13 @@ static int run_batches(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, lo
         if (rc) return rc;
         rc = upload_pairs(ctx, pairs + p0, np);
         if (rc) return rc;
-        PVP_CUDA(cudaMemsetAsync(ctx->ctl_dev, 0, 2 * sizeof(unsigned long long), ctx->stream));  // count, head
-        // queue order: tiles of R image rows (lean2 walks two vertically adjacent pixels per lane); 1 = plain row-major
+        PVP_CUDA(cudaMemsetAsync(ctx->ctl_dev, 0, 3 * sizeof(unsigned long long), ctx->stream));  // count, head, n_paired
+        // queue order (k1_row_group): 0 = auto: Z-order for the lock-step kernels (motion_compact_morton_kernel; blocks of 4 rows while an
+        // x-plane of the grid stays within 2 MiB, of 8 rows above), row-major for variants 1-3; -4 / -8 = Z-order with blocks of that many
+        // rows, 1 = plain row-major, 2 / 4 / 8 = the round-1 tiles of that many image rows (kept for A/B runs)
         const int ev = effective_variant(ctx);
-        const int row_group = ctx->opt_k1_row_group > 0 ? (int)ctx->opt_k1_row_group : ev == 0 ? auto_row_group(g, accum_mode) : ev >= 4 ? 2 : 1;
+        const int row_group = ctx->opt_k1_row_group != 0 ? (int)ctx->opt_k1_row_group
+                              : (ev == 0 || ev >= 4) ? (plane_bytes(g, accum_mode) <= PLANE_LARGE ? -4 : -8) : 1;
         // snake order of the tile columns: default for tiles of 4 rows and more (k1_snake: -1 auto, 0 off, 1 on)
         const bool snake = ctx->opt_k1_snake >= 0 ? ctx->opt_k1_snake != 0 : row_group >= 4;
         rc = frame_dtype == PVP_FRAME_U8 ? launch_k1<uint8_t>(ctx, frames_dev, frame_stride, n_pix, np, threshold, width, height, row_group, snake)
@@ -1322,7 +1530,7 @@ static int run_batches(pvp_ctx *ctx, const void *frames_dev, int frame_dtype, lo
         if (rc) return rc;
         // "integral" fixed-point sums: uint8 frames have integer diffs <= 255 (see LeanVal<FIXED, true>)
         const bool narrow_ok = frame_dtype == PVP_FRAME_U8;
-        rc = launch_k2(ctx, g, accum_mode, narrow_ok, lean_geometry_ok(g, pairs + p0, np), grid_dev, width, height);
+        rc = launch_k2(ctx, g, accum_mode, narrow_ok, lean_geometry_ok(g, pairs + p0, np), grid_dev, width, height, (unsigned long long)np * (unsigned long long)n_pix);
         if (rc) return rc;
     }
     return PVP_OK;
@@ -1408,6 +1616,7 @@ int pvp_motion_accumulate(pvp_ctx *ctx, const void *frames_dev, int frame_dtype,
     if (n_pairs > 0) {
         rc = run_batches(ctx, frames_dev, frame_dtype, frame_stride, width, height, pairs, n_pairs, threshold, grid_dev, g, grid->accum_mode);
         if (rc) return rc;
+        if ((rc = checked_verify(ctx, "pvp_motion_accumulate"))) return rc;
     }
     return fetch_stats(ctx, stats);
 }
@@ -1482,6 +1691,7 @@ int pvp_motion_accumulate_host(pvp_ctx *ctx, const void *frames_host, int frame_
         if (rc) return rc;
         PVP_CUDA(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
     }
+    if ((rc = checked_verify(ctx, "pvp_motion_accumulate_host"))) return rc;
     return fetch_stats(ctx, stats);
 }
 

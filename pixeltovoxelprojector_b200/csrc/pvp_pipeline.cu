@@ -23,6 +23,8 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "pvp_internal.h"
 
 namespace {
@@ -269,28 +271,32 @@ void pvp_run_options_default(pvp_run_options *o)
 
 namespace {
 
-struct Slot { int cam_pos; };  // index into the camera's sorted frame list
-
-struct PinnedChunk {
-    uint8_t *buf = nullptr;
-    size_t cap = 0;
-    cudaEvent_t done = nullptr;
-};
-
-// Decode prefetcher: once K2 is fast, decoding 1080p/4K files is what limits frames/s through the CLI.
-// The frames a run will visit are known up front (metadata order), so a pool of host threads decodes them ahead of
-// the consumer into a bounded ring; the consumer sees them strictly in order, so skip-on-error / size-mismatch /
-// prev<-curr semantics (ray_voxel.cpp:464-481, :534) are untouched.
+// ---- frame stream: files -> pinned ring -> device ring -> K1/K2 batches ----------------------------------------
+// Once K2 is fast, getting frames to it is what limits frames/s through the CLI.  The frames a run will visit are known up front
+// (metadata order), so:
+//   * a pool of host threads decodes them ahead of the consumer STRAIGHT INTO a ring of pinned slots (a raw PGM frame is one copy,
+//     page cache -> pinned memory; no heap traffic, no consumer-side memcpy);
+//   * the consumer sees the frames strictly in order -- skip-on-error / size-mismatch / prev<-curr semantics (ray_voxel.cpp:464-481,
+//     :534) are decided there, untouched -- and sends each loadable frame ONCE over PCIe into a ring of device slots (the previous
+//     frame of a pair is already there: it was the current frame of the pair before);
+//   * every `batch` pairs one K1 + K2 batch is launched on the device ring; the copy stream runs ahead of the kernels by up to two
+//     batches (a device slot is rewritten only after the batch that last read it has finished: event wait on the copy stream), the
+//     decoders run ahead of the copies by the pinned ring.
+// Nothing here blocks the consumer on the GPU except ring pressure.
 class DecodePool {
 public:
-    struct Item { bool ok = false; int w = 0, h = 0; std::vector<uint8_t> px; };
+    struct Item { int status = 0; int w = 0, h = 0; std::vector<uint8_t> spill; };   // status: 1 pixels in the slot, -1 in spill (larger than a slot), 0 failed
 
-    DecodePool(std::vector<std::string> paths, int threads) : paths_(std::move(paths))
+    // ring: n_slots pinned slots of slot_stride bytes; a worker decodes into slot + dst_off, capacity dst_cap bytes.  copied[slot]: the
+    // event the consumer records after enqueueing the slot's H2D copy; a worker waits for it before it overwrites the slot.
+    DecodePool(std::vector<std::string> paths, int threads, uint8_t *ring, size_t slot_stride, size_t dst_off, size_t dst_cap, int n_slots,
+               cudaEvent_t *copied, int device)
+        : paths_(std::move(paths)), ring_(ring), stride_(slot_stride), off_(dst_off), cap_(dst_cap), copied_(copied), device_(device)
     {
         const int n = (int)paths_.size();
         threads = std::max(1, std::min(threads, std::max(1, n)));
-        ring_.resize((size_t)std::min(n, 2 * threads + 2));
-        state_.assign(ring_.size(), -1);
+        items_.resize((size_t)std::max(1, n_slots));
+        state_.assign(items_.size(), -1);
         for (int t = 0; t < threads && n > 0; ++t) workers_.emplace_back([this] { work(); });
     }
     ~DecodePool()
@@ -302,18 +308,20 @@ public:
         cv_.notify_all();
         for (auto &t : workers_) t.join();
     }
+    int slot_of(int idx) const { return (int)((size_t)idx % items_.size()); }
+    uint8_t *pixels(int idx) { return ring_ + (size_t)slot_of(idx) * stride_; }
     // frame `idx` (consumed in increasing order); valid until release(idx)
     Item &get(int idx)
     {
         std::unique_lock<std::mutex> g(m_);
-        cv_.wait(g, [&] { return state_[(size_t)idx % ring_.size()] == idx; });
-        return ring_[(size_t)idx % ring_.size()];
+        cv_.wait(g, [&] { return state_[(size_t)slot_of(idx)] == idx; });
+        return items_[(size_t)slot_of(idx)];
     }
     void release(int idx)
     {
         {
             std::lock_guard<std::mutex> g(m_);
-            state_[(size_t)idx % ring_.size()] = -1;
+            state_[(size_t)slot_of(idx)] = -1;
             consumed_ = idx + 1;
         }
         cv_.notify_all();
@@ -322,18 +330,20 @@ public:
 private:
     void work()
     {
+        cudaSetDevice(device_);   // the slots' events belong to the context's device
         for (;;) {
             const int idx = next_.fetch_add(1);
             if (idx >= (int)paths_.size()) return;
-            const size_t slot = (size_t)idx % ring_.size();
+            const size_t slot = (size_t)slot_of(idx);
             {
                 std::unique_lock<std::mutex> g(m_);
-                cv_.wait(g, [&] { return stop_ || (idx < consumed_ + (int)ring_.size() && state_[slot] == -1); });
+                cv_.wait(g, [&] { return stop_ || (idx < consumed_ + (int)items_.size() && state_[slot] == -1); });
                 if (stop_) return;
                 state_[slot] = -2;  // being filled
             }
-            Item &it = ring_[slot];
-            it.ok = pvp::decode_gray_file(paths_[(size_t)idx].c_str(), it.px, &it.w, &it.h);
+            if (copied_[slot]) cudaEventSynchronize(copied_[slot]);   // the slot's previous frame has left for the device
+            Item &it = items_[slot];
+            it.status = pvp::decode_gray_file_into(paths_[(size_t)idx].c_str(), ring_ + slot * stride_ + off_, cap_, &it.w, &it.h, it.spill);
             {
                 std::lock_guard<std::mutex> g(m_);
                 state_[slot] = idx;
@@ -342,7 +352,11 @@ private:
         }
     }
     std::vector<std::string> paths_;
-    std::vector<Item> ring_;
+    uint8_t *ring_;
+    size_t stride_, off_, cap_;
+    cudaEvent_t *copied_;
+    int device_;
+    std::vector<Item> items_;
     std::vector<int> state_;  // -1 free, -2 being filled, else the frame index it holds
     std::vector<std::thread> workers_;
     std::mutex m_;
@@ -352,69 +366,168 @@ private:
     bool stop_ = false;
 };
 
-struct Runner {
+double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct FrameStream {
     pvp_ctx *ctx;
     const pvp_run_options *opt;
     void *grid_dev;
-    std::string folder;
-    PinnedChunk chunk[2];
-    int cur = 0;
-    // open chunk
-    int W = 0, H = 0, n_frames = 0;
+    // pinned ring (host side of PCIe)
+    uint8_t *hring = nullptr;
+    size_t hslot = 0;               // bytes per pinned slot
+    int n_hslots = 0;
+    std::vector<cudaEvent_t> copied;  // per pinned slot: its H2D copy has finished
+    // device ring
+    uint8_t *dring = nullptr;
+    size_t dslot = 0;               // bytes per device slot (a multiple of 16)
+    int n_dslots = 0, dnext = 0;
+    std::vector<long long> dslot_batch;  // id of the last batch that reads the slot (-1: none)
+    static constexpr int NB = 64;
+    cudaEvent_t batch_done[NB] = {};
+    cudaEvent_t ev_up = nullptr;
+    long long open_batch = 0;
+    // open batch
+    int W = 0, H = 0, prev_ds = -1, batch_pairs = 32;
     std::vector<pvp_pair> pairs;
-    int max_frames = 32;
     uint64_t frames_loaded = 0, pairs_done = 0;
+    double s_wait = 0, s_upload = 0, s_launch = 0;
     // loader noise (ray_voxel.cpp:203-218): frames become float32, one generator for the whole run, seeded once
     bool noise = false;
     size_t elem = 1;
     std::mt19937 gen;
+    std::vector<float> noise_tmp, spill_f32;
 
-    int ensure(PinnedChunk &c, size_t bytes)
+    ~FrameStream()
     {
-        if (c.cap >= bytes) return PVP_OK;
-        if (c.buf) { PVP_CUDA(cudaEventSynchronize(c.done)); cudaFreeHost(c.buf); c.buf = nullptr; c.cap = 0; }
-        PVP_CUDA(cudaMallocHost((void **)&c.buf, bytes));
-        c.cap = bytes;
-        return PVP_OK;
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        for (auto e : copied) if (e) cudaEventDestroy(e);
+        for (auto e : batch_done) if (e) cudaEventDestroy(e);
+        if (ev_up) cudaEventDestroy(ev_up);
+        // the rings stay with the context for the next call (pvp_ctx_destroy frees them)
     }
-    int init()
+    int init(size_t frame_px, int host_slots)
     {
-        for (auto &c : chunk) PVP_CUDA(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
-        return PVP_OK;
-    }
-    // the pinned chunk buffers and their events go with the Runner on every path out of the frame loop, error returns and
-    // exceptions (caught at the C ABI) included
-    ~Runner()
-    {
-        for (auto &c : chunk) {
-            if (c.done) { cudaEventSynchronize(c.done); cudaEventDestroy(c.done); c.done = nullptr; }
-            if (c.buf) { cudaFreeHost(c.buf); c.buf = nullptr; c.cap = 0; }
+        const size_t px = std::max<size_t>(frame_px, 16);
+        hslot = (px * elem + 4095) / 4096 * 4096;
+        n_hslots = std::max(2, host_slots);
+        if (ctx->fs_hring_bytes < hslot * (size_t)n_hslots) {
+            if (ctx->fs_hring) cudaFreeHost(ctx->fs_hring);
+            ctx->fs_hring = nullptr; ctx->fs_hring_bytes = 0;
+            PVP_CUDA(cudaMallocHost((void **)&ctx->fs_hring, hslot * (size_t)n_hslots));
+            ctx->fs_hring_bytes = hslot * (size_t)n_hslots;
         }
+        hring = ctx->fs_hring;
+        copied.assign((size_t)n_hslots, nullptr);
+        for (auto &e : copied) PVP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : batch_done) PVP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        PVP_CUDA(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
+        n_dslots = 3 * batch_pairs + 3;   // three batches of frames in flight + the carried previous frame
+        return grow_device(px * elem);
     }
-    // Submit the open chunk; keep its last frame as frame 0 of the next chunk when `carry`.
-    int flush(bool carry)
+    // (re)allocate the device ring with slots of at least `bytes`; the previous frame, if any, moves to slot 0 of the new ring
+    int grow_device(size_t bytes)
     {
-        PinnedChunk &c = chunk[cur];
-        const size_t fbytes = (size_t)W * H * elem;
-        if (!pairs.empty()) {
-            int rc = pvp_motion_accumulate_host(ctx, c.buf, noise ? PVP_FRAME_F32 : PVP_FRAME_U8, (int64_t)W * H, W, H, n_frames, pairs.data(),
-                                                (int)pairs.size(), opt->threshold, grid_dev, &opt->grid, nullptr);
-            if (rc) return rc;
-            PVP_CUDA(cudaEventRecord(c.done, ctx->stream));
-            pairs_done += pairs.size();
-        }
-        PinnedChunk &nx = chunk[cur ^ 1];
-        if (carry && n_frames > 0) {
-            int rc = ensure(nx, (size_t)max_frames * fbytes);
-            if (rc) return rc;
-            PVP_CUDA(cudaEventSynchronize(nx.done));  // the other buffer's previous submission has been copied
-            memcpy(nx.buf, c.buf + (size_t)(n_frames - 1) * fbytes, fbytes);
-            n_frames = 1;
+        const size_t want = (bytes + 255) / 256 * 256;
+        if (dring && want <= dslot) return PVP_OK;
+        int rc = flush();
+        if (rc) return rc;
+        PVP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+        uint8_t *nr = nullptr;
+        if (!dring && ctx->fs_dring_bytes >= want * (size_t)n_dslots) {
+            nr = ctx->fs_dring;            // the ring of an earlier call is large enough
         } else {
-            n_frames = 0;
+            PVP_CUDA(cudaMalloc((void **)&nr, want * (size_t)n_dslots));
+            if (dring && prev_ds >= 0) PVP_CUDA(cudaMemcpy(nr, dring + (size_t)prev_ds * dslot, (size_t)W * H * elem, cudaMemcpyDeviceToDevice));
+            if (ctx->fs_dring) cudaFree(ctx->fs_dring);
+            ctx->fs_dring = nr; ctx->fs_dring_bytes = want * (size_t)n_dslots;
         }
+        dring = nr; dslot = want;
+        dslot_batch.assign((size_t)n_dslots, -1);
+        if (prev_ds >= 0) { prev_ds = 0; dnext = 1; } else { dnext = 0; }
+        return PVP_OK;
+    }
+    // launch K1 + K2 over the open batch's pairs (device ring slots); the previous frame stays where it is
+    int flush()
+    {
+        if (pairs.empty()) return PVP_OK;
+        const double t0 = wall_s();
+        nvtxRangePushA("pvp:K1+K2 batch");
+        PVP_CUDA(cudaEventRecord(ev_up, ctx->copy_stream));
+        PVP_CUDA(cudaStreamWaitEvent(ctx->stream, ev_up, 0));   // the batch's frames are on the device
+        int rc = pvp_motion_accumulate(ctx, dring, noise ? PVP_FRAME_F32 : PVP_FRAME_U8, (int64_t)(dslot / elem), W, H, n_dslots, pairs.data(),
+                                       (int)pairs.size(), opt->threshold, grid_dev, &opt->grid, nullptr);
+        nvtxRangePop();
+        if (rc) return rc;
+        PVP_CUDA(cudaEventRecord(batch_done[open_batch % NB], ctx->stream));
+        pairs_done += pairs.size();
         pairs.clear();
-        cur ^= 1;
+        ++open_batch;
+        s_launch += wall_s() - t0;
+        return PVP_OK;
+    }
+    // One decoded frame (w x h, 8-bit gray at src: a pinned slot, or pageable memory with pinned_slot < 0) -> a free device slot.
+    // Returns the device slot through *ds_out.  Pinned source: asynchronous, `copied[pinned_slot]` marks the end of the copy.
+    int upload(uint8_t *src, int pinned_slot, int w, int h, int *ds_out)
+    {
+        const double t0 = wall_s();
+        const size_t npx = (size_t)w * h, bytes = npx * elem;
+        int rc = grow_device(bytes);
+        if (rc) return rc;
+        const void *from = src;
+        if (noise) {  // load_image_gray, ray_voxel.cpp:203-218: same generator, same distribution, same draw order (pixel order, frame after frame)
+            std::uniform_real_distribution<float> noise_dist(-1.0f, 1.0f);
+            noise_tmp.resize(npx);
+            for (size_t i = 0; i < npx; ++i) noise_tmp[i] = noise_dist(gen);
+            float *dst;
+            const uint8_t *px = src;
+            if (pinned_slot >= 0) {
+                dst = reinterpret_cast<float *>(hring + (size_t)pinned_slot * hslot);   // the 8-bit pixels sit in the last quarter of the slot: expand in place, forwards
+            } else {
+                spill_f32.resize(npx);
+                dst = spill_f32.data();
+            }
+            for (size_t i = 0; i < npx; ++i) {
+                float val = static_cast<float>(px[i]);
+                val += noise_tmp[i];
+                if (val < 0.0f) val = 0.0f;
+                if (val > 255.0f) val = 255.0f;
+                dst[i] = val;
+            }
+            from = dst;
+        }
+        int ds = dnext;
+        if (ds == prev_ds) ds = (ds + 1) % n_dslots;   // the previous frame is still needed by the next pair
+        dnext = (ds + 1) % n_dslots;
+        if (dslot_batch[(size_t)ds] == open_batch) {   // read by the batch that is still open: submit it first
+            if ((rc = flush())) return rc;
+        }
+        if (dslot_batch[(size_t)ds] >= 0)              // read by a submitted batch: the copy waits for that batch's kernels
+            PVP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, batch_done[dslot_batch[(size_t)ds] % NB], 0));
+        nvtxRangePushA("pvp:H2D frame");
+        PVP_CUDA(cudaMemcpyAsync(dring + (size_t)ds * dslot, from, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (pinned_slot >= 0) PVP_CUDA(cudaEventRecord(copied[(size_t)pinned_slot], ctx->copy_stream));
+        nvtxRangePop();
+        dslot_batch[(size_t)ds] = -1;
+        ++frames_loaded;
+        *ds_out = ds;
+        s_upload += wall_s() - t0;
+        return PVP_OK;
+    }
+    // the frame in device slot ds becomes the current frame of a pair with the previous one (pose of the CURRENT frame, :486-491)
+    int add_pair(int ds, const pvp_frame_info &ci, int w)
+    {
+        pvp_pair p;
+        memcpy(p.cam, ci.camera_position, sizeof(p.cam));
+        pvp_rotation_matrix(ci.yaw, ci.pitch, ci.roll, p.R);
+        p.focal = pvp_focal_length(ci.fov_degrees, w);
+        p.prev = prev_ds; p.curr = ds;
+        pairs.push_back(p);
+        dslot_batch[(size_t)prev_ds] = open_batch;
+        dslot_batch[(size_t)ds] = open_batch;
+        prev_ds = ds;
+        if ((int)pairs.size() >= batch_pairs) return flush();
         return PVP_OK;
     }
 };
@@ -435,6 +548,7 @@ static int ray_voxel_accumulate_impl(pvp_ctx *ctx, const char *metadata_json, co
                 opt->shard_rank, opt->shard_count);
     PVP_REQUIRE(!(opt->loader_noise && opt->shard_count > 1),
                 "loader_noise draws one pseudo-random stream over all frames in load order (ray_voxel.cpp:203-209); it cannot be frame-sharded");
+    const double t_begin = wall_s();
     pvp_frame_info *frames = nullptr;
     int n = 0;
     int rc = pvp_load_metadata(metadata_json, &frames, &n);
@@ -453,20 +567,7 @@ static int ray_voxel_accumulate_impl(pvp_ctx *ctx, const char *metadata_json, co
     const long long lo = total_slots * opt->shard_rank / opt->shard_count, hi = total_slots * (opt->shard_rank + 1) / opt->shard_count;
 
     DeviceGuard guard(ctx->device);
-    Runner R{ctx, opt, grid_dev, image_folder};
-    R.max_frames = opt->chunk_frames > 1 ? opt->chunk_frames : 32;
-    if (opt->loader_noise) {
-        R.noise = true; R.elem = sizeof(float);
-        R.gen.seed(opt->noise_seed);  // the reference: static std::mt19937 gen(rd()) -- here rd() is the caller's seed
-    }
-    if ((rc = R.init())) return rc;
-    std::vector<uint8_t> tmp;
-    uint64_t skipped = 0, mismatched = 0;
-
-    auto load = [&](const pvp_frame_info &fi, int *w, int *h) -> bool {  // serial load (shard look-back only)
-        std::string path = R.folder + "/" + fi.image_file;  // :467
-        return decode_gray_file(path.c_str(), tmp, w, h);
-    };
+    const std::string folder = image_folder;
     // every frame of this rank's block, in visiting order, goes through the decode pool
     std::vector<std::string> visit;
     {
@@ -477,48 +578,44 @@ static int ray_voxel_accumulate_impl(pvp_ctx *ctx, const char *metadata_json, co
             const long long cam_lo = s0, cam_hi = s0 + (long long)cf.size();
             s0 = cam_hi;
             const long long a = std::max(lo, cam_lo) - cam_lo, b = std::min(hi, cam_hi) - cam_lo;
-            for (long long k = a; k < b; ++k) visit.push_back(R.folder + "/" + cf[(size_t)k].image_file);
+            for (long long k = a; k < b; ++k) visit.push_back(folder + "/" + cf[(size_t)k].image_file);  // :467
         }
     }
     int decode_threads = opt->decode_threads;
     if (decode_threads <= 0) {
         const char *env = getenv("PVP_DECODE_THREADS");
-        decode_threads = env ? atoi(env) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    }
-    DecodePool pool(std::move(visit), decode_threads);
-    int visit_idx = 0;
-    auto load_next = [&](int *w, int *h) -> bool {  // next frame of the visiting order -> tmp
-        const int idx = visit_idx++;
-        DecodePool::Item &it = pool.get(idx);
-        const bool ok = it.ok;
-        if (ok) { *w = it.w; *h = it.h; tmp.swap(it.px); }  // the slot keeps the old buffer for its next decode
-        pool.release(idx);
-        return ok;
-    };
-    auto push_frame = [&](int w, int h) -> int {  // append tmp as a new frame of the open chunk
-        const size_t fbytes = (size_t)w * h * R.elem;
-        PinnedChunk &c = R.chunk[R.cur];
-        int rc2 = R.ensure(c, (size_t)R.max_frames * fbytes);
-        if (rc2) return rc2;
-        if (R.n_frames == 0) PVP_CUDA(cudaEventSynchronize(c.done));
-        if (R.noise) {  // load_image_gray, ray_voxel.cpp:203-218: same generator, same distribution, same draw order
-            std::uniform_real_distribution<float> noise_dist(-1.0f, 1.0f);
-            float *dst = reinterpret_cast<float *>(c.buf + (size_t)R.n_frames * fbytes);
-            const size_t n_px = (size_t)w * h;
-            for (size_t i = 0; i < n_px; ++i) {
-                float val = static_cast<float>(tmp[i]);
-                val += noise_dist(R.gen);
-                if (val < 0.0f) val = 0.0f;
-                if (val > 255.0f) val = 255.0f;
-                dst[i] = val;
-            }
-        } else {
-            memcpy(c.buf + (size_t)R.n_frames * fbytes, tmp.data(), fbytes);
+        if (env) {
+            decode_threads = atoi(env);
+        } else {  // up to 32 threads, sharing the host's cores with the other ranks of the node (torchrun exports LOCAL_WORLD_SIZE)
+            const char *lws = getenv("LOCAL_WORLD_SIZE");
+            const unsigned ranks = lws && atoi(lws) > 0 ? (unsigned)atoi(lws) : 1u;
+            decode_threads = (int)std::min(32u, std::max(2u, std::thread::hardware_concurrency() / ranks));
         }
-        R.W = w; R.H = h; R.n_frames++;
-        R.frames_loaded++;
-        return PVP_OK;
-    };
+    }
+    decode_threads = std::max(1, decode_threads);
+
+    FrameStream R{ctx, opt, grid_dev};
+    R.batch_pairs = opt->chunk_frames > 1 ? opt->chunk_frames - 1 : 32;
+    if (opt->loader_noise) {
+        R.noise = true; R.elem = sizeof(float);
+        R.gen.seed(opt->noise_seed);  // the reference: static std::mt19937 gen(rd()) -- here rd() is the caller's seed
+    }
+    // ring slots are sized by the first frame that decodes (a sequence normally has one resolution); larger frames later on take
+    // the spill path of the pool and grow the device ring
+    std::vector<uint8_t> tmp;
+    size_t first_px = 0;
+    for (size_t i = 0; i < visit.size() && !first_px; ++i) {
+        int w, h;
+        if (decode_gray_file(visit[i].c_str(), tmp, &w, &h)) first_px = (size_t)w * h;
+    }
+    if ((rc = R.init(first_px, 2 * decode_threads + 4))) return rc;
+    uint64_t skipped = 0, mismatched = 0;
+
+    // noise mode: the 8-bit pixels go into the last quarter of the (4 bytes per pixel) slot and are expanded in place
+    const size_t cap_px = R.hslot / R.elem;
+    DecodePool pool(std::move(visit), decode_threads, R.hring, R.hslot, R.noise ? 3 * cap_px : 0, cap_px, R.n_hslots, R.copied.data(), ctx->device);
+    int visit_idx = 0;
+    const double t_loop = wall_s();
 
     long long slot = 0;
     for (auto &kv : by_cam) {
@@ -528,59 +625,66 @@ static int ray_voxel_accumulate_impl(pvp_ctx *ctx, const char *metadata_json, co
         slot = cam_hi;
         const long long a = std::max(lo, cam_lo) - cam_lo, b = std::min(hi, cam_hi) - cam_lo;
         if (a >= b) continue;
-        bool prev_valid = false;
-        // the frame a pair starting this block compares against: last loadable frame before it
-        for (long long k = a - 1; k >= 0 && !prev_valid; --k) {
+        R.prev_ds = -1;   // no pair across cameras
+        // the frame a pair starting this block compares against: last loadable frame before it (serial load, pageable source)
+        for (long long k = a - 1; k >= 0 && R.prev_ds < 0; --k) {
             int w, h;
-            if (load(cf[(size_t)k], &w, &h)) {
-                if ((rc = push_frame(w, h))) return rc;
-                prev_valid = true;
+            const std::string path = folder + "/" + cf[(size_t)k].image_file;
+            if (decode_gray_file(path.c_str(), tmp, &w, &h)) {
+                int ds;
+                if ((rc = R.upload(tmp.data(), -1, w, h, &ds))) return rc;
+                R.W = w; R.H = h; R.prev_ds = ds;
             }
         }
         for (long long k = a; k < b; ++k) {
             const pvp_frame_info &ci = cf[(size_t)k];
-            int w, h;
-            if (!load_next(&w, &h)) {  // :470-473
-                if (opt->verbose) fprintf(stderr, "Failed to load image: %s/%s\nSkipping frame due to load error.\n", R.folder.c_str(), ci.image_file);
+            const int idx = visit_idx++;
+            const double t0 = wall_s();
+            nvtxRangePushA("pvp:decode wait");
+            DecodePool::Item &it = pool.get(idx);
+            nvtxRangePop();
+            R.s_wait += wall_s() - t0;
+            if (it.status == 0) {  // :470-473
+                pool.release(idx);
+                if (opt->verbose) fprintf(stderr, "Failed to load image: %s/%s\nSkipping frame due to load error.\n", folder.c_str(), ci.image_file);
                 ++skipped;
                 continue;
             }
-            if (!prev_valid) {  // :475-481
-                if ((rc = push_frame(w, h))) return rc;
-                prev_valid = true;
-                continue;
-            }
-            if (w != R.W || h != R.H) {  // detect_motion's size check, :238-243: no rays, prev still advances (:534)
+            const int w = it.w, h = it.h;
+            const bool in_slot = it.status == 1;
+            uint8_t *src = in_slot ? pool.pixels(idx) + (R.noise ? 3 * cap_px : 0) : it.spill.data();
+            const bool first = R.prev_ds < 0;                      // :475-481
+            const bool mismatch = !first && (w != R.W || h != R.H);  // detect_motion's size check, :238-243: no rays, prev still advances (:534)
+            if (mismatch) {
                 if (opt->verbose) fprintf(stderr, "Images differ in size. Can't do motion detection!\n");
                 ++mismatched;
-                if ((rc = R.flush(false))) return rc;
-                if ((rc = push_frame(w, h))) return rc;
+                if ((rc = R.flush())) return rc;   // a batch has one frame size
+                R.prev_ds = -1;                   // the old previous frame is not needed any more
+            }
+            int ds;
+            rc = R.upload(src, in_slot ? pool.slot_of(idx) : -1, w, h, &ds);
+            pool.release(idx);   // a pinned slot is rewritten only after its `copied` event
+            if (rc) return rc;
+            if (first || mismatch) {
+                R.W = w; R.H = h; R.prev_ds = ds;
                 continue;
             }
-            if (R.n_frames >= R.max_frames) {
-                std::vector<uint8_t> keep;
-                keep.swap(tmp);  // flush() carries the previous frame over; tmp holds the current one
-                rc = R.flush(true);
-                tmp.swap(keep);
-                if (rc) return rc;
-            }
-            if ((rc = push_frame(w, h))) return rc;
-            pvp_pair p;  // pose of the CURRENT frame, :486-491
-            memcpy(p.cam, ci.camera_position, sizeof(p.cam));
-            pvp_rotation_matrix(ci.yaw, ci.pitch, ci.roll, p.R);
-            p.focal = pvp_focal_length(ci.fov_degrees, w);
-            p.prev = R.n_frames - 2; p.curr = R.n_frames - 1;
-            R.pairs.push_back(p);
+            if ((rc = R.add_pair(ds, ci, w))) return rc;
         }
-        if ((rc = R.flush(false))) return rc;  // camera boundary: no pair across cameras
+        if ((rc = R.flush())) return rc;  // camera boundary
     }
+    const double t_drain = wall_s();
     pvp_stats st = {0, 0, 0, 0};
     rc = pvp_motion_accumulate(ctx, nullptr, PVP_FRAME_U8, 1, 1, 1, 0, nullptr, 0, 0.f, grid_dev, &opt->grid, &st);  // sync + counters
     if (rc) return rc;
+    const double t_end = wall_s();
     if (stats) { stats->n_rays += st.n_rays; stats->n_steps += st.n_steps; stats->n_written += st.n_written; stats->n_atomics += st.n_atomics; }
     if (report) {
         report->n_frames_listed = (uint64_t)n; report->n_frames_loaded = R.frames_loaded; report->n_frames_skipped = skipped;
         report->n_pairs = R.pairs_done; report->n_size_mismatch = mismatched;
+        report->seconds_total = wall_s() - t_begin; report->seconds_decode_wait = R.s_wait; report->seconds_upload = R.s_upload;
+        report->seconds_launch = R.s_launch; report->decode_threads = decode_threads;
+        report->seconds_setup = t_loop - t_begin; report->seconds_drain = t_end - t_drain;
     }
     return PVP_OK;
 }
@@ -633,6 +737,7 @@ int pvp_ray_voxel_main(int argc, char **argv)
     pvp_stats st = {0, 0, 0, 0};
     pvp_run_report rep;
     memset(&rep, 0, sizeof(rep));
+    if (want_stats) pvp_ctx_profile(ctx, 1);   // CUDA events around every K1 / K2 launch: the GPU side of the stage split below
     if (!rc) rc = pvp_ray_voxel_accumulate(ctx, argv[1], argv[2], grid_dev, &opt, &st, &rep);
     if (rc) {
         fprintf(stderr, "%s\n", pvp_last_error());
@@ -641,6 +746,9 @@ int pvp_ray_voxel_main(int argc, char **argv)
         return 1;
     }
     const auto t_run = now();
+    pvp_profile prof;
+    memset(&prof, 0, sizeof(prof));
+    if (want_stats) pvp_ctx_get_profile(ctx, &prof, 1);
     // .bin payload is always float32 (ray_voxel.cpp:552); it streams from the device to the file (:542-555)
     const float *cells_dev = (const float *)grid_dev;
     if (opt.grid.accum_mode == PVP_ACCUM_FIXED) {
@@ -655,10 +763,12 @@ int pvp_ray_voxel_main(int argc, char **argv)
     pvp_ctx_destroy(ctx);
     if (rc) { fprintf(stderr, "%s\n", pvp_last_error()); return 1; }
     printf("Saved voxel grid to %s\n", argv[3]);  // :554
-    if (want_stats)
-        fprintf(stderr, "frames=%llu pairs=%llu rays=%llu voxel_steps=%llu  seconds: context %.2f, frames %.2f, .bin %.2f\n",
+    if (want_stats)   // the host stages carry the same names as NVTX ranges (pvp:decode wait, pvp:H2D frame, pvp:K1+K2 batch, pvp:.bin)
+        fprintf(stderr, "frames=%llu pairs=%llu rays=%llu voxel_steps=%llu  seconds: context %.2f, frames %.2f, .bin %.2f | frame loop: decode wait %.3f, "
+                "H2D enqueue %.3f, batch launch %.3f, set-up %.3f, final drain %.3f (host, %d decode threads); GPU K1 %.3f, K2 %.3f\n",
                 (unsigned long long)rep.n_frames_loaded, (unsigned long long)rep.n_pairs, (unsigned long long)st.n_rays,
-                (unsigned long long)st.n_steps, secs(t_start, t_ctx), secs(t_ctx, t_run), secs(t_run, t_write));
+                (unsigned long long)st.n_steps, secs(t_start, t_ctx), secs(t_ctx, t_run), secs(t_run, t_write), rep.seconds_decode_wait,
+                rep.seconds_upload, rep.seconds_launch, rep.seconds_setup, rep.seconds_drain, rep.decode_threads, prof.ms_k1 * 1e-3, prof.ms_k2 * 1e-3);
     return 0;
 }
 

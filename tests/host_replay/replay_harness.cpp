@@ -3,7 +3,7 @@
 // The product's own orchestration sources (csrc/pvp_pipeline.cu: metadata, camera grouping, frame order, skip-on-error, size
 // mismatch, prev<-curr, frame sharding with look-back, chunking, the decode pool; csrc/pvp_imageio.cpp: the decoder) are compiled
 // as they are; only what they call on the device is replaced by a recorder: every frame pair handed to
-// pvp_motion_accumulate_host is printed (checksums of the two frames, size, camera, pose).  The test compares that list with a
+// pvp_motion_accumulate is printed (checksums of the two frames, size, camera, pose).  The test compares that list with a
 // Python model of ray_voxel.cpp:450-537.  Nothing here computes voxels.
 #include "pvp_pipeline.cu"
 #include "pvp_imageio.cpp"
@@ -16,9 +16,16 @@ void pvp::set_error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnpr
 int pvp::cuda_fail(cudaError_t, const char *, const char *, int) { return PVP_ERR_CUDA; }
 
 extern "C" {
-// CUDA runtime entry points the orchestration uses for its pinned staging buffers
+// CUDA runtime entry points the orchestration uses for its pinned ring, its device ring ("device memory" is plain host memory here) and
+// the events that recycle their slots
 cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (cudaEvent_t)1; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
@@ -26,14 +33,14 @@ cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 
-// the recorder
-int pvp_motion_accumulate_host(pvp_ctx *, const void *frames, int dtype, int64_t stride, int w, int h, int n_frames, const pvp_pair *pairs,
-                               int n_pairs, float threshold, void *, const pvp_grid_desc *, pvp_stats *)
+// the recorder: every batch the frame loop submits (frames = the device ring, pairs index its slots)
+int pvp_motion_accumulate(pvp_ctx *, const void *frames, int dtype, int64_t stride, int w, int h, int n_frames, const pvp_pair *pairs,
+                          int n_pairs, float threshold, void *, const pvp_grid_desc *, pvp_stats *)
 {
     const size_t elem = dtype == PVP_FRAME_F32 ? 4 : 1;
     for (int i = 0; i < n_pairs; ++i) {
         const pvp_pair &p = pairs[i];
-        if (p.prev < 0 || p.curr < 0 || p.prev >= n_frames || p.curr >= n_frames) { printf("BAD pair index %d %d of %d\n", p.prev, p.curr, n_frames); continue; }
+        if (p.prev < 0 || p.curr < 0 || p.prev >= n_frames || p.curr >= n_frames || p.prev == p.curr) { printf("BAD pair index %d %d of %d\n", p.prev, p.curr, n_frames); continue; }
         const unsigned long a = crc32(0, (const Bytef *)frames + (size_t)p.prev * stride * elem, (uInt)((size_t)w * h * elem));
         const unsigned long b = crc32(0, (const Bytef *)frames + (size_t)p.curr * stride * elem, (uInt)((size_t)w * h * elem));
         printf("PAIR %08lx %08lx %d %d cam %a %a %a ypr %a %a %a focal %a thr %a dtype %d\n", a, b, w, h, p.cam[0], p.cam[1], p.cam[2], p.R[0], p.R[1],
@@ -41,7 +48,7 @@ int pvp_motion_accumulate_host(pvp_ctx *, const void *frames, int dtype, int64_t
     }
     return PVP_OK;
 }
-int pvp_motion_accumulate(pvp_ctx *, const void *, int, int64_t, int, int, int, const pvp_pair *, int, float, void *, const pvp_grid_desc *, pvp_stats *) { return PVP_OK; }
+int pvp_motion_accumulate_host(pvp_ctx *, const void *, int, int64_t, int, int, int, const pvp_pair *, int, float, void *, const pvp_grid_desc *, pvp_stats *) { return PVP_OK; }
 // pose helpers: transparent stand-ins, so the record shows WHICH frame's pose went into a pair (ray_voxel.cpp:486-491: the current one)
 void pvp_rotation_matrix(float yaw, float pitch, float roll, float R[9]) { for (int i = 0; i < 9; ++i) R[i] = 0.f; R[0] = yaw; R[1] = pitch; R[2] = roll; }
 float pvp_focal_length(float fov_degrees, int width) { return fov_degrees * 65536.f + (float)width; }

@@ -442,3 +442,49 @@ def test_multiply_high_division_used_by_the_k2_slow_path():
             q = (xs * np.uint64(m)) >> np.uint64(32)
             q = q + ((xs - q * np.uint64(d)) >= d)
             assert np.array_equal(q, xs // np.uint64(d)), (n, d)
+
+
+@pytest.mark.gpu
+def test_checked_build_catches_an_injected_out_of_bounds_index():
+    """libpvp_b200_checked.so (make checked; tools/checked_run.sh runs the whole GPU suite against it) must actually see a bad index:
+    told a quarter of the queue's capacity (K1) or half of the grid's span (K3), the kernels skip the offending writes, count them,
+    and the call returns PVP_ERR_CHECK.  Runs in a subprocess: the library variant is chosen at import time."""
+    import subprocess
+    import sys
+    checked = os.path.join(ROOT, "pixeltovoxelprojector_b200", "libpvp_b200_checked.so")
+    if not os.path.exists(checked):
+        pytest.skip("libpvp_b200_checked.so not built (make -C pixeltovoxelprojector_b200/csrc checked)")
+    code = r'''
+import numpy as np, torch
+import pixeltovoxelprojector_b200 as pvp
+from pixeltovoxelprojector_b200 import synth, _lib
+assert _lib.load().pvp_build_flags() & 1
+ctx = pvp.default_context()
+frames = torch.as_tensor(synth.dense_frames(3, 64, 96, seed=1), device="cuda")
+poses = synth.orbit_poses(3, 32, 8.0, (0.0, 0.0, 500.0), seed=2)
+pairs, _ = pvp.make_pairs(poses, 96)
+grid = pvp.VoxelGrid(32, 8.0, (0.0, 0.0, 500.0))
+assert pvp.accumulate_motion(frames, pairs, grid, 2.0)["n_steps"] > 0           # clean run: no violation
+ctx.set_option("inject_fault", 1)
+try:
+    pvp.accumulate_motion(frames, pairs, grid, 2.0)
+    print("K1 MISSED")
+except pvp.PvpError as e:
+    print("K1 CAUGHT", e.status, "queue write" in str(e))
+ctx.set_option("inject_fault", 0)
+assert pvp.accumulate_motion(frames, pairs, grid, 2.0)["n_steps"] > 0           # and clean again
+img = torch.as_tensor(np.random.default_rng(3).random((32, 32)), device="cuda")
+g = torch.zeros((24, 24, 24), dtype=torch.float64, device="cuda"); t = torch.zeros((16, 16), dtype=torch.float64, device="cuda")
+call = lambda: pvp.process_image_cpp(img, [0.1, 0.2, -5.0], [0.02, 0.01, 1.0], 0.7, 32, 32, g, [(-10.0, 10.0), (-10.0, 10.0), (20.0, 40.0)], 80.0, 400, t, 1.5, 1.5, 0.8, 0.8, True, False)
+call()
+ctx.set_option("inject_fault", 2)
+try:
+    call()
+    print("K3 MISSED")
+except pvp.PvpError as e:
+    print("K3 CAUGHT", e.status, "voxel grid" in str(e))
+'''
+    env = dict(os.environ, PVP_LIB_VARIANT="checked", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "K1 CAUGHT -6 True" in r.stdout and "K3 CAUGHT -6 True" in r.stdout, r.stdout

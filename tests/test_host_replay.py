@@ -29,7 +29,7 @@ def replay(tmp_path_factory):
     if cxx is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
         pytest.skip("needs g++ and the CUDA headers")
     exe = str(tmp_path_factory.mktemp("replay") / "replay")
-    cmd = [cxx, "-std=c++17", "-O1", "-x", "c++", "-include", "cuda_runtime.h", "-I", CSRC, "-I", cuda_inc, HARNESS, "-o", exe, "-lz", "-lpthread"]
+    cmd = [cxx, "-std=c++17", "-O1", "-x", "c++", "-include", "cuda_runtime.h", "-I", CSRC, "-I", cuda_inc, HARNESS, "-o", exe, "-lz", "-lpthread", "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
 
@@ -198,3 +198,46 @@ def test_frame_loop_is_blind_to_the_container_format(replay, tmp_path):
         lists[ext], rep = replay(str(d / "metadata.json"), str(d), threads=3, chunk=3)
         assert rep["pairs"] == 6 and rep["loaded"] == 7
     assert lists["pgm"] == lists["png"] == lists["bmp"] and len(lists["pgm"]) == 6
+
+
+def test_pgm_header_forms_take_the_same_path(replay, tmp_path):
+    """The decode pool reads a plain binary PGM straight into its pinned slot (header parsed from the first 64 bytes, payload by pread);
+    headers with comments, long runs of white space, 16-bit samples or a header longer than 64 bytes fall back to the general decoder.
+    All forms of the same frames must give the same pairs; a payload one byte short is a failed load in either path."""
+    rng = np.random.default_rng(12)
+    frames = [rng.integers(0, 256, (9, 13), dtype=np.uint8) for _ in range(8)]
+
+    def write(path, img, form):
+        h, w = img.shape
+        if form == "plain":
+            head, body = b"P5\n%d %d\n255\n" % (w, h), img.tobytes()
+        elif form == "comment":
+            head, body = b"P5\n# made by a camera\n%d %d\n# another\n255\n" % (w, h), img.tobytes()
+        elif form == "spaces":
+            head, body = b"P5 \t\r\n%d\n\n%d\t255 " % (w, h), img.tobytes()
+        elif form == "long":
+            head, body = b"P5\n" + b" " * 80 + b"%d %d\n255\n" % (w, h), img.tobytes()
+        elif form == "maxval16":     # 16-bit big-endian samples: stb_image's 16 -> 8 bit conversion keeps the high byte
+            head, body = b"P5\n%d %d\n65535\n" % (w, h), (img.astype(np.uint16) * 256 + 7).astype(">u2").tobytes()
+        open(path, "wb").write(head + body)
+
+    lists = {}
+    for form in ("plain", "comment", "spaces", "long", "maxval16"):
+        d = tmp_path / form
+        d.mkdir()
+        entries = []
+        for k, img in enumerate(frames):
+            name = f"f{k}.pgm"
+            write(str(d / name), img, form)
+            entries.append({"camera_index": 0, "frame_index": k, "camera_position": [0.0, 1.0, 2.0], "image_file": name})
+        json.dump(entries, open(d / "metadata.json", "w"))
+        lists[form], rep = replay(str(d / "metadata.json"), str(d), threads=3, chunk=4)
+        assert rep["pairs"] == 7 and rep["loaded"] == 8, form
+    for f in lists:
+        assert lists[f] == lists["plain"], f
+    # truncated payload: one byte short -> the frame is skipped (ray_voxel.cpp:470-473), its neighbours pair up across it
+    d = tmp_path / "plain"
+    data = open(d / "f3.pgm", "rb").read()
+    open(d / "f3.pgm", "wb").write(data[:-1])
+    got, rep = replay(str(d / "metadata.json"), str(d), threads=2)
+    assert rep["skipped"] == 1 and rep["pairs"] == 6 and rep["loaded"] == 7
