@@ -378,6 +378,7 @@ def rooflines(env, workload, kernel, units_per_launch, launch_ms, algo_bytes, cl
            "algorithmic_model": model}
     if e.get("warp_inst_per_launch") and e.get("voxel_steps_per_launch") and peak_issue > 0:
         per_unit = e["warp_inst_per_launch"] / e["voxel_steps_per_launch"]
+        out["kernel"] = e.get("kernel", kernel)
         out = {"bound": "issue", "achieved": per_unit * rate, "peak": peak_issue, "unit": "warp-instructions/s", "frac": per_unit * rate / peak_issue,
                "warp_inst_per_voxel_step": per_unit, "sass_md5_ok": sass_fresh(workload),
                "peak_source": f"{env.sms} SMs x 4 schedulers x {mhz:.0f} MHz (SM clock sampled during the timed region)",
@@ -799,7 +800,7 @@ def run_ours(args):
     line = pick(wl)(env, args, args.workload, args.steps, args.warmup, full=True)
     if args.workload == "1080p_dense_512" and not args.no_also:
         also = {}
-        for name, st, wu in ALSO_DEFAULT + (ALSO_8GPU if env.world == 8 else []):
+        for name, st, wu in ALSO_DEFAULT + (ALSO_8GPU if (env.world == 8 or (args.also_multi and env.world > 1)) else []):
             if name not in WORKLOADS:
                 continue
             try:
@@ -825,6 +826,7 @@ def main():
     ap.add_argument("--reduce", default="peers", choices=["peers", "nccl"], help="N>1: grid merge by our peer-memory kernel (default) or by NCCL")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments only)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads of the default run")
+    ap.add_argument("--also-multi", action="store_true", help="run the 8-GPU secondary workloads (1024^3 as slabs and as frames + merge) at any N > 1")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -59,11 +59,10 @@ __device__ __forceinline__ unsigned long long vadd(unsigned long long a, unsigne
 
 // V = float4 | float | unsigned long long; elements [lo, hi) of V; dst < 0: every rank receives the sum.
 // UNROLL independent loads per thread are in flight before the first add: NVLink round trips are ~2 us.
-template <typename V, bool MC>
+template <typename V, bool MC, int UNROLL>
 __global__ void __launch_bounds__(256)
 grid_reduce_peers_kernel(PeerPtrs peers, int world, int dst, V *__restrict__ mc, long long lo, long long hi)
 {
-    constexpr int UNROLL = 4;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long base = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; base < hi; base += stride * UNROLL) {
         V acc[UNROLL];
@@ -104,9 +103,12 @@ template <typename V, bool MC>
 static void launch_reduce(pvp_ctx *ctx, const PeerPtrs &pp, int world, int dst, void *mc, long long lo, long long hi)
 {
     if (hi <= lo) return;
-    const int blocks = (int)std::min<long long>((hi - lo + 1023) / 1024, (long long)ctx->sm_count * 8);
+    // bytes in flight = blocks x 256 threads x UNROLL x sizeof(V); options reduce_blocks_per_sm (default 8) and reduce_unroll (4, 8; default 4)
+    const int per_sm = ctx->opt_reduce_blocks_per_sm > 0 ? (int)ctx->opt_reduce_blocks_per_sm : 8;
+    const int blocks = (int)std::min<long long>((hi - lo + 1023) / 1024, (long long)ctx->sm_count * per_sm);
     ++ctx->prof.launches_other;
-    grid_reduce_peers_kernel<V, MC><<<blocks, 256, 0, ctx->stream>>>(pp, world, dst, (V *)mc, lo, hi);
+    if (ctx->opt_reduce_unroll == 8) grid_reduce_peers_kernel<V, MC, 8><<<blocks, 256, 0, ctx->stream>>>(pp, world, dst, (V *)mc, lo, hi);
+    else grid_reduce_peers_kernel<V, MC, 4><<<blocks, 256, 0, ctx->stream>>>(pp, world, dst, (V *)mc, lo, hi);
 }
 
 }  // namespace pvp

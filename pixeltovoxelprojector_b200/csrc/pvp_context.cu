@@ -100,9 +100,6 @@ int ensure_pairs(pvp_ctx *ctx, int n_pairs)
     PVP_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->pairs_dev) cudaFree(ctx->pairs_dev);
     if (ctx->pairs_pinned) cudaFreeHost(ctx->pairs_pinned);
-    if (ctx->fs_hring) cudaFreeHost(ctx->fs_hring);
-    if (ctx->fs_dring) cudaFree(ctx->fs_dring);
-    for (auto p : ctx->bin_pin) if (p) cudaFreeHost(p);
     ctx->pairs_dev = nullptr; ctx->pairs_pinned = nullptr; ctx->pairs_cap = 0;
     int cap = n_pairs < 64 ? 64 : n_pairs;
     PVP_CUDA(cudaMalloc(&ctx->pairs_dev, sizeof(pvp_pair) * (size_t)cap));
@@ -212,6 +209,9 @@ int pvp_ctx_destroy(pvp_ctx *ctx)
     if (ctx->queue.pair) cudaFree(ctx->queue.pair);
     if (ctx->pairs_dev) cudaFree(ctx->pairs_dev);
     if (ctx->pairs_pinned) cudaFreeHost(ctx->pairs_pinned);
+    if (ctx->fs_hring) cudaFreeHost(ctx->fs_hring);
+    if (ctx->fs_dring) cudaFree(ctx->fs_dring);
+    for (auto p : ctx->bin_pin) if (p) cudaFreeHost(p);
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
@@ -286,6 +286,8 @@ int pvp_ctx_set_option(pvp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "lean_regs")) ctx->opt_lean_regs = value;
     else if (!strcmp(key, "image_variant")) ctx->opt_image_variant = value;
     else if (!strcmp(key, "reduce_pull")) ctx->opt_reduce_pull = value;
+    else if (!strcmp(key, "reduce_unroll")) ctx->opt_reduce_unroll = value;
+    else if (!strcmp(key, "reduce_blocks_per_sm")) ctx->opt_reduce_blocks_per_sm = value;
     else if (!strcmp(key, "image_tile_h")) ctx->opt_image_tile_h = value;
     else if (!strcmp(key, "k1_row_group")) ctx->opt_k1_row_group = value;
     else if (!strcmp(key, "k1_snake")) ctx->opt_k1_snake = value;

@@ -93,6 +93,8 @@ struct pvp_ctx {
     int64_t opt_ctas_per_sm = 0;       // 0 = occupancy query
     int64_t opt_k1_snake = -1;         // K1 queue order inside a tile: odd columns bottom-up (-1 = auto: on for tiles of 4+ rows, 0 off, 1 on)
     int64_t opt_k1_row_group = 0;      // K1 queue order: tiles of this many image rows (0 = default of the K2 variant, 1 = row major, 2, 4, 8)
+    int64_t opt_reduce_unroll = 0;     // grid merge kernel: independent 16-byte loads per thread (0/4 default, 8)
+    int64_t opt_reduce_blocks_per_sm = 0;  // grid merge kernel: CTAs per SM (0 = 8)
     int64_t opt_reduce_pull = 0;       // grid merge to one rank with multicast: 0 = every rank reduces a slice (default), 1 = the destination pulls the whole grid
     int64_t opt_image_tile_h = 0;      // lock-step path-B kernel: rows of a warp's pixel tile (0/2 default, 1, 4, 8)
     int64_t opt_image_variant = 0;     // path B kernel: 0 = auto, 1 = generic per-pixel, 2 = lock-step

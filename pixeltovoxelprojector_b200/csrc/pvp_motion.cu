@@ -1256,7 +1256,9 @@ __global__ void fixed_to_f64_kernel(const long long *__restrict__ src, double *_
 static int make_gridp(const pvp_grid_desc *d, GridP *g)
 {
     PVP_REQUIRE(d != nullptr, "grid descriptor is NULL");
-    PVP_REQUIRE(d->n > 0 && d->n <= 2048, "grid n=%d out of range (1..2048)", d->n);
+    // up to 2048 the lock-step kernels' per-ray limits are proven (axis_limit: rem < 2^11); larger grids -- the ones that need slab
+    // sharding because they exceed one GPU's memory, e.g. 4096^3 float32 = 256 GiB -- run the reference-structured kernel (variant 3)
+    PVP_REQUIRE(d->n > 0 && d->n <= 4096, "grid n=%d out of range (1..4096)", d->n);
     PVP_REQUIRE(d->slab_lo >= 0 && d->slab_lo <= d->slab_hi && d->slab_hi <= d->n, "bad slab [%d,%d) for n=%d",
                 d->slab_lo, d->slab_hi, d->n);
     PVP_REQUIRE(d->accum_mode == PVP_ACCUM_F32 || d->accum_mode == PVP_ACCUM_FIXED, "bad accum_mode %d", d->accum_mode);
@@ -1430,7 +1432,7 @@ static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_o
     const bool slab = !(g.slab_lo == 0 && g.slab_hi == g.n);
     const unsigned long long cells = (unsigned long long)(g.slab_hi - g.slab_lo) * g.n * g.n;
     const unsigned long long full = (unsigned long long)g.n * g.n * g.n;
-    if (cells >= 0xffffffffull) variant = 3;
+    if (cells >= 0xffffffffull || g.n > 2048) variant = 3;
     const bool lockstep = variant == 0 || variant >= 4;
     if (lockstep && (slab ? full > (1ull << 31) : full >= 0xffffffffull)) variant = 3;  // slab test relies on wrapped offsets
     if (lockstep && !lean_ok) variant = 3;

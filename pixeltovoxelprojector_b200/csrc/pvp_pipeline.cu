@@ -506,7 +506,20 @@ struct FrameStream {
         if (dslot_batch[(size_t)ds] >= 0)              // read by a submitted batch: the copy waits for that batch's kernels
             PVP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, batch_done[dslot_batch[(size_t)ds] % NB], 0));
         nvtxRangePushA("pvp:H2D frame");
-        PVP_CUDA(cudaMemcpyAsync(dring + (size_t)ds * dslot, from, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        {
+            const cudaError_t e = cudaMemcpyAsync(dring + (size_t)ds * dslot, from, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e != cudaSuccess) {   // say what was asked for: the ring arithmetic is the only thing that can be wrong here
+                cudaPointerAttributes pa = {}, pb = {};
+                cudaPointerGetAttributes(&pa, dring + (size_t)ds * dslot);
+                cudaPointerGetAttributes(&pb, from);
+                cuda_fail(e, "cudaMemcpyAsync(frame H2D)", __FILE__, __LINE__);
+                std::string why = pvp_last_error();
+                set_error("%s [device ring %p + slot %d x %zu B of %d slots (memory type %d), source %p (type %d, pinned ring %p, %d slots x %zu B, slot %d), %zu bytes, frame %dx%d]",
+                          why.c_str(), (void *)dring, ds, dslot, n_dslots, (int)pa.type, from, (int)pb.type, (void *)hring, n_hslots, hslot, pinned_slot, bytes, w, h);
+                nvtxRangePop();
+                return PVP_ERR_CUDA;
+            }
+        }
         if (pinned_slot >= 0) PVP_CUDA(cudaEventRecord(copied[(size_t)pinned_slot], ctx->copy_stream));
         nvtxRangePop();
         dslot_batch[(size_t)ds] = -1;

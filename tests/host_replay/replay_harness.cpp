@@ -11,6 +11,8 @@
 #include <stdarg.h>
 #include <zlib.h>
 
+#include <map>
+
 static char g_err[512];
 void pvp::set_error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
 int pvp::cuda_fail(cudaError_t, const char *, const char *, int) { return PVP_ERR_CUDA; }
@@ -18,13 +20,41 @@ int pvp::cuda_fail(cudaError_t, const char *, const char *, int) { return PVP_ER
 extern "C" {
 // CUDA runtime entry points the orchestration uses for its pinned ring, its device ring ("device memory" is plain host memory here) and
 // the events that recycle their slots
-cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
-cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+// allocations are tracked so that every copy the frame loop enqueues can be range-checked: the destination must lie inside ONE live
+// "device" allocation, a source inside the pinned ring must lie inside ONE live pinned allocation (anything else is pageable memory)
+static std::map<const char *, size_t> g_dev, g_pin;
+static bool inside(const std::map<const char *, size_t> &m, const void *p, size_t n)
+{
+    auto it = m.upper_bound((const char *)p);
+    if (it == m.begin()) return false;
+    --it;
+    return (const char *)p >= it->first && (const char *)p + n <= it->first + it->second;
+}
+static bool touches(const std::map<const char *, size_t> &m, const void *p)
+{
+    auto it = m.upper_bound((const char *)p);
+    if (it == m.begin()) return false;
+    --it;
+    return (const char *)p < it->first + it->second;
+}
+cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n); if (*p) g_pin[(const char *)*p] = n; return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void *p) { if (p && !g_pin.erase((const char *)p)) printf("BAD cudaFreeHost of an unknown pointer\n"); free(p); return cudaSuccess; }
+cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n); if (*p) g_dev[(const char *)*p] = n; return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void *p) { if (p && !g_dev.erase((const char *)p)) printf("BAD cudaFree of an unknown pointer\n"); free(p); return cudaSuccess; }
+static cudaError_t checked_copy(void *d, const void *s, size_t n, cudaMemcpyKind kind)
+{
+    if (!inside(g_dev, d, n)) { printf("BAD copy: destination [%p, +%zu) is not inside a live device allocation\n", d, n); return cudaErrorInvalidValue; }
+    if (kind == cudaMemcpyDeviceToDevice ? !inside(g_dev, s, n) : (touches(g_pin, s) && !inside(g_pin, s, n)) || touches(g_dev, s)) {
+        printf("BAD copy: source [%p, +%zu) of kind %d is out of range\n", s, n, (int)kind);
+        return cudaErrorInvalidValue;
+    }
+    memcpy(d, s, n);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind kind, cudaStream_t) { return checked_copy(d, s, n, kind); }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind kind) { return checked_copy(d, s, n, kind); }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { memset(a, 0, sizeof *a); return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (cudaEvent_t)1; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
@@ -38,6 +68,7 @@ int pvp_motion_accumulate(pvp_ctx *, const void *frames, int dtype, int64_t stri
                           int n_pairs, float threshold, void *, const pvp_grid_desc *, pvp_stats *)
 {
     const size_t elem = dtype == PVP_FRAME_F32 ? 4 : 1;
+    if (n_pairs > 0 && !inside(g_dev, frames, (size_t)n_frames * stride * elem)) printf("BAD frames: the ring handed to K1 is not a live device allocation\n");
     for (int i = 0; i < n_pairs; ++i) {
         const pvp_pair &p = pairs[i];
         if (p.prev < 0 || p.curr < 0 || p.prev >= n_frames || p.curr >= n_frames || p.prev == p.curr) { printf("BAD pair index %d %d of %d\n", p.prev, p.curr, n_frames); continue; }
@@ -80,7 +111,12 @@ int main(int argc, char **argv)
     pvp_stats st = {0, 0, 0, 0};
     pvp_run_report rep;
     memset(&rep, 0, sizeof rep);
-    const int rc = pvp_ray_voxel_accumulate(&ctx, argv[1], argv[2], &cell, &opt, &st, &rep);
+    int rc = pvp_ray_voxel_accumulate(&ctx, argv[1], argv[2], &cell, &opt, &st, &rep);
+    if (rc != PVP_OK) { printf("ERROR %d %s\n", rc, g_err); return 1; }
+    // a second run on the same context reuses the rings the first one left behind; its record must be the same (printed after AGAIN)
+    printf("AGAIN\n");
+    memset(&rep, 0, sizeof rep);
+    rc = pvp_ray_voxel_accumulate(&ctx, argv[1], argv[2], &cell, &opt, &st, &rep);
     if (rc != PVP_OK) { printf("ERROR %d %s\n", rc, g_err); return 1; }
     printf("REPORT listed %llu loaded %llu skipped %llu pairs %llu mismatch %llu\n", (unsigned long long)rep.n_frames_listed,
            (unsigned long long)rep.n_frames_loaded, (unsigned long long)rep.n_frames_skipped, (unsigned long long)rep.n_pairs,

@@ -126,3 +126,13 @@ def _f32_of(rank, n):
 def test_world2_gloo_reduce_and_slab_assembly(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+
+
+def test_auto_mode_prefers_frames_while_a_private_grid_fits():
+    """mode="auto" of ray_voxel_distributed: frames + one merge whenever a private full grid fits the GPU, slabs only beyond that."""
+    hbm = 180 << 30
+    assert pd.pick_mode(512, "f32", world=8, hbm_bytes=hbm) == "frames"
+    assert pd.pick_mode(1024, "f32", world=8, hbm_bytes=hbm) == "frames"         # BASELINE config 4's grid: 4 GiB
+    assert pd.pick_mode(2048, "fixed", world=8, hbm_bytes=hbm) == "frames"       # 64 GiB
+    assert pd.pick_mode(3072, "f32", world=8, hbm_bytes=hbm) == "slabs"          # 108 GiB: more than half of one GPU
+    assert pd.pick_mode(4096, "f32", world=1, hbm_bytes=hbm) == "frames"         # one rank: nothing to shard

@@ -156,3 +156,26 @@ def test_grid_near_the_32bit_offset_limit_variants_agree(ctx):
         ctx.set_option("dda_variant", 0)
         del ref
         torch.cuda.empty_cache()
+
+
+def test_slab_of_a_grid_beyond_one_gpu_vs_oracle(ctx, oracle):
+    """A grid too large for one GPU is what slab sharding exists for: N = 3000 float32 is 108 GB of cells.  One rank's slab (x-planes
+    [1496, 1512): 576 MB) of that grid against the C port walking the same rays with full-grid arithmetic and writing into the same
+    slab -- counters and every cell.  (N > 2048 runs the reference-structured kernel: the lock-step kernels' per-ray limits are proven
+    for N <= 2048.)"""
+    H, W, N, vs, center = 60, 80, 3000, 0.34, (0.0, 0.0, 500.0)
+    frames = synth.dense_frames(2, H, W, seed=301)
+    poses = synth.orbit_poses(2, N, vs, center, seed=302)
+    lo, hi = 1496, 1512
+    want = np.zeros((hi - lo, N, N), np.float32)
+    R = oracle.rotation_matrix(poses[1].yaw, poses[1].pitch, poses[1].roll)
+    nr, ns, nw = oracle.accumulate_pair(frames[0], frames[1], np.array(poses[1].camera_position, np.float32), R, oracle.focal_length(poses[1].fov_degrees, W),
+                                        want, N, vs, np.array(center, np.float32), 2.0, slab=(lo, hi))
+    tab, _ = pvp.make_pairs(poses, W)
+    slab = pvp.VoxelGrid(N, vs, center, slab=(lo, hi))
+    st = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), tab, slab, 2.0)
+    assert (st["n_rays"], st["n_written"]) == (nr, nw) and nw > 1000 and ns > 1000 * nr > 0
+    got = slab.data.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    with pytest.raises(pvp.PvpError):
+        pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), tab, pvp.VoxelGrid(4097, 1.0, center, slab=(0, 0)), 2.0)   # n <= 4096

@@ -16,3 +16,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-fil
 $I > gpurun_out/plain_k3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:process_image_lockstep2 -s 3 -c 1 -o gpurun_out/${P}_k3_lockstep2 $I > gpurun_out/ncu_f3.log 2>&1
 ls -la gpurun_out | grep ${P}
+# scattered motion (10 % iid): the auto pick is the one-ray-per-lane kernel
+S="python bench.py --workload 1080p_scatter10_512 --steps 2 --warmup 3 --no-cpu --no-also"
+$S > gpurun_out/plain_sc.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:dda_accumulate_lean_kernel -s 6 -c 1 -o gpurun_out/${P}_k2_lean_scatter10 $S > gpurun_out/ncu_fs.log 2>&1
+ls -la gpurun_out | grep ${P}

@@ -43,6 +43,14 @@ def main():
         "peers plain loads -> rank 0": timed(lambda: pd.reduce_grid_peers(g, dst=0, ctx=ctx, multicast=False)),
         "two symmetric-memory barriers alone": timed(lambda: (g.symm.barrier(channel=0), g.symm.barrier(channel=1))),
     }
+    for unroll in (4, 8):                 # bytes in flight of the merge kernel: loads per thread x CTAs per SM
+        for per_sm in (4, 8, 16):
+            ctx.set_option("reduce_unroll", unroll)
+            ctx.set_option("reduce_blocks_per_sm", per_sm)
+            res[f"peers multicast -> all, unroll {unroll}, {per_sm} CTAs/SM"] = timed(lambda: pd.reduce_grid_peers(g, dst=None, ctx=ctx, multicast=True))
+            res[f"peers multicast -> rank 0, unroll {unroll}, {per_sm} CTAs/SM"] = timed(lambda: pd.reduce_grid_peers(g, dst=0, ctx=ctx, multicast=True))
+    ctx.set_option("reduce_unroll", 0)
+    ctx.set_option("reduce_blocks_per_sm", 0)
     if rank == 0:
         mib = n ** 3 * 4 / 2 ** 20
         for k, v in res.items():
