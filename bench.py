@@ -794,6 +794,11 @@ ALSO_8GPU = [("1080p_dense_1024_slab8", 10, 3), ("1080p_dense_1024", 10, 3)]
 
 
 def run_ours(args):
+    # the contract is ONE JSON line on stdout: libraries that print there from C (NCCL's version banner, whatever NCCL_DEBUG says in
+    # this environment) are sent to stderr for the duration of the run; the line itself goes to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     env = Env(args)
     wl = WORKLOADS[args.workload]
     pick = lambda w: measure_image if w.get("path") == "B" else measure_files if w.get("path") == "files" else measure_motion   # noqa: E731
@@ -809,9 +814,12 @@ def run_ours(args):
                 also[name] = {"error": repr(e)}
         if line is not None:
             line["also"] = also
-    if line is not None:
-        print(json.dumps(line))
     env.close()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 def main():

@@ -103,11 +103,16 @@ template <typename V, bool MC>
 static void launch_reduce(pvp_ctx *ctx, const PeerPtrs &pp, int world, int dst, void *mc, long long lo, long long hi)
 {
     if (hi <= lo) return;
-    // bytes in flight = blocks x 256 threads x UNROLL x sizeof(V); options reduce_blocks_per_sm (default 8) and reduce_unroll (4, 8; default 4)
-    const int per_sm = ctx->opt_reduce_blocks_per_sm > 0 ? (int)ctx->opt_reduce_blocks_per_sm : 8;
+    // loads in flight = blocks x 256 threads x UNROLL x sizeof(V); options reduce_blocks_per_sm and reduce_unroll (4, 8).  Measured at 8
+    // GPUs (tools/reduce_bench.py, profiles/r2_n8_reduce_*.log): the all-ranks variant does not care (512 MiB 1.20-1.23 ms, 4 GiB 9.0-9.3 ms
+    // for every setting); the one-destination variant, whose results leave as peer stores into ONE GPU, is best with 8 loads per thread and
+    // a grid of 16 CTAs per SM (512 MiB 1.44 -> 1.28 ms, 4 GiB 10.4 -> 9.1 ms)
+    const bool to_one = dst >= 0;
+    const int per_sm = ctx->opt_reduce_blocks_per_sm > 0 ? (int)ctx->opt_reduce_blocks_per_sm : to_one ? 16 : 8;
+    const int unroll = ctx->opt_reduce_unroll > 0 ? (int)ctx->opt_reduce_unroll : to_one ? 8 : 4;
     const int blocks = (int)std::min<long long>((hi - lo + 1023) / 1024, (long long)ctx->sm_count * per_sm);
     ++ctx->prof.launches_other;
-    if (ctx->opt_reduce_unroll == 8) grid_reduce_peers_kernel<V, MC, 8><<<blocks, 256, 0, ctx->stream>>>(pp, world, dst, (V *)mc, lo, hi);
+    if (unroll == 8) grid_reduce_peers_kernel<V, MC, 8><<<blocks, 256, 0, ctx->stream>>>(pp, world, dst, (V *)mc, lo, hi);
     else grid_reduce_peers_kernel<V, MC, 4><<<blocks, 256, 0, ctx->stream>>>(pp, world, dst, (V *)mc, lo, hi);
 }
 
