@@ -394,7 +394,7 @@ motion_compact_morton_kernel(const T *__restrict__ frames, long long frame_strid
                 T pa[C], pb[C];
                 memcpy(pa, &a[r], sizeof(pa));
                 memcpy(pb, &b[r], sizeof(pb));
-                s_pix[pos] = (uint32_t)((v0 + r) * width + u0 + k);
+                s_pix[pos] = (uint32_t)(v0 + r) * (uint32_t)width + (uint32_t)(u0 + k);   // < 2^32: the host bounds width * height
                 s_diff[pos] = motion_diff(pa[k], pb[k]);
                 ++pos;
             }
