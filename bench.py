@@ -383,6 +383,12 @@ def rooflines(env, workload, kernel, units_per_launch, launch_ms, algo_bytes, cl
                "warp_inst_per_voxel_step": per_unit, "sass_md5_ok": sass_fresh(workload),
                "peak_source": f"{env.sms} SMs x 4 schedulers x {mhz:.0f} MHz (SM clock sampled during the timed region)",
                "source": f"{e.get('source', 'profiles/traffic.json')}: smsp__inst_executed.sum per voxel step x live rate", **out}
+        lim = e.get("limiter")
+        if lim:   # ncu found another unit busier than the issue slots (e.g. the L2 / RED path on scattered motion): that is the bound
+            cap_rate = e["voxel_steps_per_launch"] / (lim["launch_ms"] * 1e-3)
+            out["issue"] = {k: out[k] for k in ("achieved", "peak", "unit", "frac")}
+            out.update({"bound": lim["bound"], "unit": "% of peak (" + lim["ncu_metric"] + ")", "peak": 100.0, "achieved": lim["ncu_pct"] * rate / cap_rate,
+                        "frac": lim["ncu_pct"] / 100.0 * rate / cap_rate, "limiter_note": lim.get("note")})
     else:   # no ncu capture committed for this workload: only the nominal model can be stated
         out = {"bound": "hbm", "achieved": model["achieved"], "peak": model["peak"], "unit": "GB/s", "frac": model["frac"], **out}
     return out

@@ -468,3 +468,42 @@ def test_opt_in_distance_attenuation(ctx, oracle):
             ctx.set_option("dda_variant", 0)
     with pytest.raises(pvp.PvpError, match="attenuation_alpha"):
         pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, pvp.VoxelGrid(N, vs, center, attenuation_alpha=-1.0), 2.0)
+
+
+@pytest.mark.parametrize("kind", ["dense", "scatter", "object", "float"])
+def test_zorder_queue_all_motion_kinds_vs_oracle(ctx, oracle, kind):
+    """The Z-order ray queue (motion_compact_morton_kernel) on frames that span several 64 x 64 footprints, with widths that are
+    and are not multiples of 4 (vector / scalar loads), for every kind of motion the order treats differently: dense frames (strip
+    order inside footprints, lean2 picked), iid-scattered motion (Morton order, lean picked by the paired share), a moving textured
+    object (dense and empty footprints side by side), float frames; blocks of 4 and of 8 rows.  Counters and grids against the C port,
+    bit-exact (uint8 frames, and fixed point always)."""
+    rng = np.random.default_rng({"dense": 1, "scatter": 2, "object": 3, "float": 4}[kind])
+    N, vs, center = 48, 6.0, (0.0, 0.0, 500.0)
+    for (H, W) in ((150, 200), (97, 131), (64, 64), (65, 257)):
+        F = 3
+        if kind == "dense":
+            frames = synth.dense_frames(F, H, W, seed=int(rng.integers(1 << 30)))
+        elif kind == "scatter":
+            frames = synth.scatter_frames(F, H, W, seed=int(rng.integers(1 << 30)), fraction=0.1)
+        elif kind == "object":
+            frames = synth.object_frames(F, H, W, seed=int(rng.integers(1 << 30)))
+        else:
+            frames = (synth.dense_frames(F, H, W, seed=int(rng.integers(1 << 30))).astype(np.float32) + rng.random((F, H, W)).astype(np.float32))
+        poses = synth.orbit_poses(F, N, vs, center, seed=int(rng.integers(1 << 30)))
+        pairs, _ = pvp.make_pairs(poses, W)
+        for mode, accum in ((1, "fixed"), (0, "f32")):
+            want, tot = _oracle_run(oracle, frames, poses, N, vs, center, 2.0, accum_mode=mode, frac_bits=10)
+            for rg in (-4, -8):
+                ctx.set_option("k1_row_group", rg)
+                try:
+                    grid = pvp.VoxelGrid(N, vs, center, accum=accum, frac_bits=10)
+                    st = pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), pairs, grid, 2.0)
+                finally:
+                    ctx.set_option("k1_row_group", 0)
+                assert (st["n_rays"], st["n_steps"], st["n_written"]) == tuple(tot), (kind, H, W, accum, rg)
+                assert st["n_rays"] > 0
+                got = grid.data.cpu().numpy()
+                if accum == "fixed" or kind != "float":
+                    assert np.array_equal(got, want), (kind, H, W, accum, rg)
+                else:
+                    np.testing.assert_allclose(got, want, rtol=1e-5, atol=0)
