@@ -112,3 +112,41 @@ def test_field_of_view_matches_the_reference_lines():
     for c, want in zip(cases, g["fov_rad"]):
         got = pvp.field_of_view_rad(c["header"], c["width"], c["height"])
         assert np.float64(got).tobytes() == np.float64(want).tobytes(), c
+
+
+def _golden_check(device):
+    """tests/golden/sky_golden.npz: outputs of the reference's OWN statements (spacevoxelviewer.py:179-184 and :320-347, cut out of the
+    unmodified source and executed by tests/golden/make_golden_sky.py) -- this is what pins SURVEY 8f N2, bit for bit."""
+    import os
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sky_golden.npz"))
+    for k in range(int(g["n_norm"])):
+        src, want = g[f"norm_{k}_in"], g[f"norm_{k}_out"]
+        if src.dtype.kind != "f":
+            continue                                        # integer FITS data: the reference promotes through numpy; torch callers pass floats
+        got = sky.normalize_image(torch.as_tensor(src, device=device))
+        assert got.cpu().numpy().dtype == want.dtype and np.array_equal(bits(got.cpu().numpy()), bits(want)), k
+    with pytest.raises(ValueError, match=str(g["norm_constant_error"])):
+        sky.normalize_image(torch.full((4, 4), 2.5, device=device))
+    assert int(g["n_an"]) >= 6
+    for k in range(int(g["n_an"])):
+        grid = g[f"an_{k}_grid"]
+        ext = [tuple(r) for r in g[f"an_{k}_extent"]]
+        out = sky.analyze_voxel_grid(torch.as_tensor(grid, device=device), int(g[f"an_{k}_n_files"]), ext, float(g[f"an_{k}_pct"]))
+        assert np.array_equal(bits(out["voxel_grid_avg"].cpu().numpy()), bits(g[f"an_{k}_avg"])), k
+        assert float(out["threshold"]) == float(g[f"an_{k}_threshold"]), (k, out["threshold"], g[f"an_{k}_threshold"])
+        for name in ("x_coords", "y_coords", "z_coords", "intensities"):
+            assert np.array_equal(bits(out[name].cpu().numpy()), bits(g[f"an_{k}_{name}"])), (k, name)
+        want_b = g[f"an_{k}_brightest"]
+        assert (out["brightest"] is None) == (want_b.size == 0)
+        if want_b.size:
+            assert out["brightest"] == tuple(float(v) for v in want_b), k
+
+
+def test_sky_matches_the_reference_lines_cpu():
+    _golden_check("cpu")
+
+
+@pytest.mark.gpu
+def test_sky_matches_the_reference_lines_gpu():
+    _golden_check("cuda")
