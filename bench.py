@@ -554,7 +554,30 @@ def measure_motion(env, args, name, steps, warmup, full):
     if slabs:
         from pixeltovoxelprojector_b200.distributed import slab_range
         n_slabs = world if world > 1 else slabs     # --gpus N: N slabs, one per rank (N = 8 is BASELINE config 4); 1 GPU: rank 4 of 8
-        lo, hi = slab_range(wl["N"], rank if world > 1 else slabs // 2, n_slabs)
+        one_gpu_rank = int(os.environ.get("PVP_BENCH_SLAB_RANK", slabs // 2))       # which of the slabs a 1-GPU run plays
+        lo, hi = slab_range(wl["N"], rank if world > 1 else one_gpu_rank, n_slabs)
+        if os.environ.get("PVP_BENCH_SLAB_BALANCE", "1") != "0":   # slabs of equal estimated work (pilot over a sample of the pose table, same on every rank)
+            from pixeltovoxelprojector_b200.distributed import balanced_slabs, estimate_plane_work
+            sample = [(i, i + 1) for i in range(0, wl["pool"] - 1, max(1, (wl["pool"] - 1) // 8))]
+            work = estimate_plane_work(frames_dev, poses, wl["N"], wl["voxel_size"], wl["center"], pairs=sample, ctx=ctx)
+            cut = balanced_slabs(work, n_slabs)
+            if world > 1:    # one correction from measured times: every rank runs the sample on its slab, the times are gathered, the planes re-cut
+                from pixeltovoxelprojector_b200.distributed import refine_slabs_by_time
+                tab_s, n_s = pvp.make_pairs(poses, wl["W"], pairs=sample)
+                trial = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev, slab=cut[rank])
+                for rep in range(2):
+                    a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a_ev.record()
+                    pvp.accumulate_motion(frames_dev, tab_s, trial, 2.0, ctx=ctx, want_stats=False)
+                    b_ev.record()
+                    torch.cuda.synchronize(dev)
+                times = torch.zeros(world, dtype=torch.float64, device=dev)
+                times[rank] = a_ev.elapsed_time(b_ev)
+                dist.all_reduce(times)
+                del trial
+                torch.cuda.empty_cache()
+                cut = refine_slabs_by_time(cut, work, times.tolist())
+            lo, hi = cut[rank if world > 1 else one_gpu_rank]
         grid = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], accum=wl["accum"], device=dev, slab=(lo, hi))
         reduce_how = f"none (slab sharding: rank writes x-planes [{lo}, {hi}) of the .bin)"
     if world > 1 and not slabs:

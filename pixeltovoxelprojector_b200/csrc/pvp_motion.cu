@@ -848,6 +848,43 @@ __device__ __forceinline__ bool pick_lean2(const Ctl *ctl, unsigned long long co
     return paired_pct == 0 || 200ull * ctl->n_paired >= paired_pct * count;
 }
 
+// Slab kernels: FAST-FORWARD a ray that starts outside the slab to the moment it enters it, without walking the voxels in between
+// and without changing a single rounding of the reference's walk.  The walk is a 3-way merge of three independent sequences: axis
+// a's t_max takes the values S_a[0] = t_max_a, S_a[j+1] = fl(S_a[j] + t_delta_a) whatever the other axes do, and the loop always
+// steps the axis with the smallest head, ties to the later axis (ray_voxel.cpp:375-387: x only if strictly below y and z, y only if
+// strictly below z).  Hence the k-th x step, taken at t = X = S_x[k-1], comes exactly after every y step with S_y[j] <= X and every z
+// step with S_z[j] <= X -- three short scalar loops (one rounded add and one compare per skipped voxel step instead of a full
+// lock-step iteration) give the state at the slab's near face: voxel, the three t_max, t_current = X.  The ray never gets there if
+// X > t_end (the loop condition :365 fails first: the chosen t values are non-decreasing, X is the largest before the entry) or if y
+// or z would have left [0, N) before (:388-391).  x moves one way along a ray, so "entering the slab" is its k-th x step with
+// k = distance from the start plane to the slab's near plane.  rem_x becomes the x steps that stay inside the slab.
+__device__ __forceinline__ bool slab_enter(Ray &r, float cam_x, float dir_x, const GridP &g, int &rem_x)
+{
+    if (!slab_reach(r, cam_x, dir_x, g, rem_x)) return false;
+    const int kx = r.sx > 0 ? g.slab_lo - r.ix : r.ix - (g.slab_hi - 1);
+    if (kx <= 0) return true;  // starts inside the slab
+    float X = r.tmx;
+    for (int j = 1; j < kx; ++j) X = fadd(X, r.tdx);
+    if (!(X <= r.t_end)) return false;  // ends before it reaches the slab (also: x never steps, t_max_x = inf)
+    const int N = g.n;
+    const int rem_y = r.sy > 0 ? N - 1 - r.iy : r.iy, rem_z = r.sz > 0 ? N - 1 - r.iz : r.iz;
+    int ky = 0, kz = 0;
+    float y = r.tmy, z = r.tmz;
+    while (y <= X) {
+        if (++ky > rem_y) return false;  // that y step leaves the grid: the walk ends before the slab
+        y = fadd(y, r.tdy);
+    }
+    while (z <= X) {
+        if (++kz > rem_z) return false;
+        z = fadd(z, r.tdz);
+    }
+    r.ix += r.sx * kx; r.iy += r.sy * ky; r.iz += r.sz * kz;
+    r.tmx = fadd(X, r.tdx); r.tmy = y; r.tmz = z;
+    r.t_cur = X;
+    rem_x -= kx;
+    return true;
+}
+
 template <int MODE, bool SLAB, bool NARROW, int MINB>
 __global__ void __launch_bounds__(LEAN_THREADS, MINB)
 dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
@@ -890,7 +927,7 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
             Ray r;
             int rem_x = 0;
             if (ray_setup(__ldg(&P->cam[0]), __ldg(&P->cam[1]), __ldg(&P->cam[2]), dx, dy, dz, g, r) && r.t_cur <= r.t_end &&
-                (!SLAB || slab_reach(r, __ldg(&P->cam[0]), dx, g, rem_x))) {
+                (!SLAB || slab_enter(r, __ldg(&P->cam[0]), dx, g, rem_x))) {
                 if (!SLAB) rem_x = r.sx > 0 ? N - 1 - r.ix : r.ix;
                 t_end = r.t_end;
                 tmx = r.tmx; tmy = r.tmy; tmz = r.tmz; tdx = r.tdx; tdy = r.tdy; tdz = r.tdz;
@@ -1038,7 +1075,7 @@ __device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, uns
     if (!(ray_setup(__ldg(&P->cam[0]), __ldg(&P->cam[1]), __ldg(&P->cam[2]), dx, dy, dz, g, r) && r.t_cur <= r.t_end)) return 0;
     const int N = g.n;
     int rem_x = r.sx > 0 ? N - 1 - r.ix : r.ix;
-    if (SLAB && !slab_reach(r, __ldg(&P->cam[0]), dx, g, rem_x)) return 0;  // never writes into this slab: not walked here
+    if (SLAB && !slab_enter(r, __ldg(&P->cam[0]), dx, g, rem_x)) return 0;  // never writes into this slab: not walked here; else fast-forwarded to its near face
     s.t_end = r.t_end; s.t_cur = r.t_cur;
     raw_diff = diff;
     s.tmx = r.tmx; s.tmy = r.tmy; s.tmz = r.tmz; s.tdx = r.tdx; s.tdy = r.tdy; s.tdz = r.tdz;

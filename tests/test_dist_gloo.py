@@ -136,3 +136,25 @@ def test_auto_mode_prefers_frames_while_a_private_grid_fits():
     assert pd.pick_mode(2048, "fixed", world=8, hbm_bytes=hbm) == "frames"       # 64 GiB
     assert pd.pick_mode(3072, "f32", world=8, hbm_bytes=hbm) == "slabs"          # 108 GiB: more than half of one GPU
     assert pd.pick_mode(4096, "f32", world=1, hbm_bytes=hbm) == "frames"         # one rank: nothing to shard
+
+
+def test_balanced_slabs_partition_and_balance():
+    rng = np.random.default_rng(4)
+    for n, world in ((1024, 8), (100, 7), (8, 8), (33, 2)):
+        w = rng.gamma(0.5, 1.0, n) * np.exp(-((np.arange(n) - n * 0.45) / (n * 0.12)) ** 2)      # work concentrated around the camera
+        slabs = pd.balanced_slabs(w, world)
+        assert slabs[0][0] == 0 and slabs[-1][1] == n and all(a[1] == b[0] for a, b in zip(slabs, slabs[1:]))
+        assert all(hi > lo for lo, hi in slabs)
+        if n == 1024:
+            per = [w[lo:hi].sum() for lo, hi in slabs]
+            eq = [w[lo:hi].sum() for lo, hi in (pd.slab_range(n, r, world) for r in range(world))]
+            assert max(per) < 0.6 * max(eq) and max(per) < 1.3 * w.sum() / world
+    assert pd.balanced_slabs(np.zeros(64), 4) == [pd.slab_range(64, r, 4) for r in range(4)]     # no information: equal widths
+    # measured-time refinement: a rank that took twice as long as the others gives planes away
+    w = np.ones(800)
+    first = pd.balanced_slabs(w, 8)
+    again = pd.refine_slabs_by_time(first, w, [1.0, 1.0, 2.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+    assert again[2][1] - again[2][0] < first[2][1] - first[2][0] and again[0][0] == 0 and again[-1][1] == 800
+    assert abs((again[2][1] - again[2][0]) - 100 * 9 / 8 / 2) <= 2
+    with pytest.raises(ValueError):
+        pd.balanced_slabs(np.ones(3), 4)
