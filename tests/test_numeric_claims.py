@@ -9,7 +9,8 @@ themselves are compared with the oracle on the GPU; these tests pin the *reasons
   samples inside the grid whenever A*K <= 2^49 (the host's `affine_ok`) and the safe range's 32-unit margin holds.
 * K3 `div_by_extent`: the five-operation FMA sequence is the correctly rounded quotient (exact rationals).
 * K2 axis choice from one three-input minimum == the reference's strict-comparison chain; K2 `slab_reach`: the box-exit x index
-  bounds the planes a ray visits."""
+  bounds the planes a ray visits; K2 `slab_enter`: the fast-forward to a slab's near face (three independent scalar loops) reproduces the
+  reference loop's state after its k-th x step, ties and early ends included."""
 from fractions import Fraction
 
 import numpy as np
@@ -319,3 +320,79 @@ def test_k3_safe_range_samples_pass_the_reference_bounds_test():
             accepted += 1
             assert ok[a:b + 1].all(), (case, a, b)
     assert accepted > 150 and grazing > 50
+
+
+def test_k2_slab_fast_forward_is_the_reference_walk():
+    """`slab_enter` (csrc/pvp_motion.cu): the state of the reference's DDA loop (ray_voxel.cpp:365-391) right after its k-th x step --
+    voxel, the three t_max, t_current, emitted voxels -- equals the three independent loops of the fast-forward: X = S_x[k-1]; every y step
+    with S_y[j] <= X and every z step with S_z[j] <= X precede it (ties go to the later axis); the ray dies first if X > t_end or if y / z
+    leave [0, N).  float32 throughout, incl. exact ties (equal t_max on two axes, t_delta that are multiples of each other) and parallel
+    axes (t_max = inf)."""
+    rng = np.random.default_rng(21)
+    N = 40
+    checked = died = 0
+    for trial in range(4000):
+        tie = trial % 5 == 0
+        td = (np.array([1.0, 2.0, 0.5], np.float32) * F32(rng.choice([0.25, 1.0, 3.0])) if tie
+              else np.exp(rng.uniform(np.log(0.05), np.log(20.0), 3)).astype(F32))
+        tm = (td * rng.integers(1, 4, 3).astype(F32)).astype(F32) if tie else (rng.uniform(0.0, 1.0, 3).astype(F32) * td).astype(F32)
+        par = rng.integers(0, 12)
+        if par in (1, 2):                                     # y or z parallel to the ray: never steps (safe_div -> inf)
+            tm[par], td[par] = np.inf, np.inf
+        idx = rng.integers(0, N, 3)
+        step = rng.choice([-1, 1], 3)
+        t_end = F32(rng.uniform(5.0, 200.0))
+        k = int(rng.integers(1, N))                          # the slab's near face is k x-steps away
+        if not (0 <= idx[0] + step[0] * k < N):
+            continue
+        # ---- the reference loop, run until its k-th x step (or until it ends)
+        t_cur, m, i, xs, emitted, alive = F32(0.0), tm.copy(), idx.copy(), 0, 0, True
+        while True:
+            if not (t_cur <= t_end):
+                alive = False
+                break
+            emitted += 1
+            if m[0] < m[1] and m[0] < m[2]:
+                a = 0
+            elif m[1] < m[2]:
+                a = 1
+            else:
+                a = 2
+            i[a] += step[a]
+            t_cur = m[a]
+            m[a] = F32(m[a] + td[a])
+            if not (0 <= i[a] < N):
+                alive = False
+                break
+            if a == 0:
+                xs += 1
+                if xs == k:
+                    break
+        # ---- the fast-forward
+        X = tm[0]
+        for _ in range(1, k):
+            X = F32(X + td[0])
+        ff_alive = bool(X <= t_end)
+        cnt, val = [0, 0], [tm[1], tm[2]]
+        if ff_alive:
+            for ax in (1, 2):
+                rem = N - 1 - idx[ax] if step[ax] > 0 else idx[ax]
+                while val[ax - 1] <= X:
+                    cnt[ax - 1] += 1
+                    if cnt[ax - 1] > rem:
+                        ff_alive = False
+                        break
+                    val[ax - 1] = F32(val[ax - 1] + td[ax])
+                if not ff_alive:
+                    break
+        # the loop only notices "X > t_end" at the NEXT iteration's check: the k-th x step itself is taken, the voxel after it is not emitted
+        ref_enters = alive and bool(t_cur <= t_end)
+        assert ref_enters == ff_alive, (trial, alive, ff_alive)
+        if ff_alive:
+            checked += 1
+            assert emitted == k + cnt[0] + cnt[1]
+            assert i[0] == idx[0] + step[0] * k and i[1] == idx[1] + step[1] * cnt[0] and i[2] == idx[2] + step[2] * cnt[1]
+            assert t_cur == X and m[0] == F32(X + td[0]) and m[1] == val[0] and m[2] == val[1]
+        else:
+            died += 1
+    assert checked > 500 and died > 200, (checked, died)
