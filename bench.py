@@ -308,6 +308,7 @@ class Env:
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.ctx = pvp.default_context(self.dev)
+        self.args = args
         if args.variant:
             self.ctx.set_option("dda_variant", args.variant)
         for kv in args.opt or []:
@@ -350,7 +351,7 @@ def sass_fresh(workload):
         return None
 
 
-def rooflines(env, workload, kernel, units_per_launch, launch_ms, algo_bytes, clocks, share):
+def rooflines(env, workload, kernel, units_per_launch, launch_ms, algo_bytes, clocks, share, pick=None):
     """`roofline` of the dominant kernel.  PRIMARY bound = the one the lock-step kernels sit on: warp-instruction issue (ncu: ~80 % of the
     issue slots busy, DRAM at 1-2 % of its peak).  achieved = warp instructions per voxel step (committed ncu capture of this very SASS,
     see sass_md5_ok) x the live rate; peak = SMs x 4 schedulers x the SM clock sampled in this run.  `algorithmic_model` keeps SURVEY 8(d)'s
@@ -363,6 +364,8 @@ def rooflines(env, workload, kernel, units_per_launch, launch_ms, algo_bytes, cl
         e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload) or {}
     except Exception:
         pass
+    if pick and e.get("k2_pick") not in (None, pick):   # the capture belongs to another lock-step kernel than the one that ran: its figures do not apply
+        e = {}
     algo_bytes_launch = algo_bytes * units_per_launch
     traffic = None
     if "bytes_per_launch" in e and e.get("voxel_steps_per_launch"):
@@ -524,18 +527,28 @@ def measure_image(env, args, name, steps, warmup, full):
     }
 
 
-def parity_of_pair(env, wl, frames_dev, poses, pair, ref_grid, ref_rays, ref_steps):
+def parity_of_pair(env, wl, frames_dev, poses, pair, ref_grid, ref_rays, ref_steps, pick=0):
     """The pair the cpu_baseline leg has just run through the reference: the same pair on the GPU (float32 atomics and fixed point),
-    compared cell by cell (oracle.parity_report; this is the checker at work inside the cpu_baseline leg, not a product path)."""
+    compared cell by cell (oracle.parity_report; this is the checker at work inside the cpu_baseline leg, not a product path).
+    pick: the lock-step kernel the timed region's batches ran on (Context.last_k2_pick) -- the float32 grid of this single pair is made
+    by that same kernel (a one-pair batch alone would fall below lean4's ray threshold and go to lean2)."""
     import oracle
     pvp, ctx = env.pvp, env.ctx
     tab, _ = pvp.make_pairs(poses, wl["W"], pairs=[pair])
     g32 = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], device=env.dev)
-    st = pvp.accumulate_motion(frames_dev, tab, g32, 2.0, ctx=ctx)
+    forced = {1: 4, 2: 5, 4: 6}.get(pick, 0) if not getattr(env.args, "variant", 0) else 0
+    if forced:
+        ctx.set_option("dda_variant", forced)
+    try:
+        st = pvp.accumulate_motion(frames_dev, tab, g32, 2.0, ctx=ctx)
+    finally:
+        if forced:
+            ctx.set_option("dda_variant", 0)
     gfx = pvp.VoxelGrid(wl["N"], wl["voxel_size"], wl["center"], accum="fixed", frac_bits=8, device=env.dev)
     stx = pvp.accumulate_motion(frames_dev, tab, gfx, 2.0, ctx=ctx)
     rep = oracle.parity_report(g32.data.cpu().numpy(), ref_grid, gfx.data.cpu().numpy() >> 8)
     rep["counters_equal"] = bool((st["n_rays"], st["n_steps"]) == (ref_rays, ref_steps) == (stx["n_rays"], stx["n_steps"]))
+    rep["k2_kernel"] = {1: "lean", 2: "lean2", 4: "lean4"}.get(pick, "as configured")
     rep["against"] = "unmodified ray_voxel.cpp (oracle/_ref), one frame pair of the workload, serial fp32 sum; exact = the GPU's int64 fixed-point grid"
     rep["fixed_point_equals_reference_below_2p24"] = rep.pop("reference_equals_exact_below_2p24")
     return rep
@@ -646,7 +659,17 @@ def measure_motion(env, args, name, steps, warmup, full):
     reduce_ms = ev[-1][0].elapsed_time(ev[-1][1])
     prof = ctx.get_profile(reset=True)
     ctx.profile(False)
+    k2_pick = ctx.last_k2_pick()    # which lock-step kernel the device-side pick gave the batches to: 1 lean, 2 lean2, 4 lean4 (0: a forced other variant)
     stats = pvp.accumulate_motion(frames_dev, pairs_for(0)[1], grid, 2.0, ctx=ctx, n_pairs=0, want_stats=True)
+    if k2_pick == 4:
+        # lean4 leaves the RED counter out of its loop (4 of 106 instructions, ~5 %); one extra, untimed step through the instantiation
+        # that counts gives the REDs per voxel step of this workload
+        ctx.set_option("count_atomics", 1)
+        try:
+            c = pvp.accumulate_motion(frames_dev, pairs_for(warmup)[1], grid, 2.0, ctx=ctx, n_pairs=B, want_stats=True)
+        finally:
+            ctx.set_option("count_atomics", 0)
+        stats["n_atomics"] = int(round(c["n_atomics"] / max(1, c["n_steps"]) * stats["n_steps"]))
     # slab mode over several ranks: the job's voxel steps are the ranks' WRITES (each step lands in exactly one slab); a rank's n_steps is what it walked
     ms_max, = env.reduce([ms], "max")
     all_steps, all_rays, all_atomics = env.reduce([stats["n_written"] if (slabs and world > 1) else stats["n_steps"], stats["n_rays"], stats["n_atomics"]], "sum")
@@ -677,8 +700,10 @@ def measure_motion(env, args, name, steps, warmup, full):
     # a batch (at most max_queue / pixels = 32 1080p pairs) is one K1 + one K2 launch; in the default auto mode a batch launches both
     # lock-step kernels and the one the ray count does not pick exits in ~2.5 us, so "launch" here means the batch's working K2 launch
     n_batches = max(1, int(prof["launches_k1"]))
-    roofline = rooflines(env, name, "dda_accumulate_lean2_kernel (K2)", per_rank_steps / n_batches, prof["ms_k2"] / n_batches, ALGO_BYTES_PER_STEP[wl["accum"]],
-                         clocks, prof["ms_k2"] / ms if ms > 0 else None)
+    k2_name = {1: "dda_accumulate_lean_kernel (K2)", 2: "dda_accumulate_lean2_kernel (K2)", 4: "dda_accumulate_lean4_kernel (K2)"}.get(k2_pick, "K2 as configured")
+    roofline = rooflines(env, name, k2_name, per_rank_steps / n_batches, prof["ms_k2"] / n_batches, ALGO_BYTES_PER_STEP[wl["accum"]],
+                         clocks, prof["ms_k2"] / ms if ms > 0 else None, pick=k2_pick)
+    roofline["k2_pick"] = k2_pick
     roofline["k2_kernels_launched"] = int(prof["launches_k2"])
     roofline["k1_ms_total"] = prof["ms_k1"]
     line = {
@@ -724,7 +749,7 @@ def measure_motion(env, args, name, steps, warmup, full):
         line["cpu_baseline"] = {"value": c_steps / c_s, "unit": "voxel-steps/s", "cores": 1, "kind": kind,
                                 "sample": f"one {W}x{H} frame pair of the workload ({c_steps} voxel-steps, {c_s:.1f} s); reference is single-threaded: 1 of {os.cpu_count()} host cores"}
         try:
-            line["parity"] = parity_of_pair(env, wl, frames_dev, poses, p0[0], c_grid, c_rays, c_steps)
+            line["parity"] = parity_of_pair(env, wl, frames_dev, poses, p0[0], c_grid, c_rays, c_steps, pick=k2_pick)
         except Exception as e:
             line["parity"] = {"error": repr(e)}
     return line

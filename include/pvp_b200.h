@@ -92,7 +92,7 @@ typedef struct pvp_stats {
                          * count and >= n_written (the default kernels; dda_variant 1-3 walk every ray in full) */
     uint64_t n_written; /* grid updates = voxel steps inside the grid's x-planes (== n_steps for a whole grid; over the slabs of a grid
                          * they add up to the whole-grid n_steps) */
-    uint64_t n_atomics; /* global atomic operations actually issued (<= n_written after aggregation) */
+    uint64_t n_atomics; /* global atomic operations actually issued (<= n_written after aggregation); lean4 counts them only with option "count_atomics" */
 } pvp_stats;
 
 /* ---- library / context ---------------------------------------------------- */
@@ -107,7 +107,9 @@ int pvp_ctx_destroy(pvp_ctx *ctx);
 int pvp_ctx_set_stream(pvp_ctx *ctx, void *stream);
 int pvp_ctx_sync(pvp_ctx *ctx);
 /* Tuning / experiment switches (all default to "auto"; none changes results, only which kernel or queue order is used -- DESIGN.md 4):
- *   "dda_variant"   0 auto | 1 scan aggregation | 2 match.any | 3 one RED per step (any grid size) | 4 lean | 5 lean2
+ *   "dda_variant"   0 auto | 1 scan aggregation | 2 match.any | 3 one RED per step (any grid size) | 4 lean | 5 lean2 | 6 lean4
+ *   "lean4"         0 auto | -1 the auto mode never picks lean4                              "lean2_paired" percent of rays in vertical pairs from which lean2 / lean4 run (50)
+ *   "count_atomics" 1: lean4 counts its REDs (pvp_stats.n_atomics; 4 instructions of its loop, ~5 %); 0 (default): lean4 reports n_atomics = 0
  *   "k1_row_group"  0 auto | 1 row-major queue | 2, 4, 8 image rows per queue tile        "k1_snake"  -1 auto | 0 | 1
  *   "lean_regs"     0 auto | 64, 80, 128 register budget of the lock-step kernels         "ctas_per_sm" 0 = by occupancy
  *   "max_queue"     ray queue capacity in entries (>= 1024)
@@ -125,6 +127,9 @@ typedef struct pvp_profile {
     double ms_k1, ms_k2, ms_k3;                                     /* summed event time (profiling enabled only) */
 } pvp_profile;
 int pvp_ctx_profile(pvp_ctx *ctx, int enable);
+/* Which lock-step kernel the device-side pick gave the LAST batch to: 1 lean (one ray per lane), 2 lean2, 4 lean4; 0 when the last
+ * batch ran a non-lock-step variant (or nothing ran yet).  Diagnostics for bench.py / the tests; synchronises the stream. */
+int pvp_ctx_last_k2_pick(pvp_ctx *ctx, int *out_pick);
 int pvp_ctx_get_profile(pvp_ctx *ctx, pvp_profile *out, int reset); /* synchronises the stream */
 
 /* plain device-memory helpers for hosts that do not bring their own allocator (the CLI) */

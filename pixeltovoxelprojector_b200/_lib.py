@@ -97,6 +97,7 @@ SIGNATURES = {
     "pvp_ctx_sync": (C.c_int, [_P]),
     "pvp_ctx_profile": (C.c_int, [_P, C.c_int]),
     "pvp_ctx_get_profile": (C.c_int, [_P, C.POINTER(Profile), C.c_int]),
+    "pvp_ctx_last_k2_pick": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "pvp_ctx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "pvp_dev_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "pvp_dev_free": (C.c_int, [_P, _P]),
@@ -147,8 +148,12 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = LIB_PATH
-    if os.environ.get("PVP_LIB_VARIANT") == "checked":   # the same sources with -DPVP_CHECKED: every index a kernel computes is tested (make checked)
-        path = LIB_PATH.replace("libpvp_b200.so", "libpvp_b200_checked.so")
+    variant = os.environ.get("PVP_LIB_VARIANT", "")
+    if variant:   # "checked": the same sources with -DPVP_CHECKED, every index a kernel computes is tested (make checked); other names: kernel
+        # experiments built from the same sources with extra -D flags (tools/build_exp.sh), for A/B runs on one GPU box
+        if not variant.replace("_", "").isalnum():
+            raise ImportError(f"bad PVP_LIB_VARIANT {variant!r}")
+        path = LIB_PATH.replace("libpvp_b200.so", f"libpvp_b200_{variant}.so")
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing. Build it with `make -C pixeltovoxelprojector_b200/csrc` "

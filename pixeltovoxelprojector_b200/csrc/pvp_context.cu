@@ -259,6 +259,19 @@ int pvp_ctx_profile(pvp_ctx *ctx, int enable)
     return PVP_OK;
 }
 
+int pvp_ctx_last_k2_pick(pvp_ctx *ctx, int *out_pick)
+{
+    PVP_REQUIRE(ctx && out_pick, "pvp_ctx_last_k2_pick: NULL argument");
+    DeviceGuard guard(ctx->device);
+    *out_pick = 0;
+    if (!ctx->ctl_dev || !ctx->last_k2_lockstep) return PVP_OK;
+    unsigned long long sel[3] = {0, 0, 0};
+    PVP_CUDA(cudaMemcpyAsync(sel, ctx->ctl_dev->sel_count, sizeof(sel), cudaMemcpyDeviceToHost, ctx->stream));
+    PVP_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out_pick = sel[2] ? 4 : sel[1] ? 2 : sel[0] ? 1 : 0;
+    return PVP_OK;
+}
+
 int pvp_ctx_get_profile(pvp_ctx *ctx, pvp_profile *out, int reset)
 {
     PVP_REQUIRE(ctx && out, "pvp_ctx_get_profile: NULL argument");
@@ -293,6 +306,8 @@ int pvp_ctx_set_option(pvp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "k1_snake")) ctx->opt_k1_snake = value;
     else if (!strcmp(key, "lean2_paired")) ctx->opt_lean2_density = value;
     else if (!strcmp(key, "inject_fault")) ctx->opt_inject_fault = value;
+    else if (!strcmp(key, "count_atomics")) ctx->opt_count_atomics = value;
+    else if (!strcmp(key, "lean4")) ctx->opt_lean4 = value;
     else { set_error("pvp_ctx_set_option: unknown key '%s'", key); return PVP_ERR_INVALID; }
     return PVP_OK;
 }

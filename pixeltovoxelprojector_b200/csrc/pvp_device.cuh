@@ -27,6 +27,7 @@ struct GridP {
     int frac_shift;     // frac_bits (0 for float32 grids)
     float alpha;        // opt-in distance attenuation (0 = off, the reference's behaviour)
     unsigned mul_n, mul_nn;  // floor(2^32 / n), floor(2^32 / n^2): division of a voxel offset by a multiply (udiv_by)
+    int one;            // 1, but not known to the compiler: the z stride of rays_step_mad (a multiply by a literal 1 would be turned back into an add)
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }

@@ -25,6 +25,12 @@ struct Ctl {
     unsigned long long img_samples;
     unsigned long long n_pairs;    // checked build: pairs of the batch (written by K1)
     unsigned long long check[8];   // checked build: violations per PVP_CHK_* site class
+    // the lock-step K2 kernels (lean / lean2 / lean4 = slots 0 / 1 / 2) each read their own copy of the queue length and claim chunks from
+    // their own head: select_lockstep_kernel gives the whole queue to the one kernel that suits the batch and 0 to the others, which then
+    // leave through their normal "queue is empty" exit.  (A pick tested at the top of a kernel, with an early return, costs the four-ray
+    // kernel 6 instructions of its 106-instruction loop: ptxas lays the loop out differently.)
+    unsigned long long sel_count[3];
+    unsigned long long sel_head[3];
 };
 
 // ---- checked build (make checked -> libpvp_b200_checked.so, -DPVP_CHECKED) ---------------------------------------------------------
@@ -101,6 +107,9 @@ struct pvp_ctx {
     int64_t opt_lean2_density = 0;     // auto K2 ("lean2_paired"): lean2 from this percentage of the rays in vertical pairs up (0 = default 50), lean below
     int64_t opt_inject_fault = 0;      // checked build only: 1 = K1 is told a quarter of the queue's capacity, 2 = K3 half of the grid's span (tests of the checks themselves)
     int64_t opt_lean_regs = 0;         // register budget of the lean K2 kernel: 0/72, 80 or 64
+    bool last_k2_lockstep = false;     // the last K2 batch went through select_lockstep_kernel (pvp_ctx_last_k2_pick)
+    int64_t opt_lean4 = 0;             // auto K2: -1 = never pick lean4 (the round-2 pair lean / lean2 only)
+    int64_t opt_count_atomics = 0;     // lean4 (four rays per lane): 1 = the instantiation that counts its REDs (pvp_stats.n_atomics); 0 = n_atomics is 0 for that kernel
 };
 
 namespace pvp {

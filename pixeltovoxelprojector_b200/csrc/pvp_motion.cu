@@ -698,6 +698,10 @@ struct LaneMasks {
     unsigned w1, w2, w4, w8, w16, next;
 };
 
+// CAP < 32 (8 or 16): runs are cut at every CAP-th lane, so the scan needs log2(CAP) levels only.  The cut costs no instruction: bit 0 of
+// the head ballot is always set, so a window that contains a multiple of CAP simply gets bit 0 as well (its test is then always "head
+// inside"), and the lane below a cut issues through the same bit.
+template <int CAP = 32>
 __device__ __forceinline__ LaneMasks lane_masks(unsigned lane)
 {
     LaneMasks m;
@@ -708,6 +712,17 @@ __device__ __forceinline__ LaneMasks lane_masks(unsigned lane)
     asm volatile("" : "+r"(m.w1));  // opaque: otherwise "heads & w1" is compiled as ((heads >> lane) & 1) != 1, three instructions instead of one LOP3
     m.w16 = lane + 1 >= 16 ? (0xffffu << (lane - 15)) : ((2u << lane) - 1u);
     m.next = lane == 31 ? 1u : (1u << (lane + 1));  // lane 31 always ends a run: bit 0 is always set
+    if (CAP < 32) {
+        const unsigned in_group = lane % CAP;  // a window of d lanes reaches a cut iff d > in_group
+        if (1 > in_group) m.w1 |= 1u;
+        if (2 > in_group) m.w2 |= 1u;
+        if (4 > in_group) m.w4 |= 1u;
+        if (8 > in_group) m.w8 |= 1u;
+        if (16 > in_group) m.w16 |= 1u;
+        if (in_group == CAP - 1) m.next |= 1u;
+        // opaque: under register pressure the compiler otherwise re-derives the masks from the lane number inside the loop (27 extra instructions)
+        asm volatile("" : "+r"(m.w1), "+r"(m.w2), "+r"(m.w4), "+r"(m.next));
+    }
     return m;
 }
 
@@ -762,6 +777,9 @@ __device__ __forceinline__ bool run_head(unsigned key)
 
 #ifndef PVP_LEAN_THREADS
 #define PVP_LEAN_THREADS 256  // measured at 1080p -> 512^3: 256-thread CTAs 503 G steps/s, 128 and 64 threads 489 G (same resident warps)
+#endif
+#ifndef PVP_RUN_CAP
+#define PVP_RUN_CAP 32  // longest run of lanes that the lean2 / lean4 scans merge (32 = no cut; 8 / 16: fewer scan levels, a few more REDs)
 #endif
 #ifndef PVP_LEAN2_MINB
 #define PVP_LEAN2_MINB 3  // resident CTAs of the default lean2 instantiation (80 registers at 256 threads)
@@ -841,11 +859,29 @@ __device__ __forceinline__ bool slab_reach(const Ray &r, float cam_x, float dir_
 // of the rays in vertical pairs (counted by K1), i.e. locally dense motion -- with scattered motion the second ray of a lane rarely
 // shares the first one's voxel, every lane issues two REDs and lean does the same work better (10 % iid motion: 493 against 444 G
 // voxel-steps/s; a moving object covering 3.6 % of the frame is locally dense: 730 against 566 G the other way round).
-// Forced variants: min_rays = 0, paired_pct = 0 (always lean2) or min_rays = ~0 (never).
-__device__ __forceinline__ bool pick_lean2(const Ctl *ctl, unsigned long long count, unsigned long long min_rays, unsigned long long paired_pct)
+// lean4 (four rays per lane, 128-ray chunks) takes the batches that lean2 would take from min_rays4 rays up (float32 cells, small planes:
+// the host passes ~0 otherwise): dense 1080p 966 against 829 G voxel-steps/s, 60 % iid motion 855 against 794, but a moving object of
+// 75 k rays per pair 685 against 706.  Returns 1 (lean), 2 (lean2) or 4 (lean4).
+// Forced variants: (min_rays, paired_pct, min_rays4) = (~0, 0, ~0) lean, (0, 0, ~0) lean2, (0, 0, 0) lean4.  (count == 0 falls to lean2 or
+// lean4 under the forced settings and to lean otherwise; with an empty queue it does not matter.)
+__device__ __forceinline__ int pick_lockstep(const Ctl *ctl, unsigned long long count, unsigned long long min_rays, unsigned long long paired_pct,
+                                             unsigned long long min_rays4)
 {
-    if (count < min_rays) return false;
-    return paired_pct == 0 || 200ull * ctl->n_paired >= paired_pct * count;
+    if (count < min_rays) return 1;
+    if (paired_pct != 0 && 200ull * ctl->n_paired < paired_pct * count) return 1;
+    return count >= min_rays4 ? 4 : 2;
+}
+
+// One thread, between K1 and the lock-step K2 kernels of a batch: hands the queue to the kernel pick_lockstep names (Ctl::sel_count) and
+// resets the three chunk heads.  The others see an empty queue.
+__global__ void select_lockstep_kernel(Ctl *__restrict__ ctl, unsigned long long min_rays, unsigned long long paired_pct, unsigned long long min_rays4)
+{
+    const unsigned long long count = ctl->count;
+    const int pick = pick_lockstep(ctl, count, min_rays, paired_pct, min_rays4);
+    ctl->sel_count[0] = pick == 1 ? count : 0ull;
+    ctl->sel_count[1] = pick == 2 ? count : 0ull;
+    ctl->sel_count[2] = pick == 4 ? count : 0ull;
+    ctl->sel_head[0] = ctl->sel_head[1] = ctl->sel_head[2] = 0ull;
 }
 
 // Slab kernels: FAST-FORWARD a ray that starts outside the slab to the moment it enters it, without walking the voxels in between
@@ -888,7 +924,7 @@ __device__ __forceinline__ bool slab_enter(Ray &r, float cam_x, float dir_x, con
 template <int MODE, bool SLAB, bool NARROW, int MINB>
 __global__ void __launch_bounds__(LEAN_THREADS, MINB)
 dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
-                           int width, int height, Ctl *__restrict__ ctl, unsigned long long min_rays, unsigned long long paired_pct)
+                           int width, int height, Ctl *__restrict__ ctl)
 {
     using A = Accum<MODE>;
     using V = LeanVal<MODE, NARROW>;
@@ -896,15 +932,14 @@ dda_accumulate_lean_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g,
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
     const LaneMasks lm = lane_masks(lane);
-    const unsigned long long count = ctl->count;
-    if (pick_lean2(ctl, count, min_rays, paired_pct)) return;  // auto mode launches both lock-step kernels; the batch's rays pick one on the device
+    const unsigned long long count = ctl->sel_count[0];  // the whole queue, or 0 when another lock-step kernel takes the batch (select_lockstep_kernel)
     const int N = g.n;
     const unsigned slab_cells = (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)N * (unsigned)N;
     unsigned steps32 = 0, written32 = 0, atomics32 = 0;  // per lane; see lean2
 
     for (;;) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&ctl->head, 32ull);
+        if (lane == 0) base = atomicAdd(&ctl->sel_head[0], 32ull);
         base = __shfl_sync(FULL, base, 0);
         if (base >= count) break;
         const unsigned long long i = base + lane;
@@ -1057,7 +1092,8 @@ __device__ __forceinline__ void rays_retire(RayS &r)
 }
 
 // queue entry -> walking state; returns the value to accumulate (0 when the ray casts no step)
-template <typename V, bool SLAB>
+// SIGNS: dix / diy / diz hold the step signs (+-1) instead of the offset strides; the step multiplies them by n^2 / n / 1 (rays_step_mad)
+template <typename V, bool SLAB, int SIGNS = 0>
 __device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, unsigned long long i, unsigned long long count,
                                                     const pvp_pair *__restrict__ pairs, const GridP &g, int width, int height, float &raw_diff, Ctl *ctl)
 {
@@ -1080,7 +1116,7 @@ __device__ __forceinline__ typename V::T rays_setup(RayS &s, const Queue &q, uns
     raw_diff = diff;
     s.tmx = r.tmx; s.tmy = r.tmy; s.tmz = r.tmz; s.tdx = r.tdx; s.tdy = r.tdy; s.tdz = r.tdz;
     s.idx = (unsigned)((r.ix - g.slab_lo) * N + r.iy) * (unsigned)N + (unsigned)r.iz;
-    s.dix = r.sx * N * N; s.diy = r.sy * N; s.diz = r.sz;
+    s.dix = SIGNS ? r.sx : r.sx * N * N; s.diy = SIGNS == 1 ? r.sy : r.sy * N; s.diz = r.sz;
     s.lim = fminf(fminf(axis_limit(r.tmx, r.tdx, rem_x), axis_limit(r.tmy, r.tdy, r.sy > 0 ? N - 1 - r.iy : r.iy)),
                   fminf(axis_limit(r.tmz, r.tdz, r.sz > 0 ? N - 1 - r.iz : r.iz), r.t_end));
     return V::make(diff, g);
@@ -1104,6 +1140,16 @@ __device__ __forceinline__ void dda_advance(float m, float &tmx, float &tmy, flo
         "@pz add.s32 %3, %3, %10;\n\t}"
         : "+f"(tmx), "+f"(tmy), "+f"(tmz), "+r"(idx)
         : "f"(m), "f"(tdx), "f"(tdy), "f"(tdz), "r"(dix), "r"(diy), "r"(diz));
+}
+
+// a += b where p (the join of two rays of a lane that sit in the same voxel) as one predicated add
+__device__ __forceinline__ void add_if(bool p, float &a, float b)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q add.rn.f32 %0, %0, %2;\n\t}" : "+f"(a) : "r"((unsigned)p), "f"(b));
+}
+__device__ __forceinline__ void add_if(bool p, unsigned long long &a, unsigned long long b)
+{
+    if (p) a += b;
 }
 
 // one DDA step (ray_voxel.cpp:375-391); returns the step's t (the minimum of the three t_max).  While it is below the ray's
@@ -1130,6 +1176,55 @@ __device__ __forceinline__ float rays_step(RayS &s)
     return m;
 }
 
+// rays_step with the voxel offset advanced by multiply-adds: offset += sign * stride, the signs (+-1) per ray in dix / diy / diz, the
+// strides n^2 / n / 1 the same for every ray.  Same arithmetic as dda_advance; the point is the pipe: IMAD issues on the FMA pipe, and
+// the lock-step loops saturate the ALU pipe (compares, min3, selects, integer adds: 76 % busy at 77 % of the issue slots in lean4,
+// the FMA pipe at 23 % -- profiles/r2j_k2_lean4_dense_full_raw.csv), so the three offset adds of every ray step move over.
+template <bool X_ONLY>
+__device__ __forceinline__ float rays_step_mad(RayS &s, int nn, int n, int one)
+{
+    const float m = fmin3(s.tmx, s.tmy, s.tmz);
+    if (X_ONLY) {   // diy holds the y stride itself (rays_setup<..., SIGNS = 2>)
+        asm("{\n\t.reg .pred pz, py, px;\n\t"
+            "setp.eq.f32 pz, %2, %4;\n\t"
+            "setp.eq.and.f32 py, %1, %4, !pz;\n\t"
+            "setp.neu.and.f32 px, %1, %4, !pz;\n\t"
+            "@px add.rn.f32 %0, %0, %5;\n\t"
+            "@py add.rn.f32 %1, %1, %6;\n\t"
+            "@pz add.rn.f32 %2, %2, %7;\n\t"
+            "@px mad.lo.s32 %3, %8, %11, %3;\n\t"
+            "@py add.s32 %3, %3, %9;\n\t"
+            "@pz add.s32 %3, %3, %10;\n\t}"
+            : "+f"(s.tmx), "+f"(s.tmy), "+f"(s.tmz), "+r"(s.idx)
+            : "f"(m), "f"(s.tdx), "f"(s.tdy), "f"(s.tdz), "r"(s.dix), "r"(s.diy), "r"(s.diz), "r"(nn));
+        s.t_cur = m;
+        return m;
+    }
+    asm("{\n\t.reg .pred pz, py, px;\n\t"
+        "setp.eq.f32 pz, %2, %4;\n\t"
+        "setp.eq.and.f32 py, %1, %4, !pz;\n\t"
+        "setp.neu.and.f32 px, %1, %4, !pz;\n\t"
+        "@px add.rn.f32 %0, %0, %5;\n\t"
+        "@py add.rn.f32 %1, %1, %6;\n\t"
+        "@pz add.rn.f32 %2, %2, %7;\n\t"
+        "@px mad.lo.s32 %3, %8, %11, %3;\n\t"
+        "@py mad.lo.s32 %3, %9, %12, %3;\n\t"
+        "@pz mad.lo.s32 %3, %10, %13, %3;\n\t}"
+        : "+f"(s.tmx), "+f"(s.tmy), "+f"(s.tmz), "+r"(s.idx)
+        : "f"(m), "f"(s.tdx), "f"(s.tdy), "f"(s.tdz), "r"(s.dix), "r"(s.diy), "r"(s.diz), "r"(nn), "r"(n), "r"(one));
+    s.t_cur = m;
+    return m;
+}
+
+// rays_ended for rays whose dix / diy / diz hold signs (rays_setup<..., SIGNS = true>)
+template <bool SLAB, bool Y_SIGN>
+__device__ __forceinline__ bool rays_ended_signs(const RayS &s, unsigned cur, float m, const GridP &g)
+{
+    const int d = (int)(s.idx - cur);
+    const bool cz = d == s.diz, cy = !cz && (Y_SIGN ? d == s.diy * g.n : d == s.diy);
+    return step_leaves<SLAB>(cur, cz, cy, s.dix, s.diy, s.diz, g) || !(m <= s.t_end);
+}
+
 // exact end-of-ray test of the step (t = m) just taken from voxel `cur` (:388-391 and the loop condition :365).  The axis of the
 // step is read back from the offset change (for N == 1 the strides coincide, and every step leaves whatever its axis).
 template <bool SLAB>
@@ -1143,22 +1238,21 @@ __device__ __forceinline__ bool rays_ended(const RayS &s, unsigned cur, float m,
 template <int MODE, bool SLAB, bool NARROW, int MINB, bool ATT = false>
 __global__ void __launch_bounds__(LEAN_THREADS, MINB)
 dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
-                            int width, int height, Ctl *__restrict__ ctl, unsigned long long min_rays, unsigned long long paired_pct)
+                            int width, int height, Ctl *__restrict__ ctl)
 {
     using V = LeanVal<MODE, NARROW>;
     using T = typename V::T;
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
-    const LaneMasks lm = lane_masks(lane);
-    const unsigned long long count = ctl->count;
-    if (!pick_lean2(ctl, count, min_rays, paired_pct)) return;  // auto mode launches both lock-step kernels; the batch's rays pick one on the device
+    const LaneMasks lm = lane_masks<PVP_RUN_CAP>(lane);
+    const unsigned long long count = ctl->sel_count[1];  // the whole queue, or 0 when another lock-step kernel takes the batch (select_lockstep_kernel)
     const unsigned slab_cells = (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)g.n * (unsigned)g.n;
     // per-lane counters in 32 bits (a lane walks count / 113 664 rays of at most 3 n steps each; the queue holds < 2^32 entries): three
     // registers less in a loop that sits at its register cap; widened for the warp reduction below
     unsigned steps32 = 0, written32 = 0, atomics32 = 0;
     for (;;) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&ctl->head, 64ull);
+        if (lane == 0) base = atomicAdd(&ctl->sel_head[1], 64ull);
         base = __shfl_sync(FULL, base, 0);
         if (base >= count) break;
         RayS a, b;
@@ -1196,13 +1290,15 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
             t = __shfl_up_sync(FULL, sum, 1);  if (!(heads & lm.w1))  sum = V::add(sum, t);
             t = __shfl_up_sync(FULL, sum, 2);  if (!(heads & lm.w2))  sum = V::add(sum, t);
             t = __shfl_up_sync(FULL, sum, 4);  if (!(heads & lm.w4))  sum = V::add(sum, t);
-            t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t);
-            t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t);
+            if (PVP_RUN_CAP > 8)  { t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t); }
+            if (PVP_RUN_CAP > 16) { t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t); }
             const bool issue = (heads & lm.next) && ka != KEY_NONE;
             red_if(issue && PVP_DEV_CHECK(ctl, PVP_CHK_GRID, ka < slab_cells), grid + ka, V::cell_value(sum, g));
             red_if(b_alone && PVP_DEV_CHECK(ctl, PVP_CHK_GRID, kb < slab_cells), grid + kb, V::cell_value(sb, g));
+#ifndef PVP_NO_ATOMIC_COUNT
             if (issue) n_issued += 1.f;
             if (b_alone) n_issued += 1.f;
+#endif
             heads = __ballot_sync(FULL, next_head);
             // ---- rays that ended: park them; leave when every ray of the warp is parked ----------------------------
             if (any_unsure) {
@@ -1233,6 +1329,166 @@ dda_accumulate_lean2_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g
         atomicAdd(&ctl->n_steps, my_steps);
         atomicAdd(&ctl->n_written, my_written);
         atomicAdd(&ctl->n_atomics, my_atomics);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->n_rays, count);
+}
+
+// ---- variant 6: "lean4", four rays per lane -------------------------------------------------------------------------
+// A warp takes 128 consecutive queue entries; lane l walks entries 4l .. 4l+3, which K1's column-snake order makes one
+// column of a 4-row block (or half a column of an 8-row block).  The per-iteration overhead of the lock-step loop -- the
+// run scan, the run-head ballot and shuffle, the end-of-ray vote, the loop itself -- is paid once per 128 voxel
+// steps instead of once per 64.  Inside a lane the four rays are chained bottom-up: ray j joins ray j-1 where both sit in
+// the same voxel (a predicated add), otherwise it issues its own RED; ray 0 carries the lane's sum into the run scan.
+// Runs are cut at every 8th lane (lane_masks<8>): 32 columns of the image span ~5 voxels, so a natural run is ~7 lanes long
+// anyway; the cut costs ~0.02 REDs per voxel step and saves two of the five scan levels.
+// COUNT: count the REDs (pvp_stats.n_atomics; context option count_atomics) -- a diagnostic that costs four instructions
+// of the loop, so the default instantiation leaves it out and reports n_atomics = 0.
+// Per ray the arithmetic, the step order and the counters are those of variants 4 and 5 (same bit-exact visited sets).
+// Measured 1080p dense -> 512^3 float32 (G voxel-steps/s; lean2: 829): 256-thread CTAs x 2 (108 registers, 16 warps per SM) 898, 128 x 5 (96
+// registers, 20 warps) 941, 192 x 3 at 104 registers 816, 128 x 5 at 88 registers (a 124-instruction loop) 790; run cap 4 / 8 / 16 / none
+// 817 / 898 / 894 / 775 (256 x 2); counting the REDs 852 against 898; the loop unrolled twice 954, the chain's joins as predicated adds
+// 966 (not unrolled; both together 960); three rays per lane 876-908, two rays per lane in this form 790-800 (profiles/r2_lean4_tuning.log).
+#ifndef PVP_LEAN4_THREADS
+#define PVP_LEAN4_THREADS 128
+#endif
+#ifndef PVP_LEAN4_MINB
+#define PVP_LEAN4_MINB 5  // resident CTAs: 96 registers at 128 threads, 20 warps per SM
+#endif
+#ifndef PVP_LEAN4_CAP
+#define PVP_LEAN4_CAP 8
+#endif
+#ifndef PVP_LEAN4_UNROLL
+#define PVP_LEAN4_UNROLL 1
+#endif
+#ifndef PVP_LEAN4_MAD
+#define PVP_LEAN4_MAD 1  // voxel offset advanced by IMAD (FMA pipe) instead of IADD (ALU pipe), see rays_step_mad
+#endif
+#ifndef PVP_LEAN4_NR
+#define PVP_LEAN4_NR 4  // rays per lane
+#endif
+constexpr int LEAN4_THREADS = PVP_LEAN4_THREADS;
+#ifdef PVP_LEAN4_MAXNREG
+#define PVP_LEAN4_BOUNDS __maxnreg__(PVP_LEAN4_MAXNREG)
+#else
+#define PVP_LEAN4_BOUNDS __launch_bounds__(LEAN4_THREADS, PVP_LEAN4_MINB)
+#endif
+template <int MODE, bool SLAB, bool NARROW, bool COUNT>
+__global__ void PVP_LEAN4_BOUNDS
+dda_accumulate_lean4_kernel(Queue q, const pvp_pair *__restrict__ pairs, GridP g, typename Accum<MODE>::cell *__restrict__ grid,
+                            int width, int height, Ctl *__restrict__ ctl)
+{
+    using V = LeanVal<MODE, NARROW>;
+    using T = typename V::T;
+    constexpr int NR = PVP_LEAN4_NR, CAP = PVP_LEAN4_CAP;
+    constexpr bool L4_MAD = PVP_LEAN4_MAD != 0;
+    // PVP_LEAN4_MAD: 1 = x and y offsets by IMAD, z by IADD (literal stride 1); 2 = all three by IMAD (stride g.one, a run-time 1: 149
+    // instructions, ptxas runs out of predicate registers); 3 = x only
+    const int stride_x = g.n * g.n, stride_y = (PVP_LEAN4_MAD == 3) ? 0 : g.n, stride_z = (PVP_LEAN4_MAD == 2) ? g.one : 1;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const LaneMasks lm = lane_masks<CAP>(lane);
+    const unsigned long long count = ctl->sel_count[2];  // the whole queue, or 0 when another lock-step kernel takes the batch (select_lockstep_kernel)
+    const unsigned slab_cells = (unsigned)(g.slab_hi - g.slab_lo) * (unsigned)g.n * (unsigned)g.n;
+    unsigned steps32 = 0, written32 = 0, atomics32 = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->sel_head[2], (unsigned long long)(32 * NR));
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= count) break;
+        RayS r[NR];
+        T v[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            float raw;
+            v[j] = rays_setup<V, SLAB, (PVP_LEAN4_MAD == 3 ? 2 : PVP_LEAN4_MAD != 0 ? 1 : 0)>(r[j], q, base + NR * lane + j, count, pairs, g, width, height, raw, ctl);
+        }
+        float n_issued = 0.f, n_inslab = 0.f;
+        float walked = 0.f;
+        bool none_live = true;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) none_live = none_live && !rays_live(r[j]);
+        if (__all_sync(FULL, none_live)) continue;
+
+        unsigned heads = __ballot_sync(FULL, run_head(SLAB ? (r[0].idx < slab_cells ? r[0].idx : KEY_NONE) : r[0].idx));
+        // one lock-step iteration; true when every ray of the warp has ended
+        auto iteration = [&]() -> bool {
+            unsigned k[NR], k0[NR];
+            float m[NR];
+            T s[NR];
+            bool unsure = false;
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                k[j] = k0[j] = r[j].idx;
+                // the predicated-PTX forms: with four rays the compiler's own form of the C++ turns into divergent branches
+                m[j] = L4_MAD ? rays_step_mad<PVP_LEAN4_MAD == 3>(r[j], stride_x, stride_y, stride_z) : rays_step<true>(r[j]);
+                unsure = unsure || !(m[j] < r[j].lim);
+                s[j] = v[j];
+            }
+            const bool any_unsure = __any_sync(FULL, unsure);
+            walked += 1.f;
+            if (SLAB) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const bool in = k[j] < slab_cells;
+                    k[j] = in ? k[j] : KEY_NONE;
+                    s[j] = in ? s[j] : (T)0;
+                    n_inslab += in ? 1.f : 0.f;
+                }
+            }
+            const bool next_head = run_head(SLAB ? (r[0].idx < slab_cells ? r[0].idx : KEY_NONE) : r[0].idx);
+            // ---- the lane's chain: ray j joins ray j-1 where they share the voxel, else it issues its own RED ------------
+#pragma unroll
+            for (int j = NR - 1; j > 0; --j) {
+                const bool same = (k[j] == k[j - 1]);
+                const bool alone = !same && k[j] != KEY_NONE;
+                red_if(alone && PVP_DEV_CHECK(ctl, PVP_CHK_GRID, k[j] < slab_cells), grid + k[j], V::cell_value(s[j], g));
+                if (COUNT && alone) n_issued += 1.f;
+                add_if(same, s[j - 1], s[j]);
+            }
+            T sum = s[0], t;
+            t = __shfl_up_sync(FULL, sum, 1);  if (!(heads & lm.w1))  sum = V::add(sum, t);
+            t = __shfl_up_sync(FULL, sum, 2);  if (!(heads & lm.w2))  sum = V::add(sum, t);
+            if (CAP > 4)  { t = __shfl_up_sync(FULL, sum, 4);  if (!(heads & lm.w4))  sum = V::add(sum, t); }
+            if (CAP > 8)  { t = __shfl_up_sync(FULL, sum, 8);  if (!(heads & lm.w8))  sum = V::add(sum, t); }
+            if (CAP > 16) { t = __shfl_up_sync(FULL, sum, 16); if (!(heads & lm.w16)) sum = V::add(sum, t); }
+            const bool issue = (heads & lm.next) && k[0] != KEY_NONE;
+            red_if(issue && PVP_DEV_CHECK(ctl, PVP_CHK_GRID, k[0] < slab_cells), grid + k[0], V::cell_value(sum, g));
+            if (COUNT && issue) n_issued += 1.f;
+            heads = __ballot_sync(FULL, next_head);
+            // ---- rays that ended: park them; leave when every ray of the warp is parked ----------------------------
+            if (any_unsure) {
+                bool live = false;
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    if (!(m[j] < r[j].lim) && rays_live(r[j]) && (L4_MAD ? rays_ended_signs<SLAB, PVP_LEAN4_MAD != 3>(r[j], k0[j], m[j], g) : rays_ended<SLAB>(r[j], k0[j], m[j], g))) {
+                        steps32 += (unsigned)walked;
+                        rays_retire(r[j]); v[j] = 0;
+                    }
+                    live = live || rays_live(r[j]);
+                }
+                if (__all_sync(FULL, !live)) return true;
+                heads = __ballot_sync(FULL, run_head(SLAB ? (r[0].idx < slab_cells ? r[0].idx : KEY_NONE) : r[0].idx));
+            }
+            return false;
+        };
+        for (;;) {
+            if (iteration()) break;
+            if (PVP_LEAN4_UNROLL > 1 && iteration()) break;
+        }
+        if (COUNT) atomics32 += (unsigned)n_issued;
+        if (SLAB) written32 += (unsigned)n_inslab;
+    }
+    unsigned long long my_steps = steps32, my_written = SLAB ? written32 : steps32, my_atomics = atomics32;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_steps += __shfl_xor_sync(FULL, my_steps, o);
+        my_written += __shfl_xor_sync(FULL, my_written, o);
+        if (COUNT) my_atomics += __shfl_xor_sync(FULL, my_atomics, o);
+    }
+    if (lane == 0 && my_steps) {
+        atomicAdd(&ctl->n_steps, my_steps);
+        atomicAdd(&ctl->n_written, my_written);
+        if (COUNT) atomicAdd(&ctl->n_atomics, my_atomics);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->n_rays, count);
 }
@@ -1314,6 +1570,7 @@ static int make_gridp(const pvp_grid_desc *d, GridP *g)
     g->alpha = d->attenuation_alpha;
     g->mul_n = (unsigned)(0x100000000ull / (unsigned long long)d->n);  // n >= 2 here; n == 1 divides by shifting nothing: see udiv_by
     g->mul_nn = (unsigned)(0x100000000ull / ((unsigned long long)d->n * d->n));
+    g->one = 1;
     return PVP_OK;
 }
 
@@ -1398,30 +1655,36 @@ static void launch_agg(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, 
 
 // lean_regs: register budget = resident warps per SM: 0/72 -> 28 warps at 128-thread CTAs (24 at 256), 80 -> 24 warps, 64 -> 32 warps
 template <int MODE, bool SLAB, bool NARROW>
-static void launch_lean(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height, unsigned long long min_rays = ~0ull,
-                        unsigned long long paired_pct = 0)  // defaults: lean2 is never picked, this kernel always runs
+static void launch_lean(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height)
 {
     auto k = ctx->opt_lean_regs == 64 ? dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_C>
            : ctx->opt_lean_regs == 80 ? dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_B> : dda_accumulate_lean_kernel<MODE, SLAB, NARROW, LEAN_CTAS_A>;
     k<<<k2_grid_size(ctx, (const void *)k, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
-                                                                                           width, height, ctx->ctl_dev, min_rays, paired_pct);
+                                                                                           width, height, ctx->ctl_dev);
 }
 
 template <int MODE, bool SLAB, bool NARROW>
-static void launch_lean2(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height, unsigned long long min_rays = 0,
-                         unsigned long long paired_pct = 0)  // defaults: always picked
+static void launch_lean2(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height)
 {
     if (g.alpha > 0.f) {  // opt-in distance attenuation: values change every step, so no integral shortcut (NARROW is false here)
         auto ka = dda_accumulate_lean2_kernel<MODE, SLAB, false, 3, true>;
         ka<<<k2_grid_size(ctx, (const void *)ka, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
-                                                                                                 width, height, ctx->ctl_dev, min_rays, paired_pct);
+                                                                                                 width, height, ctx->ctl_dev);
         return;
     }
     // lean_regs: 0/80 -> 3 resident CTAs (24 warps; measured best: 780 G voxel-steps/s at 512^3 on 2-row tiles), 128 -> 2 CTAs (686 G), 64 -> 4 CTAs (722 G)
     auto k = ctx->opt_lean_regs == 128 ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 2>
            : ctx->opt_lean_regs == 64  ? dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, 4> : dda_accumulate_lean2_kernel<MODE, SLAB, NARROW, PVP_LEAN2_MINB>;
     k<<<k2_grid_size(ctx, (const void *)k, LEAN_THREADS), LEAN_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
-                                                                                           width, height, ctx->ctl_dev, min_rays, paired_pct);
+                                                                                           width, height, ctx->ctl_dev);
+}
+
+template <int MODE, bool SLAB, bool NARROW>
+static void launch_lean4(pvp_ctx *ctx, const GridP &g, void *grid_dev, int width, int height)
+{
+    auto k = ctx->opt_count_atomics ? dda_accumulate_lean4_kernel<MODE, SLAB, NARROW, true> : dda_accumulate_lean4_kernel<MODE, SLAB, NARROW, false>;
+    k<<<k2_grid_size(ctx, (const void *)k, LEAN4_THREADS), LEAN4_THREADS, 0, ctx->stream>>>(ctx->queue, ctx->pairs_dev, g, (typename Accum<MODE>::cell *)grid_dev,
+                                                                                             width, height, ctx->ctl_dev);
 }
 
 // See the lean kernel's header: no t value of the batch can overflow to -inf.
@@ -1437,14 +1700,16 @@ static bool lean_geometry_ok(const GridP &g, const pvp_pair *pairs, int n_pairs)
     return true;
 }
 
-// 0 = auto: both lock-step kernels are launched and the ray count of the batch picks one on the device (lean2 from
-// LEAN2_MIN_RAYS_PER_WARP rays per resident warp up: with fewer rays its 64-ray chunks leave SMs idle)
+// 0 = auto: the lock-step kernels are all launched and the batch's ray count and paired share pick one on the device (select_lockstep_kernel:
+// lean2 from LEAN2_MIN_RAYS_PER_WARP rays per resident warp up -- with fewer rays its 64-ray chunks leave SMs idle --, lean4 from
+// LEAN4_MIN_RAYS_PER_WARP)
 static int effective_variant(const pvp_ctx *ctx)
 {
     const int v = (int)ctx->opt_dda_variant;
-    return (v < 0 || v > 5) ? 0 : v;
+    return (v < 0 || v > 6) ? 0 : v;
 }
 constexpr unsigned long long LEAN2_MIN_RAYS_PER_WARP = 256;
+constexpr unsigned long long LEAN4_MIN_RAYS_PER_WARP = 2048;  // 6 M rays on a B200: a moving object of 2.4 M rays per batch runs better on lean2, 38 M rays of 60 % iid motion on lean4
 
 // Bytes of one x-plane of the grid (n * n cells).  Neighbouring image columns land in neighbouring x-planes, i.e. this
 // far apart in memory; once a plane outgrows a 2 MiB page the RED misses of a wide, flat ray tile dominate K2 (measured at
@@ -1460,7 +1725,8 @@ static size_t plane_bytes(const GridP &g, int accum_mode)
 constexpr size_t PLANE_LARGE = 2u << 20;
 // dda_variant: 0 = auto (lean2 / lean by ray count where their 32-bit voxel keys allow, else 3), 1 = segmented-scan aggregation (round-1
 // baseline), 2 = match.any aggregation, 3 = one RED per lane and step (no aggregation, any grid size),
-// 4 = lean lock-step kernel (one ray per lane), 5 = lean2 (two rays per lane, vertical neighbours of K1's tile order).  narrow_ok: uint8 frames, i.e. integer addends (LeanVal<FIXED, true>).
+// 4 = lean lock-step kernel (one ray per lane), 5 = lean2 (two rays per lane, vertical neighbours of K1's tile order),
+// 6 = lean4 (four rays per lane: a column of K1's 4-row blocks).  narrow_ok: uint8 frames, i.e. integer addends (LeanVal<FIXED, true>).
 static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_ok, bool lean_ok, void *grid_dev, int width, int height,
                      unsigned long long batch_pixels)  // NOLINT
 {
@@ -1474,30 +1740,49 @@ static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_o
     if (lockstep && (slab ? full > (1ull << 31) : full >= 0xffffffffull)) variant = 3;  // slab test relies on wrapped offsets
     if (lockstep && !lean_ok) variant = 3;
     const bool f32 = accum_mode == PVP_ACCUM_F32;
+    ctx->last_k2_lockstep = false;
     if (g.alpha > 0.f && variant != 3) { variant = 5; narrow_ok = false; }  // only lean2 and variant 3 implement the attenuation
     if (variant == 0 && plane_bytes(g, accum_mode) > PLANE_LARGE) variant = 4;
     if (variant == 0) {
-        ++ctx->prof.launches_k2;  // two kernels are launched (the scope above counted one); the one not chosen exits at once
-        // both lock-step kernels are launched; K1's counters pick one on the device (pick_lean2): lean2 from LEAN2_MIN_RAYS_PER_WARP rays per
-        // resident warp up AND lean2_paired percent of the rays in vertical pairs (default 50), lean otherwise
+        // all eligible lock-step kernels are launched; K1's counters pick one on the device (pick_lockstep): lean2 / lean4 from
+        // LEAN2_MIN_RAYS_PER_WARP rays per resident warp up AND lean2_paired percent of the rays in vertical pairs (default 50), lean otherwise;
+        // of the two, lean4 from LEAN4_MIN_RAYS_PER_WARP rays per resident warp up -- float32 cells without attenuation only (with int64
+        // cells lean4 is no faster than lean2: 751 against 754 G voxel-steps/s).  The kernels that are not chosen exit at once.
         const unsigned long long T = (unsigned long long)ctx->sm_count * 3 * (LEAN_THREADS / 32) * LEAN2_MIN_RAYS_PER_WARP;
         const unsigned long long pct = (unsigned long long)(ctx->opt_lean2_density > 0 ? ctx->opt_lean2_density : 50);
+        const bool lean4_ok = f32 && g.alpha == 0.f && ctx->opt_lean4 >= 0;
+        const unsigned long long T4 = lean4_ok ? (unsigned long long)ctx->sm_count * PVP_LEAN4_MINB * (LEAN4_THREADS / 32) * LEAN4_MIN_RAYS_PER_WARP : ~0ull;
+        ctx->prof.launches_k2 += lean4_ok ? 3 : 2;  // the selector and two or three kernels (the scope above counted one)
         (void)batch_pixels;
+        ctx->last_k2_lockstep = true;
+        select_lockstep_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl_dev, T, pct, T4);
         if (f32) {
-            if (slab) { launch_lean<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height, T, pct); }
-            else { launch_lean<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height, T, pct); }
+            if (slab) { launch_lean<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height); launch_lean2<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height);
+                        if (lean4_ok) launch_lean4<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height); }
+            else { launch_lean<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height); launch_lean2<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height);
+                   if (lean4_ok) launch_lean4<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height); }
         } else if (narrow_ok) {
-            if (slab) { launch_lean<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height, T, pct); }
-            else { launch_lean<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height, T, pct); }
+            if (slab) { launch_lean<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height); launch_lean2<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height); }
+            else { launch_lean<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height); launch_lean2<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height); }
         } else {
-            if (slab) { launch_lean<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height, T, pct); }
-            else { launch_lean<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height, T, pct); launch_lean2<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height, T, pct); }
+            if (slab) { launch_lean<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height); launch_lean2<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height); }
+            else { launch_lean<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height); launch_lean2<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height); }
         }
+    } else if (variant == 6) {
+        ctx->last_k2_lockstep = true; ++ctx->prof.launches_k2;
+        select_lockstep_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl_dev, 0ull, 0ull, 0ull);  // forced: (min_rays, paired_pct, min_rays4) = (0, 0, 0) is always lean4
+        if (f32) { if (slab) launch_lean4<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height); else launch_lean4<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height); }
+        else if (narrow_ok) { if (slab) launch_lean4<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height); else launch_lean4<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height); }
+        else { if (slab) launch_lean4<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height); else launch_lean4<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height); }
     } else if (variant == 5) {
+        ctx->last_k2_lockstep = true; ++ctx->prof.launches_k2;
+        select_lockstep_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl_dev, 0ull, 0ull, ~0ull);  // always lean2
         if (f32) { if (slab) launch_lean2<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height); else launch_lean2<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height); }
         else if (narrow_ok) { if (slab) launch_lean2<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height); else launch_lean2<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height); }
         else { if (slab) launch_lean2<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height); else launch_lean2<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height); }
     } else if (variant == 4) {
+        ctx->last_k2_lockstep = true; ++ctx->prof.launches_k2;
+        select_lockstep_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl_dev, ~0ull, 0ull, ~0ull);  // always lean
         if (f32) { if (slab) launch_lean<PVP_ACCUM_F32, true, false>(ctx, g, grid_dev, width, height); else launch_lean<PVP_ACCUM_F32, false, false>(ctx, g, grid_dev, width, height); }
         else if (narrow_ok) { if (slab) launch_lean<PVP_ACCUM_FIXED, true, true>(ctx, g, grid_dev, width, height); else launch_lean<PVP_ACCUM_FIXED, false, true>(ctx, g, grid_dev, width, height); }
         else { if (slab) launch_lean<PVP_ACCUM_FIXED, true, false>(ctx, g, grid_dev, width, height); else launch_lean<PVP_ACCUM_FIXED, false, false>(ctx, g, grid_dev, width, height); }

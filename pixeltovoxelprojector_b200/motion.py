@@ -68,6 +68,12 @@ class Context:
         check(self._lib.pvp_ctx_get_profile(self.handle, C.byref(p), int(reset)))
         return p.as_dict()
 
+    def last_k2_pick(self) -> int:
+        """Which lock-step kernel took the last K2 batch: 1 lean, 2 lean2, 4 lean4 (0: another variant, or nothing ran)."""
+        v = C.c_int(0)
+        check(self._lib.pvp_ctx_last_k2_pick(self.handle, C.byref(v)))
+        return int(v.value)
+
     def sync(self) -> None:
         check(self._lib.pvp_ctx_sync(self.handle))
 

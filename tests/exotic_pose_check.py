@@ -69,7 +69,7 @@ def main():
                                          grid, N, np.float32(vs), np.array(center, np.float32), 2.0, accum_mode=mode, frac_bits=8)
             want[accum] = (grid, tot)
         with_steps += want["f32"][1][1] > 0
-        for variant in (() if a.oracle_only else (0, 1, 2, 3, 4, 5)):
+        for variant in (() if a.oracle_only else (0, 1, 2, 3, 4, 5, 6)):
             ctx.set_option("dda_variant", variant)
             for accum in ("f32", "fixed"):
                 g = pvp.VoxelGrid(N, vs, center, accum=accum, frac_bits=8)

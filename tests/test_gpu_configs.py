@@ -95,7 +95,7 @@ def test_config4_1024_grid_eight_x_slabs(ctx):
 
 def test_headline_shape_all_variants_agree_1080p_dense_512(ctx):
     """The bench workload's shape (1080p dense motion -> 512^3, 2 M rays and 1.2 G voxel steps per pair): every K2 variant --
-    the default auto pick (lean2), lean, the first scan kernel and the plain one-RED-per-step kernel, whose code shares nothing
+    the default auto pick (lean2 for this batch of two pairs), lean, lean2, lean4, the first scan kernel and the plain one-RED-per-step kernel, whose code shares nothing
     with the lock-step kernels beyond the ray set-up -- must produce the same int64 grid and the same counters, and the float32
     grid must equal the fixed-point one exactly wherever the integer sum is below 2^24."""
     H, W, N, vs, center = 1080, 1920, 512, 2.0, (0.0, 0.0, 500.0)
@@ -104,7 +104,8 @@ def test_headline_shape_all_variants_agree_1080p_dense_512(ctx):
     tab, _ = pvp.make_pairs(poses, W)
     ref_grid, ref_stats = None, None
     try:
-        for variant in (3, 0, 4, 5, 1):
+        ctx.set_option("count_atomics", 1)     # lean4 leaves its RED counter out unless asked
+        for variant in (3, 0, 4, 5, 6, 1):
             ctx.set_option("dda_variant", variant)
             g = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=4)
             st = pvp.accumulate_motion(frames, tab, g, 2.0)
@@ -117,16 +118,21 @@ def test_headline_shape_all_variants_agree_1080p_dense_512(ctx):
                 assert torch.equal(g.data, ref_grid), variant
                 assert st["n_atomics"] < 0.3 * st["n_written"]          # aggregated
                 del g
-        ctx.set_option("dda_variant", 0)
-        gf = pvp.VoxelGrid(N, vs, center)
-        pvp.accumulate_motion(frames, tab, gf, 2.0)
         exact = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=4, data=ref_grid).to_float32()
         small = exact < 2 ** 24                     # integer sums below 2^24 are exact in fp32 whatever the order
-        assert torch.equal(gf.data[small], exact[small]) and int((~small).sum()) > 0
-        # the few cells every ray crosses (around the camera: up to 1.8e8 here) round at each of ~10^5 atomic adds
-        torch.testing.assert_close(gf.data[~small], exact[~small], rtol=1e-4, atol=0)
+        for variant, want_pick in ((0, 2), (6, 4), (4, 1)):     # float32 cells: the auto pick (4 M rays: lean2), lean4 and lean
+            ctx.set_option("dda_variant", variant)
+            gf = pvp.VoxelGrid(N, vs, center)
+            st = pvp.accumulate_motion(frames, tab, gf, 2.0)
+            assert ctx.last_k2_pick() == want_pick, variant
+            assert (st["n_rays"], st["n_steps"], st["n_written"]) == ref_stats and 0 < st["n_atomics"] < 0.3 * st["n_written"], variant
+            assert torch.equal(gf.data[small], exact[small]) and int((~small).sum()) > 0, variant
+            # the few cells every ray crosses (around the camera: up to 1.8e8 here) round at each of ~10^5 atomic adds
+            torch.testing.assert_close(gf.data[~small], exact[~small], rtol=1e-4, atol=0)
+            del gf
     finally:
         ctx.set_option("dda_variant", 0)
+        ctx.set_option("count_atomics", 0)
 
 
 def test_grid_near_the_32bit_offset_limit_variants_agree(ctx):

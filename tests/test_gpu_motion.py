@@ -192,7 +192,7 @@ def test_sequence_float_frames_tolerance_and_fixed_exact(ctx, oracle):
                           bits(oracle.fixed_to_f32(want_fx, 20)))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("accum", ["f32", "fixed"])
 def test_k2_variants_bit_exact(ctx, oracle, variant, accum):
     """Every K2 variant (segmented-scan aggregation, match.any aggregation, plain per-lane RED, lean lock-step) must give the
@@ -245,7 +245,7 @@ def test_queue_tile_heights_bit_exact(ctx, oracle, rows):
     wantf, totf = _oracle_run(oracle, ff, poses, N, vs, center, 2.0, accum_mode=1, frac_bits=10)
     ctx.set_option("k1_row_group", rows)
     try:
-        for variant in (4, 5):
+        for variant in (4, 5, 6):
             ctx.set_option("dda_variant", variant)
             for fr, w, t in ((frames, want, tot), (ff, wantf, totf)):
                 grid = pvp.VoxelGrid(N, vs, center, accum="fixed", frac_bits=10)
@@ -345,7 +345,7 @@ def test_rays_leaving_through_low_corners_and_tiny_grids(ctx, oracle):
         pairs, _ = pvp.make_pairs(poses, W)
         want, tot = _oracle_run(oracle, frames, poses, N, vs, center, 2.0)
         assert tot[1] > 500
-        for variant in (0, 1, 3, 5):
+        for variant in (0, 1, 3, 5, 6):
             ctx.set_option("dda_variant", variant)
             try:
                 grid = pvp.VoxelGrid(N, vs, center)
@@ -360,7 +360,7 @@ def test_rays_leaving_through_low_corners_and_tiny_grids(ctx, oracle):
                         # variants 1-3 walk every ray in full on a slab; the default kernels clip (rays that cannot reach the slab are
                         # not walked, a walk stops once x has passed it)
                         assert ss["n_rays"] == tot[0] and ss["n_written"] <= ss["n_steps"] <= tot[1], (N, variant, lo, hi)
-                        assert variant in (0, 5) or ss["n_steps"] == tot[1], (N, variant, lo, hi)
+                        assert variant in (0, 5, 6) or ss["n_steps"] == tot[1], (N, variant, lo, hi)
                         assert np.array_equal(s.data.cpu().numpy(), want[lo:hi]), (N, variant, lo, hi)
                         if hi == lo + 1:
                             planes_written += ss["n_written"]
@@ -369,7 +369,7 @@ def test_rays_leaving_through_low_corners_and_tiny_grids(ctx, oracle):
                 ctx.set_option("dda_variant", 0)
 
 
-@pytest.mark.parametrize("variant", [0, 5])
+@pytest.mark.parametrize("variant", [0, 5, 6])
 def test_random_geometry_sweep_vs_oracle(ctx, oracle, variant):
     """Broad randomised parity sweep of the default (lean lock-step) kernel: cameras inside and outside the grid (outside ones
     look in through min or max faces -- the latter cast no steps, ray_voxel.cpp:329-334), full-range yaw / pitch / roll, fov
@@ -507,3 +507,47 @@ def test_zorder_queue_all_motion_kinds_vs_oracle(ctx, oracle, kind):
                     assert np.array_equal(got, want), (kind, H, W, accum, rg)
                 else:
                     np.testing.assert_allclose(got, want, rtol=1e-5, atol=0)
+
+
+def test_lockstep_pick_follows_ray_count_pairing_and_cell_type(ctx):
+    """The device-side choice between the three lock-step kernels (select_lockstep_kernel): dense batches of >= 6 M rays into float32
+    cells run on lean4 (four rays per lane), smaller or int64 batches on lean2, scattered motion and tiny batches on lean (one ray per
+    lane); option lean4 = -1 keeps lean4 out.  lean4 reports n_atomics only when asked (count_atomics).  Whatever is picked, the grid is
+    the same (uint8 frames: exact)."""
+    H, W, N, vs, center = 1080, 1920, 256, 4.0, (0.0, 0.0, 500.0)
+    F = 5
+    dense = torch.as_tensor(synth.dense_frames(F, H, W, seed=5), device=DEV)
+    scat = torch.as_tensor(synth.scatter_frames(F, H, W, seed=6, fraction=0.1), device=DEV)
+    poses = synth.orbit_poses(F, N, vs, center, seed=7)
+    tab, _ = pvp.make_pairs(poses, W)                         # 4 pairs: 8 M rays when everything moves
+    one, _ = pvp.make_pairs(poses[:2], W)
+
+    def run(frames, table, accum="f32", **opts):
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        try:
+            g = pvp.VoxelGrid(N, vs, center, accum=accum, frac_bits=4)
+            st = pvp.accumulate_motion(frames, table, g, 2.0)
+            return ctx.last_k2_pick(), st, g.data
+        finally:
+            for k in opts:
+                ctx.set_option(k, 0)
+
+    def same(a, b):     # float32 sums are exact and order-independent below 2^24; the few hotter cells around the camera round per RED
+        small = (a < 2 ** 24) & (b < 2 ** 24)
+        return torch.equal(a[small], b[small]) and torch.allclose(a[~small], b[~small], rtol=1e-4, atol=0)
+
+    p4, st4, g4 = run(dense, tab)
+    assert p4 == 4 and st4["n_rays"] > 6_100_000 and st4["n_atomics"] == 0
+    p4c, st4c, g4c = run(dense, tab, count_atomics=1)
+    assert p4c == 4 and 0 < st4c["n_atomics"] < 0.3 * st4c["n_written"] and same(g4c, g4)
+    p2, st2, g2 = run(dense, tab, lean4=-1)
+    assert p2 == 2 and 0 < st2["n_atomics"] < 0.3 * st2["n_written"]
+    assert (st2["n_rays"], st2["n_steps"], st2["n_written"]) == (st4["n_rays"], st4["n_steps"], st4["n_written"]) and same(g2, g4)
+    assert run(dense, tab, accum="fixed")[0] == 2             # int64 cells: lean4 is no faster there
+    assert run(dense, one)[0] == 2                            # 2 M rays: below lean4's threshold
+    assert run(scat, tab)[0] == 1                             # 10 % iid motion: few vertical pairs
+    assert run(dense[:, :64, :64].contiguous(), one)[0] == 1  # 4 k rays: too few for 64-ray chunks
+    p1, st1, g1 = run(dense, tab, dda_variant=4)
+    assert p1 == 1 and same(g1, g4)
+    assert run(dense, tab, dda_variant=3)[0] == 0             # not a lock-step kernel

@@ -15,7 +15,7 @@ F, H, W, N, vs, center = 3, 20, 37, 24, 4.0, (0.0, 0.0, 500.0)
 frames = torch.as_tensor(synth.dense_frames(F, H, W, seed=1), device="cuda")
 poses = synth.orbit_poses(F, N, vs, center, seed=2)
 pairs, _ = pvp.make_pairs(poses, W)
-for variant in (0, 1, 2, 3, 4, 5):
+for variant in (0, 1, 2, 3, 4, 5, 6):
     ctx.set_option("dda_variant", variant)
     for accum in ("f32", "fixed"):
         for slab in (None, (5, 17)):
