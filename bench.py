@@ -503,7 +503,7 @@ def measure_image(env, args, name, steps, warmup, full):
     if rank != 0:
         return None
     launches = max(1, int(prof["launches_k3"]))
-    roofline = rooflines(env, name, "process_image_lockstep2_kernel (K3)", my_samples / launches, prof["ms_k3"] / launches, 16, clocks,
+    roofline = rooflines(env, name, "process_image_lockstepN_kernel (K3)", my_samples / launches, prof["ms_k3"] / launches, 16, clocks,
                          prof["ms_k3"] / ms if ms > 0 else None)
     if not full or args.no_cpu:
         cpu = {"value": 0.0, "unit": "voxel-steps/s", "cores": 0, "kind": "skipped", "sample": ""}

@@ -113,7 +113,7 @@ int pvp_ctx_sync(pvp_ctx *ctx);
  *   "k1_row_group"  0 auto | 1 row-major queue | 2, 4, 8 image rows per queue tile        "k1_snake"  -1 auto | 0 | 1
  *   "lean_regs"     0 auto | 64, 80, 128 register budget of the lock-step kernels         "ctas_per_sm" 0 = by occupancy
  *   "max_queue"     ray queue capacity in entries (>= 1024)
- *   "image_variant" 0 auto | 1 generic per-pixel kernel | 2 lock-step, one pixel per lane | 3 two pixels per lane
+ *   "image_variant" 0 auto | 1 generic per-pixel kernel | 2 lock-step, one pixel per lane | 3 two pixels per lane | 4 three pixels per lane
  *   "image_tile_h"  tile height of image_variant 2 (1, 2, 4, 8)                           "reduce_pull" pvp_grid_reduce_peers strategy
  * unknown key -> PVP_ERR_INVALID */
 int pvp_ctx_set_option(pvp_ctx *ctx, const char *key, int64_t value);

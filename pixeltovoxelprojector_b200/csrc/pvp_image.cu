@@ -83,6 +83,49 @@ template <> struct Cell<PVP_ACCUM_FIXED> {
 
 constexpr int K3_THREADS = 128;
 
+// World direction of pixel (i, j)'s ray, process_image.cpp:241-260.  A function of its own because the four-pixel kernel evaluates it
+// again (same operations, same bits) where it needs a direction that it does not keep in registers across its march loop.
+__device__ __forceinline__ void pixel_dir(const ImageP &p, long long i, long long j, double &w0, double &w1, double &w2)
+{
+    const double x_cam = dsub((double)j, p.cx), y_cam = dsub((double)i, p.cy), z_cam = p.focal;  // :241-243
+    const double norm = __dsqrt_rn(dadd(dadd(dmul(x_cam, x_cam), dmul(y_cam, y_cam)), dmul(z_cam, z_cam)));
+    const double c0 = ddiv(x_cam, norm), c1 = ddiv(y_cam, norm), c2 = ddiv(z_cam, norm);
+    w0 = dadd(dadd(dmul(p.xa[0], c0), dmul(p.ya[0], c1)), dmul(p.za[0], c2));  // :250-252
+    w1 = dadd(dadd(dmul(p.xa[1], c0), dmul(p.ya[1], c1)), dmul(p.za[1], c2));
+    w2 = dadd(dadd(dmul(p.xa[2], c0), dmul(p.ya[2], c1)), dmul(p.za[2], c2));
+    const double dn = __dsqrt_rn(dadd(dadd(dmul(w0, w0), dmul(w1, w1)), dmul(w2, w2)));  // :255-260
+    w0 = ddiv(w0, dn); w1 = ddiv(w1, dn); w2 = ddiv(w2, dn);
+}
+
+// The march bounds of a ray, process_image.cpp:24-61 (ray_aabb_intersection) and :334-340.  Like pixel_dir a function of the pixel
+// alone (no side effects), so the four-pixel kernel can evaluate it a second time instead of keeping the bounds in registers.
+__device__ __forceinline__ bool pixel_range(const ImageP &p, double w0, double w1, double w2, int &s_entry, int &s_exit)
+{
+    double tmin = -CUDART_INF, tmax = CUDART_INF;
+    bool hit = true;
+    const double dir[3] = {w0, w1, w2};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (fabs(dir[a]) > 1e-8) {
+            double t1 = ddiv(dsub(p.ext[2 * a], p.o[a]), dir[a]);
+            double t2 = ddiv(dsub(p.ext[2 * a + 1], p.o[a]), dir[a]);
+            if (t1 > t2) { double sw = t1; t1 = t2; t2 = sw; }
+            tmin = (tmin < t1) ? t1 : tmin;  // std::max(tmin, t1)
+            tmax = (t2 < tmax) ? t2 : tmax;  // std::min(tmax, t2)
+            if (tmin > tmax) hit = false;
+        } else if (p.o[a] < p.ext[2 * a] || p.o[a] > p.ext[2 * a + 1]) {
+            hit = false;
+        }
+    }
+    if (!hit) return false;
+    const double t_entry = (tmin < 0.0) ? 0.0 : tmin;                      // :334
+    const double t_exit = (p.max_distance < tmax) ? p.max_distance : tmax;  // :335
+    if (!(t_entry <= t_exit)) return false;                                 // :337
+    s_entry = trunc32_like_x86(ddiv(t_entry, p.step_size));                 // :339-340
+    s_exit = trunc32_like_x86(ddiv(t_exit, p.step_size));
+    return true;
+}
+
 // One pixel up to the march bounds (process_image.cpp:236-340): brightness filter, fp64 camera ray, RA/Dec, sky-texture
 // lookup / background subtraction / accumulate, AABB clip.  Returns true when the pixel marches samples
 // s_entry..s_exit; `counted` tells whether it reached the ray stage (statistics).
@@ -97,14 +140,7 @@ __device__ __forceinline__ bool pixel_setup(const double *__restrict__ image, ty
     double brightness = image[i * p.is0 + j * p.is1];  // :236
     if (!(brightness > 0)) return false;               // :238
 
-    const double x_cam = dsub((double)j, p.cx), y_cam = dsub((double)i, p.cy), z_cam = p.focal;  // :241-243
-    const double norm = __dsqrt_rn(dadd(dadd(dmul(x_cam, x_cam), dmul(y_cam, y_cam)), dmul(z_cam, z_cam)));
-    const double c0 = ddiv(x_cam, norm), c1 = ddiv(y_cam, norm), c2 = ddiv(z_cam, norm);
-    w0 = dadd(dadd(dmul(p.xa[0], c0), dmul(p.ya[0], c1)), dmul(p.za[0], c2));  // :250-252
-    w1 = dadd(dadd(dmul(p.xa[1], c0), dmul(p.ya[1], c1)), dmul(p.za[1], c2));
-    w2 = dadd(dadd(dmul(p.xa[2], c0), dmul(p.ya[2], c1)), dmul(p.za[2], c2));
-    const double dn = __dsqrt_rn(dadd(dadd(dmul(w0, w0), dmul(w1, w1)), dmul(w2, w2)));  // :255-260
-    w0 = ddiv(w0, dn); w1 = ddiv(w1, dn); w2 = ddiv(w2, dn);
+    pixel_dir(p, i, j, w0, w1, w2);  // :241-260
 
     if (p.update_tex || p.bg_sub) {  // RA/Dec and the texel have no other consumer (:267-314); warp-uniform
         const double r = __dsqrt_rn(dadd(dadd(dmul(w0, w0), dmul(w1, w1)), dmul(w2, w2)));   // :267
@@ -135,30 +171,7 @@ __device__ __forceinline__ bool pixel_setup(const double *__restrict__ image, ty
     counted = true;
     if (!p.grid_provided) return false;  // :317
 
-    // ray_aabb_intersection, :24-61
-    double tmin = -CUDART_INF, tmax = CUDART_INF;
-    bool hit = true;
-    const double dir[3] = {w0, w1, w2};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        if (fabs(dir[a]) > 1e-8) {
-            double t1 = ddiv(dsub(p.ext[2 * a], p.o[a]), dir[a]);
-            double t2 = ddiv(dsub(p.ext[2 * a + 1], p.o[a]), dir[a]);
-            if (t1 > t2) { double sw = t1; t1 = t2; t2 = sw; }
-            tmin = (tmin < t1) ? t1 : tmin;  // std::max(tmin, t1)
-            tmax = (t2 < tmax) ? t2 : tmax;  // std::min(tmax, t2)
-            if (tmin > tmax) hit = false;
-        } else if (p.o[a] < p.ext[2 * a] || p.o[a] > p.ext[2 * a + 1]) {
-            hit = false;
-        }
-    }
-    if (!hit) return false;
-    const double t_entry = (tmin < 0.0) ? 0.0 : tmin;                      // :334
-    const double t_exit = (p.max_distance < tmax) ? p.max_distance : tmax;  // :335
-    if (!(t_entry <= t_exit)) return false;                                 // :337
-    s_entry = trunc32_like_x86(ddiv(t_entry, p.step_size));                 // :339-340
-    s_exit = trunc32_like_x86(ddiv(t_exit, p.step_size));
-    return true;
+    return pixel_range(p, w0, w1, w2, s_entry, s_exit);
 }
 
 // Generic kernel: one thread per pixel, any grid size / strides / extent; one RED per sample.
@@ -222,6 +235,7 @@ struct ImageFastP {
     unsigned gs[3];            // element strides
     double margin[3];          // 32 units of 2^-20 voxel in world units (safe_range)
     int affine_ok;             // the safe-range march may take the scaled coordinate from one FMA per axis (sample_keys2<2>)
+    double x0[3];              // (o - ext_lo) * k20 + (2^52 - 5): the constant term of that FMA, the same for every pixel (Affine::x0)
 };
 
 __device__ __forceinline__ double div_by_extent(double a, double b, double y)
@@ -663,6 +677,273 @@ process_image_lockstep2_kernel(const double *__restrict__ image, typename Cell<M
     }
 }
 
+// ---- NP (three) pixels per lane (the lean4 idea of path A) ---------------------------------------------------------------
+// A warp's tile is 32 columns x NP rows; lane l holds the NP pixels of column l.  The per-iteration overhead of the march loop (run
+// scan, run-head ballot and shuffle, loop control) is paid once per 32 * NP samples.  Inside a lane the pixels are chained bottom-up:
+// pixel j's sample joins pixel j-1's where both sit in the same voxel, else it issues its own RED; pixel 0 carries the lane's sum into
+// the run scan, whose runs are cut at every CAP-th lane (fewer scan levels).  To hold four pixels in registers the loop over the safe
+// range keeps only what its one FMA per axis needs (the increments dx; the constant term x0 is the same for every pixel and comes from
+// the host: ImageFastP::x0); the ray directions and march bounds, which only the tested spans at either end of the march and the ~10 samples per
+// million that take the exact division read, live in shared memory (LaneRays).  Requires ImageFastP::affine_ok (else the two-pixel kernel).
+// Measured, 4096^2 -> 512^3 int64, G samples/s looking along z / y (tools/image_probe.py; two-pixel kernel: 631 / 654;
+// profiles/r2_k3n_tuning.log): pixels per lane x CTA shape x run cap -- 4 x (256 x 2, 124 registers) x 8: 656; 4 x (256 x 3, 80 registers) x 8:
+// 734 / ...; 3 x (128 x 6, 80) x 8: 746 / 798; 3 x (128 x 7, 72) x 8: 757 / 809; 3 x (128 x 7, 72) x 4: 775 / 829 <- kept; 3 x (128 x 8, 64) x 4:
+// 759 / 807; 2 x (128 x 8, 64) x 4: 771 / 787; 4 x (256 x 3) x 4: 756 / 812; run cap 16: 710-716.
+#ifndef PVP_K3N_NP
+#define PVP_K3N_NP 3        // pixels per lane (rows of a warp's 32-column tile)
+#endif
+#ifndef PVP_K3N_CAP
+#define PVP_K3N_CAP 4       // longest run of lanes the scan merges
+#endif
+#ifndef PVP_K3N_THREADS
+#define PVP_K3N_THREADS 128
+#endif
+#ifndef PVP_K3N_MINB
+#define PVP_K3N_MINB 7      // 72 registers, 28 warps per SM
+#endif
+constexpr int K3N_THREADS = PVP_K3N_THREADS;
+
+template <int CAP>
+__device__ __forceinline__ ScanMasks scan_masks_cap(unsigned lane)
+{
+    ScanMasks m;
+    auto win = [lane](unsigned d) { return lane + 1 >= d ? (((1u << d) - 1u) << (lane + 1 - d)) : ((2u << lane) - 1u); };
+    m.w1 = 1u << lane; m.w2 = win(2); m.w4 = win(4); m.w8 = win(8);
+    m.w16 = lane + 1 >= 16 ? (0xffffu << (lane - 15)) : ((2u << lane) - 1u);
+    m.next = lane == 31 ? 1u : (1u << (lane + 1));
+    if (CAP < 32) {  // bit 0 of the head ballot is always set: a window that reaches a cut gets it too, the lane below a cut issues through it
+        const unsigned in_group = lane % CAP;
+        if (1 > in_group) m.w1 |= 1u;
+        if (2 > in_group) m.w2 |= 1u;
+        if (4 > in_group) m.w4 |= 1u;
+        if (8 > in_group) m.w8 |= 1u;
+        if (16 > in_group) m.w16 |= 1u;
+        if (in_group == CAP - 1) m.next |= 1u;
+    }
+    asm volatile("" : "+r"(m.w1), "+r"(m.w2), "+r"(m.w4), "+r"(m.w8), "+r"(m.w16), "+r"(m.next));
+    return m;
+}
+
+template <int NP> struct MarchN {
+    unsigned k[NP];
+    unsigned heads, n_in;
+};
+
+// What the tested spans and the exact-division fallback need of a lane's pixels -- ray directions and march bounds -- lives in shared
+// memory, one column per thread (every thread reads back only what it wrote: no barrier, no bank conflict), so that the safe-range
+// loop holds four pixels in 96 registers: the FMA increments dx, the values, the keys.
+template <int NP> struct LaneRays {
+    double (*w)[K3N_THREADS];   // [NP * 3][threads]
+    int (*lo)[K3N_THREADS];     // [NP][threads]
+    int (*hi)[K3N_THREADS];
+};
+
+// keys of sample s of the lane's NP pixels.  TESTED: with the range and bounds tests (the spans at either end of a march).  Otherwise
+// (inside every ray's safe range): one FMA per axis, y = RN(s * dx + x0) -- see sample_keys2<2> for why its screened truncation is the
+// reference's index; a flagged sample takes the exact sequence on the reference's own operands.
+template <bool TESTED, int NP>
+__device__ __forceinline__ void sample_keysN(const ImageP &p, const ImageFastP &f, int s, const LaneRays<NP> &lr, const double (&dx)[NP][3],
+                                             unsigned has, unsigned (&k)[NP])
+{
+    const unsigned t = threadIdx.x;
+    if (TESTED) {
+        const double d = dmul((double)s, p.step_size);  // :344
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const SamplePos q = sample_pos(p, d, lr.w[3 * j][t], lr.w[3 * j + 1][t], lr.w[3 * j + 2][t]);
+            bool unsafe = false;
+            int xi = voxel_index_screened(q.ax, f, 0, unsafe), yi = voxel_index_screened(q.ay, f, 1, unsafe), zi = voxel_index_screened(q.az, f, 2, unsafe);
+            if (unsafe) { xi = voxel_index_exact(q.ax, f, 0); yi = voxel_index_exact(q.ay, f, 1); zi = voxel_index_exact(q.az, f, 2); }
+            xi = min(xi, f.n1[0]); yi = min(yi, f.n1[1]); zi = min(zi, f.n1[2]);
+            k[j] = tested_key(p, s, lr.lo[j][t], lr.hi[j][t], q, (unsigned)xi * f.gs[0] + (unsigned)yi * f.gs[1] + (unsigned)zi * f.gs[2]);
+        }
+        return;
+    }
+    const double sd = (double)s;
+    int idx[NP][3];
+    bool unsafe = false;
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double y = __fma_rn(sd, dx[j][a], f.x0[a]);
+            const unsigned l = (unsigned)__double2loint(y), h = (unsigned)__double2hiint(y);
+            unsafe = unsafe || (l & 0xFFFFFu) >= 0xFFFF6u;
+            idx[j][a] = (int)__funnelshift_r(l, h, 20);
+        }
+    if (unsafe) {
+        const double d = dmul(sd, p.step_size);  // :344
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            if (!(has & (1u << j))) continue;   // no ray: the key below is IMG_NONE whatever the indices
+            const SamplePos q = sample_pos(p, d, lr.w[3 * j][t], lr.w[3 * j + 1][t], lr.w[3 * j + 2][t]);
+            idx[j][0] = voxel_index_exact(q.ax, f, 0); idx[j][1] = voxel_index_exact(q.ay, f, 1); idx[j][2] = voxel_index_exact(q.az, f, 2);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+        k[j] = (has & (1u << j)) ? (unsigned)idx[j][0] * f.gs[0] + (unsigned)idx[j][1] * f.gs[1] + (unsigned)idx[j][2] * f.gs[2] : IMG_NONE;
+}
+
+template <bool COUNT, int NP, int CAP, typename S, typename CellT>
+__device__ __forceinline__ void marchN_accumulate(CellT *__restrict__ grid, const ScanMasks &lm, MarchN<NP> &m, const S (&val)[NP])
+{
+    const unsigned FULL = 0xffffffffu;
+    S sv[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        const bool live = m.k[j] != IMG_NONE;
+        if (COUNT) m.n_in += (unsigned)live;
+        sv[j] = live ? val[j] : (S)0;
+    }
+#pragma unroll
+    for (int j = NP - 1; j > 0; --j) {   // the lane's chain
+        const bool live = m.k[j] != IMG_NONE;
+        const bool same = live && m.k[j] == m.k[j - 1];
+        if (live && !same && PVP_IMG_CHECK_GRID(m.k[j])) img_red(grid + m.k[j], sv[j]);
+        scan_add(same, sv[j - 1], sv[j]);
+    }
+    S sum = sv[0], t;
+    t = __shfl_up_sync(FULL, sum, 1);  scan_add(!(m.heads & lm.w1), sum, t);
+    t = __shfl_up_sync(FULL, sum, 2);  scan_add(!(m.heads & lm.w2), sum, t);
+    if (CAP > 4)  { t = __shfl_up_sync(FULL, sum, 4);  scan_add(!(m.heads & lm.w4), sum, t); }
+    if (CAP > 8)  { t = __shfl_up_sync(FULL, sum, 8);  scan_add(!(m.heads & lm.w8), sum, t); }
+    if (CAP > 16) { t = __shfl_up_sync(FULL, sum, 16); scan_add(!(m.heads & lm.w16), sum, t); }
+    if ((m.heads & lm.next) && m.k[0] != IMG_NONE && PVP_IMG_CHECK_GRID(m.k[0])) img_red(grid + m.k[0], sum);
+}
+
+// iterations s .. s_stop-1; each first computes the keys of sample s+1 (their arithmetic and shuffle overlap the scan of sample s)
+template <bool TESTED, int NP, int CAP, typename S, typename CellT>
+__device__ __forceinline__ void marchN_span(CellT *__restrict__ grid, const ImageP &p, const ImageFastP &f, const ScanMasks &lm, MarchN<NP> &m, int &s, int s_stop,
+                                            const LaneRays<NP> &lr, const double (&dx)[NP][3], const S (&val)[NP], unsigned has)
+{
+    const unsigned FULL = 0xffffffffu;
+    if (s >= s_stop) return;
+    if (!TESTED) {
+        // not counted per iteration in the safe range: sample s (keys computed earlier) by its keys; samples s+1 .. s_stop-1 -- computed
+        // AND accumulated by this span -- are inside for every ray the lane has; sample s_stop is counted by whoever accumulates it
+#pragma unroll
+        for (int j = 0; j < NP; ++j) m.n_in += (unsigned)(m.k[j] != IMG_NONE);
+        m.n_in += (unsigned)(s_stop - 1 - s) * (unsigned)__popc(has);
+    }
+    for (; s < s_stop; ++s) {
+        unsigned kn[NP];
+        sample_keysN<TESTED, NP>(p, f, s + 1, lr, dx, has, kn);
+        const bool head_n = img_run_head(kn[0]);
+        marchN_accumulate<TESTED, NP, CAP, S>(grid, lm, m, val);
+        m.heads = __ballot_sync(FULL, head_n);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) m.k[j] = kn[j];
+    }
+}
+
+// [mlo, mhi]: the samples inside every active ray's safe range (empty: mlo > mhi); has: bit j = pixel j marches
+template <int NP, int CAP, typename S, typename CellT>
+__device__ __forceinline__ unsigned march_lockstepN(CellT *__restrict__ grid, const ImageP &p, const ImageFastP &f, const ScanMasks &lm,
+                                                    const LaneRays<NP> &lr, const double (&dx)[NP][3], const S (&val)[NP], unsigned has,
+                                                    int wlo, int whi, int mlo, int mhi)
+{
+    const unsigned FULL = 0xffffffffu;
+    MarchN<NP> m;
+    m.n_in = 0;
+    sample_keysN<true, NP>(p, f, wlo, lr, dx, has, m.k);
+    m.heads = __ballot_sync(FULL, img_run_head(m.k[0]));
+    int s = wlo;
+    marchN_span<true, NP, CAP, S>(grid, p, f, lm, m, s, min(whi, mlo - 1), lr, dx, val, has);    // s+1 < mlo
+    marchN_span<false, NP, CAP, S>(grid, p, f, lm, m, s, min(whi, mhi), lr, dx, val, has);       // mlo <= s+1 <= mhi
+    marchN_span<true, NP, CAP, S>(grid, p, f, lm, m, s, whi, lr, dx, val, has);
+    marchN_accumulate<true, NP, CAP, S>(grid, lm, m, val);  // sample whi
+    return m.n_in;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(K3N_THREADS, PVP_K3N_MINB)
+process_image_lockstepN_kernel(const double *__restrict__ image, typename Cell<MODE>::T *__restrict__ grid,
+                               typename Cell<MODE>::T *__restrict__ tex, ImageP p, ImageFastP f, Ctl *__restrict__ ctl)
+{
+    using C = Cell<MODE>;
+    constexpr int NP = PVP_K3N_NP, CAP = PVP_K3N_CAP;
+    __shared__ double s_w[NP * 3][K3N_THREADS];
+    __shared__ int s_lo[NP][K3N_THREADS], s_hi[NP][K3N_THREADS];
+    const LaneRays<NP> lr = {s_w, s_lo, s_hi};
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31, t = threadIdx.x;
+    const ScanMasks lm = scan_masks_cap<CAP>(lane);
+    const long long tiles_x = (p.W + 31) / 32, tiles_y = (p.row1 - p.row0 + NP - 1) / NP;
+    const unsigned long long n_groups = (unsigned long long)(tiles_x * tiles_y);
+    unsigned long long my_rays = 0, my_samples = 0;
+    for (;;) {
+        unsigned long long group = 0;
+        if (lane == 0) group = atomicAdd(&ctl->head, 1ull);
+        group = __shfl_sync(FULL, group, 0);
+        if (group >= n_groups) break;
+        const long long ty = (long long)(group / (unsigned long long)tiles_x), tx = (long long)group - ty * tiles_x;
+        const long long pj = tx * 32 + lane, pi = p.row0 + ty * NP;
+        unsigned has = 0;
+        double dx[NP][3];
+        typename C::V val[NP];
+        int lane_lo = INT32_MAX, lane_hi = INT32_MIN, lane_mlo = INT32_MIN, lane_mhi = INT32_MAX;
+        bool narrow = true;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+            int lo = INT32_MAX, hi = INT32_MIN;  // empty range
+            val[j] = 0;
+            if (pj < p.W && pi + j < p.row1) {
+                int s_entry, s_exit;
+                bool counted;
+                if (pixel_setup<MODE>(image, tex, p, (pi + j) * p.W + pj, w0, w1, w2, val[j], s_entry, s_exit, counted) && s_entry <= s_exit) {
+                    lo = s_entry; hi = s_exit;
+                    has |= 1u << j;
+                }
+                my_rays += counted;
+            }
+            s_w[3 * j][t] = w0; s_w[3 * j + 1][t] = w1; s_w[3 * j + 2][t] = w2;
+            s_lo[j][t] = lo; s_hi[j][t] = hi;
+            dx[j][0] = dmul(dmul(p.step_size, w0), f.k20[0]);   // Affine::dx
+            dx[j][1] = dmul(dmul(p.step_size, w1), f.k20[1]);
+            dx[j][2] = dmul(dmul(p.step_size, w2), f.k20[2]);
+            int slo, shi;
+            safe_range(p, f, w0, w1, w2, lo, hi, slo, shi);
+            lane_lo = min(lane_lo, lo); lane_hi = max(lane_hi, hi);
+            if (lo <= hi) { lane_mlo = max(lane_mlo, slo); lane_mhi = min(lane_mhi, shi); }
+            if (MODE == PVP_ACCUM_FIXED) narrow = narrow && (unsigned long long)val[j] < (1ull << 26);
+        }
+        const int wlo = __reduce_min_sync(FULL, lane_lo), whi = __reduce_max_sync(FULL, lane_hi);
+        if (wlo > whi) continue;
+        const int mlo = __reduce_max_sync(FULL, lane_mlo), mhi = __reduce_min_sync(FULL, lane_mhi);
+        if (MODE == PVP_ACCUM_FIXED) {
+            // a run has at most CAP * NP values: its sum fits 32 bits when every value is below 2^26
+            static_assert(CAP * NP <= 64, "32-bit run sums");
+            if (__all_sync(FULL, narrow)) {
+                unsigned v32[NP];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) v32[j] = (unsigned)val[j];
+                my_samples += march_lockstepN<NP, CAP, unsigned>((unsigned long long *)grid, p, f, lm, lr, dx, v32, has, wlo, whi, mlo, mhi);
+            } else {
+                unsigned long long v64[NP];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) v64[j] = (unsigned long long)val[j];
+                my_samples += march_lockstepN<NP, CAP, unsigned long long>((unsigned long long *)grid, p, f, lm, lr, dx, v64, has, wlo, whi, mlo, mhi);
+            }
+        } else {
+            double vd[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) vd[j] = (double)val[j];
+            my_samples += march_lockstepN<NP, CAP, double>((double *)grid, p, f, lm, lr, dx, vd, has, wlo, whi, mlo, mhi);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_rays += __shfl_xor_sync(FULL, my_rays, o);
+        my_samples += __shfl_xor_sync(FULL, my_samples, o);
+    }
+    if (lane == 0 && (my_rays | my_samples)) {
+        atomicAdd(&ctl->img_rays, my_rays);
+        atomicAdd(&ctl->img_samples, my_samples);
+    }
+}
+
 template <int MODE, int TILE_H>
 __global__ void __launch_bounds__(K3L_THREADS)
 process_image_lockstep_kernel(const double *__restrict__ image, typename Cell<MODE>::T *__restrict__ grid,
@@ -806,11 +1087,17 @@ static bool make_fastp(const ImageP &p, ImageFastP *f)
         const double A = fabs(p.o[k]) + p.max_distance + fabs(p.ext[2 * k]) + fabs(p.ext[2 * k + 1]) + f->b[k];
         if (!(A * f->k20[k] <= 0x1p49)) f->affine_ok = 0;
     }
+    for (int k = 0; k < 3; ++k) {   // the expression of affine_of, un-fused like the device's (-fmad=false)
+        volatile double d = p.o[k] - p.ext[2 * k];
+        volatile double m = d * f->k20[k];
+        volatile double x0 = m + (0x1p52 - 5.0);
+        f->x0[k] = x0;
+    }
     return span < 0xffffffffull;  // voxel offsets are 32-bit keys, 0xffffffff is reserved
 }
 
-// image_variant: 0 = auto (two-pixel lock-step where fast_ok), 1 = generic per-pixel kernel, 2 = one-pixel lock-step, 3 = two-pixel lock-step
-// (the lock-step kernels fall back to the generic one if !fast_ok)
+// image_variant: 0 = auto (three-pixel lock-step where fast_ok and affine_ok, two-pixel where only fast_ok), 1 = generic per-pixel kernel,
+// 2 = one-pixel lock-step, 3 = two-pixel lock-step, 4 = three-pixel lock-step (the lock-step kernels fall back to the generic one if !fast_ok)
 static int launch_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, void *tex_dev, const ImageP &p, int accum_mode)
 {
     const long long rows = p.row1 - p.row0, n_px = p.W * rows;
@@ -822,7 +1109,17 @@ static int launch_image(pvp_ctx *ctx, const double *image_dev, void *grid_dev, v
         int per_sm = 0;
         const int th = ctx->opt_image_tile_h == 1 ? 1 : ctx->opt_image_tile_h == 4 ? 4 : ctx->opt_image_tile_h == 8 ? 8 : 2;
         const bool f64 = accum_mode == PVP_ACCUM_F64;
-        if (ctx->opt_image_variant != 2) {  // default: two pixels per lane
+        if ((ctx->opt_image_variant == 4 || ctx->opt_image_variant == 0) && f.affine_ok) {  // default where the one-FMA coordinate is allowed: three pixels per lane
+            const void *k4 = f64 ? (const void *)process_image_lockstepN_kernel<PVP_ACCUM_F64> : (const void *)process_image_lockstepN_kernel<PVP_ACCUM_FIXED>;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4, K3N_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+            const long long groups4 = ((p.W + 31) / 32) * ((rows + PVP_K3N_NP - 1) / PVP_K3N_NP);
+            const int blocks4 = (int)std::min<long long>((groups4 + K3N_THREADS / 32 - 1) / (K3N_THREADS / 32), (long long)ctx->sm_count * per_sm);
+            void *args4[] = {(void *)&image_dev, (void *)&grid_dev, (void *)&tex_dev, (void *)&p, (void *)&f, (void *)&ctx->ctl_dev};
+            PVP_CUDA(cudaLaunchKernel(k4, dim3((unsigned)blocks4), dim3(K3N_THREADS), args4, 0, ctx->stream));
+            PVP_CUDA(cudaGetLastError());
+            return PVP_OK;
+        }
+        if (ctx->opt_image_variant != 2) {  // two pixels per lane (image_variant 3; the default where !affine_ok)
             const void *k2 = f64 ? (const void *)process_image_lockstep2_kernel<PVP_ACCUM_F64> : (const void *)process_image_lockstep2_kernel<PVP_ACCUM_FIXED>;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, K3L_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
             const long long groups2 = ((p.W + 31) / 32) * ((rows + 1) / 2);

@@ -101,7 +101,7 @@ def test_division_by_extent_equals_ieee_division(ctx):
         assert bad.value == 0, (b, bad.value)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_random_scenes_vs_oracle(ctx, oracle, variant):
     """variant 1 = generic per-pixel kernel, 2 = lock-step kernel with warp-aggregated REDs, one pixel per lane, 3 = two pixels
     per lane (the default where eligible)."""
@@ -175,7 +175,7 @@ def test_full_size_properties_4096_512_fixed(ctx):
     assert torch.equal(grids[0], grids[1]) and torch.equal(grids[2], grids[0] * 2)
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 def test_lockstep_random_sweep_fixed_point_exact(ctx, oracle, variant):
     """Broad randomised sweep of the lock-step kernel in fixed-point mode (bit-exact against the oracle): observer inside
     and outside the grid, non-cubic and strided grids, steps longer and shorter than a voxel, max_distance clipping inside
@@ -235,7 +235,7 @@ def _lockstep_sweep(oracle, pi, rng):
     return total
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_row_and_file_shards_sum_to_whole(ctx, oracle, variant):
     """SURVEY 8e, path B over several GPUs (the ranks run one after another here): row shards of one image -- ragged,
     odd boundaries that split the kernels' 2-row tiles, an empty shard -- and file shards of an observation list, each
@@ -307,7 +307,7 @@ def test_row_and_file_shards_sum_to_whole(ctx, oracle, variant):
         ctx.set_option("image_variant", 0)
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 def test_bench_geometry_and_samples_on_voxel_faces_exact(ctx, oracle, variant):
     """The bench scene's geometry at a size the oracle finishes in seconds (512^2 image -> 128^3 grid, one sample per voxel
     pitch, ~50 M samples), and an axis-aligned scene whose samples land EXACTLY on voxel faces (observer on the grid axis,

@@ -9,5 +9,5 @@ cap() { # name workload kernel-regex
 }
 cap k2_lean4_dense 1080p_dense_512 dda_accumulate_lean4
 cap k2_lean_scatter10 1080p_scatter10_512 dda_accumulate_lean_kernel
-cap k3_lockstep2 image_4096_512_fixed process_image_lockstep2
+cap k3_lockstepN image_4096_512_fixed process_image_lockstepN
 ls -la gpurun_out | grep ${P}_

@@ -28,7 +28,7 @@ pvp.accumulate_motion(frames.cpu().numpy(), pairs, pvp.VoxelGrid(N, vs, center),
 rng = np.random.default_rng(3)
 img = torch.as_tensor(rng.random((19, 45)), device="cuda")
 ext = [(-10.0, 10.0), (-10.0, 10.0), (20.0, 40.0)]
-for variant in (1, 2, 3):
+for variant in (1, 2, 3, 4):
     ctx.set_option("image_variant", variant)
     for mode, dt in (("f64", torch.float64), ("fixed", torch.int64)):
         g = torch.zeros((12, 14, 16), dtype=dt, device="cuda")
