@@ -17,4 +17,4 @@ cat gpurun_out/${P}_checked_build.log
 (python tools/sanitize_case.py; echo "sanitize_case rc=$?") > gpurun_out/${P}_checked_sanitize_case.log 2>&1
 (python tests/exotic_pose_check.py --cases 400; echo "exotic rc=$?") > gpurun_out/${P}_checked_exotic.log 2>&1
 (python -m pytest tests -m gpu -q -x --deselect tests/test_bench_contract.py; echo "pytest rc=$?") > gpurun_out/${P}_checked_pytest_gpu.log 2>&1
-tail -2 gpurun_out/${P}_checked_sanitize_case.log gpurun_out/${P}_checked_exotic.log gpurun_out/${P}_checked_pytest_gpu.log
+tail -n 2 gpurun_out/${P}_checked_sanitize_case.log gpurun_out/${P}_checked_exotic.log gpurun_out/${P}_checked_pytest_gpu.log
