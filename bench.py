@@ -366,6 +366,15 @@ def rooflines(env, workload, kernel, units_per_launch, launch_ms, algo_bytes, cl
         pass
     if pick and e.get("k2_pick") not in (None, pick):   # the capture belongs to another lock-step kernel than the one that ran: its figures do not apply
         e = {}
+    approx_from = None
+    if not e and pick:   # no capture of this workload: the capture of the SAME kernel on another workload gives its instructions per voxel step approximately
+        try:
+            for k, v in json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).items():
+                if isinstance(v, dict) and v.get("k2_pick") == pick and "limiter" not in v:
+                    e, approx_from = {kk: vv for kk, vv in v.items() if kk != "bytes_per_launch"}, k
+                    break
+        except Exception:
+            pass
     algo_bytes_launch = algo_bytes * units_per_launch
     traffic = None
     if "bytes_per_launch" in e and e.get("voxel_steps_per_launch"):
@@ -386,6 +395,9 @@ def rooflines(env, workload, kernel, units_per_launch, launch_ms, algo_bytes, cl
                "warp_inst_per_voxel_step": per_unit, "sass_md5_ok": sass_fresh(workload),
                "peak_source": f"{env.sms} SMs x 4 schedulers x {mhz:.0f} MHz (SM clock sampled during the timed region)",
                "source": f"{e.get('source', 'profiles/traffic.json')}: smsp__inst_executed.sum per voxel step x live rate", **out}
+        if approx_from:
+            out["approx_from"] = f"instructions per voxel step of the same kernel captured on {approx_from} (no capture of this workload)"
+            out["sass_md5_ok"] = sass_fresh(approx_from)
         lim = e.get("limiter")
         if lim:   # ncu found another unit busier than the issue slots (e.g. the L2 / RED path on scattered motion): that is the bound
             cap_rate = e["voxel_steps_per_launch"] / (lim["launch_ms"] * 1e-3)

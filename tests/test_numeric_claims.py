@@ -396,3 +396,79 @@ def test_k2_slab_fast_forward_is_the_reference_walk():
         else:
             died += 1
     assert checked > 500 and died > 200, (checked, died)
+
+
+def _lane_masks(lane, cap):
+    """csrc/pvp_motion.cu lane_masks<CAP> / csrc/pvp_image.cu scan_masks_cap<CAP>, restated."""
+    def win(d):
+        return (((1 << d) - 1) << (lane + 1 - d)) if lane + 1 >= d else ((2 << lane) - 1)
+    m = {1: 1 << lane, 2: win(2), 4: win(4), 8: win(8), 16: win(16), "next": 1 if lane == 31 else 1 << (lane + 1)}
+    if cap < 32:
+        g = lane % cap
+        for d in (1, 2, 4, 8, 16):
+            if d > g:
+                m[d] |= 1
+        if g == cap - 1:
+            m["next"] |= 1
+    return m
+
+
+def test_lockstep_merge_machinery_conserves_every_voxel_sum():
+    """lean4 / the N-pixel K3 restated on the CPU: per lane a bottom-up chain (ray j joins ray j-1 where their voxel keys are equal,
+    else issues its own RED), across lanes a segmented scan over run heads of ray 0's key whose runs are CUT at every CAP-th lane
+    (the cut is encoded in the lane masks only: bit 0 of the head ballot is always set), one RED per run from the run's last lane.
+    Claim: for ANY keys -- parked rays (NONE) included, equal keys that are not adjacent included -- the REDs issued add up, per voxel,
+    to exactly the sum of the values of the rays that sit in it; and no RED goes to NONE."""
+    rng = np.random.default_rng(11)
+    NONE = 0xFFFFFFFF
+    for cap, nr in ((32, 2), (8, 4), (4, 3), (16, 4), (8, 1)):
+        levels = [d for d in (1, 2, 4, 8, 16) if d < cap]
+        masks = [_lane_masks(l, cap) for l in range(32)]
+        for trial in range(300):
+            # keys with long runs, short runs, repeats and parked rays
+            n_vox = int(rng.integers(1, 12))
+            base = np.sort(rng.integers(0, n_vox, 32))
+            keys = np.empty((32, nr), np.int64)
+            for j in range(nr):
+                keys[:, j] = base + (rng.random(32) < 0.15 * j)          # vertical neighbours mostly share the voxel
+            if trial % 3 == 0:
+                rng.shuffle(keys)                                        # runs in any order, equal keys not adjacent
+            keys[rng.random((32, nr)) < 0.1] = NONE
+            vals = rng.integers(1, 256, (32, nr)).astype(np.int64)
+            vals[keys == NONE] = 0                                       # a parked ray carries value 0
+            want = {}
+            for k, v in zip(keys.ravel(), vals.ravel()):
+                if k != NONE:
+                    want[int(k)] = want.get(int(k), 0) + int(v)
+            got = {}
+
+            def red(k, v):
+                assert k != NONE
+                got[int(k)] = got.get(int(k), 0) + int(v)
+
+            s = vals.copy()
+            for l in range(32):                                          # the lane's chain
+                for j in range(nr - 1, 0, -1):
+                    same = keys[l, j] == keys[l, j - 1]
+                    if not same and keys[l, j] != NONE:
+                        red(keys[l, j], s[l, j])
+                    if same:
+                        s[l, j - 1] += s[l, j]
+            k0 = keys[:, 0]
+            heads = 0
+            for l in range(32):                                          # run_head: lane 0, or a key that differs from the lane below
+                if l == 0 or k0[l] != k0[l - 1]:
+                    heads |= 1 << l
+            assert heads & 1
+            run = s[:, 0].copy()
+            for d in levels:                                             # segmented scan, all lanes at once per level
+                prev = run.copy()
+                for l in range(32):
+                    if not (heads & masks[l][d]) and l >= d:
+                        run[l] = prev[l] + prev[l - d]
+                    else:
+                        assert (heads & masks[l][d]) or l < d            # (a window that reaches below lane 0 always contains bit 0)
+            for l in range(32):
+                if (heads & masks[l]["next"]) and k0[l] != NONE:
+                    red(k0[l], run[l])
+            assert got == want, (cap, nr, trial)
