@@ -1,7 +1,8 @@
 """One workload's dominant kernel on IDENTICAL launches, for an exact ncu capture: every launch processes the same batch, the script prints
 the voxel steps (samples) of one launch, so warp instructions and DRAM bytes per voxel step follow from the capture without guessing which
 batch ncu caught.
-    python tools/ncu_case.py 1080p_dense_512 [launches]        -> "voxel_steps_per_launch ..." (K2: one batch of 32 frame pairs)
+    python tools/ncu_case.py 1080p_dense_512 [launches [pairs]] -> "voxel_steps_per_launch ..." (K2: one batch of 32 frame pairs; 4K frames: pass 8 pairs,
+                                                                   the largest batch the ray queue holds)
     python tools/ncu_case.py image_4096_512_fixed [launches]   -> one image (K3)"""
 import json
 import os
@@ -33,7 +34,7 @@ if wl.get("path") == "B":
                               geom["num_steps"], tex, *geom["sky"], False, False, accum_mode=wl["accum"], frac_bits=wl["frac_bits"], want_stats=True)
         per = pi.last_stats["n_samples"]
 else:
-    wl = dict(wl, pool=33)
+    wl = dict(wl, pool=(int(sys.argv[3]) if len(sys.argv) > 3 else 32) + 1)
     frames, poses = bench.make_inputs(wl, seed=1000)
     fr = torch.as_tensor(frames, device="cuda")
     tab, n_pairs = pvp.make_pairs(poses, wl["W"])
