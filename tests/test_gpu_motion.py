@@ -339,7 +339,7 @@ def test_rays_leaving_through_low_corners_and_tiny_grids(ctx, oracle):
         half = N * vs / 2
         frames = synth.dense_frames(4, H, W, seed=N)
         # inside the grid, looking (mostly) towards the (-,-,-) corner / the -z face, wide field of view
-        poses = [pvp.FramePose((float(np.float32(-half + vs * 0.6 + 0.3 * i)), float(np.float32(-half + vs * 0.7)), float(np.float32(-half + vs * 1.1 + 0.2 * i))),
+        poses = [pvp.FramePose((float(np.float32(-half + vs * 0.6 + 0.3 * i)), float(np.float32(-half + vs * 0.7)), float(np.float32(-half + vs * (1.1 if N > 1 else 0.6) + 0.2 * i))),
                                yaw=float(rng.uniform(-40, 40)), pitch=float(rng.uniform(-40, 40)), roll=float(rng.uniform(-20, 20)), fov_degrees=100.0)
                  for i in range(4)]
         pairs, _ = pvp.make_pairs(poses, W)
