@@ -812,7 +812,7 @@ __device__ __forceinline__ unsigned udiv_by(unsigned x, unsigned d, unsigned m)
 }
 
 // Does the step along the chosen axis (cz / cy / else x) leave [0, N)?  Decodes the voxel the step starts from.  Slab kernels
-// hold x relative to the slab, possibly negative (N^3 <= 2^31 there, so the offset is a valid int).
+// hold x relative to the slab (the slab's cells number <= 2^31, so the offset is a valid int; the floor division also takes a negative one).
 template <bool SLAB>
 __device__ __forceinline__ bool step_leaves(unsigned cur, bool cz, bool cy, int dix, int diy, int diz, const GridP &g)
 {
@@ -1737,7 +1737,12 @@ static int launch_k2(pvp_ctx *ctx, const GridP &g, int accum_mode, bool narrow_o
     const unsigned long long full = (unsigned long long)g.n * g.n * g.n;
     if (cells >= 0xffffffffull || g.n > 2048) variant = 3;
     const bool lockstep = variant == 0 || variant >= 4;
-    if (lockstep && (slab ? full > (1ull << 31) : full >= 0xffffffffull)) variant = 3;  // slab test relies on wrapped offsets
+    // 32-bit voxel keys: the whole grid for whole-grid kernels; under slabs only the slab's own cells -- since the exact fast-forward
+    // (slab_enter) a walked ray is inside its slab from its first step to the step that passes the far face, so its slab-relative
+    // offset never leaves [0, cells) (step_leaves decodes it as an int: cells <= 2^31).  A 2048^3 grid in 8 slabs thus runs on the
+    // lock-step kernels (round 1 and the first half of round 2 fell back to the one-RED-per-step kernel above 1290^3)
+    if (lockstep && (slab ? cells > (1ull << 31) : full >= 0xffffffffull)) variant = 3;
+    if (!lockstep && variant != 3 && full >= 0xffffffffull) variant = 3;   // variants 1 / 2 walk every ray from its start with wrapped slab offsets: the whole grid must fit the key
     if (lockstep && !lean_ok) variant = 3;
     const bool f32 = accum_mode == PVP_ACCUM_F32;
     ctx->last_k2_lockstep = false;

@@ -185,3 +185,34 @@ def test_slab_of_a_grid_beyond_one_gpu_vs_oracle(ctx, oracle):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     with pytest.raises(pvp.PvpError):
         pvp.accumulate_motion(torch.as_tensor(frames, device=DEV), tab, pvp.VoxelGrid(4097, 1.0, center, slab=(0, 0)), 2.0)   # n <= 4096
+
+
+def test_slab_of_a_2048_grid_runs_on_the_lockstep_kernels_vs_oracle(ctx, oracle):
+    """2048^3 float32 is 32 GiB: the size slab sharding is for.  Since the exact fast-forward a walked ray never leaves its slab, so the
+    32-bit voxel keys only have to hold the slab's own cells and the lock-step kernels (lean by default at this plane size, lean2 and
+    lean4 when forced) take grids up to n = 2048 under slabs; before, every grid above 1290^3 fell back to the one-RED-per-step kernel.
+    One rank's slab (x-planes [1016, 1032): 256 MiB) against the C port walking the same rays with full-grid arithmetic -- counters and
+    every cell, for every kernel, float32 and fixed point; and a slab at the grid's low end whose rays start inside it."""
+    H, W, N, vs, center = 60, 80, 2048, 0.5, (0.0, 0.0, 500.0)
+    frames = synth.dense_frames(2, H, W, seed=311)
+    poses = synth.orbit_poses(2, N, vs, center, seed=312)
+    R = oracle.rotation_matrix(poses[1].yaw, poses[1].pitch, poses[1].roll)
+    tab, _ = pvp.make_pairs(poses, W)
+    fr = torch.as_tensor(frames, device=DEV)
+    cam_plane = int((poses[1].camera_position[0] - (center[0] - N * vs / 2)) / vs)
+    for lo, hi in ((1016, 1032), (max(0, cam_plane - 8), max(0, cam_plane - 8) + 16)):
+        want = np.zeros((hi - lo, N, N), np.float32)
+        nr, ns, nw = oracle.accumulate_pair(frames[0], frames[1], np.array(poses[1].camera_position, np.float32), R, oracle.focal_length(poses[1].fov_degrees, W),
+                                            want, N, vs, np.array(center, np.float32), 2.0, slab=(lo, hi))
+        assert nw > 1000 and ns > 500 * nr > 0
+        try:
+            for variant, pick in ((0, 1), (4, 1), (5, 2), (6, 4), (3, 0)):
+                ctx.set_option("dda_variant", variant)
+                slab = pvp.VoxelGrid(N, vs, center, slab=(lo, hi))
+                st = pvp.accumulate_motion(fr, tab, slab, 2.0)
+                assert ctx.last_k2_pick() == pick, (variant, lo)
+                assert (st["n_rays"], st["n_written"]) == (nr, nw), (variant, lo, st)
+                assert np.array_equal(slab.data.cpu().numpy().view(np.uint32), want.view(np.uint32)), (variant, lo)
+                del slab
+        finally:
+            ctx.set_option("dda_variant", 0)
