@@ -472,3 +472,23 @@ def test_lockstep_merge_machinery_conserves_every_voxel_sum():
                 if (heads & masks[l]["next"]) and k0[l] != NONE:
                     red(k0[l], run[l])
             assert got == want, (cap, nr, trial)
+
+
+def test_fp32_hot_cell_error_grows_like_the_square_root_of_the_adds():
+    """The tolerance of tests/test_gpu_fullsize_parity.py for cells above 2^24 (hot_tol = 1e-5 per 2^20 rays, growing with the square root
+    of the ray count) restated: the camera's own voxel receives one RED per warp chunk (~32 rays of <= 255 each), every RED into an fp32
+    accumulator above 2^24 rounds by up to half an ulp, and the roundings add up like a random walk.  Sequential float32 sums
+    (np.cumsum) of K = rays / 32 integer run sums against the exact integer sum, 40 orders each: the error stays below hot_tol, and it
+    is not far below it -- i.e. the tolerance is neither loose by an order of magnitude nor reachable at a fixed 1e-5 for 4K frames."""
+    rng = np.random.default_rng(5)
+    for n_rays in (1 << 21, 1 << 23):                       # a 1080p pair, a 4K pair
+        tol = 1e-5 * max(1.0, (n_rays / 2.0 ** 20) ** 0.5)
+        k = n_rays // 32
+        worst = 0.0
+        for _ in range(40):
+            runs = rng.integers(1, 256, (k, 32)).sum(axis=1)     # run sums of 32 rays, exact integers < 2^24
+            exact = int(runs.sum())
+            got = float(np.cumsum(runs.astype(np.float32), dtype=np.float32)[-1])
+            worst = max(worst, abs(got - exact) / exact)
+        assert exact > 2 ** 24 and worst <= tol, (n_rays, worst, tol)
+        assert worst >= tol / 30, (n_rays, worst, tol)           # the same order of magnitude: 2.5e-6 ... at 1080p
