@@ -10,11 +10,11 @@ I="python bench.py --workload image_4096_512_fixed --steps 2 --warmup 3 --no-cpu
 $B > gpurun_out/plain_k2.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${P}_launches_bench_1080p_dense_512.csv $B > gpurun_out/ncu_l2.log 2>&1
 $B > gpurun_out/plain_k2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:dda_accumulate_lean2 -s 6 -c 2 -o gpurun_out/${P}_k2_lean2 $B > gpurun_out/ncu_f2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:dda_accumulate_lean4 -s 6 -c 2 -o gpurun_out/${P}_k2_lean4 $B > gpurun_out/ncu_f2.log 2>&1
 $I > gpurun_out/plain_k3.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/${P}_launches_bench_image_4096_512_fixed.csv $I > gpurun_out/ncu_l3.log 2>&1
 $I > gpurun_out/plain_k3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:process_image_lockstep2 -s 3 -c 1 -o gpurun_out/${P}_k3_lockstep2 $I > gpurun_out/ncu_f3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:process_image_lockstepN -s 3 -c 1 -o gpurun_out/${P}_k3_lockstepN $I > gpurun_out/ncu_f3.log 2>&1
 ls -la gpurun_out | grep ${P}
 # scattered motion (10 % iid): the auto pick is the one-ray-per-lane kernel
 S="python bench.py --workload 1080p_scatter10_512 --steps 2 --warmup 3 --no-cpu --no-also"
