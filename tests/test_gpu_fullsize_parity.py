@@ -11,8 +11,7 @@ Bars (uint8 frames: every addend is an integer <= 255):
   * cells at or above 2^24 (the few voxels around the camera that every ray crosses): BOTH float sums round -- the reference at each
     of its ~2 M serial adds, the GPU at each RED of a run sum.  The distance is measured and written to gpurun_out/ (committed under
     profiles/ by the round); asserted: the GPU grid is no further from the exact integer sum than hot_tol(rays) = RTOL_HOT (1e-5) per
-    2^20 rays of the pair, growing with the square root of the ray count; it is at least as close to the exact sum as the reference
-    itself; and its distance from the reference is explained by the reference's own distance from the exact sum (triangle inequality).
+    2^20 rays of the pair, growing with the square root of the ray count; wherever the reference's own sum is off by more than three tolerances it is closer to the exact sum than the reference; and its distance from the reference is explained by the reference's own distance from the exact sum (triangle inequality).
     Why a square root: the camera's own voxel receives one RED from every warp chunk of the pair (K ~ rays / 32), each RED into an
     accumulator above 2^24 rounds by up to half an ulp (2^-24 relative), and the roundings add up like a random walk, ~0.3 * 2^-24 *
     sqrt(K): ~5e-6 for a 1080p pair (measured 3.1e-6 ... 7.3e-6 over the round's runs, lean2 and lean4), ~1e-5 for a 4K pair
@@ -70,7 +69,8 @@ def _check(case, got_f32, ref, exact_from_gpu_fixed, n_rays):
     assert rep["reference_equals_exact_below_2p24"], rep
     assert rep["gpu_max_rel_err_vs_exact"] <= hot_tol(n_rays), rep
     re_, ge_ = rep["reference_max_rel_err_vs_exact"], rep["gpu_max_rel_err_vs_exact"]
-    assert rep["cells_at_or_above_2p24"] == 0 or ge_ <= re_, rep          # never further from the exact sum than the reference is
+    # where the reference's serial sum is clearly off (more than three tolerances), the GPU grid is the one closer to the exact sum
+    assert re_ <= 3 * hot_tol(n_rays) or ge_ <= re_, rep
     assert rep["max_rel_err_vs_reference_at_or_above_2p24"] <= (re_ + ge_) / (1.0 - re_) + 1e-7, rep     # |g - r| <= |g - e| + |e - r|, relative to r >= e (1 - re_)
     return rep
 
